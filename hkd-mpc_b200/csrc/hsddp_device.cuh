@@ -1,0 +1,641 @@
+// Device-side data layout and per-problem building blocks of the batched HS-DDP
+// solver.  One thread block owns one problem; every *_block function below is
+// executed by the whole block (kThreads threads) and contains block barriers, so
+// it must be called under block-uniform control flow.
+//
+// Reference functions restated here (all FP64, <double,24,24,0> instantiation):
+//   SinglePhase::hybrid_rollout      HSDDPSolver/source/SinglePhase.cpp:182-233
+//   SinglePhase::compute_cost        :236-262   (+ ReB/AL folding :370-378,402-411)
+//   SinglePhase::LQ_approximation    :265-296   (+ :381-394,414-426)
+//   SinglePhase::linear_rollout      :145-178
+//   MultiPhaseDDP::{hybrid_rollout,linear_rollout,compute_cost,LQ_approximation,
+//     update_nominal_trajectory,measure_dynamics_feasibility,update_AL_params,update_REB_params}
+//                                     HSDDPSolver/source/MultiPhaseDDP.cpp:20-95,431-448,487-529
+//   costs / constraints / reset map  HKDMPC/HKD-TrajOpt/{HKDCost.h,HKDCost.cpp,HKDConstraints.cpp,HKDReset.h}
+//   ReB / AL formulas and updates    HSDDPSolver/header/ConstraintsBase.h:168-263,349-399
+// The Riccati recursion lives in hsddp_sweep.cuh, the iteration control in hsddp_kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/hsddp_b200.h"
+#include "hkd_model.cuh"
+
+namespace hsddp {
+
+constexpr int kThreads = 128;
+constexpr int kWarps = kThreads / 32;
+constexpr int MAXPH = HSDDP_MAX_PHASES;
+
+// compact per-stage LQ record (doubles)
+constexpr int LQ_AT = 0;                     // [6][24] rows {0,1,2,6,7,8} of A - I
+constexpr int LQ_BT = LQ_AT + hkd::kAtSize;  // [3][12] rows {6,7,8} of B, GRF columns
+constexpr int LQ_LX = LQ_BT + hkd::kBtSize;  // [24]
+constexpr int LQ_LU = LQ_LX + 24;            // [24]
+constexpr int LQ_LUU = LQ_LU + 24;           // [4][3][3] ReB Hessian blocks per leg (dt folded in)
+constexpr int LQ_STRIDE = LQ_LUU + 36;       // 264
+// per-phase terminal record
+constexpr int TQ_PHIX = 0;   // [24]
+constexpr int TQ_HX = 24;    // [4][24] touchdown-constraint gradients, by leg
+constexpr int TQ_WH = 120;   // [4] AL Hessian weights sigma(1+h)+lambda (0: no constraint on that leg)
+constexpr int TQ_STRIDE = 128;
+
+struct DevSchedule {
+    int n_phases, n_stages, n_nodes, _pad;
+    int horizon[MAXPH];
+    int node_off[MAXPH];    // first state node of the phase
+    int stage_off[MAXPH];   // first control stage of the phase
+    unsigned cmask[MAXPH];  // contact bit mask of the phase
+    unsigned nmask[MAXPH];  // contact after the phase
+    long long ref_off;      // node offset of this schedule inside the concatenated reference arrays
+    double dt;
+};
+
+// solver scalars of one problem (MultiPhaseDDP.h:92-104) + bookkeeping
+struct SolverState {
+    double actual_cost, merit, feas, dV_1, dV_2;
+    double max_tconstr_prev, max_pconstr_prev, max_tconstr, max_pconstr, merit_rho;
+    double reg;
+    int rollout_ok, sweep_ok;
+};
+
+struct BatchPtrs {
+    int n_problems, max_stages, max_nodes, _pad;
+    const DevSchedule* sched;
+    const int* sched_id;
+    const double *xr, *ur, *prel, *xinit;  // concatenated over schedules, per node
+    double* x0;                            // [P][24]
+    // problem-major workspace
+    double *Xbar, *X, *Xsim_t, *Defect, *dX;  // [P][max_nodes][24]
+    double *Ubar, *U, *U_t, *dU;              // [P][max_stages][24]
+    double* K;                                // [P][max_stages][576]
+    double* lq;                               // [P][max_stages][LQ_STRIDE]
+    double* tq;                               // [P][MAXPH][TQ_STRIDE]
+    double* gcon;                             // [P][max_stages][20]
+    double* reb;                              // [P][max_stages][20][2]  (eps, delta)
+    double* hcon;                             // [P][MAXPH][4]
+    double* al;                               // [P][MAXPH][4][2]        (sigma, lambda)
+    double* g0h0;                             // [P][600] value gradient / Hessian at the first node
+    SolverState* state;                       // [P]
+    hsddp_info* info;                         // [P]
+    hsddp_iter_record* trace;                 // [P][HSDDP_TRACE_CAP]
+    unsigned long long* counters;             // [0] = sum over problems of (backward sweeps x stages)
+    int* work_counter;                        // dynamic problem queue of the persistent kernel
+    hsddp_constraint_params cp;
+};
+
+// Shared-memory working set of one block.
+struct __align__(16) Smem {
+    double H[576], Y[576], Z[576], Quu[576], Qux[576], Qxx[576];
+    double G[24], Gn[24], Qx[24], Qu[24], wu[24], dfc[24], vtmp[24], vtmp2[24];
+    double lq[LQ_STRIDE];
+    double red[kThreads];
+    DevSchedule sc;
+    SolverState st;
+    hsddp_constraint_params cp;
+    hsddp_options opt;
+    // per-problem base pointers
+    double *Xbar, *X, *Xsim_t, *Defect, *dX, *Ubar, *U, *U_t, *dU, *K, *lqg, *tq, *gcon, *reb, *hcon, *al, *g0h0;
+    const double *xr, *ur, *prel, *xinit, *x0;
+    int pid;
+    int flag;
+    int ibuf[4];
+    double dbuf[8];
+};
+
+// ---------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// block-wide reductions; result valid in every thread.  Contains barriers.
+template <int OP>  // 0 sum, 1 min, 2 max
+__device__ __forceinline__ double block_reduce(Smem& sm, double v) {
+    v = (OP == 0) ? warp_sum(v) : (OP == 1) ? warp_min(v) : warp_max(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm.red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = sm.red[0];
+#pragma unroll
+    for (int w = 1; w < kWarps; ++w) r = (OP == 0) ? r + sm.red[w] : (OP == 1) ? fmin(r, sm.red[w]) : fmax(r, sm.red[w]);
+    return r;
+}
+
+__device__ __forceinline__ void phase_of_stage(const DevSchedule& sc, int s, int& ph, int& k) {
+    ph = 0;
+    while (ph + 1 < sc.n_phases && s >= sc.stage_off[ph + 1]) ++ph;
+    k = s - sc.stage_off[ph];
+}
+__device__ __forceinline__ void phase_of_node(const DevSchedule& sc, int n, int& ph, int& k) {
+    ph = 0;
+    while (ph + 1 < sc.n_phases && n >= sc.node_off[ph + 1]) ++ph;
+    k = n - sc.node_off[ph];
+}
+
+// tracking weights (HKDCost.h:11-37)
+__device__ __forceinline__ double weight_Q(int j, unsigned cmask) {
+    switch (j) {
+        case 0: return 1; case 1: return 4; case 2: return 5; case 3: return 1; case 4: return 1; case 5: return 30;
+        case 6: case 7: case 8: return .2; case 9: return 4; case 10: return 1; case 11: return .5;
+        default: return .2 * (double)(1 - (int)((cmask >> ((j - 12) / 3)) & 1u));
+    }
+}
+__device__ __forceinline__ double weight_Qf(int j, unsigned cmask) {
+    double scale;
+    switch (j) {
+        case 2: scale = 2; break; case 5: scale = 20; break; case 6: case 7: case 8: scale = .3; break;
+        case 10: scale = 3; break; case 0: case 1: case 3: case 4: case 9: case 11: scale = 1; break;
+        default: scale = .01; break;
+    }
+    return (20 * scale) * weight_Q(j, cmask);
+}
+__device__ __forceinline__ double weight_R(int j) { return j < 12 ? .2 : .1; }
+// foot-placement regulariser weight 20*diag(3c, c, 0) (HKDCost.h:56-69)
+__device__ __forceinline__ double weight_foot(int l, int j, unsigned cmask) {
+    const double c = (double)((cmask >> l) & 1u);
+    return ((j == 0) ? 3 * c : (j == 1) ? c : 0.0) * 20;
+}
+// GRF friction-pyramid rows (HKDConstraints.cpp:17-24)
+__device__ __forceinline__ void grf_rows(double mu, double rows[5][3]) {
+    const double r[5][3] = {{0, 0, 1}, {-1, 0, mu}, {1, 0, mu}, {0, -1, mu}, {0, 1, mu}};
+    for (int i = 0; i < 5; ++i) for (int j = 0; j < 3; ++j) rows[i][j] = r[i][j];
+}
+
+__device__ inline void bind_problem(Smem& sm, const BatchPtrs& bp, int pid) {
+    if (threadIdx.x == 0) {
+        sm.pid = pid;
+        const size_t sn = (size_t)bp.max_nodes * 24, ss = (size_t)bp.max_stages * 24;
+        sm.Xbar = bp.Xbar + pid * sn; sm.X = bp.X + pid * sn; sm.Xsim_t = bp.Xsim_t + pid * sn;
+        sm.Defect = bp.Defect + pid * sn; sm.dX = bp.dX + pid * sn;
+        sm.Ubar = bp.Ubar + pid * ss; sm.U = bp.U + pid * ss; sm.U_t = bp.U_t + pid * ss; sm.dU = bp.dU + pid * ss;
+        sm.K = bp.K + (size_t)pid * bp.max_stages * 576;
+        sm.lqg = bp.lq + (size_t)pid * bp.max_stages * LQ_STRIDE;
+        sm.tq = bp.tq + (size_t)pid * MAXPH * TQ_STRIDE;
+        sm.gcon = bp.gcon + (size_t)pid * bp.max_stages * 20;
+        sm.reb = bp.reb + (size_t)pid * bp.max_stages * 40;
+        sm.hcon = bp.hcon + (size_t)pid * MAXPH * 4;
+        sm.al = bp.al + (size_t)pid * MAXPH * 8;
+        sm.g0h0 = bp.g0h0 + (size_t)pid * 600;
+        sm.x0 = bp.x0 + (size_t)pid * 24;
+        sm.cp = bp.cp;
+        sm.st = bp.state[pid];
+    }
+    const DevSchedule* src = bp.sched + bp.sched_id[pid];
+    const int nw = (int)(sizeof(DevSchedule) / sizeof(int));
+    for (int i = threadIdx.x; i < nw; i += kThreads) ((int*)&sm.sc)[i] = ((const int*)src)[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const size_t ro = (size_t)sm.sc.ref_off;
+        sm.xr = bp.xr + ro * 24; sm.ur = bp.ur + ro * 24; sm.prel = bp.prel + ro * 12; sm.xinit = bp.xinit + ro * 24;
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// reset map (HKDReset.h:41-75) — single thread
+// ---------------------------------------------------------------------------
+__device__ inline void resetmap_thread(const double* x, unsigned c, unsigned cn, double* xn) {
+    for (int i = 0; i < 24; ++i) xn[i] = x[i];
+    for (int l = 0; l < 4; ++l) {
+        const bool cl = (c >> l) & 1u, nl = (cn >> l) & 1u;
+        if (cl && !nl) { xn[12 + 3 * l] = 0.0; xn[13 + 3 * l] = -0.8; xn[14 + 3 * l] = 1.7; }
+        if (!cl && nl) {
+            double pf[3];
+            hkd::foot_position(x + 3, x, x + 12 + 3 * l, l, pf);
+            xn[12 + 3 * l] = 1.0 * pf[0]; xn[13 + 3 * l] = 1.0 * pf[1]; xn[14 + 3 * l] = 0.0 * pf[2];
+        }
+    }
+}
+
+// dense Px (HKDReset.h:78-136), column-major into P[576]
+__device__ inline void resetmap_partial_block(const double* x, unsigned c, unsigned cn, double* P) {
+    for (int e = threadIdx.x; e < 576; e += kThreads) P[e] = ((e % 24) == (e / 24)) ? 1.0 : 0.0;
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        const int l = threadIdx.x;
+        const bool cl = (c >> l) & 1u, nl = (cn >> l) & 1u;
+        if (cl && !nl)
+            for (int r = 0; r < 3; ++r) P[(12 + 3 * l + r) * 25] = 0.0;
+        if (!cl && nl) {
+            double Jc[18];
+            hkd::foot_jacobian_compact(x, x + 12 + 3 * l, l, Jc);
+            const double cmap[3] = {1.0, 1.0, 0.0};
+            for (int r = 0; r < 3; ++r) {
+                const int row = 12 + 3 * l + r;
+                for (int cc = 0; cc < 24; ++cc) P[row + 24 * cc] = 0.0;
+                for (int cc = 0; cc < 3; ++cc) {
+                    P[row + 24 * cc] = cmap[r] * Jc[r * 6 + cc];                     // d/d eul
+                    P[row + 24 * (3 + cc)] = cmap[r] * ((r == cc) ? 1.0 : 0.0);      // d/d pos
+                    P[row + 24 * (12 + 3 * l + cc)] = cmap[r] * Jc[r * 6 + 3 + cc];  // d/d qleg
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// hybrid rollout (MultiPhaseDDP::hybrid_rollout + SinglePhase::hybrid_rollout).
+// With multiple shooting every node is a shooting node (update_SS_config(horizon+1),
+// HKDProblem.cpp:104), so all stages are rolled out concurrently.  Pass 1 writes
+// trial controls / simulated states; the commit pass reproduces the reference's
+// partial-update semantics when a stage diverges.
+// ---------------------------------------------------------------------------
+__device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
+    const DevSchedule& sc = sm.sc;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = sc.n_stages;
+    double* wdx = sm.Y + 32 * warp;  // per-warp scratch
+    // (a) controls: U = (Ubar + eps dU) + K (X - Xbar), one warp per stage
+    for (int s = warp; s < N; s += kWarps) {
+        int ph, k;
+        phase_of_stage(sc, s, ph, k);
+        const int n = sc.node_off[ph] + k;
+        if (lane < 24) {
+            const double xb = sm.Xbar[24 * n + lane];
+            const double x = xb + eps * sm.dX[24 * n + lane];
+            wdx[lane] = x - xb;
+        }
+        __syncwarp();
+        if (lane < 24) {
+            const double* Kk = sm.K + 576 * (size_t)s;
+            double acc = 0.0;
+#pragma unroll 8
+            for (int j = 0; j < 24; ++j) acc += Kk[lane + 24 * j] * wdx[j];
+            sm.U_t[24 * s + lane] = (sm.Ubar[24 * s + lane] + eps * sm.dU[24 * s + lane]) + acc;
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    // (b) dynamics, one thread per stage; phase-initial simulated states
+    int first_bad = 0x7fffffff;
+    for (int s = tid; s < N; s += kThreads) {
+        int ph, k;
+        phase_of_stage(sc, s, ph, k);
+        const int n = sc.node_off[ph] + k;
+        double x[24], u[24], xn[24];
+#pragma unroll
+        for (int j = 0; j < 24; ++j) { x[j] = sm.Xbar[24 * n + j] + eps * sm.dX[24 * n + j]; u[j] = sm.U_t[24 * s + j]; }
+        hkd::dynamics(x, u, sc.dt, sc.cmask[ph], xn);
+        double nrm2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 24; ++j) { nrm2 += xn[j] * xn[j]; sm.Xsim_t[24 * (n + 1) + j] = xn[j]; }
+        if (sqrt(nrm2) > 1e6) first_bad = min(first_bad, s);
+    }
+    if (tid < sc.n_phases) {
+        const int ph = tid;
+        double xi[24];
+        if (ph == 0) {
+            for (int j = 0; j < 24; ++j) xi[j] = sm.x0[j];
+        } else {
+            const int ne = sc.node_off[ph - 1] + sc.horizon[ph - 1];
+            double xe[24];
+            for (int j = 0; j < 24; ++j) xe[j] = sm.Xbar[24 * ne + j] + eps * sm.dX[24 * ne + j];
+            resetmap_thread(xe, sc.cmask[ph - 1], sc.nmask[ph - 1], xi);
+        }
+        for (int j = 0; j < 24; ++j) sm.Xsim_t[24 * sc.node_off[ph] + j] = xi[j];
+    }
+    // first diverged stage in the reference's sequential order
+    const int bad = (int)block_reduce<1>(sm, (double)first_bad);
+    int bad_ph = sc.n_phases, bad_k = 0;
+    if (bad != 0x7fffffff) phase_of_stage(sc, bad, bad_ph, bad_k);
+    // (c) commit exactly what the sequential reference would have written
+    for (int e = tid; e < sc.n_nodes * 24; e += kThreads) {
+        const int n = e / 24;
+        int ph, k;
+        phase_of_node(sc, n, ph, k);
+        if (ph < bad_ph || (ph == bad_ph && k <= bad_k)) {
+            const double x = sm.Xbar[e] + eps * sm.dX[e];
+            sm.X[e] = x;
+            if (ph < bad_ph) sm.Defect[e] = sm.Xsim_t[e] - x;  // compute_defect only after a complete phase
+        }
+    }
+    double gmin = 0.0;
+    const double mu = sm.cp.mu;
+    for (int e = tid; e < N * 24; e += kThreads) {
+        const int s = e / 24;
+        int ph, k;
+        phase_of_stage(sc, s, ph, k);
+        if (ph < bad_ph || (ph == bad_ph && k <= bad_k)) sm.U[e] = sm.U_t[e];
+    }
+    for (int e = tid; e < N * 4; e += kThreads) {  // GRFConstraint::compute_violation, one (stage, leg) per thread
+        const int s = e >> 2, l = e & 3;
+        int ph, k;
+        phase_of_stage(sc, s, ph, k);
+        if (((sc.cmask[ph] >> l) & 1u) && (ph < bad_ph || (ph == bad_ph && k < bad_k))) {
+            const double fx = sm.U_t[24 * s + 3 * l], fy = sm.U_t[24 * s + 3 * l + 1], fz = sm.U_t[24 * s + 3 * l + 2];
+            double* g = sm.gcon + 20 * s + 5 * l;
+            g[0] = fz; g[1] = -fx + mu * fz; g[2] = fx + mu * fz; g[3] = -fy + mu * fz; g[4] = fy + mu * fz;
+            if (ph < bad_ph) gmin = fmin(gmin, fmin(fmin(fmin(g[0], g[1]), fmin(g[2], g[3])), g[4]));
+        }
+    }
+    double hmax = 0.0;
+    if (tid < sc.n_phases * 4) {  // TouchDownConstraint::compute_violation
+        const int ph = tid >> 2, l = tid & 3;
+        const bool td = !((sc.cmask[ph] >> l) & 1u) && ((sc.nmask[ph] >> l) & 1u);
+        if (td && ph < bad_ph) {
+            const int ne = sc.node_off[ph] + sc.horizon[ph];
+            double xe[24], pf[3];
+            for (int j = 0; j < 24; ++j) xe[j] = sm.Xbar[24 * ne + j] + eps * sm.dX[24 * ne + j];
+            hkd::foot_position(xe + 3, xe, xe + 12 + 3 * l, l, pf);
+            sm.hcon[4 * ph + l] = pf[2] - 0.0;
+            hmax = fabs(pf[2]);
+        }
+    }
+    const double gm = block_reduce<1>(sm, gmin);
+    const double hm = block_reduce<2>(sm, hmax);
+    if (tid == 0) {
+        sm.st.actual_cost = 0.0;
+        sm.st.max_pconstr = gm;
+        sm.st.max_tconstr = hm;
+        sm.st.rollout_ok = (bad_ph == sc.n_phases);
+    }
+    __syncthreads();
+    return bad_ph == sc.n_phases;
+}
+
+// ---------------------------------------------------------------------------
+// compute_cost + measure_dynamics_feasibility (MultiPhaseDDP.cpp:431-439,514-529)
+// ---------------------------------------------------------------------------
+__device__ inline void foot_rel_error(const double* x, const double* prel_r, double d[12]) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) d[3 * l + j] = (x[12 + 3 * l + j] - x[3 + j]) - prel_r[3 * l + j];
+}
+
+__device__ inline void compute_cost_block(Smem& sm) {
+    const DevSchedule& sc = sm.sc;
+    const int tid = threadIdx.x;
+    const int N = sc.n_stages;
+    const double dt = sc.dt;
+    double csum = 0.0;
+    for (int s = tid; s < N; s += kThreads) {
+        int ph, k;
+        phase_of_stage(sc, s, ph, k);
+        const int n = sc.node_off[ph] + k;
+        const unsigned cm = sc.cmask[ph];
+        const double* x = sm.X + 24 * n;
+        const double* u = sm.U + 24 * s;
+        const double* xr = sm.xr + 24 * n;
+        const double* ur = sm.ur + 24 * n;
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 24; ++j) { const double dx = x[j] - xr[j]; s1 += (0.5 * dx * weight_Q(j, cm)) * dx; }
+#pragma unroll
+        for (int j = 0; j < 24; ++j) { const double du = u[j] - ur[j]; s2 += (0.5 * du * weight_R(j)) * du; }
+        double l = (s1 + s2) * dt;
+        double d[12];
+        foot_rel_error(x, sm.prel + 12 * n, d);
+        double lf = 0.0;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) lf += (.5 * d[j] * weight_foot(j / 3, j % 3, cm)) * d[j];
+        l += lf * dt;
+        if (sm.opt.ReB_active && cm) {  // compute_ReB_cost, ConstraintsBase.h:204-222
+            double reb_cost = 0.0;
+            for (int ll = 0; ll < 4; ++ll) {
+                if (!((cm >> ll) & 1u)) continue;
+                for (int r = 0; r < 5; ++r) {
+                    const double g = sm.gcon[20 * s + 5 * ll + r];
+                    const double eps_b = sm.reb[40 * s + 2 * (5 * ll + r)], delta = sm.reb[40 * s + 2 * (5 * ll + r) + 1];
+                    double barr;
+                    if (g > delta) barr = -log(g);
+                    else { const double z = (g - 2 * delta) / delta; barr = .5 * (z * z - 1); barr -= log(delta); }
+                    reb_cost += eps_b * barr;
+                }
+            }
+            l += dt * reb_cost;
+        }
+        csum += l;
+    }
+    if (tid < sc.n_phases) {  // terminal cost of each phase
+        const int ph = tid;
+        const unsigned cm = sc.cmask[ph];
+        const int n = sc.node_off[ph] + sc.horizon[ph];
+        const double* x = sm.X + 24 * n;
+        const double* xr = sm.xr + 24 * n;
+        double s1 = 0.0;
+        for (int j = 0; j < 24; ++j) { const double dx = x[j] - xr[j]; s1 += (dx * weight_Qf(j, cm)) * dx; }
+        double Phi = 0.5 * s1;
+        double d[12];
+        foot_rel_error(x, sm.prel + 12 * n, d);
+        double sf = 0.0;
+        for (int j = 0; j < 12; ++j) sf += (10 * d[j] * weight_foot(j / 3, j % 3, cm)) * d[j];
+        Phi += sf;
+        if (sm.opt.AL_active) {  // compute_AL_cost, ConstraintsBase.h:374-385
+            double al_cost = 0.0;
+            for (int l = 0; l < 4; ++l) {
+                const bool td = !((cm >> l) & 1u) && ((sc.nmask[ph] >> l) & 1u);
+                if (!td) continue;
+                const double h = sm.hcon[4 * ph + l], sigma = sm.al[8 * ph + 2 * l], lambda = sm.al[8 * ph + 2 * l + 1];
+                al_cost += 0.5 * sigma * h * h;
+                al_cost += lambda * h;
+            }
+            Phi += al_cost;
+        }
+        csum += Phi;
+    }
+    double dsum = 0.0;
+    for (int e = tid; e < sc.n_nodes * 24; e += kThreads) { const double d = sm.Defect[e]; dsum += d * d; }
+    const double cost = block_reduce<0>(sm, csum);
+    const double f2 = block_reduce<0>(sm, dsum);
+    if (tid == 0) { sm.st.actual_cost = cost; sm.st.feas = sqrt(f2); }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// LQ_approximation: one thread per stage writes the compact record; one thread per
+// phase the terminal record.
+// ---------------------------------------------------------------------------
+__device__ inline void lq_approximation_block(Smem& sm) {
+    const DevSchedule& sc = sm.sc;
+    const int tid = threadIdx.x;
+    const int N = sc.n_stages;
+    const double dt = sc.dt;
+    for (int s = tid; s < N; s += kThreads) {
+        int ph, k;
+        phase_of_stage(sc, s, ph, k);
+        const int n = sc.node_off[ph] + k;
+        const unsigned cm = sc.cmask[ph];
+        double x[24], u[24];
+#pragma unroll
+        for (int j = 0; j < 24; ++j) { x[j] = sm.X[24 * n + j]; u[j] = sm.U[24 * s + j]; }
+        double* rec = sm.lqg + (size_t)s * LQ_STRIDE;
+        hkd::dynamics_partial_compact(x, u, dt, cm, rec + LQ_AT, rec + LQ_BT);
+        const double* xr = sm.xr + 24 * n;
+        const double* ur = sm.ur + 24 * n;
+        double lx[24], lu[24];
+#pragma unroll
+        for (int j = 0; j < 24; ++j) {
+            lx[j] = (dt * weight_Q(j, cm)) * (x[j] - xr[j]);
+            lu[j] = (dt * weight_R(j)) * (u[j] - ur[j]);
+        }
+        double d[12];
+        foot_rel_error(x, sm.prel + 12 * n, d);
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const double c = (double)((cm >> l) & 1u);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const double w = dt * c * weight_foot(l, j, cm);
+                lx[3 + j] += -(w * d[3 * l + j]);
+                lx[12 + 3 * l + j] += w * d[3 * l + j];
+            }
+        }
+        // ReB folding (compute_ReB_partials, ConstraintsBase.h:224-263); only gu is non-zero
+        double rows[5][3];
+        grf_rows(sm.cp.mu, rows);
+        for (int l = 0; l < 4; ++l) {
+            double hess[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, grad[3] = {0, 0, 0};
+            if (sm.opt.ReB_active && ((cm >> l) & 1u)) {
+                for (int r = 0; r < 5; ++r) {
+                    const double g = sm.gcon[20 * s + 5 * l + r];
+                    const double eps_b = sm.reb[40 * s + 2 * (5 * l + r)], delta = sm.reb[40 * s + 2 * (5 * l + r) + 1];
+                    double bd, bdd;
+                    if (g > delta) { bd = -1.0 / g; bdd = 1.0 / (g * g); }
+                    else { bd = (g - 2 * delta) / delta / delta; bdd = 1.0 / (delta * delta); }
+                    for (int a = 0; a < 3; ++a) grad[a] += eps_b * bd * rows[r][a];
+                    for (int a = 0; a < 3; ++a)
+                        for (int b = 0; b < 3; ++b) hess[3 * a + b] += eps_b * (bdd * rows[r][a] * rows[r][b]);
+                }
+            }
+            for (int a = 0; a < 3; ++a) lu[3 * l + a] += dt * grad[a];
+            for (int a = 0; a < 9; ++a) rec[LQ_LUU + 9 * l + a] = dt * hess[a];
+        }
+#pragma unroll
+        for (int j = 0; j < 24; ++j) { rec[LQ_LX + j] = lx[j]; rec[LQ_LU + j] = lu[j]; }
+    }
+    if (tid < sc.n_phases) {
+        const int ph = tid;
+        const unsigned cm = sc.cmask[ph];
+        const int n = sc.node_off[ph] + sc.horizon[ph];
+        const double* x = sm.X + 24 * n;
+        const double* xr = sm.xr + 24 * n;
+        double* rec = sm.tq + ph * TQ_STRIDE;
+        double phix[24];
+        for (int j = 0; j < 24; ++j) phix[j] = weight_Qf(j, cm) * (x[j] - xr[j]);
+        double d[12];
+        foot_rel_error(x, sm.prel + 12 * n, d);
+        for (int l = 0; l < 4; ++l) {
+            const double c = (double)((cm >> l) & 1u);
+            for (int j = 0; j < 3; ++j) {
+                const double w = 20 * c * weight_foot(l, j, cm);
+                phix[3 + j] += -(w * d[3 * l + j]);
+                phix[12 + 3 * l + j] += w * d[3 * l + j];
+            }
+        }
+        for (int l = 0; l < 4; ++l) {
+            double* hx = rec + TQ_HX + 24 * l;
+            for (int j = 0; j < 24; ++j) hx[j] = 0.0;
+            rec[TQ_WH + l] = 0.0;
+            const bool td = !((cm >> l) & 1u) && ((sc.nmask[ph] >> l) & 1u);
+            if (td && sm.opt.AL_active) {
+                double Jc[18];
+                hkd::foot_jacobian_compact(x, x + 12 + 3 * l, l, Jc);
+                for (int c = 0; c < 3; ++c) { hx[c] = Jc[2 * 6 + c]; hx[12 + 3 * l + c] = Jc[2 * 6 + 3 + c]; }
+                hx[5] = 1.0;
+                const double h = sm.hcon[4 * ph + l], sigma = sm.al[8 * ph + 2 * l], lambda = sm.al[8 * ph + 2 * l + 1];
+                const double wg = sigma * h + lambda;
+                for (int j = 0; j < 24; ++j) phix[j] += wg * hx[j];
+                rec[TQ_WH + l] = sigma * (1 + h) + lambda;  // Q3
+            }
+        }
+        for (int j = 0; j < 24; ++j) rec[TQ_PHIX + j] = phix[j];
+    }
+    __syncthreads();
+}
+
+// running-cost Hessian lxx(i,j) of a phase: dt*Q on the diagonal + the foot regulariser block
+__device__ __forceinline__ double lxx_entry(int i, int j, unsigned cm, double scale_track, double scale_foot, bool terminal) {
+    double v = 0.0;
+    if (i == j) v = terminal ? weight_Qf(i, cm) : scale_track * weight_Q(i, cm);
+    // foot block: rows/cols {3,4,5} and {12+3l+jj}
+    if (i >= 3 && i < 6) {
+        const int jj = i - 3;
+        if (j == i) { for (int l = 0; l < 4; ++l) { const double c = (double)((cm >> l) & 1u); v += (scale_foot * c * weight_foot(l, jj, cm)) * c; } }
+        else if (j >= 12 && (j - 12) % 3 == jj) { const int l = (j - 12) / 3; const double c = (double)((cm >> l) & 1u); v += -((scale_foot * c * weight_foot(l, jj, cm)) * c); }
+    } else if (i >= 12) {
+        const int l = (i - 12) / 3, jj = (i - 12) % 3;
+        const double c = (double)((cm >> l) & 1u);
+        if (j == i) v += (scale_foot * c * weight_foot(l, jj, cm)) * c;
+        else if (j == 3 + jj) v += -((scale_foot * c * weight_foot(l, jj, cm)) * c);
+    }
+    return v;
+}
+
+// ---------------------------------------------------------------------------
+// update_nominal_trajectory (TrajectoryManagement.cpp:110-115)
+// ---------------------------------------------------------------------------
+__device__ inline void update_nominal_block(Smem& sm) {
+    for (int e = threadIdx.x; e < sm.sc.n_nodes * 24; e += kThreads) sm.Xbar[e] = sm.X[e];
+    for (int e = threadIdx.x; e < sm.sc.n_stages * 24; e += kThreads) sm.Ubar[e] = sm.U[e];
+    __syncthreads();
+}
+
+// update_AL_params / update_REB_params (ConstraintsBase.h:168-183,349-365)
+__device__ inline void update_al_block(Smem& sm) {
+    const DevSchedule& sc = sm.sc;
+    if (threadIdx.x < sc.n_phases * 4) {
+        const int ph = threadIdx.x >> 2, l = threadIdx.x & 3;
+        const bool td = !((sc.cmask[ph] >> l) & 1u) && ((sc.nmask[ph] >> l) & 1u);
+        if (td) {
+            const double h = sm.hcon[4 * ph + l];
+            double& sigma = sm.al[8 * ph + 2 * l];
+            double& lambda = sm.al[8 * ph + 2 * l + 1];
+            if (!(fabs(h) < sm.opt.tconstr_thresh)) {
+                if (fabs(h) > 0.005) { sigma *= sm.opt.update_penalty; sigma = fmin(sigma, sm.cp.td_sigma_max); }
+                else lambda += h * sigma;
+            }
+        }
+    }
+    __syncthreads();
+}
+__device__ inline void update_reb_block(Smem& sm) {
+    const DevSchedule& sc = sm.sc;
+    for (int e = threadIdx.x; e < sc.n_stages * 20; e += kThreads) {
+        const int s = e / 20, l = (e % 20) / 5;
+        int ph, k;
+        phase_of_stage(sc, s, ph, k);
+        if (!((sc.cmask[ph] >> l) & 1u)) continue;
+        if (sm.gcon[e] > -sm.opt.pconstr_thresh) continue;
+        sm.reb[2 * e] *= sm.opt.update_ReB;
+        double delta = sm.reb[2 * e + 1] * sm.opt.update_relax;
+        sm.reb[2 * e + 1] = fmax(delta, sm.cp.grf_delta_min);
+    }
+    __syncthreads();
+}
+
+// cold start (HKDProblem.cpp:84-90, TrajectoryManagement.cpp:11-32, constraint initialize_params)
+__device__ inline void cold_start_block(Smem& sm) {
+    const DevSchedule& sc = sm.sc;
+    for (int e = threadIdx.x; e < sc.n_nodes * 24; e += kThreads) {
+        const double v = sm.xinit[e];
+        sm.Xbar[e] = v; sm.X[e] = v; sm.dX[e] = 0.0; sm.Defect[e] = 0.0; sm.Xsim_t[e] = 0.0;
+    }
+    for (int e = threadIdx.x; e < sc.n_stages * 24; e += kThreads) { sm.Ubar[e] = 0.0; sm.U[e] = 0.0; sm.dU[e] = 0.0; sm.U_t[e] = 0.0; }
+    for (size_t e = threadIdx.x; e < (size_t)sc.n_stages * 576; e += kThreads) sm.K[e] = 0.0;
+    for (int e = threadIdx.x; e < sc.n_stages * 20; e += kThreads) {
+        sm.gcon[e] = 0.0; sm.reb[2 * e] = sm.cp.grf_eps; sm.reb[2 * e + 1] = sm.cp.grf_delta;
+    }
+    for (int e = threadIdx.x; e < MAXPH * 4; e += kThreads) { sm.hcon[e] = 0.0; sm.al[2 * e] = sm.cp.td_sigma; sm.al[2 * e + 1] = sm.cp.td_lambda; }
+    if (threadIdx.x == 0) {
+        SolverState z = {};
+        z.rollout_ok = 1; z.sweep_ok = 1;
+        sm.st = z;
+    }
+    __syncthreads();
+}
+
+}  // namespace hsddp

@@ -1,0 +1,691 @@
+// Kernels, iteration control and the C ABI of the batched HS-DDP solver (sm_100a).
+//
+//   MultiPhaseDDP::solve            HSDDPSolver/source/MultiPhaseDDP.cpp:232-428  -> solve_block / k_solve
+//   MultiPhaseDDP::line_search      :98-138                                       -> line_search_block
+//   step-level public methods       HSDDPSolver/header/MultiPhaseDDP.h:42-69      -> k_step<OP>
+// One thread block per problem; k_solve is persistent (blocks pull problem indices
+// from a device-side queue so problems with few iterations retire early).
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "hsddp_device.cuh"
+#include "hsddp_sweep.cuh"
+
+namespace hsddp {
+
+// ---------------------------------------------------------------------------
+// iteration control
+// ---------------------------------------------------------------------------
+__device__ inline void prepare_merit_block(Smem& sm) {  // MultiPhaseDDP.cpp:331-337 (Q5)
+    if (threadIdx.x == 0) {
+        SolverState& st = sm.st;
+        const double dV_abs = fabs(st.dV_1 + 0.5 * st.dV_2);
+        st.merit_rho = (st.feas > sm.opt.dynamics_feas_thresh) ? dV_abs / ((1 - sm.opt.merit_scale) * st.feas) + sm.opt.merit_offset : 0;
+        st.merit = st.actual_cost + st.merit_rho * st.feas;
+    }
+    __syncthreads();
+}
+
+// MultiPhaseDDP::line_search.  Returns success; eps_out = accepted step (0 if none).
+__device__ inline bool line_search_block(Smem& sm, double& eps_out, int& n_trials) {
+    double eps = 1;
+    const double merit_prev = sm.st.merit;
+    const double feas_prev = sm.st.feas;
+    const double merit_rho = sm.st.merit_rho;
+    const double dV_1 = sm.st.dV_1, dV_2 = sm.st.dV_2;
+    bool success = false;
+    n_trials = 0;
+    __syncthreads();
+    while (eps > 1e-3) {  // 1, .1, .010000000000000002, .0010000000000000002 (Q6)
+        const bool rollout_success = hybrid_rollout_block(sm, eps);
+        compute_cost_block(sm);
+        const double merit = sm.st.actual_cost + merit_rho * sm.st.feas;
+        ++n_trials;
+        const double exp_cost_change = eps * dV_1 + 0.5 * eps * eps * dV_2;
+        const double exp_merit_change = exp_cost_change - eps * merit_rho * feas_prev;
+        __syncthreads();
+        if (threadIdx.x == 0) sm.st.merit = merit;
+        __syncthreads();
+        if ((merit <= merit_prev + sm.opt.gamma * exp_merit_change) && rollout_success) { success = true; break; }
+        eps *= sm.opt.alpha;
+    }
+    eps_out = success ? eps : 0.0;
+    return success;
+}
+
+__device__ inline void solve_block(Smem& sm, const BatchPtrs& bp) {
+    const int tid = threadIdx.x;
+    const hsddp_options opt = sm.opt;
+    hsddp_iter_record* trace = bp.trace + (size_t)sm.pid * HSDDP_TRACE_CAP;
+    int iter = 0, iter_ou = 0, iter_in = 0, n_sweeps_total = 0, n_trials_total = 0;
+    int status = HSDDP_STATUS_MAX_ITER;
+    bool success = true;
+    if (tid == 0) {
+        sm.st.actual_cost = 0; sm.st.max_pconstr = 0; sm.st.max_pconstr_prev = 0; sm.st.max_tconstr = 0; sm.st.max_tconstr_prev = 0;
+    }
+    __syncthreads();
+    hybrid_rollout_block(sm, 0.0);
+    update_nominal_block(sm);
+    compute_cost_block(sm);
+    const double cost0 = sm.st.actual_cost, feas0 = sm.st.feas;
+
+    while (iter_ou < opt.max_AL_iter) {
+        iter_ou++;
+        __syncthreads();
+        if (tid == 0) { sm.st.max_tconstr_prev = sm.st.max_tconstr; sm.st.max_pconstr_prev = sm.st.max_pconstr; sm.st.reg = 0; }
+        __syncthreads();
+        iter_in = 0;
+        while (iter_in < opt.max_DDP_iter) {
+            compute_cost_block(sm);
+            iter_in++; iter++;
+            hsddp_iter_record rec;
+            rec.outer = iter_ou; rec.inner = iter_in; rec.cost_before = sm.st.actual_cost; rec.feas_before = sm.st.feas;
+            rec.dV_1 = rec.dV_2 = rec.merit_rho = rec.eps_accepted = rec.n_trials = 0; rec._pad = 0;
+            rec.cost_after = rec.feas_after = rec.max_tconstr = rec.max_pconstr = 0;
+
+            lq_approximation_block(sm);
+            int nsw = 0;
+            success = backward_sweep_regularized_block(sm, nsw);
+            n_sweeps_total += nsw;
+            rec.n_sweeps = nsw; rec.reg_after = sm.st.reg;
+            if (!success) {
+                if (tid == 0 && iter <= HSDDP_TRACE_CAP) trace[iter - 1] = rec;
+                goto bad_solve;
+            }
+            if (opt.MS) linear_rollout_block(sm, 1.0);
+            prepare_merit_block(sm);
+            {
+                const double cost_prev = sm.st.actual_cost, merit_prev = sm.st.merit;
+                const double dV_abs = fabs(sm.st.dV_1 + 0.5 * sm.st.dV_2);
+                rec.dV_1 = sm.st.dV_1; rec.dV_2 = sm.st.dV_2; rec.merit_rho = sm.st.merit_rho;
+                if ((dV_abs < opt.cost_thresh) && (sm.st.feas <= opt.dynamics_feas_thresh)) {
+                    rec.eps_accepted = -1; rec.n_trials = 0;
+                    rec.cost_after = sm.st.actual_cost; rec.feas_after = sm.st.feas; rec.max_tconstr = sm.st.max_tconstr; rec.max_pconstr = sm.st.max_pconstr;
+                    if (tid == 0 && iter <= HSDDP_TRACE_CAP) trace[iter - 1] = rec;
+                    break;
+                }
+                double eps_acc = 0;
+                int ntr = 0;
+                if (line_search_block(sm, eps_acc, ntr)) {
+                    update_nominal_block(sm);
+                } else {  // Q2: only the scalars are restored
+                    __syncthreads();
+                    if (tid == 0) { sm.st.actual_cost = cost_prev; sm.st.merit = merit_prev; }
+                    __syncthreads();
+                }
+                n_trials_total += ntr;
+                rec.eps_accepted = eps_acc; rec.n_trials = ntr;
+                rec.cost_after = sm.st.actual_cost; rec.feas_after = sm.st.feas; rec.max_tconstr = sm.st.max_tconstr; rec.max_pconstr = sm.st.max_pconstr;
+                if (tid == 0 && iter <= HSDDP_TRACE_CAP) trace[iter - 1] = rec;
+                if ((fabs((cost_prev - sm.st.actual_cost) / cost_prev) < opt.cost_thresh) && (sm.st.feas <= opt.dynamics_feas_thresh)) break;
+            }
+        }
+        if (opt.AL_active) update_al_block(sm);
+        if (opt.ReB_active) update_reb_block(sm);
+        {
+            const SolverState& st = sm.st;
+            if (st.max_tconstr < opt.tconstr_thresh && fabs(st.max_pconstr) < opt.pconstr_thresh && st.feas <= opt.dynamics_feas_thresh) { status = HSDDP_STATUS_CONVERGED; break; }
+            if (fabs(st.max_tconstr - st.max_tconstr_prev) < 0.0001 && fabs(st.max_pconstr - st.max_pconstr_prev) < 0.0001 && st.feas <= opt.dynamics_feas_thresh) { status = HSDDP_STATUS_STALLED; break; }
+        }
+    }
+bad_solve:
+    if (!success) status = HSDDP_STATUS_REG_OVERFLOW;
+    __syncthreads();
+    if (tid == 0) {
+        hsddp_info& info = bp.info[sm.pid];
+        info.status = status; info.n_iter = iter; info.n_outer = iter_ou; info.n_sweeps = n_sweeps_total; info.n_trials = n_trials_total; info._pad = 0;
+        info.cost = sm.st.actual_cost; info.feas = sm.st.feas; info.max_tconstr = sm.st.max_tconstr; info.max_pconstr = sm.st.max_pconstr;
+        info.cost0 = cost0; info.feas0 = feas0;
+        atomicAdd(bp.counters, (unsigned long long)n_sweeps_total * (unsigned long long)sm.sc.n_stages);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads) k_solve(BatchPtrs bp, hsddp_options opt, int cold_start) {
+    __shared__ Smem sm;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) sm.ibuf[3] = atomicAdd(bp.work_counter, 1);
+        __syncthreads();
+        const int pid = sm.ibuf[3];
+        if (pid >= bp.n_problems) break;
+        bind_problem(sm, bp, pid);
+        if (threadIdx.x == 0) sm.opt = opt;
+        __syncthreads();
+        if (cold_start) cold_start_block(sm);
+        solve_block(sm, bp);
+        if (threadIdx.x == 0) bp.state[pid] = sm.st;
+    }
+}
+
+enum StepOp { OP_RESET = 0, OP_ROLLOUT, OP_COST, OP_LQ, OP_SWEEP, OP_SWEEP_REG, OP_LINEAR, OP_MERIT, OP_FORWARD, OP_NOMINAL, OP_AL, OP_REB };
+
+// step-level kernel: one block per problem, state round-trips through HBM
+__global__ void __launch_bounds__(kThreads) k_step(BatchPtrs bp, hsddp_options opt, int op, double arg, double* darg, int* ok) {
+    __shared__ Smem sm;
+    const int pid = blockIdx.x;
+    bind_problem(sm, bp, pid);
+    if (threadIdx.x == 0) sm.opt = opt;
+    __syncthreads();
+    int okv = 1;
+    switch (op) {
+        case OP_RESET: cold_start_block(sm); break;
+        case OP_ROLLOUT: okv = hybrid_rollout_block(sm, arg) ? 1 : 0; break;
+        case OP_COST: compute_cost_block(sm); break;
+        case OP_LQ: lq_approximation_block(sm); break;
+        case OP_SWEEP: okv = backward_sweep_block(sm, arg) ? 1 : 0; break;
+        case OP_SWEEP_REG: {
+            if (threadIdx.x == 0) sm.st.reg = darg[pid];
+            __syncthreads();
+            int nsw;
+            okv = backward_sweep_regularized_block(sm, nsw) ? 1 : 0;
+            if (threadIdx.x == 0) darg[pid] = sm.st.reg;
+        } break;
+        case OP_LINEAR: linear_rollout_block(sm, arg); break;
+        case OP_MERIT: prepare_merit_block(sm); break;
+        case OP_FORWARD: {
+            const double cost_prev = sm.st.actual_cost, merit_prev = sm.st.merit;
+            double eps_acc; int ntr;
+            okv = line_search_block(sm, eps_acc, ntr) ? 1 : 0;
+            if (!okv) { __syncthreads(); if (threadIdx.x == 0) { sm.st.actual_cost = cost_prev; sm.st.merit = merit_prev; } }
+            if (threadIdx.x == 0 && darg) darg[pid] = eps_acc;
+        } break;
+        case OP_NOMINAL: update_nominal_block(sm); break;
+        case OP_AL: update_al_block(sm); break;
+        case OP_REB: update_reb_block(sm); break;
+        default: break;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { bp.state[pid] = sm.st; if (ok) ok[pid] = okv; }
+}
+
+// FP64 throughput probes (roofline denominators measured on the box)
+__global__ void k_dfma_probe(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+__global__ void k_dmma_probe(double* out, int iters) {
+    double c0[2] = {0, 0}, c1[2] = {0, 0}, c2[2] = {0, 0}, c3[2] = {0, 0};
+    const double a = 1.0 + threadIdx.x * 1e-6, b = 1.0 - threadIdx.x * 1e-6;
+    for (int i = 0; i < iters; ++i) {
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0[0]), "+d"(c0[1]) : "d"(a), "d"(b));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c1[0]), "+d"(c1[1]) : "d"(a), "d"(b));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c2[0]), "+d"(c2[1]) : "d"(a), "d"(b));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c3[0]), "+d"(c3[1]) : "d"(a), "d"(b));
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = c0[0] + c0[1] + c1[0] + c1[1] + c2[0] + c2[1] + c3[0] + c3[1];
+}
+
+}  // namespace hsddp
+
+// ===========================================================================
+// host side: the C ABI
+// ===========================================================================
+using namespace hsddp;
+
+static thread_local std::string g_last_error;
+const char* hsddp_last_error(void) { return g_last_error.c_str(); }
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            g_last_error = std::string(#call) + ": " + cudaGetErrorString(e_);                     \
+            return HSDDP_ERR_CUDA;                                                                 \
+        }                                                                                          \
+    } while (0)
+
+struct hsddp_batch {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int n_sm = 0, blocks_per_sm = 1;
+    BatchPtrs bp{};
+    std::vector<void*> allocs;
+    std::vector<DevSchedule> h_sched;
+    std::vector<int> h_sched_id;
+    bool has_problems = false;
+    bool cold = true;
+    float last_ms = 0.f;
+    int* d_ok = nullptr;
+    double* d_darg = nullptr;
+};
+
+namespace {
+
+template <class T>
+int dalloc(hsddp_batch* b, T** p, size_t n) {
+    void* q = nullptr;
+    CK(cudaMalloc(&q, n * sizeof(T)));
+    b->allocs.push_back(q);
+    *p = (T*)q;
+    return HSDDP_OK;
+}
+
+void free_problem_allocs(hsddp_batch* b) {
+    for (void* p : b->allocs) cudaFree(p);
+    b->allocs.clear();
+    b->has_problems = false;
+}
+
+hsddp_options default_options() {
+    hsddp_options o;
+    std::memset(&o, 0, sizeof o);
+    o.alpha = 0.1; o.gamma = 0.01; o.update_penalty = 5; o.update_relax = 1; o.update_regularization = 2; o.update_ReB = 1;
+    o.max_DDP_iter = 10; o.max_AL_iter = 5; o.cost_thresh = 1e-3; o.tconstr_thresh = 1e-3; o.pconstr_thresh = 1e-3;
+    o.dynamics_feas_thresh = 1e-3; o.merit_scale = 0.2; o.merit_offset = 1e2; o.AL_active = 1; o.ReB_active = 1; o.MS = 1;
+    return o;
+}
+
+int check_opt(const hsddp_options* opt) {
+    if (!opt) return HSDDP_OK;
+    if (!opt->MS) { g_last_error = "single shooting (MS = false) is not implemented: the reference ships MS = true"; return HSDDP_ERR_UNSUPPORTED; }
+    return HSDDP_OK;
+}
+
+int launch_step(hsddp_batch* b, const hsddp_options* opt, int op, double arg, double* darg_dev, int32_t* ok_host, bool sync = true) {
+    if (!b || !b->has_problems) { g_last_error = "no problems set"; return HSDDP_ERR_STATE; }
+    int rc = check_opt(opt);
+    if (rc) return rc;
+    CK(cudaSetDevice(b->device));
+    const hsddp_options o = opt ? *opt : default_options();
+    k_step<<<b->bp.n_problems, kThreads, 0, b->stream>>>(b->bp, o, op, arg, darg_dev, b->d_ok);
+    CK(cudaGetLastError());
+    if (ok_host) CK(cudaMemcpyAsync(ok_host, b->d_ok, sizeof(int) * b->bp.n_problems, cudaMemcpyDeviceToHost, b->stream));
+    if (sync || ok_host) CK(cudaStreamSynchronize(b->stream));
+    if (op != OP_RESET) b->cold = false;
+    return HSDDP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hsddp_batch_create(int device, hsddp_batch** out) {
+    if (!out) return HSDDP_ERR_ARG;
+    int n = 0;
+    CK(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) { g_last_error = "no such CUDA device (this library has no CPU fallback)"; return HSDDP_ERR_CUDA; }
+    CK(cudaSetDevice(device));
+    hsddp_batch* b = new hsddp_batch();
+    b->device = device;
+    CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&b->ev0));
+    CK(cudaEventCreate(&b->ev1));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    b->n_sm = prop.multiProcessorCount;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->blocks_per_sm, k_solve, kThreads, 0));
+    if (b->blocks_per_sm < 1) b->blocks_per_sm = 1;
+    *out = b;
+    return HSDDP_OK;
+}
+
+int hsddp_batch_destroy(hsddp_batch* b) {
+    if (!b) return HSDDP_OK;
+    cudaSetDevice(b->device);
+    free_problem_allocs(b);
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+    return HSDDP_OK;
+}
+
+int hsddp_batch_set_problems(hsddp_batch* b, int n_schedules, const hsddp_schedule* schedules, int n_problems,
+                             const int32_t* schedule_id, const hsddp_constraint_params* cparams) {
+    if (!b || n_schedules <= 0 || !schedules || n_problems <= 0 || !schedule_id) return HSDDP_ERR_ARG;
+    CK(cudaSetDevice(b->device));
+    free_problem_allocs(b);
+    // flatten schedules
+    b->h_sched.assign(n_schedules, DevSchedule{});
+    size_t total_nodes = 0;
+    int max_stages = 0, max_nodes = 0;
+    for (int i = 0; i < n_schedules; ++i) {
+        const hsddp_schedule& s = schedules[i];
+        if (s.n_phases < 1 || s.n_phases > MAXPH || s.n_stages > HSDDP_MAX_STAGES || !s.xr || !s.ur || !s.prel_r || !s.xinit) {
+            g_last_error = "invalid schedule";
+            return HSDDP_ERR_ARG;
+        }
+        DevSchedule& d = b->h_sched[i];
+        d.n_phases = s.n_phases; d.n_stages = s.n_stages; d.n_nodes = s.n_nodes; d.dt = s.dt; d.ref_off = (long long)total_nodes;
+        int no = 0, so = 0;
+        for (int p = 0; p < s.n_phases; ++p) {
+            if (s.horizon[p] < 1) { g_last_error = "phase with empty horizon"; return HSDDP_ERR_ARG; }
+            d.horizon[p] = s.horizon[p]; d.node_off[p] = no; d.stage_off[p] = so;
+            unsigned cm = 0, nm = 0;
+            for (int l = 0; l < 4; ++l) { cm |= (s.contact[p][l] ? 1u : 0u) << l; nm |= (s.next_contact[p][l] ? 1u : 0u) << l; }
+            d.cmask[p] = cm; d.nmask[p] = nm;
+            no += s.horizon[p] + 1; so += s.horizon[p];
+        }
+        if (no != s.n_nodes || so != s.n_stages) { g_last_error = "schedule node/stage counts inconsistent"; return HSDDP_ERR_ARG; }
+        total_nodes += (size_t)s.n_nodes;
+        max_stages = std::max(max_stages, s.n_stages);
+        max_nodes = std::max(max_nodes, s.n_nodes);
+    }
+    for (int i = 0; i < n_problems; ++i)
+        if (schedule_id[i] < 0 || schedule_id[i] >= n_schedules) { g_last_error = "schedule_id out of range"; return HSDDP_ERR_ARG; }
+    b->h_sched_id.assign(schedule_id, schedule_id + n_problems);
+
+    BatchPtrs& bp = b->bp;
+    std::memset(&bp, 0, sizeof bp);
+    bp.n_problems = n_problems; bp.max_stages = max_stages; bp.max_nodes = max_nodes;
+    if (cparams) bp.cp = *cparams;
+    else { bp.cp.grf_delta = 0.1; bp.cp.grf_delta_min = 0.1; bp.cp.grf_eps = 0.1; bp.cp.td_sigma = 50; bp.cp.td_sigma_max = 1e4; bp.cp.td_lambda = 0; bp.cp.mu = 0.7; }
+
+    std::vector<double> xr(total_nodes * 24), ur(total_nodes * 24), prel(total_nodes * 12), xinit(total_nodes * 24);
+    for (int i = 0; i < n_schedules; ++i) {
+        const hsddp_schedule& s = schedules[i];
+        const size_t o = (size_t)b->h_sched[i].ref_off, nn = (size_t)s.n_nodes;
+        std::memcpy(&xr[o * 24], s.xr, nn * 24 * sizeof(double));
+        std::memcpy(&ur[o * 24], s.ur, nn * 24 * sizeof(double));
+        std::memcpy(&prel[o * 12], s.prel_r, nn * 12 * sizeof(double));
+        std::memcpy(&xinit[o * 24], s.xinit, nn * 24 * sizeof(double));
+    }
+    DevSchedule* d_sched; int* d_sid; double *d_xr, *d_ur, *d_prel, *d_xinit;
+    int rc;
+    if ((rc = dalloc(b, &d_sched, (size_t)n_schedules))) return rc;
+    if ((rc = dalloc(b, &d_sid, (size_t)n_problems))) return rc;
+    if ((rc = dalloc(b, &d_xr, xr.size()))) return rc;
+    if ((rc = dalloc(b, &d_ur, ur.size()))) return rc;
+    if ((rc = dalloc(b, &d_prel, prel.size()))) return rc;
+    if ((rc = dalloc(b, &d_xinit, xinit.size()))) return rc;
+    CK(cudaMemcpy(d_sched, b->h_sched.data(), sizeof(DevSchedule) * n_schedules, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_sid, schedule_id, sizeof(int) * n_problems, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_xr, xr.data(), xr.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_ur, ur.data(), ur.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_prel, prel.data(), prel.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_xinit, xinit.data(), xinit.size() * sizeof(double), cudaMemcpyHostToDevice));
+    bp.sched = d_sched; bp.sched_id = d_sid; bp.xr = d_xr; bp.ur = d_ur; bp.prel = d_prel; bp.xinit = d_xinit;
+
+    const size_t P = (size_t)n_problems, SN = (size_t)max_nodes * 24, SS = (size_t)max_stages * 24;
+    if ((rc = dalloc(b, &bp.x0, P * 24))) return rc;
+    if ((rc = dalloc(b, &bp.Xbar, P * SN))) return rc;
+    if ((rc = dalloc(b, &bp.X, P * SN))) return rc;
+    if ((rc = dalloc(b, &bp.Xsim_t, P * SN))) return rc;
+    if ((rc = dalloc(b, &bp.Defect, P * SN))) return rc;
+    if ((rc = dalloc(b, &bp.dX, P * SN))) return rc;
+    if ((rc = dalloc(b, &bp.Ubar, P * SS))) return rc;
+    if ((rc = dalloc(b, &bp.U, P * SS))) return rc;
+    if ((rc = dalloc(b, &bp.U_t, P * SS))) return rc;
+    if ((rc = dalloc(b, &bp.dU, P * SS))) return rc;
+    if ((rc = dalloc(b, &bp.K, P * max_stages * 576))) return rc;
+    if ((rc = dalloc(b, &bp.lq, P * max_stages * LQ_STRIDE))) return rc;
+    if ((rc = dalloc(b, &bp.tq, P * MAXPH * TQ_STRIDE))) return rc;
+    if ((rc = dalloc(b, &bp.gcon, P * max_stages * 20))) return rc;
+    if ((rc = dalloc(b, &bp.reb, P * max_stages * 40))) return rc;
+    if ((rc = dalloc(b, &bp.hcon, P * MAXPH * 4))) return rc;
+    if ((rc = dalloc(b, &bp.al, P * MAXPH * 8))) return rc;
+    if ((rc = dalloc(b, &bp.g0h0, P * 600))) return rc;
+    if ((rc = dalloc(b, &bp.state, P))) return rc;
+    if ((rc = dalloc(b, &bp.info, P))) return rc;
+    if ((rc = dalloc(b, &bp.trace, P * HSDDP_TRACE_CAP))) return rc;
+    if ((rc = dalloc(b, &bp.counters, (size_t)4))) return rc;
+    if ((rc = dalloc(b, &bp.work_counter, (size_t)4))) return rc;
+    if ((rc = dalloc(b, &b->d_ok, P))) return rc;
+    if ((rc = dalloc(b, &b->d_darg, P))) return rc;
+    CK(cudaMemset(bp.x0, 0, P * 24 * sizeof(double)));
+    CK(cudaMemset(bp.info, 0, P * sizeof(hsddp_info)));
+    CK(cudaMemset(bp.trace, 0, P * HSDDP_TRACE_CAP * sizeof(hsddp_iter_record)));
+    CK(cudaMemset(bp.state, 0, P * sizeof(SolverState)));
+    CK(cudaMemset(bp.counters, 0, 4 * sizeof(unsigned long long)));
+    CK(cudaMemset(bp.tq, 0, P * MAXPH * TQ_STRIDE * sizeof(double)));
+    CK(cudaMemset(bp.lq, 0, P * max_stages * LQ_STRIDE * sizeof(double)));
+    CK(cudaMemset(bp.g0h0, 0, P * 600 * sizeof(double)));
+    b->has_problems = true;
+    return hsddp_batch_reset(b);
+}
+
+int hsddp_batch_set_initial_condition(hsddp_batch* b, const double* x0) {
+    if (!b || !b->has_problems || !x0) return HSDDP_ERR_ARG;
+    CK(cudaSetDevice(b->device));
+    CK(cudaMemcpyAsync(b->bp.x0, x0, sizeof(double) * 24 * b->bp.n_problems, cudaMemcpyHostToDevice, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return HSDDP_OK;
+}
+
+int hsddp_batch_reset(hsddp_batch* b) {
+    // queued on the handle's stream without a host synchronise, so reset + solve run back to back
+    int rc = launch_step(b, nullptr, OP_RESET, 0.0, nullptr, nullptr, false);
+    if (rc == HSDDP_OK) b->cold = true;
+    return rc;
+}
+
+int hsddp_batch_solve_async(hsddp_batch* b, const hsddp_options* opt) {
+    if (!b || !b->has_problems) { g_last_error = "no problems set"; return HSDDP_ERR_STATE; }
+    int rc = check_opt(opt);
+    if (rc) return rc;
+    CK(cudaSetDevice(b->device));
+    const hsddp_options o = opt ? *opt : default_options();
+    CK(cudaMemsetAsync(b->bp.work_counter, 0, sizeof(int), b->stream));
+    const int grid = std::min(b->bp.n_problems, b->n_sm * b->blocks_per_sm);
+    CK(cudaEventRecord(b->ev0, b->stream));
+    k_solve<<<grid, kThreads, 0, b->stream>>>(b->bp, o, 0);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(b->ev1, b->stream));
+    b->cold = false;
+    return HSDDP_OK;
+}
+
+int hsddp_batch_sync(hsddp_batch* b) {
+    if (!b) return HSDDP_ERR_ARG;
+    CK(cudaSetDevice(b->device));
+    CK(cudaStreamSynchronize(b->stream));
+    return HSDDP_OK;
+}
+
+int hsddp_batch_solve(hsddp_batch* b, const hsddp_options* opt) {
+    int rc = hsddp_batch_solve_async(b, opt);
+    if (rc) return rc;
+    return hsddp_batch_sync(b);
+}
+
+int hsddp_batch_last_solve_ms(hsddp_batch* b, float* ms) {
+    if (!b || !ms) return HSDDP_ERR_ARG;
+    CK(cudaSetDevice(b->device));
+    CK(cudaEventSynchronize(b->ev1));
+    CK(cudaEventElapsedTime(ms, b->ev0, b->ev1));
+    return HSDDP_OK;
+}
+
+int hsddp_batch_hybrid_rollout(hsddp_batch* b, double eps, const hsddp_options* opt, int32_t* ok) { return launch_step(b, opt, OP_ROLLOUT, eps, nullptr, ok); }
+int hsddp_batch_compute_cost(hsddp_batch* b, const hsddp_options* opt) { return launch_step(b, opt, OP_COST, 0, nullptr, nullptr); }
+int hsddp_batch_lq_approximation(hsddp_batch* b, const hsddp_options* opt) { return launch_step(b, opt, OP_LQ, 0, nullptr, nullptr); }
+int hsddp_batch_backward_sweep(hsddp_batch* b, double regularization, int32_t* ok) { return launch_step(b, nullptr, OP_SWEEP, regularization, nullptr, ok); }
+int hsddp_batch_backward_sweep_regularized(hsddp_batch* b, double* regularization, const hsddp_options* opt, int32_t* ok) {
+    if (!b || !b->has_problems || !regularization) return HSDDP_ERR_ARG;
+    CK(cudaSetDevice(b->device));
+    CK(cudaMemcpy(b->d_darg, regularization, sizeof(double) * b->bp.n_problems, cudaMemcpyHostToDevice));
+    int rc = launch_step(b, opt, OP_SWEEP_REG, 0, b->d_darg, ok);
+    if (rc) return rc;
+    CK(cudaMemcpy(regularization, b->d_darg, sizeof(double) * b->bp.n_problems, cudaMemcpyDeviceToHost));
+    return HSDDP_OK;
+}
+int hsddp_batch_linear_rollout(hsddp_batch* b, double eps, const hsddp_options* opt) { return launch_step(b, opt, OP_LINEAR, eps, nullptr, nullptr); }
+int hsddp_batch_prepare_merit(hsddp_batch* b, const hsddp_options* opt) { return launch_step(b, opt, OP_MERIT, 0, nullptr, nullptr); }
+int hsddp_batch_forward_sweep(hsddp_batch* b, const hsddp_options* opt, int32_t* ok, double* eps_accepted) {
+    int rc = launch_step(b, opt, OP_FORWARD, 0, b ? b->d_darg : nullptr, ok);
+    if (rc) return rc;
+    if (eps_accepted) CK(cudaMemcpy(eps_accepted, b->d_darg, sizeof(double) * b->bp.n_problems, cudaMemcpyDeviceToHost));
+    return HSDDP_OK;
+}
+int hsddp_batch_update_nominal(hsddp_batch* b) { return launch_step(b, nullptr, OP_NOMINAL, 0, nullptr, nullptr); }
+int hsddp_batch_update_al_params(hsddp_batch* b, const hsddp_options* opt) { return launch_step(b, opt, OP_AL, 0, nullptr, nullptr); }
+int hsddp_batch_update_reb_params(hsddp_batch* b, const hsddp_options* opt) { return launch_step(b, opt, OP_REB, 0, nullptr, nullptr); }
+
+int hsddp_batch_dims(hsddp_batch* b, int32_t* n_problems, int32_t* max_stages, int32_t* max_nodes) {
+    if (!b || !b->has_problems) return HSDDP_ERR_STATE;
+    if (n_problems) *n_problems = b->bp.n_problems;
+    if (max_stages) *max_stages = b->bp.max_stages;
+    if (max_nodes) *max_nodes = b->bp.max_nodes;
+    return HSDDP_OK;
+}
+
+int hsddp_batch_get_info(hsddp_batch* b, hsddp_info* out) {
+    if (!b || !b->has_problems || !out) return HSDDP_ERR_ARG;
+    CK(cudaSetDevice(b->device));
+    CK(cudaMemcpyAsync(out, b->bp.info, sizeof(hsddp_info) * b->bp.n_problems, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return HSDDP_OK;
+}
+
+int hsddp_batch_get_trace(hsddp_batch* b, hsddp_iter_record* out) {
+    if (!b || !b->has_problems || !out) return HSDDP_ERR_ARG;
+    CK(cudaSetDevice(b->device));
+    CK(cudaMemcpyAsync(out, b->bp.trace, sizeof(hsddp_iter_record) * HSDDP_TRACE_CAP * b->bp.n_problems, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return HSDDP_OK;
+}
+
+int hsddp_batch_get_scalars(hsddp_batch* b, double* out) {
+    if (!b || !b->has_problems || !out) return HSDDP_ERR_ARG;
+    CK(cudaSetDevice(b->device));
+    std::vector<SolverState> st(b->bp.n_problems);
+    CK(cudaMemcpy(st.data(), b->bp.state, sizeof(SolverState) * st.size(), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < st.size(); ++i) {
+        double* o = out + 8 * i;
+        o[0] = st[i].actual_cost; o[1] = st[i].merit; o[2] = st[i].feas; o[3] = st[i].dV_1; o[4] = st[i].dV_2;
+        o[5] = st[i].max_tconstr; o[6] = st[i].max_pconstr; o[7] = st[i].merit_rho;
+    }
+    return HSDDP_OK;
+}
+
+static int array_spec(hsddp_batch* b, int which, double** dev, size_t* per_problem) {
+    const BatchPtrs& bp = b->bp;
+    const size_t SN = (size_t)bp.max_nodes * 24, SS = (size_t)bp.max_stages * 24;
+    switch (which) {
+        case HSDDP_ARR_XBAR: *dev = bp.Xbar; *per_problem = SN; return 0;
+        case HSDDP_ARR_X: *dev = bp.X; *per_problem = SN; return 0;
+        case HSDDP_ARR_DEFECT: *dev = bp.Defect; *per_problem = SN; return 0;
+        case HSDDP_ARR_DX: *dev = bp.dX; *per_problem = SN; return 0;
+        case HSDDP_ARR_UBAR: *dev = bp.Ubar; *per_problem = SS; return 0;
+        case HSDDP_ARR_U: *dev = bp.U; *per_problem = SS; return 0;
+        case HSDDP_ARR_DU: *dev = bp.dU; *per_problem = SS; return 0;
+        case HSDDP_ARR_K: *dev = bp.K; *per_problem = (size_t)bp.max_stages * 576; return 0;
+        case HSDDP_ARR_GCON: *dev = bp.gcon; *per_problem = (size_t)bp.max_stages * 20; return 0;
+        case HSDDP_ARR_HCON: *dev = bp.hcon; *per_problem = (size_t)MAXPH * 4; return 0;
+        case HSDDP_ARR_AL: *dev = bp.al; *per_problem = (size_t)MAXPH * 8; return 0;
+        case HSDDP_ARR_G0: *dev = bp.g0h0; *per_problem = 600; return 1;  // strided special cases
+        case HSDDP_ARR_H0: *dev = bp.g0h0; *per_problem = 600; return 2;
+        default: return -1;
+    }
+}
+
+int hsddp_batch_get_array(hsddp_batch* b, int which, double* out) {
+    if (!b || !b->has_problems || !out) return HSDDP_ERR_ARG;
+    CK(cudaSetDevice(b->device));
+    const BatchPtrs& bp = b->bp;
+    const size_t P = (size_t)bp.n_problems;
+    if (which == HSDDP_ARR_A || which == HSDDP_ARR_B || which == HSDDP_ARR_LX || which == HSDDP_ARR_LU ||
+        which == HSDDP_ARR_LUU || which == HSDDP_ARR_LXX) {
+        // dense views reconstructed on the host from the compact LQ records
+        std::vector<double> lq(P * bp.max_stages * LQ_STRIDE);
+        CK(cudaMemcpy(lq.data(), bp.lq, lq.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        const bool vec = (which == HSDDP_ARR_LX || which == HSDDP_ARR_LU);
+        const size_t per = (size_t)bp.max_stages * (vec ? 24 : 576);
+        std::memset(out, 0, P * per * sizeof(double));
+        for (size_t p = 0; p < P; ++p) {
+            const DevSchedule& sc = b->h_sched[b->h_sched_id[p]];
+            for (int ph = 0; ph < sc.n_phases; ++ph)
+                for (int k = 0; k < sc.horizon[ph]; ++k) {
+                    const int s = sc.stage_off[ph] + k;
+                    const double* rec = &lq[(p * bp.max_stages + s) * LQ_STRIDE];
+                    double* o = out + p * per + (size_t)s * (vec ? 24 : 576);
+                    const unsigned cm = sc.cmask[ph];
+                    if (which == HSDDP_ARR_LX) std::memcpy(o, rec + LQ_LX, 24 * sizeof(double));
+                    else if (which == HSDDP_ARR_LU) std::memcpy(o, rec + LQ_LU, 24 * sizeof(double));
+                    else if (which == HSDDP_ARR_A || which == HSDDP_ARR_B) {
+                        double A[576], B[576];
+                        hkd::expand_AB(rec + LQ_AT, rec + LQ_BT, sc.dt, cm, A, B);
+                        std::memcpy(o, which == HSDDP_ARR_A ? A : B, 576 * sizeof(double));
+                    } else if (which == HSDDP_ARR_LUU) {
+                        for (int i = 0; i < 24; ++i) o[i * 25] = sc.dt * (i < 12 ? .2 : .1);
+                        for (int l = 0; l < 4; ++l)
+                            for (int a = 0; a < 3; ++a)
+                                for (int c = 0; c < 3; ++c) o[(3 * l + a) + 24 * (3 * l + c)] += rec[LQ_LUU + 9 * l + 3 * a + c];
+                    } else {  // LXX: dt*Q + foot regulariser block (HKDCost.cpp:36-37)
+                        const double q[12] = {1, 4, 5, 1, 1, 30, .2, .2, .2, 4, 1, .5};
+                        for (int i = 0; i < 24; ++i) {
+                            const double Q = i < 12 ? q[i] : .2 * (1 - (int)((cm >> ((i - 12) / 3)) & 1u));
+                            o[i * 25] = sc.dt * Q;
+                        }
+                        for (int l = 0; l < 4; ++l) {
+                            const double c = (double)((cm >> l) & 1u);
+                            const double wf[3] = {3 * c * 20, c * 20, 0.0};
+                            for (int j = 0; j < 3; ++j) {
+                                const double wc = (sc.dt * c * wf[j]) * c;
+                                o[(3 + j) * 25] += wc; o[(12 + 3 * l + j) * 25] += wc;
+                                o[(3 + j) + 24 * (12 + 3 * l + j)] += -wc; o[(12 + 3 * l + j) + 24 * (3 + j)] += -wc;
+                            }
+                        }
+                    }
+                }
+        }
+        return HSDDP_OK;
+    }
+    double* dev; size_t per;
+    const int kind = array_spec(b, which, &dev, &per);
+    if (kind < 0) return HSDDP_ERR_ARG;
+    if (kind == 0) {
+        CK(cudaMemcpyAsync(out, dev, P * per * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+    } else {
+        const size_t off = (kind == 1) ? 0 : 24, cnt = (kind == 1) ? 24 : 576;
+        CK(cudaMemcpy2DAsync(out, cnt * sizeof(double), dev + off, 600 * sizeof(double), cnt * sizeof(double), P, cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+    }
+    return HSDDP_OK;
+}
+
+int hsddp_batch_set_array(hsddp_batch* b, int which, const double* in) {
+    if (!b || !b->has_problems || !in) return HSDDP_ERR_ARG;
+    if (which != HSDDP_ARR_XBAR && which != HSDDP_ARR_X && which != HSDDP_ARR_UBAR && which != HSDDP_ARR_U &&
+        which != HSDDP_ARR_DX && which != HSDDP_ARR_DU && which != HSDDP_ARR_K) return HSDDP_ERR_ARG;
+    CK(cudaSetDevice(b->device));
+    double* dev; size_t per;
+    if (array_spec(b, which, &dev, &per) != 0) return HSDDP_ERR_ARG;
+    CK(cudaMemcpyAsync(dev, in, (size_t)b->bp.n_problems * per * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    b->cold = false;
+    return HSDDP_OK;
+}
+
+int hsddp_fp64_peak_tflops(int device, int kind, double* tflops) {
+    if (!tflops) return HSDDP_ERR_ARG;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+    double* d = nullptr;
+    CK(cudaMalloc(&d, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(e0));
+        if (kind == 0) k_dfma_probe<<<blocks, threads>>>(d, iters);
+        else k_dmma_probe<<<blocks, threads>>>(d, iters);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flop = (kind == 0) ? (double)blocks * threads * iters * 8.0 * 2.0
+                                        : (double)blocks * (threads / 32) * iters * 4.0 * (8.0 * 8.0 * 4.0 * 2.0);
+        if (rep > 0) best = std::max(best, flop / (ms * 1e-3) / 1e12);
+    }
+    CK(cudaEventDestroy(e0));
+    CK(cudaEventDestroy(e1));
+    CK(cudaFree(d));
+    *tflops = best;
+    return HSDDP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,220 @@
+/*
+ * hsddp_b200.h — C ABI of the B200-native batched Hybrid-Systems DDP solver.
+ *
+ * Drop-in boundary for ONE path of heli-sudoo/HKD-MPC: MultiPhaseDDP<double>::solve()
+ * and the SinglePhase<double,24,24,0> sweeps under it, for the Mini Cheetah HKD
+ * problem.  The reference has no C ABI (it exports C++ template instantiations
+ * from libhsddp.so, HSDDPSolver/CMakeLists.txt:1-3); every entry point below cites
+ * the reference interface it replaces.  Plain pointers and sizes only; all
+ * `double*`/`int*` arguments are HOST pointers unless a name ends in `_dev`.
+ *
+ * Conventions
+ *   - state x[24]  = [eul(yaw,pitch,roll) pos omega_body v_world qdummy(12)]
+ *     control u[24] = [GRF(12) qJd(12)]                       (HKDModel.h:12-14)
+ *   - matrices are column-major 24x24 (Eigen default), K is (u-row, x-col)
+ *   - "node" layout: phases concatenated; phase i contributes horizon_i+1 state
+ *     nodes (the last one is the phase's terminal state) and horizon_i control stages
+ *   - a *schedule* is what HKDProblem::initialization derives from a reference
+ *     window: the phase table plus per-node reference rows.  Many problems of a
+ *     batch may share one schedule (e.g. perturbed initial states).
+ *   - every function returns HSDDP_OK (0) or a negative HSDDP_ERR_* code; there
+ *     is no CPU fallback: without a CUDA device the batch functions fail.
+ */
+#ifndef HSDDP_B200_H
+#define HSDDP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HSDDP_NX 24
+#define HSDDP_NU 24
+#define HSDDP_MAX_PHASES 16
+#define HSDDP_MAX_STAGES 128
+
+#define HSDDP_OK 0
+#define HSDDP_ERR_ARG (-1)
+#define HSDDP_ERR_CUDA (-2)
+#define HSDDP_ERR_UNSUPPORTED (-3)
+#define HSDDP_ERR_STATE (-4)
+#define HSDDP_ERR_IO (-5)
+
+/* per-problem termination status (hsddp_info.status) — replaces the printf-only
+ * outcomes of MultiPhaseDDP::solve, HSDDPSolver/source/MultiPhaseDDP.cpp:397-427 */
+#define HSDDP_STATUS_CONVERGED 0     /* "all constraints satisfied"            :397-402 */
+#define HSDDP_STATUS_STALLED 1       /* "constraints stop decreasing"          :403-408 */
+#define HSDDP_STATUS_MAX_ITER 2      /* "maximum iteration reached"            :410-413 */
+#define HSDDP_STATUS_REG_OVERFLOW 3  /* "too large regularization" (bad_solve) :162-167,421-427 */
+
+/* HSDDP_OPTION, HSDDPSolver/common/HSDDP_CompoundTypes.h:18-60 (fields solve() reads). */
+typedef struct hsddp_options {
+    double alpha, gamma, update_penalty, update_relax, update_regularization, update_ReB;
+    int32_t max_DDP_iter, max_AL_iter;
+    double cost_thresh, tconstr_thresh, pconstr_thresh, dynamics_feas_thresh;
+    double merit_scale, merit_offset;
+    int32_t AL_active, ReB_active, MS, _pad;
+} hsddp_options;
+
+/* REB_Param_Struct / AL_Param_Struct initial values (ConstraintsBase.h:58-86,
+ * HKDMPC/settings/constraint_params.info) and the friction coefficient (HKDConstraints.h:17). */
+typedef struct hsddp_constraint_params {
+    double grf_delta, grf_delta_min, grf_eps;
+    double td_sigma, td_sigma_max, td_lambda;
+    double mu;
+} hsddp_constraint_params;
+
+/* One reference window flattened: what HKDProblem::initialization
+ * (HKDMPC/HKD-TrajOpt/HKDProblem.cpp:15-111,225-310) builds into phase objects. */
+typedef struct hsddp_schedule {
+    int32_t n_phases;
+    int32_t n_stages;                         /* sum of horizons            */
+    int32_t n_nodes;                          /* n_stages + n_phases        */
+    int32_t horizon[HSDDP_MAX_PHASES];
+    int32_t contact[HSDDP_MAX_PHASES][4];      /* phase contact flags        */
+    int32_t next_contact[HSDDP_MAX_PHASES][4]; /* contact after the phase    */
+    float start_time[HSDDP_MAX_PHASES];        /* pdata->phase_start_times   */
+    double dt;                                 /* (double)(float)0.01        */
+    /* per node (n_nodes rows): reference rows exactly as the cost callbacks see them */
+    double* xr;     /* [n_nodes][24]  HKDSinglePhaseReference::get_reference_at_t     */
+    double* ur;     /* [n_nodes][24]  (terminal nodes: unused)                        */
+    double* prel_r; /* [n_nodes][12]  foot_placements - rep4(pos_ref), HKDCost.cpp:15 */
+    double* xinit;  /* [n_nodes][24]  initial guess Xbar = X, HKDProblem.cpp:84-90    */
+} hsddp_schedule;
+
+/* per-problem result record (replaces reading MultiPhaseDDP privates / stdout) */
+typedef struct hsddp_info {
+    int32_t status, n_iter, n_outer, n_sweeps, n_trials, _pad;
+    double cost, feas, max_tconstr, max_pconstr; /* final actual_cost, feas, violations */
+    double cost0, feas0;                         /* after the initial rollout           */
+} hsddp_info;
+
+/* one row per DDP iteration (the natural per-iteration parity record; superset of
+ * the four get_solver_info buffers, MultiPhaseDDP.cpp:277-280,368-371,532-541) */
+typedef struct hsddp_iter_record {
+    double outer, inner, cost_before, feas_before, reg_after, n_sweeps, dV_1, dV_2, merit_rho,
+        eps_accepted, n_trials, cost_after, feas_after, max_tconstr, max_pconstr, _pad;
+} hsddp_iter_record;
+#define HSDDP_TRACE_CAP 64
+
+/* ------------------------------------------------------------------------
+ * Host-side problem assembly (CPU; no GPU needed)
+ * ---------------------------------------------------------------------- */
+typedef struct hkd_gait hkd_gait; /* QuadReference::tp_data, Reference/QuadReference.h:144-153 */
+
+/* QuadReference::load_top_level_data(fname), Reference/QuadReference.cpp:129-285 */
+int hkd_gait_load(const char* path, hkd_gait** out);
+/* same table from arrays already parsed to float (n rows) */
+int hkd_gait_create(int n, float dt, const float* body_state, const float* qJ, const float* foot_placements,
+                    const float* grf, const int32_t* contact, hkd_gait** out);
+int hkd_gait_size(const hkd_gait* g);
+void hkd_gait_destroy(hkd_gait* g);
+
+/* QuadReference::initialize + HKDProblem::initialization for the window that
+ * starts at sample `window_start`; allocates the schedule's arrays. */
+int hkd_schedule_build(const hkd_gait* g, int window_start, float plan_duration, hsddp_schedule* out);
+void hkd_schedule_free(hsddp_schedule* s);
+
+/* compute_hkd_state, HKDMPC/HKD-TrajOpt/HKDModel.h:65-96 */
+void hkd_compute_state(const double eul[3], const double pos[3], const double qJ[12], const int32_t contact[4], double qdummy[12]);
+/* initial condition of HKDMPCSolver::initialize, HKDMPC/HKDMPC.cpp:44-54 */
+void hkd_default_x0(const hsddp_schedule* s, double x0[24]);
+
+/* model functions on the host (same code the kernels run; unit-test hooks)
+ * HKD::Model::dynamics / dynamics_partial (HKDModel.h:33-61), foot position /
+ * Jacobian as used by HKDReset.h:41-136 and HKDConstraints.cpp:69-171.
+ * A,B: 24x24 column-major; J: 3x18 column-major, columns [pos eul qJ(12)]. */
+void hkd_model_dynamics(const double x[24], const double u[24], double dt, const int32_t contact[4], double xnext[24]);
+void hkd_model_dynamics_partial(const double x[24], const double u[24], double dt, const int32_t contact[4], double A[576], double B[576]);
+void hkd_model_foot_position(const double pos[3], const double eul[3], const double qleg[3], int leg, double p[3]);
+void hkd_model_foot_jacobian(const double pos[3], const double eul[3], const double qleg[3], int leg, double J[54]);
+
+/* ------------------------------------------------------------------------
+ * Batched solver (one handle = one GPU + one stream; MultiPhaseDDP x n_problems)
+ * ---------------------------------------------------------------------- */
+typedef struct hsddp_batch hsddp_batch;
+
+int hsddp_batch_create(int device, hsddp_batch** out);
+int hsddp_batch_destroy(hsddp_batch* b);
+const char* hsddp_last_error(void);
+
+/* MultiPhaseDDP::set_multiPhaseProblem (MultiPhaseDDP.h:27-35): uploads the
+ * schedules, allocates the problem-major workspace and resets every problem to
+ * the cold-start guess (Xbar = X = reference states, Ubar = K = dU = 0,
+ * HKDProblem.cpp:84-90, TrajectoryManagement.cpp:11-32). */
+int hsddp_batch_set_problems(hsddp_batch* b, int n_schedules, const hsddp_schedule* schedules, int n_problems,
+                             const int32_t* schedule_id, const hsddp_constraint_params* cparams);
+/* MultiPhaseDDP::set_initial_condition (MultiPhaseDDP.h:37): x0 is [n_problems][24] on the host */
+int hsddp_batch_set_initial_condition(hsddp_batch* b, const double* x0);
+/* re-arm the cold-start guess and the ReB/AL parameters without re-uploading schedules */
+int hsddp_batch_reset(hsddp_batch* b);
+
+/* MultiPhaseDDP::solve(HSDDP_OPTION) (MultiPhaseDDP.cpp:232-428) for every problem:
+ * one persistent kernel, one thread block per problem, iteration control on the device. */
+int hsddp_batch_solve(hsddp_batch* b, const hsddp_options* opt);
+/* same, without the trailing stream synchronise (pair with hsddp_batch_sync) */
+int hsddp_batch_solve_async(hsddp_batch* b, const hsddp_options* opt);
+int hsddp_batch_sync(hsddp_batch* b);
+/* milliseconds of the last solve kernel, CUDA events on the handle's stream */
+int hsddp_batch_last_solve_ms(hsddp_batch* b, float* ms);
+
+/* Step-level API: the public methods of MultiPhaseDDP (MultiPhaseDDP.h:42-69),
+ * each applied to all problems.  `ok` (optional, [n_problems]) receives the bool
+ * the reference method returns. */
+int hsddp_batch_hybrid_rollout(hsddp_batch* b, double eps, const hsddp_options* opt, int32_t* ok); /* :57-95  */
+int hsddp_batch_compute_cost(hsddp_batch* b, const hsddp_options* opt);  /* :431-439 + measure_dynamics_feasibility :514-529 */
+int hsddp_batch_lq_approximation(hsddp_batch* b, const hsddp_options* opt);                         /* :442-448 */
+int hsddp_batch_backward_sweep(hsddp_batch* b, double regularization, int32_t* ok);                 /* :190-229 */
+int hsddp_batch_backward_sweep_regularized(hsddp_batch* b, double* regularization /*[n] in/out*/, const hsddp_options* opt, int32_t* ok); /* :141-181 */
+int hsddp_batch_linear_rollout(hsddp_batch* b, double eps, const hsddp_options* opt);               /* :20-50   */
+/* forward sweep = line_search (:98-138): backtracking over the reference's step sizes,
+ * hybrid rollout + cost + feasibility + Armijo test on the merit; needs merit/merit_rho
+ * set by hsddp_batch_prepare_merit. `eps_accepted` gets the accepted step (0 = none). */
+int hsddp_batch_prepare_merit(hsddp_batch* b, const hsddp_options* opt);                            /* :331-337 */
+int hsddp_batch_forward_sweep(hsddp_batch* b, const hsddp_options* opt, int32_t* ok, double* eps_accepted);
+int hsddp_batch_update_nominal(hsddp_batch* b);                                                      /* :505-511 */
+int hsddp_batch_update_al_params(hsddp_batch* b, const hsddp_options* opt);                          /* :496-502 */
+int hsddp_batch_update_reb_params(hsddp_batch* b, const hsddp_options* opt);                         /* :487-493 */
+
+/* Results.  Trajectory getters copy [n_problems][rows][cols] with the batch-wide
+ * row stride returned by hsddp_batch_dims (rows beyond a problem's own count are zero). */
+int hsddp_batch_dims(hsddp_batch* b, int32_t* n_problems, int32_t* max_stages, int32_t* max_nodes);
+int hsddp_batch_get_info(hsddp_batch* b, hsddp_info* out /*[n_problems]*/);
+int hsddp_batch_get_trace(hsddp_batch* b, hsddp_iter_record* out /*[n_problems][HSDDP_TRACE_CAP]*/);
+/* solver scalars per problem: [actual_cost, merit, feas, dV_1, dV_2, max_tconstr, max_pconstr, merit_rho] */
+int hsddp_batch_get_scalars(hsddp_batch* b, double* out /*[n_problems][8]*/);
+
+#define HSDDP_ARR_XBAR 0   /* [nodes][24]  Trajectory::Xbar (TrajectoryManagement.h:57) */
+#define HSDDP_ARR_X 1      /* [nodes][24]  */
+#define HSDDP_ARR_DEFECT 3 /* [nodes][24]  */
+#define HSDDP_ARR_DX 4     /* [nodes][24]  */
+#define HSDDP_ARR_UBAR 10  /* [stages][24] */
+#define HSDDP_ARR_U 11     /* [stages][24] */
+#define HSDDP_ARR_DU 12    /* [stages][24]  feed-forward dU */
+#define HSDDP_ARR_K 20     /* [stages][576] feedback gains, column-major */
+#define HSDDP_ARR_A 21     /* [stages][576] dense A reconstructed from the compact LQ record */
+#define HSDDP_ARR_B 22     /* [stages][576] */
+#define HSDDP_ARR_LX 30    /* [stages][24]  */
+#define HSDDP_ARR_LU 31    /* [stages][24]  */
+#define HSDDP_ARR_LUU 25   /* [stages][576] */
+#define HSDDP_ARR_LXX 24   /* [stages][576] */
+#define HSDDP_ARR_G0 5     /* [1][24]   value gradient at the first node after the last sweep */
+#define HSDDP_ARR_H0 27    /* [1][576]  value Hessian at the first node after the last sweep  */
+#define HSDDP_ARR_GCON 52  /* [stages][20] GRF constraint values, 5 per leg (swing legs zero) */
+#define HSDDP_ARR_HCON 50  /* [HSDDP_MAX_PHASES][4] touchdown constraint values per phase/leg */
+#define HSDDP_ARR_AL 51    /* [HSDDP_MAX_PHASES][4][2] (sigma, lambda) */
+int hsddp_batch_get_array(hsddp_batch* b, int which, double* out);
+/* overwrite Xbar/X/Ubar/U (warm start); same layout as the getter */
+int hsddp_batch_set_array(hsddp_batch* b, int which, const double* in);
+/* first `n_ctrl` controls and the 12x12 body-feedback block is NOT extracted here
+ * (that is HKDMPCSolver::publish_mpc_cmd). */
+
+/* device-side FP64 FMA throughput probe (TFLOP/s) used as the measured roofline
+ * denominator by bench.py; kind 0 = DFMA on CUDA cores, 1 = DMMA m8n8k4 tensor tiles */
+int hsddp_fp64_peak_tflops(int device, int kind, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSDDP_B200_H */
