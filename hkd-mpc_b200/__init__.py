@@ -146,6 +146,11 @@ def lib():
         L.hsddp_batch_get_array.argtypes = [vp, C.c_int, dp]
         L.hsddp_batch_set_array.argtypes = [vp, C.c_int, dp]
         L.hsddp_fp64_peak_tflops.argtypes = [C.c_int, C.c_int, dp]
+        L.hsddp_batch_get_array_rows.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp]
+        L.hsddp_batch_event_record.argtypes = [vp, C.c_int]
+        L.hsddp_batch_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
+        L.hsddp_batch_get_counters.argtypes = [vp, C.POINTER(C.c_ulonglong)]
+        L.hsddp_batch_reset_counters.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -384,6 +389,29 @@ class MultiPhaseDDPBatch:
         if name in ("K", "A", "B", "lxx", "luu", "H0"):
             out = np.ascontiguousarray(np.swapaxes(out, -1, -2))  # column-major blocks -> [row, col]
         return out
+
+    def get_rows(self, name, row0, nrows, out=None):
+        cols = {"K": 576, "g": 20, "h": 4, "al": 8}.get(name, 24)
+        if out is None:
+            out = np.zeros((self.n, nrows, cols))
+        _check(lib().hsddp_batch_get_array_rows(self.h, ARR[name], int(row0), int(nrows), _dp(out)), "get_array_rows")
+        return out
+
+    def event_record(self, slot):
+        _check(lib().hsddp_batch_event_record(self.h, int(slot)), "event_record")
+
+    def event_elapsed_ms(self, slot0, slot1):
+        ms = C.c_float()
+        _check(lib().hsddp_batch_event_elapsed_ms(self.h, int(slot0), int(slot1), C.byref(ms)), "event_elapsed_ms")
+        return ms.value
+
+    def counters(self):
+        out = (C.c_ulonglong * 4)()
+        _check(lib().hsddp_batch_get_counters(self.h, out), "get_counters")
+        return dict(sweep_stages=int(out[0]), solve_launches=int(out[1]), step_launches=int(out[2]))
+
+    def reset_counters(self):
+        _check(lib().hsddp_batch_reset_counters(self.h), "reset_counters")
 
     def set(self, name, arr):
         arr = np.ascontiguousarray(arr, np.float64)

@@ -67,7 +67,7 @@ struct BatchPtrs {
     // problem-major workspace
     double *Xbar, *X, *Xsim_t, *Defect, *dX;  // [P][max_nodes][24]
     double *Ubar, *U, *U_t, *dU;              // [P][max_stages][24]
-    double* K;                                // [P][max_stages][576]
+    double* K;                                // [P][max_stages][12][24] compact gains K_r (row c <-> coupled control of leg c/3)
     double* lq;                               // [P][max_stages][LQ_STRIDE]
     double* tq;                               // [P][MAXPH][TQ_STRIDE]
     double* gcon;                             // [P][max_stages][20]
@@ -180,7 +180,7 @@ __device__ inline void bind_problem(Smem& sm, const BatchPtrs& bp, int pid) {
         sm.Xbar = bp.Xbar + pid * sn; sm.X = bp.X + pid * sn; sm.Xsim_t = bp.Xsim_t + pid * sn;
         sm.Defect = bp.Defect + pid * sn; sm.dX = bp.dX + pid * sn;
         sm.Ubar = bp.Ubar + pid * ss; sm.U = bp.U + pid * ss; sm.U_t = bp.U_t + pid * ss; sm.dU = bp.dU + pid * ss;
-        sm.K = bp.K + (size_t)pid * bp.max_stages * 576;
+        sm.K = bp.K + (size_t)pid * bp.max_stages * 288;
         sm.lqg = bp.lq + (size_t)pid * bp.max_stages * LQ_STRIDE;
         sm.tq = bp.tq + (size_t)pid * MAXPH * TQ_STRIDE;
         sm.gcon = bp.gcon + (size_t)pid * bp.max_stages * 20;
@@ -258,11 +258,13 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = sc.n_stages;
     double* wdx = sm.Y + 32 * warp;  // per-warp scratch
-    // (a) controls: U = (Ubar + eps dU) + K (X - Xbar), one warp per stage
+    // (a) controls: U = (Ubar + eps dU) + K (X - Xbar), one warp per stage.  K is stored compactly as
+    //     K_r[12][24] (only the coupled control of each leg has a non-zero gain row, see hsddp_sweep.cuh)
     for (int s = warp; s < N; s += kWarps) {
         int ph, k;
         phase_of_stage(sc, s, ph, k);
         const int n = sc.node_off[ph] + k;
+        const unsigned cm = sc.cmask[ph];
         if (lane < 24) {
             const double xb = sm.Xbar[24 * n + lane];
             const double x = xb + eps * sm.dX[24 * n + lane];
@@ -270,10 +272,13 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
         }
         __syncwarp();
         if (lane < 24) {
-            const double* Kk = sm.K + 576 * (size_t)s;
+            const bool stance = (cm >> ((lane % 12) / 3)) & 1u;
             double acc = 0.0;
+            if ((lane < 12) == stance) {
+                const double* Kr = sm.K + 288 * (size_t)s + 24 * (lane % 12);
 #pragma unroll 8
-            for (int j = 0; j < 24; ++j) acc += Kk[lane + 24 * j] * wdx[j];
+                for (int j = 0; j < 24; ++j) acc = fma(Kr[j], wdx[j], acc);
+            }
             sm.U_t[24 * s + lane] = (sm.Ubar[24 * s + lane] + eps * sm.dU[24 * s + lane]) + acc;
         }
         __syncwarp();
@@ -625,7 +630,7 @@ __device__ inline void cold_start_block(Smem& sm) {
         sm.Xbar[e] = v; sm.X[e] = v; sm.dX[e] = 0.0; sm.Defect[e] = 0.0; sm.Xsim_t[e] = 0.0;
     }
     for (int e = threadIdx.x; e < sc.n_stages * 24; e += kThreads) { sm.Ubar[e] = 0.0; sm.U[e] = 0.0; sm.dU[e] = 0.0; sm.U_t[e] = 0.0; }
-    for (size_t e = threadIdx.x; e < (size_t)sc.n_stages * 576; e += kThreads) sm.K[e] = 0.0;
+    for (size_t e = threadIdx.x; e < (size_t)sc.n_stages * 288; e += kThreads) sm.K[e] = 0.0;
     for (int e = threadIdx.x; e < sc.n_stages * 20; e += kThreads) {
         sm.gcon[e] = 0.0; sm.reb[2 * e] = sm.cp.grf_eps; sm.reb[2 * e + 1] = sm.cp.grf_delta;
     }

@@ -143,7 +143,7 @@ bad_solve:
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kThreads) k_solve(BatchPtrs bp, hsddp_options opt, int cold_start) {
+__global__ void __launch_bounds__(kThreads, 4) k_solve(BatchPtrs bp, hsddp_options opt, int cold_start) {
     __shared__ Smem sm;
     for (;;) {
         __syncthreads();
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kThreads) k_solve(BatchPtrs bp, hsddp_options 
 enum StepOp { OP_RESET = 0, OP_ROLLOUT, OP_COST, OP_LQ, OP_SWEEP, OP_SWEEP_REG, OP_LINEAR, OP_MERIT, OP_FORWARD, OP_NOMINAL, OP_AL, OP_REB };
 
 // step-level kernel: one block per problem, state round-trips through HBM
-__global__ void __launch_bounds__(kThreads) k_step(BatchPtrs bp, hsddp_options opt, int op, double arg, double* darg, int* ok) {
+__global__ void __launch_bounds__(kThreads, 4) k_step(BatchPtrs bp, hsddp_options opt, int op, double arg, double* darg, int* ok) {
     __shared__ Smem sm;
     const int pid = blockIdx.x;
     bind_problem(sm, bp, pid);
@@ -246,6 +246,8 @@ struct hsddp_batch {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t slots[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    unsigned long long n_solve_launches = 0, n_step_launches = 0;
     int n_sm = 0, blocks_per_sm = 1;
     BatchPtrs bp{};
     std::vector<void*> allocs;
@@ -298,6 +300,7 @@ int launch_step(hsddp_batch* b, const hsddp_options* opt, int op, double arg, do
     const hsddp_options o = opt ? *opt : default_options();
     k_step<<<b->bp.n_problems, kThreads, 0, b->stream>>>(b->bp, o, op, arg, darg_dev, b->d_ok);
     CK(cudaGetLastError());
+    b->n_step_launches++;
     if (ok_host) CK(cudaMemcpyAsync(ok_host, b->d_ok, sizeof(int) * b->bp.n_problems, cudaMemcpyDeviceToHost, b->stream));
     if (sync || ok_host) CK(cudaStreamSynchronize(b->stream));
     if (op != OP_RESET) b->cold = false;
@@ -319,6 +322,7 @@ int hsddp_batch_create(int device, hsddp_batch** out) {
     CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&b->ev0));
     CK(cudaEventCreate(&b->ev1));
+    for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&b->slots[i]));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     b->n_sm = prop.multiProcessorCount;
@@ -334,6 +338,7 @@ int hsddp_batch_destroy(hsddp_batch* b) {
     free_problem_allocs(b);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
+    for (int i = 0; i < 8; ++i) if (b->slots[i]) cudaEventDestroy(b->slots[i]);
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
     return HSDDP_OK;
@@ -416,7 +421,7 @@ int hsddp_batch_set_problems(hsddp_batch* b, int n_schedules, const hsddp_schedu
     if ((rc = dalloc(b, &bp.U, P * SS))) return rc;
     if ((rc = dalloc(b, &bp.U_t, P * SS))) return rc;
     if ((rc = dalloc(b, &bp.dU, P * SS))) return rc;
-    if ((rc = dalloc(b, &bp.K, P * max_stages * 576))) return rc;
+    if ((rc = dalloc(b, &bp.K, P * max_stages * 288))) return rc;
     if ((rc = dalloc(b, &bp.lq, P * max_stages * LQ_STRIDE))) return rc;
     if ((rc = dalloc(b, &bp.tq, P * MAXPH * TQ_STRIDE))) return rc;
     if ((rc = dalloc(b, &bp.gcon, P * max_stages * 20))) return rc;
@@ -469,6 +474,7 @@ int hsddp_batch_solve_async(hsddp_batch* b, const hsddp_options* opt) {
     CK(cudaEventRecord(b->ev0, b->stream));
     k_solve<<<grid, kThreads, 0, b->stream>>>(b->bp, o, 0);
     CK(cudaGetLastError());
+    b->n_solve_launches++;
     CK(cudaEventRecord(b->ev1, b->stream));
     b->cold = false;
     return HSDDP_OK;
@@ -557,6 +563,33 @@ int hsddp_batch_get_scalars(hsddp_batch* b, double* out) {
     return HSDDP_OK;
 }
 
+// Dense column-major 24x24 feedback gains for stages [row0, row0+nrows) from the compact K_r store.
+static int get_gains(hsddp_batch* b, int row0, int nrows, double* out) {
+    const BatchPtrs& bp = b->bp;
+    const size_t P = (size_t)bp.n_problems;
+    if (row0 < 0 || nrows <= 0 || row0 + nrows > bp.max_stages) return HSDDP_ERR_ARG;
+    std::vector<double> kr(P * nrows * 288);
+    CK(cudaMemcpy2DAsync(kr.data(), (size_t)nrows * 288 * sizeof(double), bp.K + (size_t)row0 * 288, (size_t)bp.max_stages * 288 * sizeof(double),
+                         (size_t)nrows * 288 * sizeof(double), P, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    std::memset(out, 0, P * nrows * 576 * sizeof(double));
+    for (size_t p = 0; p < P; ++p) {
+        const DevSchedule& sc = b->h_sched[b->h_sched_id[p]];
+        for (int ph = 0; ph < sc.n_phases; ++ph)
+            for (int k = 0; k < sc.horizon[ph]; ++k) {
+                const int s = sc.stage_off[ph] + k;
+                if (s < row0 || s >= row0 + nrows) continue;
+                const double* src = &kr[(p * nrows + (s - row0)) * 288];
+                double* o = out + (p * nrows + (s - row0)) * 576;
+                for (int c = 0; c < 12; ++c) {
+                    const int i = ((sc.cmask[ph] >> (c / 3)) & 1u) ? c : 12 + c;
+                    for (int j = 0; j < 24; ++j) o[i + 24 * j] = src[c * 24 + j];
+                }
+            }
+    }
+    return HSDDP_OK;
+}
+
 static int array_spec(hsddp_batch* b, int which, double** dev, size_t* per_problem) {
     const BatchPtrs& bp = b->bp;
     const size_t SN = (size_t)bp.max_nodes * 24, SS = (size_t)bp.max_stages * 24;
@@ -568,7 +601,7 @@ static int array_spec(hsddp_batch* b, int which, double** dev, size_t* per_probl
         case HSDDP_ARR_UBAR: *dev = bp.Ubar; *per_problem = SS; return 0;
         case HSDDP_ARR_U: *dev = bp.U; *per_problem = SS; return 0;
         case HSDDP_ARR_DU: *dev = bp.dU; *per_problem = SS; return 0;
-        case HSDDP_ARR_K: *dev = bp.K; *per_problem = (size_t)bp.max_stages * 576; return 0;
+        case HSDDP_ARR_K: *dev = bp.K; *per_problem = (size_t)bp.max_stages * 288; return 3;
         case HSDDP_ARR_GCON: *dev = bp.gcon; *per_problem = (size_t)bp.max_stages * 20; return 0;
         case HSDDP_ARR_HCON: *dev = bp.hcon; *per_problem = (size_t)MAXPH * 4; return 0;
         case HSDDP_ARR_AL: *dev = bp.al; *per_problem = (size_t)MAXPH * 8; return 0;
@@ -633,6 +666,7 @@ int hsddp_batch_get_array(hsddp_batch* b, int which, double* out) {
     double* dev; size_t per;
     const int kind = array_spec(b, which, &dev, &per);
     if (kind < 0) return HSDDP_ERR_ARG;
+    if (kind == 3) return get_gains(b, 0, bp.max_stages, out);
     if (kind == 0) {
         CK(cudaMemcpyAsync(out, dev, P * per * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
         CK(cudaStreamSynchronize(b->stream));
@@ -647,13 +681,66 @@ int hsddp_batch_get_array(hsddp_batch* b, int which, double* out) {
 int hsddp_batch_set_array(hsddp_batch* b, int which, const double* in) {
     if (!b || !b->has_problems || !in) return HSDDP_ERR_ARG;
     if (which != HSDDP_ARR_XBAR && which != HSDDP_ARR_X && which != HSDDP_ARR_UBAR && which != HSDDP_ARR_U &&
-        which != HSDDP_ARR_DX && which != HSDDP_ARR_DU && which != HSDDP_ARR_K) return HSDDP_ERR_ARG;
+        which != HSDDP_ARR_DX && which != HSDDP_ARR_DU) return HSDDP_ERR_ARG;
     CK(cudaSetDevice(b->device));
     double* dev; size_t per;
     if (array_spec(b, which, &dev, &per) != 0) return HSDDP_ERR_ARG;
     CK(cudaMemcpyAsync(dev, in, (size_t)b->bp.n_problems * per * sizeof(double), cudaMemcpyHostToDevice, b->stream));
     CK(cudaStreamSynchronize(b->stream));
     b->cold = false;
+    return HSDDP_OK;
+}
+
+int hsddp_batch_get_array_rows(hsddp_batch* b, int which, int row0, int nrows, double* out) {
+    if (!b || !b->has_problems || !out || row0 < 0 || nrows <= 0) return HSDDP_ERR_ARG;
+    CK(cudaSetDevice(b->device));
+    if (which == HSDDP_ARR_K) return get_gains(b, row0, nrows, out);
+    double* dev; size_t per;
+    if (array_spec(b, which, &dev, &per) != 0) return HSDDP_ERR_ARG;
+    size_t cols;
+    switch (which) {
+        case HSDDP_ARR_K: cols = 576; break;
+        case HSDDP_ARR_GCON: cols = 20; break;
+        case HSDDP_ARR_HCON: cols = 4; break;
+        case HSDDP_ARR_AL: cols = 8; break;
+        default: cols = 24; break;
+    }
+    if ((size_t)(row0 + nrows) * cols > per) return HSDDP_ERR_ARG;
+    CK(cudaMemcpy2DAsync(out, (size_t)nrows * cols * sizeof(double), dev + (size_t)row0 * cols, per * sizeof(double),
+                         (size_t)nrows * cols * sizeof(double), (size_t)b->bp.n_problems, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return HSDDP_OK;
+}
+
+int hsddp_batch_event_record(hsddp_batch* b, int slot) {
+    if (!b || slot < 0 || slot >= 8) return HSDDP_ERR_ARG;
+    CK(cudaSetDevice(b->device));
+    CK(cudaEventRecord(b->slots[slot], b->stream));
+    return HSDDP_OK;
+}
+
+int hsddp_batch_event_elapsed_ms(hsddp_batch* b, int slot0, int slot1, float* ms) {
+    if (!b || !ms || slot0 < 0 || slot0 >= 8 || slot1 < 0 || slot1 >= 8) return HSDDP_ERR_ARG;
+    CK(cudaSetDevice(b->device));
+    CK(cudaEventSynchronize(b->slots[slot1]));
+    CK(cudaEventElapsedTime(ms, b->slots[slot0], b->slots[slot1]));
+    return HSDDP_OK;
+}
+
+int hsddp_batch_get_counters(hsddp_batch* b, unsigned long long out[4]) {
+    if (!b || !b->has_problems || !out) return HSDDP_ERR_ARG;
+    CK(cudaSetDevice(b->device));
+    CK(cudaStreamSynchronize(b->stream));
+    CK(cudaMemcpy(out, b->bp.counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    out[1] = b->n_solve_launches; out[2] = b->n_step_launches; out[3] = 0;
+    return HSDDP_OK;
+}
+
+int hsddp_batch_reset_counters(hsddp_batch* b) {
+    if (!b || !b->has_problems) return HSDDP_ERR_ARG;
+    CK(cudaSetDevice(b->device));
+    CK(cudaMemsetAsync(b->bp.counters, 0, 4 * sizeof(unsigned long long), b->stream));
+    b->n_solve_launches = 0; b->n_step_launches = 0;
     return HSDDP_OK;
 }
 

@@ -210,6 +210,19 @@ int hsddp_batch_set_array(hsddp_batch* b, int which, const double* in);
 /* first `n_ctrl` controls and the 12x12 body-feedback block is NOT extracted here
  * (that is HKDMPCSolver::publish_mpc_cmd). */
 
+/* copy rows [row0, row0+nrows) of a per-problem array (same `which` codes; K rows are
+ * 576-double stages): out is [n_problems][nrows][cols].  This is the per-tick copy-out the
+ * MPC caller needs (first controls, states and feedback gains, HKDMPC/HKDMPC.cpp:245-275). */
+int hsddp_batch_get_array_rows(hsddp_batch* b, int which, int row0, int nrows, double* out);
+
+/* CUDA-event timing on the handle's stream (slots 0..7): record, then elapsed ms between two slots */
+int hsddp_batch_event_record(hsddp_batch* b, int slot);
+int hsddp_batch_event_elapsed_ms(hsddp_batch* b, int slot0, int slot1, float* ms);
+/* work counters of all solves since set_problems/reset_counters:
+ * out[0] = sum over problems of (backward sweeps x stages), out[1] = k_solve launches, out[2] = k_step launches */
+int hsddp_batch_get_counters(hsddp_batch* b, unsigned long long out[4]);
+int hsddp_batch_reset_counters(hsddp_batch* b);
+
 /* device-side FP64 FMA throughput probe (TFLOP/s) used as the measured roofline
  * denominator by bench.py; kind 0 = DFMA on CUDA cores, 1 = DMMA m8n8k4 tensor tiles */
 int hsddp_fp64_peak_tflops(int device, int kind, double* tflops);

