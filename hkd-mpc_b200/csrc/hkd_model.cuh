@@ -35,10 +35,13 @@ constexpr double kJxx = 3.6415571589736352e+01, kJyy = 4.1234427331951844e+00, k
 constexpr double kHipX = 1.9000000000000000e-01, kHipY = 4.9000000000000002e-02;
 constexpr double kAbad = 6.2000000000000000e-02, kThigh = -2.0899999999999999e-01, kShank = -1.9500000000000001e-01;
 
-// compact linearisation record of one stage
-constexpr int kAtRows = 6;                 // rows {0,1,2,6,7,8} of A - I, dense over 24 columns
-constexpr int kAtSize = kAtRows * 24;      // row-major [6][24]
-constexpr int kBtSize = 3 * 12;            // rows {6,7,8} of B over the 12 GRF columns, row-major [3][12]
+// Linearisation record of one stage, laid out as the Riccati kernel's tensor-core tiles read it:
+//   At12[12][24] : rows 0..11 of A - I (row-major; rows 3..5 hold dt at column 9..11, rows 9..11 are zero)
+//   Bq  [ 8][24] : rows 4..11 of B_r, the 24x12 matrix of the COUPLED controls (reduced column c = 3*leg+j;
+//                  only stance-leg columns have entries in these rows; columns 12..23 are padding)
+// Only the structural non-zeros are written; the rest of the record must be zero-initialised once.
+constexpr int kAt12Size = 12 * 24;
+constexpr int kBqSize = 8 * 24;
 
 struct Trig {
     double sy, cy, sp, cp, sr, cr;
@@ -114,31 +117,30 @@ HKD_HD void dynamics(const double* x, const double* u, double dt, unsigned cmask
     }
 }
 
-// Compact analytic linearisation (HKD::Model::dynamics_partial).
-//   At[r][c], r in 0..5 <-> state rows {0,1,2,6,7,8}: entries of A - I
-//   Bt[a][j], a in 0..2 <-> state rows {6,7,8}, j in 0..11 (GRF columns)
-HKD_HD void dynamics_partial_compact(const double* x, const double* u, double dt, unsigned cmask, double* At, double* Bt) {
-    for (int i = 0; i < kAtSize; ++i) At[i] = 0.0;
+// Analytic linearisation (HKD::Model::dynamics_partial) written straight into a stage record.
+HKD_HD void dynamics_partial_record(const double* x, const double* u, double dt, unsigned cmask, double* At12, double* Bq) {
     const Trig t = trig_of(x[0], x[1], x[2]);
     const double wx = x[6], wy = x[7], wz = x[8];
     const double s1 = t.sr * wy + t.cr * wz;
     const double s2 = t.cr * wy - t.sr * wz;
     const double icp = 1.0 / t.cp;
     const double tp = t.sp * icp;
-    // Euler-rate rows
-    At[0 * 24 + 1] = dt * (s1 * t.sp * icp * icp);
-    At[0 * 24 + 2] = dt * (s2 * icp);
-    At[0 * 24 + 7] = dt * (t.sr * icp);
-    At[0 * 24 + 8] = dt * (t.cr * icp);
-    At[1 * 24 + 2] = dt * (-s1);
-    At[1 * 24 + 7] = dt * t.cr;
-    At[1 * 24 + 8] = dt * (-t.sr);
-    At[2 * 24 + 1] = dt * (s1 * icp * icp);
-    At[2 * 24 + 2] = dt * (tp * s2);
-    At[2 * 24 + 6] = dt;
-    At[2 * 24 + 7] = dt * (tp * t.sr);
-    At[2 * 24 + 8] = dt * (tp * t.cr);
-    // angular-acceleration rows: M = dt * Jinv * R^T
+    // Euler-rate rows 0..2
+    At12[0 * 24 + 1] = dt * (s1 * t.sp * icp * icp);
+    At12[0 * 24 + 2] = dt * (s2 * icp);
+    At12[0 * 24 + 7] = dt * (t.sr * icp);
+    At12[0 * 24 + 8] = dt * (t.cr * icp);
+    At12[1 * 24 + 2] = dt * (-s1);
+    At12[1 * 24 + 7] = dt * t.cr;
+    At12[1 * 24 + 8] = dt * (-t.sr);
+    At12[2 * 24 + 1] = dt * (s1 * icp * icp);
+    At12[2 * 24 + 2] = dt * (tp * s2);
+    At12[2 * 24 + 6] = dt;
+    At12[2 * 24 + 7] = dt * (tp * t.sr);
+    At12[2 * 24 + 8] = dt * (tp * t.cr);
+    // position rows 3..5
+    At12[3 * 24 + 9] = dt; At12[4 * 24 + 10] = dt; At12[5 * 24 + 11] = dt;
+    // angular-acceleration rows 6..8: M = dt * Jinv * R^T
     double R[9], F[3], tw[3];
     rotation(t, R);
     wrench(x, u, cmask, F, tw);
@@ -148,17 +150,15 @@ HKD_HD void dynamics_partial_compact(const double* x, const double* u, double dt
     for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int i = 0; i < 3; ++i) M[3 * a + i] = jd[a] * R[3 * i + a];
-    // d/d yaw:  (dR/dyaw)^T tau = -R[1][:] tau0 + R[0][:] tau1
-    // d/d roll: (0, (R^T tau)_2, -(R^T tau)_1)
+    // d/d yaw:  (dR/dyaw)^T tau = -R[1][:] tau0 + R[0][:] tau1 ; d/d roll: (0, (R^T tau)_2, -(R^T tau)_1)
     const double rt1 = R[1] * tw[0] + R[4] * tw[1] + R[7] * tw[2];
     const double rt2 = R[2] * tw[0] + R[5] * tw[1] + R[8] * tw[2];
-    // d/d pitch: explicit dR/dpitch
     const double dP[9] = {-t.cy * t.sp, t.cy * t.cp * t.sr, t.cy * t.cp * t.cr,
                           -t.sy * t.sp, t.sy * t.cp * t.sr, t.sy * t.cp * t.cr,
                           -t.cp,        -t.sp * t.sr,       -t.sp * t.cr};
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        double* row = At + (3 + a) * 24;
+        double* row = At12 + (6 + a) * 24;
         row[0] = jd[a] * (-R[3 + a] * tw[0] + R[a] * tw[1]);
         row[1] = jd[a] * (dP[a] * tw[0] + dP[3 + a] * tw[1] + dP[6 + a] * tw[2]);
         // position columns: tau_world depends on p through r_l = foot - p  ->  column j = M (F x e_j)
@@ -166,54 +166,52 @@ HKD_HD void dynamics_partial_compact(const double* x, const double* u, double dt
         row[4] = -M[3 * a + 0] * F[2] + M[3 * a + 2] * F[0];
         row[5] = M[3 * a + 0] * F[1] - M[3 * a + 1] * F[0];
     }
-    At[3 * 24 + 2] = 0.0;
-    At[4 * 24 + 2] = jd[1] * rt2;
-    At[5 * 24 + 2] = jd[2] * (-rt1);
+    At12[6 * 24 + 2] = 0.0;
+    At12[7 * 24 + 2] = jd[1] * rt2;
+    At12[8 * 24 + 2] = jd[2] * (-rt1);
     // gyroscopic block
-    At[3 * 24 + 7] = jd[0] * (kIyy - kIzz) * wz;
-    At[3 * 24 + 8] = jd[0] * (kIyy - kIzz) * wy;
-    At[4 * 24 + 6] = jd[1] * (kIzz - kIxx) * wz;
-    At[4 * 24 + 8] = jd[1] * (kIzz - kIxx) * wx;
-    At[5 * 24 + 6] = jd[2] * (kIxx - kIyy) * wy;
-    At[5 * 24 + 7] = jd[2] * (kIxx - kIyy) * wx;
+    At12[6 * 24 + 6] = 0.0;
+    At12[6 * 24 + 7] = jd[0] * (kIyy - kIzz) * wz;
+    At12[6 * 24 + 8] = jd[0] * (kIyy - kIzz) * wy;
+    At12[7 * 24 + 6] = jd[1] * (kIzz - kIxx) * wz;
+    At12[7 * 24 + 7] = 0.0;
+    At12[7 * 24 + 8] = jd[1] * (kIzz - kIxx) * wx;
+    At12[8 * 24 + 6] = jd[2] * (kIxx - kIyy) * wy;
+    At12[8 * 24 + 7] = jd[2] * (kIxx - kIyy) * wx;
+    At12[8 * 24 + 8] = 0.0;
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
-        if ((cmask >> l) & 1u) {
-            const double rx = x[12 + 3 * l] - x[3], ry = x[13 + 3 * l] - x[4], rz = -x[5];
-            const double fx = u[3 * l], fy = u[3 * l + 1], fz = u[3 * l + 2];
+        const bool stance = (cmask >> l) & 1u;
+        const double rx = x[12 + 3 * l] - x[3], ry = x[13 + 3 * l] - x[4], rz = -x[5];
+        const double fx = u[3 * l], fy = u[3 * l + 1], fz = u[3 * l + 2];
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const double m0 = M[3 * a], m1 = M[3 * a + 1], m2 = M[3 * a + 2];
-                // foot x,y columns: M (e_j x f)
-                At[(3 + a) * 24 + 12 + 3 * l] = -m1 * fz + m2 * fy;
-                At[(3 + a) * 24 + 13 + 3 * l] = m0 * fz - m2 * fx;
-                // force columns: M (r x e_j)
-                Bt[a * 12 + 3 * l + 0] = m1 * rz - m2 * ry;
-                Bt[a * 12 + 3 * l + 1] = -m0 * rz + m2 * rx;
-                Bt[a * 12 + 3 * l + 2] = m0 * ry - m1 * rx;
-            }
-        } else {
-#pragma unroll
-            for (int a = 0; a < 3; ++a) { Bt[a * 12 + 3 * l] = 0.0; Bt[a * 12 + 3 * l + 1] = 0.0; Bt[a * 12 + 3 * l + 2] = 0.0; }
+        for (int a = 0; a < 3; ++a) {
+            const double m0 = M[3 * a], m1 = M[3 * a + 1], m2 = M[3 * a + 2];
+            // foot x,y columns: M (e_j x f) ; force columns: M (r x e_j)   (zero for a swing leg)
+            At12[(6 + a) * 24 + 12 + 3 * l] = stance ? (-m1 * fz + m2 * fy) : 0.0;
+            At12[(6 + a) * 24 + 13 + 3 * l] = stance ? (m0 * fz - m2 * fx) : 0.0;
+            Bq[(2 + a) * 24 + 3 * l + 0] = stance ? (m1 * rz - m2 * ry) : 0.0;
+            Bq[(2 + a) * 24 + 3 * l + 1] = stance ? (-m0 * rz + m2 * rx) : 0.0;
+            Bq[(2 + a) * 24 + 3 * l + 2] = stance ? (m0 * ry - m1 * rx) : 0.0;
         }
+        // linear acceleration rows 9..11: (c/m) dt on the leg's own force component
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Bq[(5 + j) * 24 + 3 * l + j] = stance ? (1.0 / kMass) * dt : 0.0;
     }
 }
 
-// expand the compact record to the dense column-major A, B of the reference
-HKD_HD void expand_AB(const double* At, const double* Bt, double dt, unsigned cmask, double* A, double* B) {
+// expand a stage record to the dense column-major A, B of the reference
+HKD_HD void expand_AB(const double* At12, const double* Bq, double dt, unsigned cmask, double* A, double* B) {
     for (int i = 0; i < 576; ++i) { A[i] = 0.0; B[i] = 0.0; }
     for (int i = 0; i < 24; ++i) A[i * 25] = 1.0;
-    const int rows[6] = {0, 1, 2, 6, 7, 8};
-    for (int r = 0; r < 6; ++r)
-        for (int c = 0; c < 24; ++c) A[rows[r] + 24 * c] += At[r * 24 + c];
-    for (int j = 0; j < 3; ++j) A[(3 + j) + 24 * (9 + j)] = dt;
-    for (int a = 0; a < 3; ++a)
-        for (int j = 0; j < 12; ++j) B[(6 + a) + 24 * j] = Bt[a * 12 + j];
+    for (int r = 0; r < 12; ++r)
+        for (int c = 0; c < 24; ++c) A[r + 24 * c] += At12[r * 24 + c];
     for (int l = 0; l < 4; ++l) {
-        const double c = ((cmask >> l) & 1u) ? 1.0 : 0.0;
+        const bool stance = (cmask >> l) & 1u;
         for (int j = 0; j < 3; ++j) {
-            B[(9 + j) + 24 * (3 * l + j)] = (c / kMass) * dt;
-            B[(12 + 3 * l + j) + 24 * (12 + 3 * l + j)] = (1.0 - c) * dt;
+            const int c = 3 * l + j;
+            if (stance) { for (int k = 4; k < 12; ++k) B[k + 24 * c] = Bq[(k - 4) * 24 + c]; }
+            else B[(12 + c) + 24 * (12 + c)] = dt;
         }
     }
 }

@@ -26,18 +26,20 @@ constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
 constexpr int MAXPH = HSDDP_MAX_PHASES;
 
-// compact per-stage LQ record (doubles)
-constexpr int LQ_AT = 0;                     // [6][24] rows {0,1,2,6,7,8} of A - I
-constexpr int LQ_BT = LQ_AT + hkd::kAtSize;  // [3][12] rows {6,7,8} of B, GRF columns
-constexpr int LQ_LX = LQ_BT + hkd::kBtSize;  // [24]
-constexpr int LQ_LU = LQ_LX + 24;            // [24]
-constexpr int LQ_LUU = LQ_LU + 24;           // [4][3][3] ReB Hessian blocks per leg (dt folded in)
-constexpr int LQ_STRIDE = LQ_LUU + 36;       // 264
+// per-stage LQ record (doubles), laid out exactly as the sweep's tensor-core tiles read it so that a
+// plain cp.async copy stages it into shared memory (see hkd_model.cuh: dynamics_partial_record)
+constexpr int LQ_AT12 = 0;                        // [12][24] rows 0..11 of A - I
+constexpr int LQ_BQ = LQ_AT12 + hkd::kAt12Size;   // [8][24]  rows 4..11 of B_r (coupled controls), cols 12..23 padding
+constexpr int LQ_LX = LQ_BQ + hkd::kBqSize;       // [24]
+constexpr int LQ_LU = LQ_LX + 24;                 // [24]
+constexpr int LQ_LUU = LQ_LU + 24;                // [4][3][3] ReB Hessian blocks per leg (dt folded in)
+constexpr int LQ_STRIDE = 576;                    // 564 used
 // per-phase terminal record
 constexpr int TQ_PHIX = 0;   // [24]
 constexpr int TQ_HX = 24;    // [4][24] touchdown-constraint gradients, by leg
 constexpr int TQ_WH = 120;   // [4] AL Hessian weights sigma(1+h)+lambda (0: no constraint on that leg)
-constexpr int TQ_STRIDE = 128;
+constexpr int TQ_JC = 124;   // [4][3][6] foot Jacobians (d/d eul, d/d qleg) at the phase's terminal state (reset-map Jacobian)
+constexpr int TQ_STRIDE = 200;
 
 struct DevSchedule {
     int n_phases, n_stages, n_nodes, _pad;
@@ -67,7 +69,7 @@ struct BatchPtrs {
     // problem-major workspace
     double *Xbar, *X, *Xsim_t, *Defect, *dX;  // [P][max_nodes][24]
     double *Ubar, *U, *U_t, *dU;              // [P][max_stages][24]
-    double* K;                                // [P][max_stages][12][24] compact gains K_r (row c <-> coupled control of leg c/3)
+    double* K;                                // [P][max_stages][24][12] compact gains, transposed: KT[j][c] = K_r[c][j] (c <-> coupled control of leg c/3)
     double* lq;                               // [P][max_stages][LQ_STRIDE]
     double* tq;                               // [P][MAXPH][TQ_STRIDE]
     double* gcon;                             // [P][max_stages][20]
@@ -85,9 +87,16 @@ struct BatchPtrs {
 
 // Shared-memory working set of one block.
 struct __align__(16) Smem {
-    double H[576], Y[576], Z[576], Quu[576], Qux[576], Qxx[576];
-    double G[24], Gn[24], Qx[24], Qu[24], wu[24], dfc[24], vtmp[24], vtmp2[24];
-    double lq[LQ_STRIDE];
+    // --- sweep tiles; contiguous, reused as streaming buffers by the linear rollout ---
+    double H[576], Y[576], Z[576];
+    double Qux[384];           // Qux_r [16][24]
+    double Quu[288];           // Quu_r [12][24]
+    double KrS[288];           // K_r transposed [24][12] of the current stage
+    double rec[2][LQ_STRIDE];  // stage records, cp.async double buffer
+    // --- vectors ---
+    double dfc2[2][24];
+    double G[24], Gn[24], Qx[24], Qu[24], wu[24], vtmp[24], vtmp2[24];
+    double lxxd[24], lxxTd[24], lxxw[12], lxxTw[12];
     double red[kThreads];
     DevSchedule sc;
     SolverState st;
@@ -219,27 +228,24 @@ __device__ inline void resetmap_thread(const double* x, unsigned c, unsigned cn,
     }
 }
 
-// dense Px (HKDReset.h:78-136), column-major into P[576]
-__device__ inline void resetmap_partial_block(const double* x, unsigned c, unsigned cn, double* P) {
+// dense Px (HKDReset.h:78-136), column-major into P[576].  Jc: the foot Jacobians cached by the
+// LQ approximation in the phase's terminal record ([4][3][6]: d/d eul, d/d qleg per leg).
+__device__ inline void resetmap_partial_block(const double* Jc_all, unsigned c, unsigned cn, double* P) {
     for (int e = threadIdx.x; e < 576; e += kThreads) P[e] = ((e % 24) == (e / 24)) ? 1.0 : 0.0;
     __syncthreads();
-    if (threadIdx.x < 4) {
-        const int l = threadIdx.x;
+    if (threadIdx.x < 12) {
+        const int l = threadIdx.x / 3, r = threadIdx.x % 3;
         const bool cl = (c >> l) & 1u, nl = (cn >> l) & 1u;
-        if (cl && !nl)
-            for (int r = 0; r < 3; ++r) P[(12 + 3 * l + r) * 25] = 0.0;
+        const int row = 12 + 3 * l + r;
+        if (cl && !nl) P[row * 25] = 0.0;
         if (!cl && nl) {
-            double Jc[18];
-            hkd::foot_jacobian_compact(x, x + 12 + 3 * l, l, Jc);
-            const double cmap[3] = {1.0, 1.0, 0.0};
-            for (int r = 0; r < 3; ++r) {
-                const int row = 12 + 3 * l + r;
-                for (int cc = 0; cc < 24; ++cc) P[row + 24 * cc] = 0.0;
-                for (int cc = 0; cc < 3; ++cc) {
-                    P[row + 24 * cc] = cmap[r] * Jc[r * 6 + cc];                     // d/d eul
-                    P[row + 24 * (3 + cc)] = cmap[r] * ((r == cc) ? 1.0 : 0.0);      // d/d pos
-                    P[row + 24 * (12 + 3 * l + cc)] = cmap[r] * Jc[r * 6 + 3 + cc];  // d/d qleg
-                }
+            const double* Jc = Jc_all + 18 * l + 6 * r;
+            const double cmap = (r == 2) ? 0.0 : 1.0;
+            P[row * 25] = 0.0;
+            for (int cc = 0; cc < 3; ++cc) {
+                P[row + 24 * cc] = cmap * Jc[cc];                          // d/d eul
+                P[row + 24 * (3 + cc)] = cmap * ((r == cc) ? 1.0 : 0.0);   // d/d pos
+                P[row + 24 * (12 + 3 * l + cc)] = cmap * Jc[3 + cc];       // d/d qleg
             }
         }
     }
@@ -259,7 +265,7 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
     const int N = sc.n_stages;
     double* wdx = sm.Y + 32 * warp;  // per-warp scratch
     // (a) controls: U = (Ubar + eps dU) + K (X - Xbar), one warp per stage.  K is stored compactly as
-    //     K_r[12][24] (only the coupled control of each leg has a non-zero gain row, see hsddp_sweep.cuh)
+    //     K_r^T [24][12] (only the coupled control of each leg has a non-zero gain row, see hsddp_sweep.cuh)
     for (int s = warp; s < N; s += kWarps) {
         int ph, k;
         phase_of_stage(sc, s, ph, k);
@@ -275,9 +281,9 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
             const bool stance = (cm >> ((lane % 12) / 3)) & 1u;
             double acc = 0.0;
             if ((lane < 12) == stance) {
-                const double* Kr = sm.K + 288 * (size_t)s + 24 * (lane % 12);
+                const double* KT = sm.K + 288 * (size_t)s + (lane % 12);  // KT[j][c]
 #pragma unroll 8
-                for (int j = 0; j < 24; ++j) acc = fma(Kr[j], wdx[j], acc);
+                for (int j = 0; j < 24; ++j) acc = fma(KT[12 * j], wdx[j], acc);
             }
             sm.U_t[24 * s + lane] = (sm.Ubar[24 * s + lane] + eps * sm.dU[24 * s + lane]) + acc;
         }
@@ -478,7 +484,7 @@ __device__ inline void lq_approximation_block(Smem& sm) {
 #pragma unroll
         for (int j = 0; j < 24; ++j) { x[j] = sm.X[24 * n + j]; u[j] = sm.U[24 * s + j]; }
         double* rec = sm.lqg + (size_t)s * LQ_STRIDE;
-        hkd::dynamics_partial_compact(x, u, dt, cm, rec + LQ_AT, rec + LQ_BT);
+        hkd::dynamics_partial_record(x, u, dt, cm, rec + LQ_AT12, rec + LQ_BQ);
         const double* xr = sm.xr + 24 * n;
         const double* ur = sm.ur + 24 * n;
         double lx[24], lu[24];
@@ -546,9 +552,13 @@ __device__ inline void lq_approximation_block(Smem& sm) {
             for (int j = 0; j < 24; ++j) hx[j] = 0.0;
             rec[TQ_WH + l] = 0.0;
             const bool td = !((cm >> l) & 1u) && ((sc.nmask[ph] >> l) & 1u);
-            if (td && sm.opt.AL_active) {
+            if (td) {  // reset-map Jacobian of a touchdown leg, cached for the sweep and the linear rollout
                 double Jc[18];
                 hkd::foot_jacobian_compact(x, x + 12 + 3 * l, l, Jc);
+                for (int c = 0; c < 18; ++c) rec[TQ_JC + 18 * l + c] = Jc[c];
+            }
+            if (td && sm.opt.AL_active) {
+                const double* Jc = rec + TQ_JC + 18 * l;
                 for (int c = 0; c < 3; ++c) { hx[c] = Jc[2 * 6 + c]; hx[12 + 3 * l + c] = Jc[2 * 6 + 3 + c]; }
                 hx[5] = 1.0;
                 const double h = sm.hcon[4 * ph + l], sigma = sm.al[8 * ph + 2 * l], lambda = sm.al[8 * ph + 2 * l + 1];

@@ -583,7 +583,7 @@ static int get_gains(hsddp_batch* b, int row0, int nrows, double* out) {
                 double* o = out + (p * nrows + (s - row0)) * 576;
                 for (int c = 0; c < 12; ++c) {
                     const int i = ((sc.cmask[ph] >> (c / 3)) & 1u) ? c : 12 + c;
-                    for (int j = 0; j < 24; ++j) o[i + 24 * j] = src[c * 24 + j];
+                    for (int j = 0; j < 24; ++j) o[i + 24 * j] = src[j * 12 + c];
                 }
             }
     }
@@ -636,7 +636,7 @@ int hsddp_batch_get_array(hsddp_batch* b, int which, double* out) {
                     else if (which == HSDDP_ARR_LU) std::memcpy(o, rec + LQ_LU, 24 * sizeof(double));
                     else if (which == HSDDP_ARR_A || which == HSDDP_ARR_B) {
                         double A[576], B[576];
-                        hkd::expand_AB(rec + LQ_AT, rec + LQ_BT, sc.dt, cm, A, B);
+                        hkd::expand_AB(rec + LQ_AT12, rec + LQ_BQ, sc.dt, cm, A, B);
                         std::memcpy(o, which == HSDDP_ARR_A ? A : B, 576 * sizeof(double));
                     } else if (which == HSDDP_ARR_LUU) {
                         for (int i = 0; i < 24; ++i) o[i * 25] = sc.dt * (i < 12 ? .2 : .1);

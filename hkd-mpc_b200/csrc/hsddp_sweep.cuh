@@ -18,7 +18,7 @@
 // One stage:
 //     Y = H A            Z = H B_r                              (DMMA m8n8k4, K = 12 / 8)
 //     Qxx = lxx + A^T Y  Qux_r = B_r^T Y   Quu_r = luu_r + B_r^T Z    Qx, Qu_r   (DMMA + fix-ups)
-//     Gauss-Jordan on the register tableau [Quu_r | Qux_r | Qu_r] (lane = column) -> -K_r, -dU_r
+//     block Gauss-Jordan (2x2 pivots) on the register tableau [Quu_r | Qux_r | Qu_r] (lane = column) -> -K_r, -dU_r
 //     PD verdict = no negative pivot of Quu_r - 1e-9 I (third warp, concurrently; Q7)
 //     H' = sym(Qxx) + Qux_r^T K_r      G' = Qx + Qux_r^T dU_r   (DMMA, accumulators kept in registers)
 #pragma once
@@ -55,60 +55,98 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
                  : "d"(a), "d"(b));
 }
 
-// Shared-memory views used by the sweep (all with row stride 24 doubles):
-//   H    [24][24]  symmetric value Hessian
-//   Y    [24][24]  H A                         (row-major)
-//   Zr   [24][24]  H B_r in columns 0..11 (12..15 zero padding)
-//   At12 [12][24]  rows 0..11 of A - I
-//   Bq   [ 8][24]  rows 4..11 of B_r in columns 0..11 (stance columns only; 12..15 zero)
-//   QuxR [16][24]  Qux_r (rows 12..15 padding)
-//   QuuR [16][24]  Quu_r in [0..11][0..11]
-//   KrS  [12][24]  K_r of the current stage
-struct SweepSmem {
-    double *H, *Y, *Zr, *At12, *Bq, *QuxR, *QuuR, *KrS;
-};
+// cp.async (LDGSTS) helpers: the next stage's record is fetched while the current stage computes
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-__device__ __forceinline__ SweepSmem sweep_views(Smem& sm) {
-    SweepSmem v;
-    v.H = sm.H; v.Y = sm.Y; v.Zr = sm.Z; v.QuxR = sm.Qux; v.QuuR = sm.Quu;
-    v.At12 = sm.Qxx; v.Bq = sm.Qxx + 288; v.KrS = sm.Qxx + 288;  // KrS aliases Bq + tail: Bq is dead after the Q phase
-    return v;
+// stage record (LQ_STRIDE doubles) and the defect of the stage's successor node -> buffer `buf`
+__device__ __forceinline__ void prefetch_stage(Smem& sm, int buf, int s, int n1) {
+    const char* src = reinterpret_cast<const char*>(sm.lqg + (size_t)s * LQ_STRIDE);
+    char* dst = reinterpret_cast<char*>(sm.rec[buf]);
+    for (int c = threadIdx.x; c < LQ_STRIDE / 2; c += kThreads) cp_async16(dst + 16 * c, src + 16 * c);
+    if (threadIdx.x < 12) cp_async16(reinterpret_cast<char*>(sm.dfc2[buf]) + 16 * threadIdx.x,
+                                     reinterpret_cast<const char*>(sm.Defect + 24 * n1) + 16 * threadIdx.x);
 }
 
-// Gauss-Jordan on 12 rows, one tableau column per lane (v[0..11]).  Lanes 0..11 of the
-// warp must hold the columns of the 12x12 pivot matrix.  `sbuf` is a 12-double per-warp
-// staging area.  Returns false if a negative pivot was met (only meaningful for the caller
-// that runs the shifted matrix).  After the call v = Quu_r^-1 * (original column).
+// Block Gauss-Jordan with 2x2 pivot blocks on 12 rows, one tableau column per lane (v[0..11]).
+// Lanes 0..11 of the warp hold the columns of the 12x12 pivot matrix.  `sbuf`: 24 doubles per warp.
+// Returns false if a negative pivot was met (pivot 1 = a, pivot 2 = det / a), which for the caller
+// that runs Quu_r - 1e-9 I is the reference's LDLT(...).isPositive() verdict (Sylvester's law of
+// inertia).  After the call v = Quu_r^-1 * (original column).
 __device__ __forceinline__ bool gauss_jordan12(double (&v)[12], double* sbuf) {
     const int lane = threadIdx.x & 31;
     bool ok = true;
 #pragma unroll
-    for (int k = 0; k < 12; ++k) {
-        if (lane == k) {
-            const double inv = 1.0 / v[k];
+    for (int k = 0; k < 12; k += 2) {
+        if (lane == k || lane == k + 1) {
+            double2* dst = reinterpret_cast<double2*>(sbuf + 12 * (lane - k));
 #pragma unroll
-            for (int r = 0; r < 12; ++r) sbuf[r] = (r == k) ? inv : v[r] * inv;  // multipliers g_r = a_rk / a_kk
-            sbuf[12] = v[k];
+            for (int r = 0; r < 12; r += 2) dst[r >> 1] = make_double2(v[r], v[r + 1]);
         }
         __syncwarp();
-        double g[12];
+        double c0[12], c1[12];
 #pragma unroll
         for (int r = 0; r < 12; r += 2) {
-            const double2 t = *reinterpret_cast<const double2*>(sbuf + r);
-            g[r] = t.x; g[r + 1] = t.y;
+            const double2 a = *reinterpret_cast<const double2*>(sbuf + r);
+            const double2 b = *reinterpret_cast<const double2*>(sbuf + 12 + r);
+            c0[r] = a.x; c0[r + 1] = a.y; c1[r] = b.x; c1[r + 1] = b.y;
         }
-        const double piv = sbuf[12];
-        if (piv < 0.0) ok = false;
-        const double vk = v[k];
+        // pivot block P = [c0[k] c1[k]; c0[k+1] c1[k+1]]
+        const double det = c0[k] * c1[k + 1] - c1[k] * c0[k + 1];
+        if (c0[k] < 0.0 || det < 0.0) ok = false;
+        const double rdet = 1.0 / det;
+        const double x0 = v[k], x1 = v[k + 1];
+        const double t0 = (c1[k + 1] * x0 - c1[k] * x1) * rdet;
+        const double t1 = (c0[k] * x1 - c0[k + 1] * x0) * rdet;
 #pragma unroll
-        for (int r = 0; r < 12; ++r) v[r] = (r == k) ? vk * g[k] : fma(-g[r], vk, v[r]);
+        for (int r = 0; r < 12; ++r) {
+            if (r == k) v[r] = t0;
+            else if (r == k + 1) v[r] = t1;
+            else v[r] = fma(-c1[r], t1, fma(-c0[r], t0, v[r]));
+        }
         __syncwarp();
     }
     return ok;
 }
 
+// running / terminal cost Hessian of a phase in table form: lxx(i,j) = [i==j] d[i] - coupling w
+__device__ __forceinline__ double lxx_tab(const double* d, const double* w, int i, int j) {
+    if (i == j) return d[i];
+    if (i >= 3 && i < 6 && j >= 12 && (j - 12) % 3 == i - 3) return -w[j - 12];
+    if (i >= 12 && j == 3 + (i - 12) % 3) return -w[i - 12];
+    return 0.0;
+}
+__device__ inline void build_lxx_tables(Smem& sm, unsigned cm, double dt) {
+    const int tid = threadIdx.x;
+    if (tid < 24) {  // [0..11] running w, [12..23] terminal w
+        const int q = tid % 12, l = q / 3, jj = q % 3;
+        const double c = (double)((cm >> l) & 1u);
+        const double scale = (tid < 12) ? dt : 20.0;
+        (tid < 12 ? sm.lxxw : sm.lxxTw)[q] = (scale * c * weight_foot(l, jj, cm)) * c;
+    }
+    __syncthreads();
+    if (tid < 48) {
+        const bool term = tid >= 24;
+        const int i = tid % 24;
+        const double* w = term ? sm.lxxTw : sm.lxxw;
+        double val = term ? weight_Qf(i, cm) : dt * weight_Q(i, cm);
+        if (i >= 3 && i < 6) { for (int l = 0; l < 4; ++l) val += w[3 * l + i - 3]; }
+        else if (i >= 12) val += w[i - 12];
+        (term ? sm.lxxTd : sm.lxxd)[i] = val;
+    }
+    __syncthreads();
+}
+
 // One phase of the backward sweep.  On entry sm.G / sm.H hold Gprime / Hprime (zero for
 // the last phase).  Returns false if a stage failed the PD test.
+//
+// Shared-memory tiles (row stride 24 doubles unless noted):
+//   H [24][24] value Hessian (symmetric) ; Y [24][24] = H A ; Zr = sm.Z [24][16 used] = H B_r
+//   rec[buf]: At12 [12][24] | Bq [8][24] | lx | lu | luu blocks  (cp.async double buffer)
+//   QuxR = sm.Qux [16][24] ; QuuR = sm.Quu [12][24] ; KT = sm.KrS [24][12] (K_r transposed)
 __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, double& dV1, double& dV2) {
     const DevSchedule& sc = sm.sc;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -118,77 +156,71 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
     const PhaseConst pc = phase_const(cm, dt);
     const int Nph = sc.horizon[ph];
     const double* trec = sm.tq + ph * TQ_STRIDE;
-    const SweepSmem v = sweep_views(sm);
+    double* const H = sm.H;
+    double* const Y = sm.Y;
+    double* const Zr = sm.Z;
+    double* const QuxR = sm.Qux;
+    double* const QuuR = sm.Quu;
+    double* const KT = sm.KrS;
+    build_lxx_tables(sm, cm, dt);
+    prefetch_stage(sm, 0, sc.stage_off[ph] + Nph - 1, sc.node_off[ph] + Nph);
     // G[N] = Phix + Gprime ; H[N] = Phixx + Hprime
     if (tid < 24) sm.G[tid] += trec[TQ_PHIX + tid];
     for (int e = tid; e < 576; e += kThreads) {
         const int i = e / 24, j = e % 24;
-        double val = lxx_entry(i, j, cm, 0.0, 20.0, true);
+        double val = lxx_tab(sm.lxxTd, sm.lxxTw, i, j);
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
             const double wh = trec[TQ_WH + l];
             if (wh != 0.0) val += wh * (trec[TQ_HX + 24 * l + i] * trec[TQ_HX + 24 * l + j]);
         }
-        v.H[e] += val;
+        H[e] += val;
     }
+    cp_async_wait_all();
     __syncthreads();
     dV1 = 0.0; dV2 = 0.0;
+    // Qxx / H' tile ownership: warp0 (0,0),(1,0) ; warp1 (1,1),(2,0) ; warp2 (2,1) ; warp3 (2,2)
+    int qi[2], qj[2], nq;
+    if (warp == 0) { nq = 2; qi[0] = 0; qj[0] = 0; qi[1] = 1; qj[1] = 0; }
+    else if (warp == 1) { nq = 2; qi[0] = 1; qj[0] = 1; qi[1] = 2; qj[1] = 0; }
+    else if (warp == 2) { nq = 1; qi[0] = 2; qj[0] = 1; qi[1] = 2; qj[1] = 1; }
+    else { nq = 1; qi[0] = 2; qj[0] = 2; qi[1] = 2; qj[1] = 2; }
     for (int k = Nph - 1; k >= 0; --k) {
         const int s = sc.stage_off[ph] + k;
-        const int n1 = sc.node_off[ph] + k + 1;
-        const double* rec = sm.lqg + (size_t)s * LQ_STRIDE;
-        // ---- stage inputs -> shared memory ----
-        for (int e = tid; e < 288; e += kThreads) {  // At12: rows 0..11 of A - I
-            const int r = e / 24, c = e % 24;
-            double val = 0.0;
-            if (r < 3) val = rec[LQ_AT + r * 24 + c];
-            else if (r < 6) val = (c == r + 6) ? dt : 0.0;
-            else if (r < 9) val = rec[LQ_AT + (r - 3) * 24 + c];
-            v.At12[e] = val;
-        }
-        for (int e = tid; e < 8 * 16; e += kThreads) {  // Bq: rows 4..11 of B_r, reduced columns 0..15
-            const int r = e / 16 + 4, c = e % 16;
-            double val = 0.0;
-            if (c < 12 && ((cm >> (c / 3)) & 1u)) {
-                if (r >= 6 && r < 9) val = rec[LQ_BT + (r - 6) * 12 + c];
-                else if (r == 9 + c % 3) val = pc.cm[c / 3];
-            }
-            v.Bq[(r - 4) * 24 + c] = val;
-        }
-        if (tid < 24) {
-            sm.dfc[tid] = sm.Defect[24 * n1 + tid];
-            sm.lq[LQ_LX + tid] = rec[LQ_LX + tid];
-            sm.lq[LQ_LU + tid] = rec[LQ_LU + tid];
-        } else if (tid >= 32 && tid < 68) {
-            sm.lq[LQ_LUU + tid - 32] = rec[LQ_LUU + tid - 32];
-        }
-        __syncthreads();
+        const int buf = (Nph - 1 - k) & 1;
+        if (k > 0) prefetch_stage(sm, buf ^ 1, s - 1, sc.node_off[ph] + k);
+        const double* At12 = sm.rec[buf] + LQ_AT12;
+        const double* Bq = sm.rec[buf] + LQ_BQ;
+        const double* lxv = sm.rec[buf] + LQ_LX;
+        const double* luv = sm.rec[buf] + LQ_LU;
+        const double* luu = sm.rec[buf] + LQ_LUU;
+        const double* dfc = sm.dfc2[buf];
         // ---- P1: Y = H A, Z = H B_r, Gn = G + H d ----
         if (warp < 3) {
             const int i0 = 8 * warp;
             double cy[3][2], cz[2] = {0.0, 0.0};
 #pragma unroll
             for (int J = 0; J < 3; ++J) {
-                const double2 h2 = *reinterpret_cast<const double2*>(v.H + (i0 + g) * 24 + 8 * J + 2 * t);
+                const double2 h2 = *reinterpret_cast<const double2*>(H + (i0 + g) * 24 + 8 * J + 2 * t);
                 cy[J][0] = h2.x; cy[J][1] = h2.y;
             }
 #pragma unroll
             for (int kk = 0; kk < 12; kk += 4) {
-                const double a = v.H[(kk + t) * 24 + i0 + g];  // H[i][k] by symmetry
+                const double a = H[(kk + t) * 24 + i0 + g];  // H[i][k] by symmetry
 #pragma unroll
-                for (int J = 0; J < 3; ++J) dmma884(cy[J], a, v.At12[(kk + t) * 24 + 8 * J + g]);
-                if (kk >= 4) dmma884(cz, a, v.Bq[(kk - 4 + t) * 24 + g]);
+                for (int J = 0; J < 3; ++J) dmma884(cy[J], a, At12[(kk + t) * 24 + 8 * J + g]);
+                if (kk >= 4) dmma884(cz, a, Bq[(kk - 4 + t) * 24 + g]);
             }
 #pragma unroll
             for (int J = 0; J < 3; ++J)
-                *reinterpret_cast<double2*>(v.Y + (i0 + g) * 24 + 8 * J + 2 * t) = make_double2(cy[J][0], cy[J][1]);
+                *reinterpret_cast<double2*>(Y + (i0 + g) * 24 + 8 * J + 2 * t) = make_double2(cy[J][0], cy[J][1]);
             // swing columns of Z: H[:, 12+3l+j] * dt
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const int c = 2 * t + q;
-                if (!((cm >> (c / 3)) & 1u)) cz[q] += v.H[(i0 + g) * 24 + 12 + c] * pc.swdt[c / 3];
+                if (!((cm >> (c / 3)) & 1u)) cz[q] += H[(i0 + g) * 24 + 12 + c] * pc.swdt[c / 3];
             }
-            *reinterpret_cast<double2*>(v.Zr + (i0 + g) * 24 + 2 * t) = make_double2(cz[0], cz[1]);
+            *reinterpret_cast<double2*>(Zr + (i0 + g) * 24 + 2 * t) = make_double2(cz[0], cz[1]);
         } else {
             // warp 3: Z columns 8..15 for all three row blocks, then Gn
 #pragma unroll
@@ -196,49 +228,41 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                 const int i0 = 8 * I;
                 double cz[2] = {0.0, 0.0};
 #pragma unroll
-                for (int kk = 4; kk < 12; kk += 4) dmma884(cz, v.H[(kk + t) * 24 + i0 + g], v.Bq[(kk - 4 + t) * 24 + 8 + g]);
+                for (int kk = 4; kk < 12; kk += 4) dmma884(cz, H[(kk + t) * 24 + i0 + g], Bq[(kk - 4 + t) * 24 + 8 + g]);
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     const int c = 8 + 2 * t + q;
-                    if (c < 12 && !((cm >> (c / 3)) & 1u)) cz[q] += v.H[(i0 + g) * 24 + 12 + c] * pc.swdt[c / 3];
+                    if (c < 12 && !((cm >> (c / 3)) & 1u)) cz[q] += H[(i0 + g) * 24 + 12 + c] * pc.swdt[c / 3];
                 }
-                *reinterpret_cast<double2*>(v.Zr + (i0 + g) * 24 + 8 + 2 * t) = make_double2(cz[0], cz[1]);
+                *reinterpret_cast<double2*>(Zr + (i0 + g) * 24 + 8 + 2 * t) = make_double2(cz[0], cz[1]);
             }
             if (lane < 24) {  // Gn = G + H d   (Q10)
                 double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
                 for (int j = 0; j < 24; j += 4) {
-                    a0 = fma(v.H[j * 24 + lane], sm.dfc[j], a0);
-                    a1 = fma(v.H[(j + 1) * 24 + lane], sm.dfc[j + 1], a1);
-                    a2 = fma(v.H[(j + 2) * 24 + lane], sm.dfc[j + 2], a2);
-                    a3 = fma(v.H[(j + 3) * 24 + lane], sm.dfc[j + 3], a3);
+                    a0 = fma(H[j * 24 + lane], dfc[j], a0);
+                    a1 = fma(H[(j + 1) * 24 + lane], dfc[j + 1], a1);
+                    a2 = fma(H[(j + 2) * 24 + lane], dfc[j + 2], a2);
+                    a3 = fma(H[(j + 3) * 24 + lane], dfc[j + 3], a3);
                 }
                 sm.Gn[lane] = sm.G[lane] + ((a0 + a1) + (a2 + a3));
             }
         }
         __syncthreads();
         // ---- P2: Qxx (lower tiles, kept in registers), Qux_r, Quu_r, Qx, Qu_r ----
-        // Qxx tile ownership: warp0 (0,0),(1,0) ; warp1 (1,1),(2,0) ; warp2 (2,1) ; warp3 (2,2)
         double cq[2][2];
-        int qi[2], qj[2];
-        int nq;
-        if (warp == 0) { nq = 2; qi[0] = 0; qj[0] = 0; qi[1] = 1; qj[1] = 0; }
-        else if (warp == 1) { nq = 2; qi[0] = 1; qj[0] = 1; qi[1] = 2; qj[1] = 0; }
-        else if (warp == 2) { nq = 1; qi[0] = 2; qj[0] = 1; qi[1] = 2; qj[1] = 1; }
-        else { nq = 1; qi[0] = 2; qj[0] = 2; qi[1] = 2; qj[1] = 2; }
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             if (q < nq) {
                 const int i0 = 8 * qi[q], j0 = 8 * qj[q];
                 const int i = i0 + g, j = j0 + 2 * t;
-                const double2 y2 = *reinterpret_cast<const double2*>(v.Y + i * 24 + j);
-                cq[q][0] = lxx_entry(i, j, cm, dt, dt, false) + y2.x + ((i == j) ? reg : 0.0);
-                cq[q][1] = lxx_entry(i, j + 1, cm, dt, dt, false) + y2.y + ((i == j + 1) ? reg : 0.0);
+                const double2 y2 = *reinterpret_cast<const double2*>(Y + i * 24 + j);
+                cq[q][0] = lxx_tab(sm.lxxd, sm.lxxw, i, j) + y2.x + ((i == j) ? reg : 0.0);
+                cq[q][1] = lxx_tab(sm.lxxd, sm.lxxw, i, j + 1) + y2.y + ((i == j + 1) ? reg : 0.0);
 #pragma unroll
-                for (int kk = 0; kk < 12; kk += 4) dmma884(cq[q], v.At12[(kk + t) * 24 + i0 + g], v.Y[(kk + t) * 24 + j0 + g]);
+                for (int kk = 0; kk < 12; kk += 4) dmma884(cq[q], At12[(kk + t) * 24 + i0 + g], Y[(kk + t) * 24 + j0 + g]);
             }
         }
-        // Qux_r tiles (Ic, J): Ic in {0,1}, J in {0,1,2}; Quu_r tiles (Ic, Jc) in {0,1}^2
         {
             // job list per warp: warp0: Qux(0,0),Qux(1,0) ; warp1: Qux(0,1),Qux(1,1) ; warp2: Qux(0,2),Qux(1,2),Quu(0,0) ; warp3: Quu(0,1),Quu(1,0),Quu(1,1)
             const int njobs = (warp < 2) ? 2 : 3;
@@ -250,10 +274,10 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                     if (warp < 2) { is_quu = false; Ic = job; J = warp; }
                     else if (warp == 2) { is_quu = (job == 2); Ic = is_quu ? 0 : job; J = is_quu ? 0 : 2; }
                     else { is_quu = true; Ic = (job == 0) ? 0 : 1; J = (job == 1) ? 0 : 1; }
-                    const double* Bop = is_quu ? v.Zr : v.Y;
+                    const double* Bop = is_quu ? Zr : Y;
                     double cc[2] = {0.0, 0.0};
 #pragma unroll
-                    for (int kk = 4; kk < 12; kk += 4) dmma884(cc, v.Bq[(kk - 4 + t) * 24 + 8 * Ic + g], Bop[(kk + t) * 24 + 8 * J + g]);
+                    for (int kk = 4; kk < 12; kk += 4) dmma884(cc, Bq[(kk - 4 + t) * 24 + 8 * Ic + g], Bop[(kk + t) * 24 + 8 * J + g]);
                     // swing rows: (B_r^T M)[c][:] = dt * M[12+c][:]
                     const int c = 8 * Ic + g;
                     if (c < 12 && !((cm >> (c / 3)) & 1u)) {
@@ -262,17 +286,19 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                         cc[1] += pc.swdt[c / 3] * m2.y;
                     }
                     if (is_quu) {  // + luu_r: dt R + reg on the diagonal, ReB blocks for stance legs
+                        if (c < 12) {
 #pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            const int c2 = 8 * J + 2 * t + q;
-                            if (c < 12 && c2 < 12) {
-                                if (c == c2) cc[q] += dt * weight_R(act_index(c, cm)) + reg;
-                                if (c / 3 == c2 / 3 && ((cm >> (c / 3)) & 1u)) cc[q] += sm.lq[LQ_LUU + 9 * (c / 3) + 3 * (c % 3) + (c2 % 3)];
+                            for (int q = 0; q < 2; ++q) {
+                                const int c2 = 8 * J + 2 * t + q;
+                                if (c2 < 12) {
+                                    if (c == c2) cc[q] += dt * weight_R(act_index(c, cm)) + reg;
+                                    if (c / 3 == c2 / 3 && ((cm >> (c / 3)) & 1u)) cc[q] += luu[9 * (c / 3) + 3 * (c % 3) + (c2 % 3)];
+                                }
                             }
+                            *reinterpret_cast<double2*>(QuuR + c * 24 + 8 * J + 2 * t) = make_double2(cc[0], cc[1]);
                         }
-                        *reinterpret_cast<double2*>(v.QuuR + c * 24 + 8 * J + 2 * t) = make_double2(cc[0], cc[1]);
                     } else {
-                        *reinterpret_cast<double2*>(v.QuxR + c * 24 + 8 * J + 2 * t) = make_double2(cc[0], cc[1]);
+                        *reinterpret_cast<double2*>(QuxR + c * 24 + 8 * J + 2 * t) = make_double2(cc[0], cc[1]);
                     }
                 }
             }
@@ -280,8 +306,8 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
         if (warp == 3 && lane < 24) {  // Qx = lx + A^T Gn
             double acc = sm.Gn[lane];
 #pragma unroll
-            for (int r = 0; r < 9; ++r) acc = fma(v.At12[r * 24 + lane], sm.Gn[r], acc);
-            sm.Qx[lane] = sm.lq[LQ_LX + lane] + acc;
+            for (int r = 0; r < 9; ++r) acc = fma(At12[r * 24 + lane], sm.Gn[r], acc);
+            sm.Qx[lane] = lxv[lane] + acc;
         }
         if (warp == 2 && lane < 12) {  // Qu_r = lu_r + B_r^T Gn
             const int c = lane;
@@ -289,11 +315,11 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
             if ((cm >> (c / 3)) & 1u) {
                 acc = 0.0;
 #pragma unroll
-                for (int r = 4; r < 12; ++r) acc = fma(v.Bq[(r - 4) * 24 + c], sm.Gn[r], acc);
+                for (int r = 4; r < 12; ++r) acc = fma(Bq[(r - 4) * 24 + c], sm.Gn[r], acc);
             } else {
                 acc = pc.swdt[c / 3] * sm.Gn[12 + c];
             }
-            sm.Qu[c] = sm.lq[LQ_LU + act_index(c, cm)] + acc;
+            sm.Qu[c] = luv[act_index(c, cm)] + acc;
         }
         __syncthreads();
         // ---- P3: Gauss-Jordan tableau (warps 0,1), shifted PD test (warp 2), inactive controls (warp 3) ----
@@ -302,28 +328,31 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
             // lanes 0..11: columns of Quu_r ; warp0 lanes 12..31: Qux_r columns 0..19 ; warp1 lanes 12..15: Qux_r 20..23, lane 16: Qu_r
             const double* src = nullptr;
             int stride = 24;
-            if (lane < 12) src = v.QuuR + lane;
-            else if (warp == 0) src = v.QuxR + (lane - 12);
-            else if (warp == 1 && lane < 16) src = v.QuxR + (lane + 8);
+            if (lane < 12) src = QuuR + lane;
+            else if (warp == 0) src = QuxR + (lane - 12);
+            else if (warp == 1 && lane < 16) src = QuxR + (lane + 8);
             else if (warp == 1 && lane == 16) { src = sm.Qu; stride = 1; }
 #pragma unroll
             for (int r = 0; r < 12; ++r) col[r] = src ? src[r * stride] : ((r == (lane % 12)) ? 1.0 : 0.0);
-            if (warp == 2 && lane < 12) col[lane] -= 1e-9;  // Quu - 1e-9 I (Q7)
-            const bool ok = gauss_jordan12(col, sm.red + 16 * warp);
+            if (warp == 2 && lane < 12) {
+#pragma unroll
+                for (int r = 0; r < 12; ++r) if (r == lane) col[r] -= 1e-9;  // Quu - 1e-9 I (Q7)
+            }
+            const bool ok = gauss_jordan12(col, sm.red + 32 * warp);
             if (warp == 2) {
                 if (lane == 0) sm.ibuf[0] = ok ? 1 : 0;
             } else if (lane >= 12) {
-                if (warp == 0) {
-                    const int j = lane - 12;
-                    double* Kg = sm.K + (size_t)s * 288;
+                const int j = (warp == 0) ? lane - 12 : lane + 8;
+                if (j < 24) {  // gain column j: K_r[:, j] = -Quu_r^-1 Qux_r[:, j]  -> KT[j][0..11] (smem + HBM)
+                    double2* ks = reinterpret_cast<double2*>(KT + 12 * j);
+                    double2* kg = reinterpret_cast<double2*>(sm.K + (size_t)s * 288 + 12 * j);
 #pragma unroll
-                    for (int r = 0; r < 12; ++r) { v.KrS[r * 24 + j] = -col[r]; Kg[r * 24 + j] = -col[r]; }
-                } else if (lane < 16) {
-                    const int j = lane + 8;
-                    double* Kg = sm.K + (size_t)s * 288;
-#pragma unroll
-                    for (int r = 0; r < 12; ++r) { v.KrS[r * 24 + j] = -col[r]; Kg[r * 24 + j] = -col[r]; }
-                } else if (lane == 16) {
+                    for (int r = 0; r < 12; r += 2) {
+                        const double2 val = make_double2(-col[r], -col[r + 1]);
+                        ks[r >> 1] = val;
+                        kg[r >> 1] = val;
+                    }
+                } else if (warp == 1 && lane == 16) {
                     double dvk = 0.0;
 #pragma unroll
                     for (int r = 0; r < 12; ++r) {
@@ -339,7 +368,7 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
             double dv = 0.0;
             if (lane < 12) {
                 const int i = inact_index(lane, cm);
-                const double qu = sm.lq[LQ_LU + i];
+                const double qu = luv[i];
                 const double du = -qu / (dt * weight_R(i) + reg);
                 sm.dU[24 * s + i] = du;
                 dv = -qu * du;
@@ -349,14 +378,14 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
             if (lane == 0) sm.dbuf[1] = dv;
         }
         __syncthreads();
-        if (!sm.ibuf[0]) return false;
+        if (!sm.ibuf[0]) { cp_async_wait_all(); return false; }
         // ---- P4: H' = sym(Qxx) + Qux_r^T K_r ; G' = Qx + Qux_r^T dU_r ----
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             if (q < nq) {
                 const int i0 = 8 * qi[q], j0 = 8 * qj[q];
 #pragma unroll
-                for (int kk = 0; kk < 12; kk += 4) dmma884(cq[q], v.QuxR[(kk + t) * 24 + i0 + g], v.KrS[(kk + t) * 24 + j0 + g]);
+                for (int kk = 0; kk < 12; kk += 4) dmma884(cq[q], QuxR[(kk + t) * 24 + i0 + g], KT[(j0 + g) * 12 + kk + t]);
                 if (i0 == j0) {
                     // symmetrise the diagonal tile: partner of (g, 2t+q') is (2t+q', g), held by lane 4*(2t+q') + g/2, slot g&1
                     const double p00 = __shfl_sync(0xffffffffu, cq[q][0], 4 * (2 * t) + (g >> 1));
@@ -365,34 +394,35 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                     const double p11 = __shfl_sync(0xffffffffu, cq[q][1], 4 * (2 * t + 1) + (g >> 1));
                     cq[q][0] = 0.5 * (cq[q][0] + ((g & 1) ? p01 : p00));
                     cq[q][1] = 0.5 * (cq[q][1] + ((g & 1) ? p11 : p10));
-                    *reinterpret_cast<double2*>(v.H + (i0 + g) * 24 + j0 + 2 * t) = make_double2(cq[q][0], cq[q][1]);
+                    *reinterpret_cast<double2*>(H + (i0 + g) * 24 + j0 + 2 * t) = make_double2(cq[q][0], cq[q][1]);
                 } else {
-                    *reinterpret_cast<double2*>(v.H + (i0 + g) * 24 + j0 + 2 * t) = make_double2(cq[q][0], cq[q][1]);
-                    v.H[(j0 + 2 * t) * 24 + i0 + g] = cq[q][0];
-                    v.H[(j0 + 2 * t + 1) * 24 + i0 + g] = cq[q][1];
+                    *reinterpret_cast<double2*>(H + (i0 + g) * 24 + j0 + 2 * t) = make_double2(cq[q][0], cq[q][1]);
+                    H[(j0 + 2 * t) * 24 + i0 + g] = cq[q][0];
+                    H[(j0 + 2 * t + 1) * 24 + i0 + g] = cq[q][1];
                 }
             }
         }
         if (warp == 3 && lane < 24) {
             double acc = sm.Qx[lane];
 #pragma unroll
-            for (int r = 0; r < 12; ++r) acc = fma(v.QuxR[r * 24 + lane], sm.wu[r], acc);
+            for (int r = 0; r < 12; ++r) acc = fma(QuxR[r * 24 + lane], sm.wu[r], acc);
             sm.G[lane] = acc;
         }
         const double dvk = sm.dbuf[0] + sm.dbuf[1];
         dV1 -= dvk;
         dV2 += dvk;
+        cp_async_wait_all();
         __syncthreads();
     }
     // G[0] += H[0] * Defect[0]
     {
         const int n0 = sc.node_off[ph];
-        if (tid < 24) sm.dfc[tid] = sm.Defect[24 * n0 + tid];
+        if (tid < 24) sm.vtmp[tid] = sm.Defect[24 * n0 + tid];
         __syncthreads();
         double acc = 0.0;
         if (tid < 24) {
 #pragma unroll
-            for (int j = 0; j < 24; ++j) acc = fma(v.H[tid * 24 + j], sm.dfc[j], acc);
+            for (int j = 0; j < 24; ++j) acc = fma(H[tid * 24 + j], sm.vtmp[j], acc);
         }
         __syncthreads();
         if (tid < 24) sm.G[tid] += acc;
@@ -414,8 +444,7 @@ __device__ inline bool backward_sweep_block(Smem& sm, double reg) {
             __syncthreads();
         } else {
             // impact-aware step: G' = Px^T G0, H' = Px^T H0 Px at the phase's terminal state
-            const int ne = sc.node_off[ph] + sc.horizon[ph];
-            resetmap_partial_block(sm.X + 24 * ne, sc.cmask[ph], sc.nmask[ph], sm.Y);
+            resetmap_partial_block(sm.tq + ph * TQ_STRIDE + TQ_JC, sc.cmask[ph], sc.nmask[ph], sm.Y);
             const double* P = sm.Y;  // column-major P[r + 24 c]
             for (int e = tid; e < 576; e += kThreads) {  // Z = P^T H  (row-major Z[i][j])
                 const int i = e / 24, j = e % 24;
@@ -477,146 +506,234 @@ __device__ inline bool backward_sweep_regularized_block(Smem& sm, int& n_sweeps)
 }
 
 // ---------------------------------------------------------------------------
-// linear rollout: dX recursion and expected cost change, warp 0 (lane i <-> component i)
+// linear rollout (MultiPhaseDDP::linear_rollout + SinglePhase::linear_rollout).
+// The dX recursion is sequential in time; it runs on warp 0 (lane i <-> component i) out of
+// shared memory while ALL threads stream the next chunk of stage data (gains, the six dense
+// rows of A, the three dense rows of B, defects, feed-forward) in with cp.async.  The expected
+// cost change (dV_1, dV_2) does not feed back into the recursion, so it is accumulated
+// afterwards by all threads in parallel.
 // ---------------------------------------------------------------------------
+constexpr int LR_SLOT = 552;   // doubles per stage slot: KT 288 | A rows 0-2 72 | A rows 6-8 72 | B rows 6-8 72 | defect 24 | dU 24
+constexpr int LR_CHUNK = 3;    // stages per chunk (2 chunks resident: 2*3*552 = 3312 doubles of the sweep's tile storage)
+constexpr int LR_UNITS = 276;  // 16-byte units per slot
+
+__device__ __forceinline__ int node_of_stage(const DevSchedule& sc, int s) {
+    int ph, k;
+    phase_of_stage(sc, s, ph, k);
+    return sc.node_off[ph] + k;
+}
+
+__device__ __forceinline__ void lr_prefetch(Smem& sm, double* buf, int s0, int s1) {
+    const int total = (s1 - s0) * LR_UNITS;
+    for (int e = threadIdx.x; e < total; e += kThreads) {
+        const int si = e / LR_UNITS, u = e % LR_UNITS;
+        const int s = s0 + si;
+        const double* rec = sm.lqg + (size_t)s * LQ_STRIDE;
+        const double* src;
+        if (u < 144) src = sm.K + (size_t)s * 288 + 2 * u;
+        else if (u < 180) src = rec + LQ_AT12 + 2 * (u - 144);
+        else if (u < 216) src = rec + LQ_AT12 + 144 + 2 * (u - 180);
+        else if (u < 252) src = rec + LQ_BQ + 48 + 2 * (u - 216);
+        else if (u < 264) src = sm.Defect + 24 * (node_of_stage(sm.sc, s) + 1) + 2 * (u - 252);
+        else src = sm.dU + 24 * s + 2 * (u - 264);
+        cp_async16(buf + si * LR_SLOT + 2 * u, src);
+    }
+}
+
 __device__ inline void linear_rollout_block(Smem& sm, double eps) {
     const DevSchedule& sc = sm.sc;
     const int tid = threadIdx.x, lane = tid & 31;
     const double dt = sc.dt;
+    const int N = sc.n_stages;
+    double* scratch = sm.H;  // H, Y, Z, Qux, Quu, KrS, rec are contiguous and free outside the sweep
     double* sdx = sm.vtmp;   // current dx, shared for broadcast
-    double* sdu = sm.vtmp2;  // current du (full 24)
-    double dV1 = 0.0, dV2 = 0.0;  // lane partial sums
-    for (int ph = 0; ph < sc.n_phases; ++ph) {
-        const unsigned cm = sc.cmask[ph];
-        const PhaseConst pc = phase_const(cm, dt);
-        const int n0 = sc.node_off[ph];
-        // dx_init = Px dX_end(prev)
-        if (ph > 0) {
-            const int ne = sc.node_off[ph - 1] + sc.horizon[ph - 1];
-            resetmap_partial_block(sm.X + 24 * ne, sc.cmask[ph - 1], sc.nmask[ph - 1], sm.Y);
-            if (tid < 24) {
-                double acc = 0.0;
-#pragma unroll
-                for (int m = 0; m < 24; ++m) acc = fma(sm.Y[tid + 24 * m], sdx[m], acc);
-                sm.Gn[tid] = acc;
-            }
-            __syncthreads();
-        } else {
-            if (tid < 24) sm.Gn[tid] = 0.0;
-            __syncthreads();
-        }
+    double* sdu = sm.vtmp2;  // coupled controls du_r[0..11]
+    __syncthreads();
+    lr_prefetch(sm, scratch, 0, min(LR_CHUNK, N));
+    cp_async_wait_all();
+    __syncthreads();
+    int ph = 0;
+    double dx = 0.0;
+    for (int c0 = 0; c0 < N; c0 += LR_CHUNK) {
+        const int c1 = min(c0 + LR_CHUNK, N);
+        double* buf = scratch + ((c0 / LR_CHUNK) & 1) * (LR_CHUNK * LR_SLOT);
+        double* nbuf = scratch + (((c0 / LR_CHUNK) & 1) ^ 1) * (LR_CHUNK * LR_SLOT);
+        if (c1 < N) lr_prefetch(sm, nbuf, c1, min(c1 + LR_CHUNK, N));
         if (tid < 32) {
-            // lane -> reduced control row it owns in K_r (lanes 0..11), and its full control index
-            const bool stance_of_lane = (lane < 24) && ((cm >> ((lane % 12) / 3)) & 1u);
-            const bool lane_active = (lane < 24) && ((lane < 12) == stance_of_lane);  // control `lane` is coupled
-            const int cred = lane % 12;
-            double dx = 0.0;
-            if (lane < 24) {
-                dx = sm.Gn[lane] + eps * sm.Defect[24 * n0 + lane];
-                sm.dX[24 * n0 + lane] = dx;
-                sdx[lane] = dx;
-            }
-            __syncwarp();
-            for (int k = 0; k < sc.horizon[ph]; ++k) {
-                const int s = sc.stage_off[ph] + k;
-                const double* rec = sm.lqg + (size_t)s * LQ_STRIDE;
-                const double* At = rec + LQ_AT;
-                const double* Bt = rec + LQ_BT;
-                double du = 0.0;
-                if (lane < 24) {
-                    double acc = 0.0;
-                    if (lane_active) {
-                        const double* Kr = sm.K + (size_t)s * 288 + cred * 24;
-#pragma unroll 8
-                        for (int j = 0; j < 24; ++j) acc = fma(Kr[j], sdx[j], acc);
+            for (int s = c0; s < c1; ++s) {
+                while (ph + 1 < sc.n_phases && s >= sc.stage_off[ph + 1]) ++ph;
+                const unsigned cm = sc.cmask[ph];
+                const int k = s - sc.stage_off[ph];
+                const int n = sc.node_off[ph] + k;
+                if (k == 0) {
+                    // phase start: dx_init = Px dX_end(prev) (zero for the first phase); dX[0] = dx_init + eps Defect[0]
+                    double dxi = 0.0;
+                    if (ph > 0 && lane < 24) {
+                        const unsigned pc_ = sc.cmask[ph - 1], pn_ = sc.nmask[ph - 1];
+                        dxi = dx;
+                        if (lane >= 12) {
+                            const int l = (lane - 12) / 3, r = (lane - 12) % 3;
+                            const bool cl = (pc_ >> l) & 1u, nl = (pn_ >> l) & 1u;
+                            if (cl && !nl) dxi = 0.0;
+                            if (!cl && nl) {
+                                if (r == 2) dxi = 0.0;
+                                else {
+                                    const double* Jc = sm.tq + (ph - 1) * TQ_STRIDE + TQ_JC + 18 * l + 6 * r;
+                                    double acc = sdx[3 + r];
+#pragma unroll
+                                    for (int c = 0; c < 3; ++c) acc = fma(Jc[c], sdx[c], acc);
+#pragma unroll
+                                    for (int c = 0; c < 3; ++c) acc = fma(Jc[3 + c], sdx[12 + 3 * l + c], acc);
+                                    dxi = acc;
+                                }
+                            }
+                        }
                     }
-                    du = eps * sm.dU[24 * s + lane] + acc;
+                    __syncwarp();
+                    if (lane < 24) {
+                        dx = dxi + eps * sm.Defect[24 * n + lane];
+                        sm.dX[24 * n + lane] = dx;
+                        sdx[lane] = dx;
+                    }
+                    __syncwarp();
+                }
+                const double* slot = buf + (s - c0) * LR_SLOT;
+                const double* KT = slot;
+                const double* A0 = slot + 288;
+                const double* A6 = slot + 360;
+                const double* B6 = slot + 432;
+                const double* dfn = slot + 504;
+                const double* dUs = slot + 528;
+                // du = eps dU + K dx : lanes 0..11 the coupled controls, lanes 12..23 the decoupled ones
+                if (lane < 12) {
+                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 24; j += 4) {
+                        a0 = fma(KT[j * 12 + lane], sdx[j], a0);
+                        a1 = fma(KT[(j + 1) * 12 + lane], sdx[j + 1], a1);
+                        a2 = fma(KT[(j + 2) * 12 + lane], sdx[j + 2], a2);
+                        a3 = fma(KT[(j + 3) * 12 + lane], sdx[j + 3], a3);
+                    }
+                    const int i = act_index(lane, cm);
+                    const double du = eps * dUs[i] + ((a0 + a1) + (a2 + a3));
                     sdu[lane] = du;
+                    sm.U_t[24 * s + i] = du;
+                } else if (lane < 24) {
+                    const int i = inact_index(lane - 12, cm);
+                    sm.U_t[24 * s + i] = eps * dUs[i];
                 }
                 __syncwarp();
-                double dxn = 0.0;
                 if (lane < 24) {
-                    // A dx
-                    double adx = dx;
+                    double acc = dx;
                     if (lane < 3 || (lane >= 6 && lane < 9)) {
-                        const int r = lane < 3 ? lane : lane - 3;
-                        double acc = 0.0;
-#pragma unroll 8
-                        for (int j = 0; j < 24; ++j) acc = fma(At[r * 24 + j], sdx[j], acc);
-                        adx += acc;
-                    } else if (lane >= 3 && lane < 6) {
-                        adx += dt * sdx[lane + 6];
-                    }
-                    // B du
-                    double bdu;
-                    if (lane >= 6 && lane < 9) {
-                        double acc = 0.0;
+                        const double* Ar = (lane < 3) ? (A0 + 24 * lane) : (A6 + 24 * (lane - 6));
+                        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-                        for (int j = 0; j < 12; ++j) acc = fma(Bt[(lane - 6) * 12 + j], sdu[j], acc);
-                        bdu = acc;
-                    } else if (lane >= 9 && lane < 12) {
-                        double acc = 0.0;
+                        for (int j = 0; j < 24; j += 4) {
+                            a0 = fma(Ar[j], sdx[j], a0);
+                            a1 = fma(Ar[j + 1], sdx[j + 1], a1);
+                            a2 = fma(Ar[j + 2], sdx[j + 2], a2);
+                            a3 = fma(Ar[j + 3], sdx[j + 3], a3);
+                        }
+                        acc += (a0 + a1) + (a2 + a3);
+                        if (lane >= 6) {
+                            const double* Br = B6 + 24 * (lane - 6);
+                            double b0 = 0.0, b1 = 0.0;
 #pragma unroll
-                        for (int l = 0; l < 4; ++l) acc = fma(pc.cm[l], sdu[3 * l + lane - 9], acc);
-                        bdu = acc;
-                    } else if (lane >= 12) {
-                        bdu = pc.swdt[(lane - 12) / 3] * du;
+                            for (int c = 0; c < 12; c += 2) { b0 = fma(Br[c], sdu[c], b0); b1 = fma(Br[c + 1], sdu[c + 1], b1); }
+                            acc += b0 + b1;
+                        }
+                    } else if (lane < 6) {
+                        acc = fma(dt, sdx[lane + 6], acc);
+                    } else if (lane < 12) {
+                        double b = 0.0;
+#pragma unroll
+                        for (int l = 0; l < 4; ++l) b = fma(((cm >> l) & 1u) ? (1.0 / hkd::kMass) * dt : 0.0, sdu[3 * l + lane - 9], b);
+                        acc += b;
                     } else {
-                        bdu = 0.0;
+                        const int l = (lane - 12) / 3;
+                        if (!((cm >> l) & 1u)) acc = fma(dt, sdu[lane - 12], acc);
                     }
-                    dxn = (adx + bdu) + eps * sm.Defect[24 * (n0 + k + 1) + lane];
-                    // expected cost change, lane-partial
-                    dV1 += rec[LQ_LX + lane] * dx + rec[LQ_LU + lane] * du;
-                    double qdx = lxx_entry(lane, lane, cm, dt, dt, false) * dx;
-                    if (lane >= 3 && lane < 6) {
-                        for (int l = 0; l < 4; ++l) qdx += lxx_entry(lane, 12 + 3 * l + lane - 3, cm, dt, dt, false) * sdx[12 + 3 * l + lane - 3];
-                    } else if (lane >= 12) {
-                        const int jj = (lane - 12) % 3;
-                        qdx += lxx_entry(lane, 3 + jj, cm, dt, dt, false) * sdx[3 + jj];
-                    }
-                    dV2 += dx * qdx;
-                    double rdu = (dt * weight_R(lane)) * du;
-                    if (lane < 12) {
-                        const int l = lane / 3, a = lane % 3;
-#pragma unroll
-                        for (int b = 0; b < 3; ++b) rdu += rec[LQ_LUU + 9 * l + 3 * a + b] * sdu[3 * l + b];
-                    }
-                    dV2 += du * rdu;
+                    dx = acc + eps * dfn[lane];
                 }
                 __syncwarp();
-                dx = dxn;
-                if (lane < 24) { sm.dX[24 * (n0 + k + 1) + lane] = dx; sdx[lane] = dx; }
+                if (lane < 24) { sm.dX[24 * (n + 1) + lane] = dx; sdx[lane] = dx; }
                 __syncwarp();
-            }
-            // terminal terms
-            if (lane < 24) {
-                const double* trec = sm.tq + ph * TQ_STRIDE;
-                dV1 += trec[TQ_PHIX + lane] * dx;
-                double qdx = lxx_entry(lane, lane, cm, 0.0, 20.0, true) * dx;
-                if (lane >= 3 && lane < 6) {
-                    for (int l = 0; l < 4; ++l) qdx += lxx_entry(lane, 12 + 3 * l + lane - 3, cm, 0.0, 20.0, true) * sdx[12 + 3 * l + lane - 3];
-                } else if (lane >= 12) {
-                    const int jj = (lane - 12) % 3;
-                    qdx += lxx_entry(lane, 3 + jj, cm, 0.0, 20.0, true) * sdx[3 + jj];
-                }
-                for (int l = 0; l < 4; ++l) {
-                    const double wh = trec[TQ_WH + l];
-                    if (wh != 0.0) {
-                        double hd = 0.0;
-                        for (int j = 0; j < 24; ++j) hd += trec[TQ_HX + 24 * l + j] * sdx[j];
-                        qdx += wh * trec[TQ_HX + 24 * l + lane] * hd;
-                    }
-                }
-                dV2 += dx * qdx;
             }
         }
+        cp_async_wait_all();
         __syncthreads();
     }
-    if (tid < 32) {
-        dV1 = warp_sum(dV1);
-        dV2 = warp_sum(dV2);
-        if (lane == 0) { sm.st.dV_1 = dV1; sm.st.dV_2 = dV2; }
+    // ---- expected cost change, all threads ----
+    double dV1 = 0.0, dV2 = 0.0;
+    for (int e = tid; e < N * 24; e += kThreads) {
+        const int s = e / 24, i = e % 24;
+        int p, k;
+        phase_of_stage(sc, s, p, k);
+        const unsigned cm = sc.cmask[p];
+        const int n = sc.node_off[p] + k;
+        const double* rec = sm.lqg + (size_t)s * LQ_STRIDE;
+        const double* dxv = sm.dX + 24 * n;
+        const double* duv = sm.U_t + 24 * s;
+        const double dxi = dxv[i], dui = duv[i];
+        dV1 += rec[LQ_LX + i] * dxi + rec[LQ_LU + i] * dui;
+        // (lxx dx)_i
+        double qdx = (dt * weight_Q(i, cm)) * dxi;
+        if (i >= 3 && i < 6) {
+            for (int l = 0; l < 4; ++l) {
+                const double c = (double)((cm >> l) & 1u);
+                const double w = (dt * c * weight_foot(l, i - 3, cm)) * c;
+                qdx += w * dxi - w * dxv[12 + 3 * l + i - 3];
+            }
+        } else if (i >= 12) {
+            const int l = (i - 12) / 3, jj = (i - 12) % 3;
+            const double c = (double)((cm >> l) & 1u);
+            const double w = (dt * c * weight_foot(l, jj, cm)) * c;
+            qdx += w * dxi - w * dxv[3 + jj];
+        }
+        dV2 += dxi * qdx;
+        // (luu du)_i
+        double rdu = (dt * weight_R(i)) * dui;
+        if (i < 12) {
+            const int l = i / 3, a = i % 3;
+#pragma unroll
+            for (int b = 0; b < 3; ++b) rdu += rec[LQ_LUU + 9 * l + 3 * a + b] * duv[3 * l + b];
+        }
+        dV2 += dui * rdu;
     }
+    for (int e = tid; e < sc.n_phases * 24; e += kThreads) {  // terminal terms
+        const int p = e / 24, i = e % 24;
+        const unsigned cm = sc.cmask[p];
+        const double* trec = sm.tq + p * TQ_STRIDE;
+        const double* dxv = sm.dX + 24 * (sc.node_off[p] + sc.horizon[p]);
+        const double dxi = dxv[i];
+        dV1 += trec[TQ_PHIX + i] * dxi;
+        double qdx = weight_Qf(i, cm) * dxi;
+        if (i >= 3 && i < 6) {
+            for (int l = 0; l < 4; ++l) {
+                const double c = (double)((cm >> l) & 1u);
+                const double w = (20.0 * c * weight_foot(l, i - 3, cm)) * c;
+                qdx += w * dxi - w * dxv[12 + 3 * l + i - 3];
+            }
+        } else if (i >= 12) {
+            const int l = (i - 12) / 3, jj = (i - 12) % 3;
+            const double c = (double)((cm >> l) & 1u);
+            const double w = (20.0 * c * weight_foot(l, jj, cm)) * c;
+            qdx += w * dxi - w * dxv[3 + jj];
+        }
+        for (int l = 0; l < 4; ++l) {
+            const double wh = trec[TQ_WH + l];
+            if (wh != 0.0) {
+                double hd = 0.0;
+                for (int j = 0; j < 24; ++j) hd = fma(trec[TQ_HX + 24 * l + j], dxv[j], hd);
+                qdx += wh * trec[TQ_HX + 24 * l + i] * hd;
+            }
+        }
+        dV2 += dxi * qdx;
+    }
+    const double d1 = block_reduce<0>(sm, dV1);
+    const double d2 = block_reduce<0>(sm, dV2);
+    if (tid == 0) { sm.st.dV_1 = d1; sm.st.dV_2 = d2; }
     __syncthreads();
 }
 
