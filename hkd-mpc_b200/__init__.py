@@ -151,6 +151,7 @@ def lib():
         L.hsddp_batch_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
         L.hsddp_batch_get_counters.argtypes = [vp, C.POINTER(C.c_ulonglong)]
         L.hsddp_batch_reset_counters.argtypes = [vp]
+        L.hsddp_batch_get_profile.argtypes = [vp, C.POINTER(C.c_ulonglong)]
         _lib = L
     return _lib
 
@@ -409,6 +410,11 @@ class MultiPhaseDDPBatch:
         out = (C.c_ulonglong * 4)()
         _check(lib().hsddp_batch_get_counters(self.h, out), "get_counters")
         return dict(sweep_stages=int(out[0]), solve_launches=int(out[1]), step_launches=int(out[2]))
+
+    def profile(self):
+        out = (C.c_ulonglong * 16)()
+        _check(lib().hsddp_batch_get_profile(self.h, out), "get_profile")
+        return [int(v) for v in out]
 
     def reset_counters(self):
         _check(lib().hsddp_batch_reset_counters(self.h), "reset_counters")

@@ -36,12 +36,13 @@ constexpr double kHipX = 1.9000000000000000e-01, kHipY = 4.9000000000000002e-02;
 constexpr double kAbad = 6.2000000000000000e-02, kThigh = -2.0899999999999999e-01, kShank = -1.9500000000000001e-01;
 
 // Linearisation record of one stage, laid out as the Riccati kernel's tensor-core tiles read it:
-//   At12[12][24] : rows 0..11 of A - I (row-major; rows 3..5 hold dt at column 9..11, rows 9..11 are zero)
-//   Bq  [ 8][24] : rows 4..11 of B_r, the 24x12 matrix of the COUPLED controls (reduced column c = 3*leg+j;
-//                  only stance-leg columns have entries in these rows; columns 12..23 are padding)
+//   R[12][40] row-major:  columns 0..23  = rows 0..11 of A - I   (rows 3..5 hold dt at column 9..11, rows 9..11 zero)
+//                         columns 24..35 = rows 0..11 of B_r, the 24x12 matrix of the COUPLED controls
+//                                          (reduced column c = 3*leg+j; only stance-leg columns have entries
+//                                          in these rows, all of them in rows 6..11); columns 36..39 padding
 // Only the structural non-zeros are written; the rest of the record must be zero-initialised once.
-constexpr int kAt12Size = 12 * 24;
-constexpr int kBqSize = 8 * 24;
+constexpr int kRld = 40;
+constexpr int kRSize = 12 * kRld;
 
 struct Trig {
     double sy, cy, sp, cp, sr, cr;
@@ -118,7 +119,7 @@ HKD_HD void dynamics(const double* x, const double* u, double dt, unsigned cmask
 }
 
 // Analytic linearisation (HKD::Model::dynamics_partial) written straight into a stage record.
-HKD_HD void dynamics_partial_record(const double* x, const double* u, double dt, unsigned cmask, double* At12, double* Bq) {
+HKD_HD void dynamics_partial_record(const double* x, const double* u, double dt, unsigned cmask, double* R40) {
     const Trig t = trig_of(x[0], x[1], x[2]);
     const double wx = x[6], wy = x[7], wz = x[8];
     const double s1 = t.sr * wy + t.cr * wz;
@@ -126,20 +127,20 @@ HKD_HD void dynamics_partial_record(const double* x, const double* u, double dt,
     const double icp = 1.0 / t.cp;
     const double tp = t.sp * icp;
     // Euler-rate rows 0..2
-    At12[0 * 24 + 1] = dt * (s1 * t.sp * icp * icp);
-    At12[0 * 24 + 2] = dt * (s2 * icp);
-    At12[0 * 24 + 7] = dt * (t.sr * icp);
-    At12[0 * 24 + 8] = dt * (t.cr * icp);
-    At12[1 * 24 + 2] = dt * (-s1);
-    At12[1 * 24 + 7] = dt * t.cr;
-    At12[1 * 24 + 8] = dt * (-t.sr);
-    At12[2 * 24 + 1] = dt * (s1 * icp * icp);
-    At12[2 * 24 + 2] = dt * (tp * s2);
-    At12[2 * 24 + 6] = dt;
-    At12[2 * 24 + 7] = dt * (tp * t.sr);
-    At12[2 * 24 + 8] = dt * (tp * t.cr);
+    R40[0 * kRld + 1] = dt * (s1 * t.sp * icp * icp);
+    R40[0 * kRld + 2] = dt * (s2 * icp);
+    R40[0 * kRld + 7] = dt * (t.sr * icp);
+    R40[0 * kRld + 8] = dt * (t.cr * icp);
+    R40[1 * kRld + 2] = dt * (-s1);
+    R40[1 * kRld + 7] = dt * t.cr;
+    R40[1 * kRld + 8] = dt * (-t.sr);
+    R40[2 * kRld + 1] = dt * (s1 * icp * icp);
+    R40[2 * kRld + 2] = dt * (tp * s2);
+    R40[2 * kRld + 6] = dt;
+    R40[2 * kRld + 7] = dt * (tp * t.sr);
+    R40[2 * kRld + 8] = dt * (tp * t.cr);
     // position rows 3..5
-    At12[3 * 24 + 9] = dt; At12[4 * 24 + 10] = dt; At12[5 * 24 + 11] = dt;
+    R40[3 * kRld + 9] = dt; R40[4 * kRld + 10] = dt; R40[5 * kRld + 11] = dt;
     // angular-acceleration rows 6..8: M = dt * Jinv * R^T
     double R[9], F[3], tw[3];
     rotation(t, R);
@@ -158,7 +159,7 @@ HKD_HD void dynamics_partial_record(const double* x, const double* u, double dt,
                           -t.cp,        -t.sp * t.sr,       -t.sp * t.cr};
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        double* row = At12 + (6 + a) * 24;
+        double* row = R40 + (6 + a) * kRld;
         row[0] = jd[a] * (-R[3 + a] * tw[0] + R[a] * tw[1]);
         row[1] = jd[a] * (dP[a] * tw[0] + dP[3 + a] * tw[1] + dP[6 + a] * tw[2]);
         // position columns: tau_world depends on p through r_l = foot - p  ->  column j = M (F x e_j)
@@ -166,19 +167,19 @@ HKD_HD void dynamics_partial_record(const double* x, const double* u, double dt,
         row[4] = -M[3 * a + 0] * F[2] + M[3 * a + 2] * F[0];
         row[5] = M[3 * a + 0] * F[1] - M[3 * a + 1] * F[0];
     }
-    At12[6 * 24 + 2] = 0.0;
-    At12[7 * 24 + 2] = jd[1] * rt2;
-    At12[8 * 24 + 2] = jd[2] * (-rt1);
+    R40[6 * kRld + 2] = 0.0;
+    R40[7 * kRld + 2] = jd[1] * rt2;
+    R40[8 * kRld + 2] = jd[2] * (-rt1);
     // gyroscopic block
-    At12[6 * 24 + 6] = 0.0;
-    At12[6 * 24 + 7] = jd[0] * (kIyy - kIzz) * wz;
-    At12[6 * 24 + 8] = jd[0] * (kIyy - kIzz) * wy;
-    At12[7 * 24 + 6] = jd[1] * (kIzz - kIxx) * wz;
-    At12[7 * 24 + 7] = 0.0;
-    At12[7 * 24 + 8] = jd[1] * (kIzz - kIxx) * wx;
-    At12[8 * 24 + 6] = jd[2] * (kIxx - kIyy) * wy;
-    At12[8 * 24 + 7] = jd[2] * (kIxx - kIyy) * wx;
-    At12[8 * 24 + 8] = 0.0;
+    R40[6 * kRld + 6] = 0.0;
+    R40[6 * kRld + 7] = jd[0] * (kIyy - kIzz) * wz;
+    R40[6 * kRld + 8] = jd[0] * (kIyy - kIzz) * wy;
+    R40[7 * kRld + 6] = jd[1] * (kIzz - kIxx) * wz;
+    R40[7 * kRld + 7] = 0.0;
+    R40[7 * kRld + 8] = jd[1] * (kIzz - kIxx) * wx;
+    R40[8 * kRld + 6] = jd[2] * (kIxx - kIyy) * wy;
+    R40[8 * kRld + 7] = jd[2] * (kIxx - kIyy) * wx;
+    R40[8 * kRld + 8] = 0.0;
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
         const bool stance = (cmask >> l) & 1u;
@@ -188,29 +189,29 @@ HKD_HD void dynamics_partial_record(const double* x, const double* u, double dt,
         for (int a = 0; a < 3; ++a) {
             const double m0 = M[3 * a], m1 = M[3 * a + 1], m2 = M[3 * a + 2];
             // foot x,y columns: M (e_j x f) ; force columns: M (r x e_j)   (zero for a swing leg)
-            At12[(6 + a) * 24 + 12 + 3 * l] = stance ? (-m1 * fz + m2 * fy) : 0.0;
-            At12[(6 + a) * 24 + 13 + 3 * l] = stance ? (m0 * fz - m2 * fx) : 0.0;
-            Bq[(2 + a) * 24 + 3 * l + 0] = stance ? (m1 * rz - m2 * ry) : 0.0;
-            Bq[(2 + a) * 24 + 3 * l + 1] = stance ? (-m0 * rz + m2 * rx) : 0.0;
-            Bq[(2 + a) * 24 + 3 * l + 2] = stance ? (m0 * ry - m1 * rx) : 0.0;
+            R40[(6 + a) * kRld + 12 + 3 * l] = stance ? (-m1 * fz + m2 * fy) : 0.0;
+            R40[(6 + a) * kRld + 13 + 3 * l] = stance ? (m0 * fz - m2 * fx) : 0.0;
+            R40[(6 + a) * kRld + 24 + 3 * l + 0] = stance ? (m1 * rz - m2 * ry) : 0.0;
+            R40[(6 + a) * kRld + 24 + 3 * l + 1] = stance ? (-m0 * rz + m2 * rx) : 0.0;
+            R40[(6 + a) * kRld + 24 + 3 * l + 2] = stance ? (m0 * ry - m1 * rx) : 0.0;
         }
         // linear acceleration rows 9..11: (c/m) dt on the leg's own force component
 #pragma unroll
-        for (int j = 0; j < 3; ++j) Bq[(5 + j) * 24 + 3 * l + j] = stance ? (1.0 / kMass) * dt : 0.0;
+        for (int j = 0; j < 3; ++j) R40[(9 + j) * kRld + 24 + 3 * l + j] = stance ? (1.0 / kMass) * dt : 0.0;
     }
 }
 
 // expand a stage record to the dense column-major A, B of the reference
-HKD_HD void expand_AB(const double* At12, const double* Bq, double dt, unsigned cmask, double* A, double* B) {
+HKD_HD void expand_AB(const double* R40, double dt, unsigned cmask, double* A, double* B) {
     for (int i = 0; i < 576; ++i) { A[i] = 0.0; B[i] = 0.0; }
     for (int i = 0; i < 24; ++i) A[i * 25] = 1.0;
     for (int r = 0; r < 12; ++r)
-        for (int c = 0; c < 24; ++c) A[r + 24 * c] += At12[r * 24 + c];
+        for (int c = 0; c < 24; ++c) A[r + 24 * c] += R40[r * kRld + c];
     for (int l = 0; l < 4; ++l) {
         const bool stance = (cmask >> l) & 1u;
         for (int j = 0; j < 3; ++j) {
             const int c = 3 * l + j;
-            if (stance) { for (int k = 4; k < 12; ++k) B[k + 24 * c] = Bq[(k - 4) * 24 + c]; }
+            if (stance) { for (int k = 0; k < 12; ++k) B[k + 24 * c] = R40[k * kRld + 24 + c]; }
             else B[(12 + c) + 24 * (12 + c)] = dt;
         }
     }

@@ -20,6 +20,23 @@
 #include "../../include/hsddp_b200.h"
 #include "hkd_model.cuh"
 
+// Optional per-phase cycle accounting (build with -DHSDDP_PROFILE): thread 0 of every block adds the
+// clock64() deltas between PROF_MARK points into BatchPtrs::counters[8 + slot].
+#ifdef HSDDP_PROFILE
+#define PROF_DECL long long prof_t0_ = clock64();
+#define PROF_MARK(sm, slot)                                                         \
+    do {                                                                            \
+        if (threadIdx.x == 0) {                                                     \
+            const long long t1_ = clock64();                                        \
+            (sm).profacc[slot] += (unsigned long long)(t1_ - prof_t0_);             \
+            prof_t0_ = t1_;                                                         \
+        }                                                                           \
+    } while (0)
+#else
+#define PROF_DECL
+#define PROF_MARK(sm, slot) do { } while (0)
+#endif
+
 namespace hsddp {
 
 constexpr int kThreads = 128;
@@ -28,9 +45,8 @@ constexpr int MAXPH = HSDDP_MAX_PHASES;
 
 // per-stage LQ record (doubles), laid out exactly as the sweep's tensor-core tiles read it so that a
 // plain cp.async copy stages it into shared memory (see hkd_model.cuh: dynamics_partial_record)
-constexpr int LQ_AT12 = 0;                        // [12][24] rows 0..11 of A - I
-constexpr int LQ_BQ = LQ_AT12 + hkd::kAt12Size;   // [8][24]  rows 4..11 of B_r (coupled controls), cols 12..23 padding
-constexpr int LQ_LX = LQ_BQ + hkd::kBqSize;       // [24]
+constexpr int LQ_R = 0;                           // [12][40] rows 0..11 of [A - I | B_r] (hkd::kRld = 40)
+constexpr int LQ_LX = LQ_R + hkd::kRSize;         // [24]
 constexpr int LQ_LU = LQ_LX + 24;                 // [24]
 constexpr int LQ_LUU = LQ_LU + 24;                // [4][3][3] ReB Hessian blocks per leg (dt folded in)
 constexpr int LQ_STRIDE = 576;                    // 564 used
@@ -97,6 +113,7 @@ struct __align__(16) Smem {
     double dfc2[2][24];
     double G[24], Gn[24], Qx[24], Qu[24], wu[24], vtmp[24], vtmp2[24];
     double lxxd[24], lxxTd[24], lxxw[12], lxxTw[12];
+    double swdt[4], cmv[4];    // per-phase constants (1-c_l) dt and (c_l/m) dt
     double red[kThreads];
     DevSchedule sc;
     SolverState st;
@@ -105,6 +122,8 @@ struct __align__(16) Smem {
     // per-problem base pointers
     double *Xbar, *X, *Xsim_t, *Defect, *dX, *Ubar, *U, *U_t, *dU, *K, *lqg, *tq, *gcon, *reb, *hcon, *al, *g0h0;
     const double *xr, *ur, *prel, *xinit, *x0;
+    unsigned long long* prof;
+    unsigned long long profacc[16];
     int pid;
     int flag;
     int ibuf[4];
@@ -198,6 +217,7 @@ __device__ inline void bind_problem(Smem& sm, const BatchPtrs& bp, int pid) {
         sm.al = bp.al + (size_t)pid * MAXPH * 8;
         sm.g0h0 = bp.g0h0 + (size_t)pid * 600;
         sm.x0 = bp.x0 + (size_t)pid * 24;
+        sm.prof = bp.counters + 8;
         sm.cp = bp.cp;
         sm.st = bp.state[pid];
     }
@@ -263,6 +283,7 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
     const DevSchedule& sc = sm.sc;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = sc.n_stages;
+    PROF_DECL
     double* wdx = sm.Y + 32 * warp;  // per-warp scratch
     // (a) controls: U = (Ubar + eps dU) + K (X - Xbar), one warp per stage.  K is stored compactly as
     //     K_r^T [24][12] (only the coupled control of each leg has a non-zero gain row, see hsddp_sweep.cuh)
@@ -290,6 +311,7 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
         __syncwarp();
     }
     __syncthreads();
+    PROF_MARK(sm, 0);
     // (b) dynamics, one thread per stage; phase-initial simulated states
     int first_bad = 0x7fffffff;
     for (int s = tid; s < N; s += kThreads) {
@@ -320,6 +342,7 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
     }
     // first diverged stage in the reference's sequential order
     const int bad = (int)block_reduce<1>(sm, (double)first_bad);
+    PROF_MARK(sm, 1);
     int bad_ph = sc.n_phases, bad_k = 0;
     if (bad != 0x7fffffff) phase_of_stage(sc, bad, bad_ph, bad_k);
     // (c) commit exactly what the sequential reference would have written
@@ -374,6 +397,7 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
         sm.st.rollout_ok = (bad_ph == sc.n_phases);
     }
     __syncthreads();
+    PROF_MARK(sm, 2);
     return bad_ph == sc.n_phases;
 }
 
@@ -390,6 +414,7 @@ __device__ inline void foot_rel_error(const double* x, const double* prel_r, dou
 __device__ inline void compute_cost_block(Smem& sm) {
     const DevSchedule& sc = sm.sc;
     const int tid = threadIdx.x;
+    PROF_DECL
     const int N = sc.n_stages;
     const double dt = sc.dt;
     double csum = 0.0;
@@ -464,6 +489,7 @@ __device__ inline void compute_cost_block(Smem& sm) {
     const double f2 = block_reduce<0>(sm, dsum);
     if (tid == 0) { sm.st.actual_cost = cost; sm.st.feas = sqrt(f2); }
     __syncthreads();
+    PROF_MARK(sm, 3);
 }
 
 // ---------------------------------------------------------------------------
@@ -473,6 +499,7 @@ __device__ inline void compute_cost_block(Smem& sm) {
 __device__ inline void lq_approximation_block(Smem& sm) {
     const DevSchedule& sc = sm.sc;
     const int tid = threadIdx.x;
+    PROF_DECL
     const int N = sc.n_stages;
     const double dt = sc.dt;
     for (int s = tid; s < N; s += kThreads) {
@@ -484,7 +511,7 @@ __device__ inline void lq_approximation_block(Smem& sm) {
 #pragma unroll
         for (int j = 0; j < 24; ++j) { x[j] = sm.X[24 * n + j]; u[j] = sm.U[24 * s + j]; }
         double* rec = sm.lqg + (size_t)s * LQ_STRIDE;
-        hkd::dynamics_partial_record(x, u, dt, cm, rec + LQ_AT12, rec + LQ_BQ);
+        hkd::dynamics_partial_record(x, u, dt, cm, rec + LQ_R);
         const double* xr = sm.xr + 24 * n;
         const double* ur = sm.ur + 24 * n;
         double lx[24], lu[24];
@@ -570,6 +597,7 @@ __device__ inline void lq_approximation_block(Smem& sm) {
         for (int j = 0; j < 24; ++j) rec[TQ_PHIX + j] = phix[j];
     }
     __syncthreads();
+    PROF_MARK(sm, 4);
 }
 
 // running-cost Hessian lxx(i,j) of a phase: dt*Q on the diagonal + the foot regulariser block

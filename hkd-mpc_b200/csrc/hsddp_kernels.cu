@@ -155,8 +155,15 @@ __global__ void __launch_bounds__(kThreads, 4) k_solve(BatchPtrs bp, hsddp_optio
         if (threadIdx.x == 0) sm.opt = opt;
         __syncthreads();
         if (cold_start) cold_start_block(sm);
+#ifdef HSDDP_PROFILE
+        if (threadIdx.x == 0) for (int i = 0; i < 16; ++i) sm.profacc[i] = 0;
+        __syncthreads();
+#endif
         solve_block(sm, bp);
         if (threadIdx.x == 0) bp.state[pid] = sm.st;
+#ifdef HSDDP_PROFILE
+        if (threadIdx.x == 0) for (int i = 0; i < 16; ++i) atomicAdd(&sm.prof[i], sm.profacc[i]);
+#endif
     }
 }
 
@@ -432,7 +439,7 @@ int hsddp_batch_set_problems(hsddp_batch* b, int n_schedules, const hsddp_schedu
     if ((rc = dalloc(b, &bp.state, P))) return rc;
     if ((rc = dalloc(b, &bp.info, P))) return rc;
     if ((rc = dalloc(b, &bp.trace, P * HSDDP_TRACE_CAP))) return rc;
-    if ((rc = dalloc(b, &bp.counters, (size_t)4))) return rc;
+    if ((rc = dalloc(b, &bp.counters, (size_t)32))) return rc;
     if ((rc = dalloc(b, &bp.work_counter, (size_t)4))) return rc;
     if ((rc = dalloc(b, &b->d_ok, P))) return rc;
     if ((rc = dalloc(b, &b->d_darg, P))) return rc;
@@ -440,7 +447,7 @@ int hsddp_batch_set_problems(hsddp_batch* b, int n_schedules, const hsddp_schedu
     CK(cudaMemset(bp.info, 0, P * sizeof(hsddp_info)));
     CK(cudaMemset(bp.trace, 0, P * HSDDP_TRACE_CAP * sizeof(hsddp_iter_record)));
     CK(cudaMemset(bp.state, 0, P * sizeof(SolverState)));
-    CK(cudaMemset(bp.counters, 0, 4 * sizeof(unsigned long long)));
+    CK(cudaMemset(bp.counters, 0, 32 * sizeof(unsigned long long)));
     CK(cudaMemset(bp.tq, 0, P * MAXPH * TQ_STRIDE * sizeof(double)));
     CK(cudaMemset(bp.lq, 0, P * max_stages * LQ_STRIDE * sizeof(double)));
     CK(cudaMemset(bp.g0h0, 0, P * 600 * sizeof(double)));
@@ -636,7 +643,7 @@ int hsddp_batch_get_array(hsddp_batch* b, int which, double* out) {
                     else if (which == HSDDP_ARR_LU) std::memcpy(o, rec + LQ_LU, 24 * sizeof(double));
                     else if (which == HSDDP_ARR_A || which == HSDDP_ARR_B) {
                         double A[576], B[576];
-                        hkd::expand_AB(rec + LQ_AT12, rec + LQ_BQ, sc.dt, cm, A, B);
+                        hkd::expand_AB(rec + LQ_R, sc.dt, cm, A, B);
                         std::memcpy(o, which == HSDDP_ARR_A ? A : B, 576 * sizeof(double));
                     } else if (which == HSDDP_ARR_LUU) {
                         for (int i = 0; i < 24; ++i) o[i * 25] = sc.dt * (i < 12 ? .2 : .1);
@@ -736,10 +743,18 @@ int hsddp_batch_get_counters(hsddp_batch* b, unsigned long long out[4]) {
     return HSDDP_OK;
 }
 
+int hsddp_batch_get_profile(hsddp_batch* b, unsigned long long out[16]) {
+    if (!b || !b->has_problems || !out) return HSDDP_ERR_ARG;
+    CK(cudaSetDevice(b->device));
+    CK(cudaStreamSynchronize(b->stream));
+    CK(cudaMemcpy(out, b->bp.counters + 8, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return HSDDP_OK;
+}
+
 int hsddp_batch_reset_counters(hsddp_batch* b) {
     if (!b || !b->has_problems) return HSDDP_ERR_ARG;
     CK(cudaSetDevice(b->device));
-    CK(cudaMemsetAsync(b->bp.counters, 0, 4 * sizeof(unsigned long long), b->stream));
+    CK(cudaMemsetAsync(b->bp.counters, 0, 32 * sizeof(unsigned long long), b->stream));
     b->n_solve_launches = 0; b->n_step_launches = 0;
     return HSDDP_OK;
 }

@@ -73,40 +73,40 @@ __device__ __forceinline__ void prefetch_stage(Smem& sm, int buf, int s, int n1)
 
 // Block Gauss-Jordan with 2x2 pivot blocks on 12 rows, one tableau column per lane (v[0..11]).
 // Lanes 0..11 of the warp hold the columns of the 12x12 pivot matrix.  `sbuf`: 24 doubles per warp.
+// The loop is deliberately NOT unrolled (the stage body must stay inside the instruction cache):
+// after every step the column registers are rotated by two, so the pivot block is always at
+// positions 0,1 and all register indices stay static; six steps rotate by 12 = identity.
 // Returns false if a negative pivot was met (pivot 1 = a, pivot 2 = det / a), which for the caller
 // that runs Quu_r - 1e-9 I is the reference's LDLT(...).isPositive() verdict (Sylvester's law of
 // inertia).  After the call v = Quu_r^-1 * (original column).
 __device__ __forceinline__ bool gauss_jordan12(double (&v)[12], double* sbuf) {
     const int lane = threadIdx.x & 31;
     bool ok = true;
-#pragma unroll
-    for (int k = 0; k < 12; k += 2) {
-        if (lane == k || lane == k + 1) {
-            double2* dst = reinterpret_cast<double2*>(sbuf + 12 * (lane - k));
+#pragma unroll 1
+    for (int step = 0; step < 6; ++step) {
+        if ((lane >> 1) == step) {  // the two pivot columns (lanes 2*step, 2*step+1 < 12)
+            double2* dst = reinterpret_cast<double2*>(sbuf + 12 * (lane & 1));
 #pragma unroll
             for (int r = 0; r < 12; r += 2) dst[r >> 1] = make_double2(v[r], v[r + 1]);
         }
         __syncwarp();
-        double c0[12], c1[12];
+        // pivot block P = [a b; c d] = [col0[0] col1[0]; col0[1] col1[1]] in the rotated frame
+        const double2 pk = *reinterpret_cast<const double2*>(sbuf);
+        const double2 pk1 = *reinterpret_cast<const double2*>(sbuf + 12);
+        const double det = pk.x * pk1.y - pk1.x * pk.y;
+        if (pk.x < 0.0 || det < 0.0) ok = false;
+        const double rdet = 1.0 / det;
+        const double t0 = (pk1.y * v[0] - pk1.x * v[1]) * rdet;
+        const double t1 = (pk.x * v[1] - pk.y * v[0]) * rdet;
 #pragma unroll
-        for (int r = 0; r < 12; r += 2) {
+        for (int r = 2; r < 12; r += 2) {  // eliminate and rotate in one go
             const double2 a = *reinterpret_cast<const double2*>(sbuf + r);
             const double2 b = *reinterpret_cast<const double2*>(sbuf + 12 + r);
-            c0[r] = a.x; c0[r + 1] = a.y; c1[r] = b.x; c1[r + 1] = b.y;
+            v[r - 2] = fma(-b.x, t1, fma(-a.x, t0, v[r]));
+            v[r - 1] = fma(-b.y, t1, fma(-a.y, t0, v[r + 1]));
         }
-        // pivot block P = [c0[k] c1[k]; c0[k+1] c1[k+1]]
-        const double det = c0[k] * c1[k + 1] - c1[k] * c0[k + 1];
-        if (c0[k] < 0.0 || det < 0.0) ok = false;
-        const double rdet = 1.0 / det;
-        const double x0 = v[k], x1 = v[k + 1];
-        const double t0 = (c1[k + 1] * x0 - c1[k] * x1) * rdet;
-        const double t1 = (c0[k] * x1 - c0[k + 1] * x0) * rdet;
-#pragma unroll
-        for (int r = 0; r < 12; ++r) {
-            if (r == k) v[r] = t0;
-            else if (r == k + 1) v[r] = t1;
-            else v[r] = fma(-c1[r], t1, fma(-c0[r], t0, v[r]));
-        }
+        v[10] = t0;
+        v[11] = t1;
         __syncwarp();
     }
     return ok;
@@ -119,13 +119,18 @@ __device__ __forceinline__ double lxx_tab(const double* d, const double* w, int 
     if (i >= 12 && j == 3 + (i - 12) % 3) return -w[i - 12];
     return 0.0;
 }
-__device__ inline void build_lxx_tables(Smem& sm, unsigned cm, double dt) {
+__device__ inline void build_phase_tables(Smem& sm, unsigned cm, double dt) {
     const int tid = threadIdx.x;
     if (tid < 24) {  // [0..11] running w, [12..23] terminal w
         const int q = tid % 12, l = q / 3, jj = q % 3;
         const double c = (double)((cm >> l) & 1u);
         const double scale = (tid < 12) ? dt : 20.0;
         (tid < 12 ? sm.lxxw : sm.lxxTw)[q] = (scale * c * weight_foot(l, jj, cm)) * c;
+    } else if (tid < 28) {
+        const int l = tid - 24;
+        const double c = (double)((cm >> l) & 1u);
+        sm.cmv[l] = (c / hkd::kMass) * dt;
+        sm.swdt[l] = (1.0 - c) * dt;
     }
     __syncthreads();
     if (tid < 48) {
@@ -144,25 +149,22 @@ __device__ inline void build_lxx_tables(Smem& sm, unsigned cm, double dt) {
 // the last phase).  Returns false if a stage failed the PD test.
 //
 // Shared-memory tiles (row stride 24 doubles unless noted):
-//   H [24][24] value Hessian (symmetric) ; Y [24][24] = H A ; Zr = sm.Z [24][16 used] = H B_r
-//   rec[buf]: At12 [12][24] | Bq [8][24] | lx | lu | luu blocks  (cp.async double buffer)
+//   H [24][24] value Hessian (symmetric); between P2 and P4 its lower tiles hold Qxx
+//   Y [24][24] = H A ; Zr = sm.Z [24][16 used] = H B_r
+//   rec[buf]: R [12][40] = [A - I | B_r] rows 0..11, then lx | lu | luu blocks  (cp.async double buffer)
 //   QuxR = sm.Qux [16][24] ; QuuR = sm.Quu [12][24] ; KT = sm.KrS [24][12] (K_r transposed)
+// Every phase of the stage is a short table-driven loop over 8x8 output tiles (3 DMMA each),
+// distributed round-robin over the 4 warps, so that the whole stage body stays i-cache resident.
 __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, double& dV1, double& dV2) {
     const DevSchedule& sc = sm.sc;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const unsigned cm = sc.cmask[ph];
     const double dt = sc.dt;
-    const PhaseConst pc = phase_const(cm, dt);
     const int Nph = sc.horizon[ph];
     const double* trec = sm.tq + ph * TQ_STRIDE;
-    double* const H = sm.H;
-    double* const Y = sm.Y;
-    double* const Zr = sm.Z;
-    double* const QuxR = sm.Qux;
-    double* const QuuR = sm.Quu;
-    double* const KT = sm.KrS;
-    build_lxx_tables(sm, cm, dt);
+    PROF_DECL
+    build_phase_tables(sm, cm, dt);
     prefetch_stage(sm, 0, sc.stage_off[ph] + Nph - 1, sc.node_off[ph] + Nph);
     // G[N] = Phix + Gprime ; H[N] = Phixx + Hprime
     if (tid < 24) sm.G[tid] += trec[TQ_PHIX + tid];
@@ -174,131 +176,97 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
             const double wh = trec[TQ_WH + l];
             if (wh != 0.0) val += wh * (trec[TQ_HX + 24 * l + i] * trec[TQ_HX + 24 * l + j]);
         }
-        H[e] += val;
+        sm.H[e] += val;
     }
     cp_async_wait_all();
     __syncthreads();
+    PROF_MARK(sm, 5);
     dV1 = 0.0; dV2 = 0.0;
-    // Qxx / H' tile ownership: warp0 (0,0),(1,0) ; warp1 (1,1),(2,0) ; warp2 (2,1) ; warp3 (2,2)
-    int qi[2], qj[2], nq;
-    if (warp == 0) { nq = 2; qi[0] = 0; qj[0] = 0; qi[1] = 1; qj[1] = 0; }
-    else if (warp == 1) { nq = 2; qi[0] = 1; qj[0] = 1; qi[1] = 2; qj[1] = 0; }
-    else if (warp == 2) { nq = 1; qi[0] = 2; qj[0] = 1; qi[1] = 2; qj[1] = 1; }
-    else { nq = 1; qi[0] = 2; qj[0] = 2; qi[1] = 2; qj[1] = 2; }
+#pragma unroll 1
     for (int k = Nph - 1; k >= 0; --k) {
         const int s = sc.stage_off[ph] + k;
         const int buf = (Nph - 1 - k) & 1;
         if (k > 0) prefetch_stage(sm, buf ^ 1, s - 1, sc.node_off[ph] + k);
-        const double* At12 = sm.rec[buf] + LQ_AT12;
-        const double* Bq = sm.rec[buf] + LQ_BQ;
+        const double* R = sm.rec[buf] + LQ_R;     // [12][40]: cols 0..23 A - I, cols 24..39 B_r
         const double* lxv = sm.rec[buf] + LQ_LX;
         const double* luv = sm.rec[buf] + LQ_LU;
         const double* luu = sm.rec[buf] + LQ_LUU;
         const double* dfc = sm.dfc2[buf];
-        // ---- P1: Y = H A, Z = H B_r, Gn = G + H d ----
-        if (warp < 3) {
-            const int i0 = 8 * warp;
-            double cy[3][2], cz[2] = {0.0, 0.0};
+        // ---- P1: [Y | Z] = H [A | B_r] : 15 tiles (3 row blocks x 5 column blocks), Gn = G + H d ----
+#pragma unroll 1
+        for (int tile = warp; tile < 16; tile += 4) {
+            if (tile < 15) {
+                const int i0 = 8 * (tile / 5), Jt = tile % 5;
+                double c2[2];
+                if (Jt < 3) {
+                    const double2 h2 = *reinterpret_cast<const double2*>(sm.H + (i0 + g) * 24 + 8 * Jt + 2 * t);
+                    c2[0] = h2.x; c2[1] = h2.y;
+                } else { c2[0] = 0.0; c2[1] = 0.0; }
 #pragma unroll
-            for (int J = 0; J < 3; ++J) {
-                const double2 h2 = *reinterpret_cast<const double2*>(H + (i0 + g) * 24 + 8 * J + 2 * t);
-                cy[J][0] = h2.x; cy[J][1] = h2.y;
-            }
+                for (int kk = 0; kk < 12; kk += 4) dmma884(c2, sm.H[(kk + t) * 24 + i0 + g], R[(kk + t) * hkd::kRld + 8 * Jt + g]);
+                if (Jt < 3) {
+                    *reinterpret_cast<double2*>(sm.Y + (i0 + g) * 24 + 8 * Jt + 2 * t) = make_double2(c2[0], c2[1]);
+                } else {
+                    // swing columns of Z: H[:, 12+c] * dt
 #pragma unroll
-            for (int kk = 0; kk < 12; kk += 4) {
-                const double a = H[(kk + t) * 24 + i0 + g];  // H[i][k] by symmetry
-#pragma unroll
-                for (int J = 0; J < 3; ++J) dmma884(cy[J], a, At12[(kk + t) * 24 + 8 * J + g]);
-                if (kk >= 4) dmma884(cz, a, Bq[(kk - 4 + t) * 24 + g]);
-            }
-#pragma unroll
-            for (int J = 0; J < 3; ++J)
-                *reinterpret_cast<double2*>(Y + (i0 + g) * 24 + 8 * J + 2 * t) = make_double2(cy[J][0], cy[J][1]);
-            // swing columns of Z: H[:, 12+3l+j] * dt
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int c = 2 * t + q;
-                if (!((cm >> (c / 3)) & 1u)) cz[q] += H[(i0 + g) * 24 + 12 + c] * pc.swdt[c / 3];
-            }
-            *reinterpret_cast<double2*>(Zr + (i0 + g) * 24 + 2 * t) = make_double2(cz[0], cz[1]);
-        } else {
-            // warp 3: Z columns 8..15 for all three row blocks, then Gn
-#pragma unroll
-            for (int I = 0; I < 3; ++I) {
-                const int i0 = 8 * I;
-                double cz[2] = {0.0, 0.0};
-#pragma unroll
-                for (int kk = 4; kk < 12; kk += 4) dmma884(cz, H[(kk + t) * 24 + i0 + g], Bq[(kk - 4 + t) * 24 + 8 + g]);
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int c = 8 + 2 * t + q;
-                    if (c < 12 && !((cm >> (c / 3)) & 1u)) cz[q] += H[(i0 + g) * 24 + 12 + c] * pc.swdt[c / 3];
+                    for (int q = 0; q < 2; ++q) {
+                        const int c = 8 * (Jt - 3) + 2 * t + q;
+                        if (c < 12) c2[q] = fma(sm.H[(i0 + g) * 24 + 12 + c], sm.swdt[c / 3], c2[q]);
+                    }
+                    *reinterpret_cast<double2*>(sm.Z + (i0 + g) * 24 + 8 * (Jt - 3) + 2 * t) = make_double2(c2[0], c2[1]);
                 }
-                *reinterpret_cast<double2*>(Zr + (i0 + g) * 24 + 8 + 2 * t) = make_double2(cz[0], cz[1]);
-            }
-            if (lane < 24) {  // Gn = G + H d   (Q10)
+            } else if (lane < 24) {  // Gn = G + H d   (Q10)
                 double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
                 for (int j = 0; j < 24; j += 4) {
-                    a0 = fma(H[j * 24 + lane], dfc[j], a0);
-                    a1 = fma(H[(j + 1) * 24 + lane], dfc[j + 1], a1);
-                    a2 = fma(H[(j + 2) * 24 + lane], dfc[j + 2], a2);
-                    a3 = fma(H[(j + 3) * 24 + lane], dfc[j + 3], a3);
+                    a0 = fma(sm.H[j * 24 + lane], dfc[j], a0);
+                    a1 = fma(sm.H[(j + 1) * 24 + lane], dfc[j + 1], a1);
+                    a2 = fma(sm.H[(j + 2) * 24 + lane], dfc[j + 2], a2);
+                    a3 = fma(sm.H[(j + 3) * 24 + lane], dfc[j + 3], a3);
                 }
                 sm.Gn[lane] = sm.G[lane] + ((a0 + a1) + (a2 + a3));
             }
         }
         __syncthreads();
-        // ---- P2: Qxx (lower tiles, kept in registers), Qux_r, Quu_r, Qx, Qu_r ----
-        double cq[2][2];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            if (q < nq) {
-                const int i0 = 8 * qi[q], j0 = 8 * qj[q];
-                const int i = i0 + g, j = j0 + 2 * t;
-                const double2 y2 = *reinterpret_cast<const double2*>(Y + i * 24 + j);
-                cq[q][0] = lxx_tab(sm.lxxd, sm.lxxw, i, j) + y2.x + ((i == j) ? reg : 0.0);
-                cq[q][1] = lxx_tab(sm.lxxd, sm.lxxw, i, j + 1) + y2.y + ((i == j + 1) ? reg : 0.0);
-#pragma unroll
-                for (int kk = 0; kk < 12; kk += 4) dmma884(cq[q], At12[(kk + t) * 24 + i0 + g], Y[(kk + t) * 24 + j0 + g]);
+        PROF_MARK(sm, 6);
+        // ---- P2: 16 tiles C = [A | B_r]^T M :  6 x Qxx (lower, M = Y, parked in H) ; 6 x Qux_r (M = Y) ; 4 x Quu_r (M = Z) ----
+#pragma unroll 1
+        for (int tile = warp; tile < 16; tile += 4) {
+            int ci, j0, kind;  // ci: column block of R (A-operand), j0: column of M
+            if (tile < 6) { const int I = (tile >= 3) ? 2 : (tile >= 1 ? 1 : 0); const int J = tile - (I * (I + 1)) / 2; ci = 8 * I; j0 = 8 * J; kind = 0; }
+            else if (tile < 12) { ci = 24 + 8 * ((tile - 6) / 3); j0 = 8 * ((tile - 6) % 3); kind = 1; }
+            else { ci = 24 + 8 * ((tile - 12) >> 1); j0 = 8 * ((tile - 12) & 1); kind = 2; }
+            const double* M = (kind == 2) ? sm.Z : sm.Y;
+            double c2[2] = {0.0, 0.0};
+            if (kind == 0) {
+                const int i = ci + g, j = j0 + 2 * t;
+                const double2 y2 = *reinterpret_cast<const double2*>(sm.Y + i * 24 + j);
+                c2[0] = lxx_tab(sm.lxxd, sm.lxxw, i, j) + y2.x + ((i == j) ? reg : 0.0);
+                c2[1] = lxx_tab(sm.lxxd, sm.lxxw, i, j + 1) + y2.y + ((i == j + 1) ? reg : 0.0);
             }
-        }
-        {
-            // job list per warp: warp0: Qux(0,0),Qux(1,0) ; warp1: Qux(0,1),Qux(1,1) ; warp2: Qux(0,2),Qux(1,2),Quu(0,0) ; warp3: Quu(0,1),Quu(1,0),Quu(1,1)
-            const int njobs = (warp < 2) ? 2 : 3;
 #pragma unroll
-            for (int job = 0; job < 3; ++job) {
-                if (job < njobs) {
-                    bool is_quu;
-                    int Ic, J;
-                    if (warp < 2) { is_quu = false; Ic = job; J = warp; }
-                    else if (warp == 2) { is_quu = (job == 2); Ic = is_quu ? 0 : job; J = is_quu ? 0 : 2; }
-                    else { is_quu = true; Ic = (job == 0) ? 0 : 1; J = (job == 1) ? 0 : 1; }
-                    const double* Bop = is_quu ? Zr : Y;
-                    double cc[2] = {0.0, 0.0};
-#pragma unroll
-                    for (int kk = 4; kk < 12; kk += 4) dmma884(cc, Bq[(kk - 4 + t) * 24 + 8 * Ic + g], Bop[(kk + t) * 24 + 8 * J + g]);
-                    // swing rows: (B_r^T M)[c][:] = dt * M[12+c][:]
-                    const int c = 8 * Ic + g;
-                    if (c < 12 && !((cm >> (c / 3)) & 1u)) {
-                        const double2 m2 = *reinterpret_cast<const double2*>(Bop + (12 + c) * 24 + 8 * J + 2 * t);
-                        cc[0] += pc.swdt[c / 3] * m2.x;
-                        cc[1] += pc.swdt[c / 3] * m2.y;
+            for (int kk = 0; kk < 12; kk += 4) dmma884(c2, R[(kk + t) * hkd::kRld + ci + g], M[(kk + t) * 24 + j0 + g]);
+            if (kind == 0) {
+                *reinterpret_cast<double2*>(sm.H + (ci + g) * 24 + j0 + 2 * t) = make_double2(c2[0], c2[1]);
+            } else {
+                const int c = ci - 24 + g;  // reduced control row
+                if (c < 12) {
+                    const bool swing = !((cm >> (c / 3)) & 1u);
+                    if (swing) {  // (B_r^T M)[c][:] = dt * M[12+c][:]
+                        const double2 m2 = *reinterpret_cast<const double2*>(M + (12 + c) * 24 + j0 + 2 * t);
+                        c2[0] = fma(sm.swdt[c / 3], m2.x, c2[0]);
+                        c2[1] = fma(sm.swdt[c / 3], m2.y, c2[1]);
                     }
-                    if (is_quu) {  // + luu_r: dt R + reg on the diagonal, ReB blocks for stance legs
-                        if (c < 12) {
+                    if (kind == 2) {  // + luu_r: dt R + reg on the diagonal, ReB blocks for stance legs
 #pragma unroll
-                            for (int q = 0; q < 2; ++q) {
-                                const int c2 = 8 * J + 2 * t + q;
-                                if (c2 < 12) {
-                                    if (c == c2) cc[q] += dt * weight_R(act_index(c, cm)) + reg;
-                                    if (c / 3 == c2 / 3 && ((cm >> (c / 3)) & 1u)) cc[q] += luu[9 * (c / 3) + 3 * (c % 3) + (c2 % 3)];
-                                }
-                            }
-                            *reinterpret_cast<double2*>(QuuR + c * 24 + 8 * J + 2 * t) = make_double2(cc[0], cc[1]);
+                        for (int q = 0; q < 2; ++q) {
+                            const int cc = j0 + 2 * t + q;
+                            if (c == cc) c2[q] += dt * weight_R(act_index(c, cm)) + reg;
+                            if (cc < 12 && c / 3 == cc / 3 && !swing) c2[q] += luu[9 * (c / 3) + 3 * (c % 3) + (cc % 3)];
                         }
+                        *reinterpret_cast<double2*>(sm.Quu + c * 24 + j0 + 2 * t) = make_double2(c2[0], c2[1]);
                     } else {
-                        *reinterpret_cast<double2*>(QuxR + c * 24 + 8 * J + 2 * t) = make_double2(cc[0], cc[1]);
+                        *reinterpret_cast<double2*>(sm.Qux + c * 24 + j0 + 2 * t) = make_double2(c2[0], c2[1]);
                     }
                 }
             }
@@ -306,62 +274,60 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
         if (warp == 3 && lane < 24) {  // Qx = lx + A^T Gn
             double acc = sm.Gn[lane];
 #pragma unroll
-            for (int r = 0; r < 9; ++r) acc = fma(At12[r * 24 + lane], sm.Gn[r], acc);
+            for (int r = 0; r < 9; ++r) acc = fma(R[r * hkd::kRld + lane], sm.Gn[r], acc);
             sm.Qx[lane] = lxv[lane] + acc;
         }
         if (warp == 2 && lane < 12) {  // Qu_r = lu_r + B_r^T Gn
             const int c = lane;
-            double acc;
+            double acc = 0.0;
             if ((cm >> (c / 3)) & 1u) {
-                acc = 0.0;
 #pragma unroll
-                for (int r = 4; r < 12; ++r) acc = fma(Bq[(r - 4) * 24 + c], sm.Gn[r], acc);
+                for (int r = 6; r < 12; ++r) acc = fma(R[r * hkd::kRld + 24 + c], sm.Gn[r], acc);
             } else {
-                acc = pc.swdt[c / 3] * sm.Gn[12 + c];
+                acc = sm.swdt[c / 3] * sm.Gn[12 + c];
             }
             sm.Qu[c] = luv[act_index(c, cm)] + acc;
         }
         __syncthreads();
+        PROF_MARK(sm, 7);
         // ---- P3: Gauss-Jordan tableau (warps 0,1), shifted PD test (warp 2), inactive controls (warp 3) ----
         if (warp < 3) {
             double col[12];
             // lanes 0..11: columns of Quu_r ; warp0 lanes 12..31: Qux_r columns 0..19 ; warp1 lanes 12..15: Qux_r 20..23, lane 16: Qu_r
-            const double* src = nullptr;
-            int stride = 24;
-            if (lane < 12) src = QuuR + lane;
-            else if (warp == 0) src = QuxR + (lane - 12);
-            else if (warp == 1 && lane < 16) src = QuxR + (lane + 8);
-            else if (warp == 1 && lane == 16) { src = sm.Qu; stride = 1; }
+            const int j = (warp == 0) ? lane - 12 : lane + 8;  // Qux_r column of this lane (valid for lane >= 12, j < 24)
+            const bool is_piv = lane < 12, is_gain = !is_piv && warp < 2 && j < 24, is_ff = (warp == 1 && lane == 16);
+            const double shift = (warp == 2) ? 1e-9 : 0.0;  // Quu - 1e-9 I (Q7)
 #pragma unroll
-            for (int r = 0; r < 12; ++r) col[r] = src ? src[r * stride] : ((r == (lane % 12)) ? 1.0 : 0.0);
-            if (warp == 2 && lane < 12) {
-#pragma unroll
-                for (int r = 0; r < 12; ++r) if (r == lane) col[r] -= 1e-9;  // Quu - 1e-9 I (Q7)
+            for (int r = 0; r < 12; ++r) {
+                double val = (r == lane % 12) ? 1.0 : 0.0;  // harmless dummy column for idle lanes
+                if (is_piv) val = sm.Quu[r * 24 + lane] - ((r == lane) ? shift : 0.0);
+                else if (is_gain) val = sm.Qux[r * 24 + j];
+                else if (is_ff) val = sm.Qu[r];
+                col[r] = val;
             }
+            PROF_MARK(sm, 13);
             const bool ok = gauss_jordan12(col, sm.red + 32 * warp);
+            PROF_MARK(sm, 14);
             if (warp == 2) {
                 if (lane == 0) sm.ibuf[0] = ok ? 1 : 0;
-            } else if (lane >= 12) {
-                const int j = (warp == 0) ? lane - 12 : lane + 8;
-                if (j < 24) {  // gain column j: K_r[:, j] = -Quu_r^-1 Qux_r[:, j]  -> KT[j][0..11] (smem + HBM)
-                    double2* ks = reinterpret_cast<double2*>(KT + 12 * j);
-                    double2* kg = reinterpret_cast<double2*>(sm.K + (size_t)s * 288 + 12 * j);
+            } else if (is_gain) {  // gain column j: K_r[:, j] = -Quu_r^-1 Qux_r[:, j]  -> KT[j][0..11] (smem + HBM)
+                double2* ks = reinterpret_cast<double2*>(sm.KrS + 12 * j);
+                double2* kg = reinterpret_cast<double2*>(sm.K + (size_t)s * 288 + 12 * j);
 #pragma unroll
-                    for (int r = 0; r < 12; r += 2) {
-                        const double2 val = make_double2(-col[r], -col[r + 1]);
-                        ks[r >> 1] = val;
-                        kg[r >> 1] = val;
-                    }
-                } else if (warp == 1 && lane == 16) {
-                    double dvk = 0.0;
-#pragma unroll
-                    for (int r = 0; r < 12; ++r) {
-                        sm.wu[r] = -col[r];                                   // dU_r
-                        sm.dU[24 * s + act_index(r, cm)] = -col[r];
-                        dvk = fma(sm.Qu[r], col[r], dvk);                     // -Qu^T dU
-                    }
-                    sm.dbuf[0] = dvk;
+                for (int r = 0; r < 12; r += 2) {
+                    const double2 val = make_double2(-col[r], -col[r + 1]);
+                    ks[r >> 1] = val;
+                    kg[r >> 1] = val;
                 }
+            } else if (is_ff) {
+                double dvk = 0.0;
+#pragma unroll
+                for (int r = 0; r < 12; ++r) {
+                    sm.wu[r] = -col[r];                                   // dU_r
+                    sm.dU[24 * s + act_index(r, cm)] = -col[r];
+                    dvk = fma(sm.Qu[r], col[r], dvk);                     // -Qu^T dU
+                }
+                sm.dbuf[0] = dvk;
             }
         } else if (lane < 16) {
             // decoupled controls: Quu_ii = dt R_i + reg, Qu_i = lu_i, K row = 0
@@ -377,42 +343,49 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
             for (int o = 8; o > 0; o >>= 1) dv += __shfl_xor_sync(0x0000ffffu, dv, o, 16);
             if (lane == 0) sm.dbuf[1] = dv;
         }
+        PROF_MARK(sm, 15);
         __syncthreads();
+        PROF_MARK(sm, 8);
         if (!sm.ibuf[0]) { cp_async_wait_all(); return false; }
-        // ---- P4: H' = sym(Qxx) + Qux_r^T K_r ; G' = Qx + Qux_r^T dU_r ----
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            if (q < nq) {
-                const int i0 = 8 * qi[q], j0 = 8 * qj[q];
-#pragma unroll
-                for (int kk = 0; kk < 12; kk += 4) dmma884(cq[q], QuxR[(kk + t) * 24 + i0 + g], KT[(j0 + g) * 12 + kk + t]);
-                if (i0 == j0) {
-                    // symmetrise the diagonal tile: partner of (g, 2t+q') is (2t+q', g), held by lane 4*(2t+q') + g/2, slot g&1
-                    const double p00 = __shfl_sync(0xffffffffu, cq[q][0], 4 * (2 * t) + (g >> 1));
-                    const double p01 = __shfl_sync(0xffffffffu, cq[q][1], 4 * (2 * t) + (g >> 1));
-                    const double p10 = __shfl_sync(0xffffffffu, cq[q][0], 4 * (2 * t + 1) + (g >> 1));
-                    const double p11 = __shfl_sync(0xffffffffu, cq[q][1], 4 * (2 * t + 1) + (g >> 1));
-                    cq[q][0] = 0.5 * (cq[q][0] + ((g & 1) ? p01 : p00));
-                    cq[q][1] = 0.5 * (cq[q][1] + ((g & 1) ? p11 : p10));
-                    *reinterpret_cast<double2*>(H + (i0 + g) * 24 + j0 + 2 * t) = make_double2(cq[q][0], cq[q][1]);
-                } else {
-                    *reinterpret_cast<double2*>(H + (i0 + g) * 24 + j0 + 2 * t) = make_double2(cq[q][0], cq[q][1]);
-                    H[(j0 + 2 * t) * 24 + i0 + g] = cq[q][0];
-                    H[(j0 + 2 * t + 1) * 24 + i0 + g] = cq[q][1];
+        // ---- P4: H' = sym(Qxx) + Qux_r^T K_r (6 lower tiles, mirrored) ; G' = Qx + Qux_r^T dU_r ----
+#pragma unroll 1
+        for (int tile = warp; tile < 8; tile += 4) {
+            if (tile < 6) {
+                const int I = (tile >= 3) ? 2 : (tile >= 1 ? 1 : 0), J = tile - (I * (I + 1)) / 2;
+                const int i0 = 8 * I, j0 = 8 * J;
+                double c2[2];
+                {
+                    const double2 q2 = *reinterpret_cast<const double2*>(sm.H + (i0 + g) * 24 + j0 + 2 * t);
+                    c2[0] = q2.x; c2[1] = q2.y;
                 }
-            }
-        }
-        if (warp == 3 && lane < 24) {
-            double acc = sm.Qx[lane];
 #pragma unroll
-            for (int r = 0; r < 12; ++r) acc = fma(QuxR[r * 24 + lane], sm.wu[r], acc);
-            sm.G[lane] = acc;
+                for (int kk = 0; kk < 12; kk += 4) dmma884(c2, sm.Qux[(kk + t) * 24 + i0 + g], sm.KrS[(j0 + g) * 12 + kk + t]);
+                if (I == J) {
+                    // symmetrise the diagonal tile: partner of (g, 2t+q') is (2t+q', g), held by lane 4*(2t+q') + g/2, slot g&1
+                    const double p00 = __shfl_sync(0xffffffffu, c2[0], 4 * (2 * t) + (g >> 1));
+                    const double p01 = __shfl_sync(0xffffffffu, c2[1], 4 * (2 * t) + (g >> 1));
+                    const double p10 = __shfl_sync(0xffffffffu, c2[0], 4 * (2 * t + 1) + (g >> 1));
+                    const double p11 = __shfl_sync(0xffffffffu, c2[1], 4 * (2 * t + 1) + (g >> 1));
+                    c2[0] = 0.5 * (c2[0] + ((g & 1) ? p01 : p00));
+                    c2[1] = 0.5 * (c2[1] + ((g & 1) ? p11 : p10));
+                } else {
+                    sm.H[(j0 + 2 * t) * 24 + i0 + g] = c2[0];
+                    sm.H[(j0 + 2 * t + 1) * 24 + i0 + g] = c2[1];
+                }
+                *reinterpret_cast<double2*>(sm.H + (i0 + g) * 24 + j0 + 2 * t) = make_double2(c2[0], c2[1]);
+            } else if (tile == 7 && lane < 24) {
+                double acc = sm.Qx[lane];
+#pragma unroll
+                for (int r = 0; r < 12; ++r) acc = fma(sm.Qux[r * 24 + lane], sm.wu[r], acc);
+                sm.G[lane] = acc;
+            }
         }
         const double dvk = sm.dbuf[0] + sm.dbuf[1];
         dV1 -= dvk;
         dV2 += dvk;
         cp_async_wait_all();
         __syncthreads();
+        PROF_MARK(sm, 9);
     }
     // G[0] += H[0] * Defect[0]
     {
@@ -422,7 +395,7 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
         double acc = 0.0;
         if (tid < 24) {
 #pragma unroll
-            for (int j = 0; j < 24; ++j) acc = fma(H[tid * 24 + j], sm.vtmp[j], acc);
+            for (int j = 0; j < 24; ++j) acc = fma(sm.H[tid * 24 + j], sm.vtmp[j], acc);
         }
         __syncthreads();
         if (tid < 24) sm.G[tid] += acc;
@@ -435,6 +408,7 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
 __device__ inline bool backward_sweep_block(Smem& sm, double reg) {
     const DevSchedule& sc = sm.sc;
     const int tid = threadIdx.x;
+    PROF_DECL
     double dV1 = 0.0, dV2 = 0.0;
     bool success = true;
     for (int ph = sc.n_phases - 1; ph >= 0; --ph) {
@@ -469,9 +443,13 @@ __device__ inline bool backward_sweep_block(Smem& sm, double reg) {
             }
             if (tid < 24) sm.G[tid] = sm.vtmp[tid];
             __syncthreads();
+            PROF_MARK(sm, 10);
         }
         double d1, d2;
         if (!phase_backward_sweep_block(sm, ph, reg, d1, d2)) { success = false; break; }
+#ifdef HSDDP_PROFILE
+        prof_t0_ = clock64();
+#endif
         dV1 += d1;
         dV2 += d2;
     }
@@ -513,9 +491,9 @@ __device__ inline bool backward_sweep_regularized_block(Smem& sm, int& n_sweeps)
 // cost change (dV_1, dV_2) does not feed back into the recursion, so it is accumulated
 // afterwards by all threads in parallel.
 // ---------------------------------------------------------------------------
-constexpr int LR_SLOT = 552;   // doubles per stage slot: KT 288 | A rows 0-2 72 | A rows 6-8 72 | B rows 6-8 72 | defect 24 | dU 24
-constexpr int LR_CHUNK = 3;    // stages per chunk (2 chunks resident: 2*3*552 = 3312 doubles of the sweep's tile storage)
-constexpr int LR_UNITS = 276;  // 16-byte units per slot
+constexpr int LR_SLOT = 516;   // doubles per stage slot: KT 288 | A rows {0,1,2,6,7,8} 144 | B_r rows {6,7,8} 36 | defect 24 | dU 24
+constexpr int LR_CHUNK = 3;    // stages per chunk (2 chunks resident: 2*3*516 = 3096 doubles of the sweep's tile storage)
+constexpr int LR_UNITS = 258;  // 16-byte units per slot
 
 __device__ __forceinline__ int node_of_stage(const DevSchedule& sc, int s) {
     int ph, k;
@@ -528,14 +506,17 @@ __device__ __forceinline__ void lr_prefetch(Smem& sm, double* buf, int s0, int s
     for (int e = threadIdx.x; e < total; e += kThreads) {
         const int si = e / LR_UNITS, u = e % LR_UNITS;
         const int s = s0 + si;
-        const double* rec = sm.lqg + (size_t)s * LQ_STRIDE;
+        const double* R = sm.lqg + (size_t)s * LQ_STRIDE + LQ_R;
         const double* src;
         if (u < 144) src = sm.K + (size_t)s * 288 + 2 * u;
-        else if (u < 180) src = rec + LQ_AT12 + 2 * (u - 144);
-        else if (u < 216) src = rec + LQ_AT12 + 144 + 2 * (u - 180);
-        else if (u < 252) src = rec + LQ_BQ + 48 + 2 * (u - 216);
-        else if (u < 264) src = sm.Defect + 24 * (node_of_stage(sm.sc, s) + 1) + 2 * (u - 252);
-        else src = sm.dU + 24 * s + 2 * (u - 264);
+        else if (u < 216) {  // six dense rows of A - I, 12 units each
+            const int q = (u - 144) / 12, o = (u - 144) % 12;
+            src = R + (q < 3 ? q : q + 3) * hkd::kRld + 2 * o;
+        } else if (u < 234) {  // rows 6..8 of B_r, 6 units each
+            const int q = (u - 216) / 6, o = (u - 216) % 6;
+            src = R + (6 + q) * hkd::kRld + 24 + 2 * o;
+        } else if (u < 246) src = sm.Defect + 24 * (node_of_stage(sm.sc, s) + 1) + 2 * (u - 234);
+        else src = sm.dU + 24 * s + 2 * (u - 246);
         cp_async16(buf + si * LR_SLOT + 2 * u, src);
     }
 }
@@ -548,6 +529,7 @@ __device__ inline void linear_rollout_block(Smem& sm, double eps) {
     double* scratch = sm.H;  // H, Y, Z, Qux, Quu, KrS, rec are contiguous and free outside the sweep
     double* sdx = sm.vtmp;   // current dx, shared for broadcast
     double* sdu = sm.vtmp2;  // coupled controls du_r[0..11]
+    PROF_DECL
     __syncthreads();
     lr_prefetch(sm, scratch, 0, min(LR_CHUNK, N));
     cp_async_wait_all();
@@ -599,11 +581,11 @@ __device__ inline void linear_rollout_block(Smem& sm, double eps) {
                 }
                 const double* slot = buf + (s - c0) * LR_SLOT;
                 const double* KT = slot;
-                const double* A0 = slot + 288;
-                const double* A6 = slot + 360;
-                const double* B6 = slot + 432;
-                const double* dfn = slot + 504;
-                const double* dUs = slot + 528;
+                const double* A0 = slot + 288;   // rows 0..2 of A - I
+                const double* A6 = slot + 360;   // rows 6..8
+                const double* B6 = slot + 432;   // rows 6..8 of B_r, [3][12]
+                const double* dfn = slot + 468;
+                const double* dUs = slot + 492;
                 // du = eps dU + K dx : lanes 0..11 the coupled controls, lanes 12..23 the decoupled ones
                 if (lane < 12) {
                     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -637,7 +619,7 @@ __device__ inline void linear_rollout_block(Smem& sm, double eps) {
                         }
                         acc += (a0 + a1) + (a2 + a3);
                         if (lane >= 6) {
-                            const double* Br = B6 + 24 * (lane - 6);
+                            const double* Br = B6 + 12 * (lane - 6);
                             double b0 = 0.0, b1 = 0.0;
 #pragma unroll
                             for (int c = 0; c < 12; c += 2) { b0 = fma(Br[c], sdu[c], b0); b1 = fma(Br[c + 1], sdu[c + 1], b1); }
@@ -664,6 +646,7 @@ __device__ inline void linear_rollout_block(Smem& sm, double eps) {
         cp_async_wait_all();
         __syncthreads();
     }
+    PROF_MARK(sm, 11);
     // ---- expected cost change, all threads ----
     double dV1 = 0.0, dV2 = 0.0;
     for (int e = tid; e < N * 24; e += kThreads) {
@@ -735,6 +718,7 @@ __device__ inline void linear_rollout_block(Smem& sm, double eps) {
     const double d2 = block_reduce<0>(sm, dV2);
     if (tid == 0) { sm.st.dV_1 = d1; sm.st.dV_2 = d2; }
     __syncthreads();
+    PROF_MARK(sm, 12);
 }
 
 }  // namespace hsddp

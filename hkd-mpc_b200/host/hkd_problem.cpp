@@ -223,10 +223,10 @@ void hkd_model_dynamics(const double x[24], const double u[24], double dt, const
 }
 
 void hkd_model_dynamics_partial(const double x[24], const double u[24], double dt, const int32_t contact[4], double A[576], double B[576]) {
-    double At12[hkd::kAt12Size] = {0}, Bq[hkd::kBqSize] = {0};
+    double R40[hkd::kRSize] = {0};
     const unsigned m = mask_of(contact);
-    hkd::dynamics_partial_record(x, u, dt, m, At12, Bq);
-    hkd::expand_AB(At12, Bq, dt, m, A, B);
+    hkd::dynamics_partial_record(x, u, dt, m, R40);
+    hkd::expand_AB(R40, dt, m, A, B);
 }
 
 void hkd_model_foot_position(const double pos[3], const double eul[3], const double qleg[3], int leg, double p[3]) {

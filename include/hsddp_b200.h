@@ -222,6 +222,8 @@ int hsddp_batch_event_elapsed_ms(hsddp_batch* b, int slot0, int slot1, float* ms
  * out[0] = sum over problems of (backward sweeps x stages), out[1] = k_solve launches, out[2] = k_step launches */
 int hsddp_batch_get_counters(hsddp_batch* b, unsigned long long out[4]);
 int hsddp_batch_reset_counters(hsddp_batch* b);
+/* per-phase cycle counters (all zero unless the library was built with -DHSDDP_PROFILE) */
+int hsddp_batch_get_profile(hsddp_batch* b, unsigned long long out[16]);
 
 /* device-side FP64 FMA throughput probe (TFLOP/s) used as the measured roofline
  * denominator by bench.py; kind 0 = DFMA on CUDA cores, 1 = DMMA m8n8k4 tensor tiles */

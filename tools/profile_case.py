@@ -17,3 +17,11 @@ for _ in range(reps):
     B.reset(); B.solve()
     info = B.info()
     print(f"{cfg} n={n}: kernel {B.last_solve_ms():.2f} ms, {n / B.last_solve_ms() * 1e3:.0f} solves/s, mean iters {info['n_iter'].mean():.2f}, sweeps {info['n_sweeps'].sum()}")
+prof = B.profile()
+if any(prof):
+    names = ["rollout:U=K dx", "rollout:dynamics", "rollout:commit", "cost", "LQ approx", "sweep:phase init", "sweep:P1 Y,Z", "sweep:P2 Q",
+             "sweep:P3 GJ", "sweep:P4 H'", "sweep:Px transform", "linear:recursion", "linear:dV pass", "P3:load tableau", "P3:gauss-jordan", "P3:stores"]
+    tot = sum(prof)
+    for nm, v in zip(names, prof):
+        print(f"  {nm:22s} {v:>14d} cyc  {100.0 * v / tot:5.1f}%")
+    print("  total cycles (thread 0 of all blocks)", tot)
