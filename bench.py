@@ -185,7 +185,7 @@ def main():
     x0_pin = torch.from_numpy(w.x0.copy()).pin_memory()
     out_u = torch.zeros((w.n, n_cmd, 24), dtype=torch.float64).pin_memory()
     out_x = torch.zeros((w.n, n_cmd, 24), dtype=torch.float64).pin_memory()
-    out_k = torch.zeros((w.n, n_cmd, 576), dtype=torch.float64).pin_memory()
+    out_k = torch.zeros((w.n, n_cmd, 24, 12), dtype=torch.float64).pin_memory()
     h2d = w.x0.nbytes
     d2h = out_u.numel() * 8 + out_x.numel() * 8 + out_k.numel() * 8 + w.n * pkg.INFO_DTYPE.itemsize
 
@@ -204,7 +204,7 @@ def main():
         B.solve_async(opt)
         B.get_rows("Ubar", 0, n_cmd, out_u.numpy())
         B.get_rows("Xbar", 0, n_cmd, out_x.numpy())
-        B.get_rows("K", 0, n_cmd, out_k.numpy())
+        B.get_gains_compact(0, n_cmd, out_k.numpy())
         return B.info()
 
     # ---- kernel-resident timing ----
@@ -285,7 +285,7 @@ def main():
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.steps,
-                    "what": "set_initial_condition(x0 from pinned host) + reset + solve + copy-out of info, first 8 states/controls/gains"},
+                    "what": "set_initial_condition(x0 from pinned host) + reset + solve + copy-out to pinned host of info and the first 8 states, controls and (compact 24x12) gains of every problem"},
             "roofline": {"bound": "tensor", "pipe": "FP64 (DFMA / DMMA m8n8k4)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": None, "kernel": "k_solve", "kernel_ms": kernel_ms,
                          "flop_per_launch": flop_launch,

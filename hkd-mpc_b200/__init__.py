@@ -147,6 +147,7 @@ def lib():
         L.hsddp_batch_set_array.argtypes = [vp, C.c_int, dp]
         L.hsddp_fp64_peak_tflops.argtypes = [C.c_int, C.c_int, dp]
         L.hsddp_batch_get_array_rows.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp]
+        L.hsddp_batch_get_gains_compact.argtypes = [vp, C.c_int, C.c_int, dp]
         L.hsddp_batch_event_record.argtypes = [vp, C.c_int]
         L.hsddp_batch_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
         L.hsddp_batch_get_counters.argtypes = [vp, C.POINTER(C.c_ulonglong)]
@@ -396,6 +397,12 @@ class MultiPhaseDDPBatch:
         if out is None:
             out = np.zeros((self.n, nrows, cols))
         _check(lib().hsddp_batch_get_array_rows(self.h, ARR[name], int(row0), int(nrows), _dp(out)), "get_array_rows")
+        return out
+
+    def get_gains_compact(self, row0, nrows, out=None):
+        if out is None:
+            out = np.zeros((self.n, nrows, 24, 12))
+        _check(lib().hsddp_batch_get_gains_compact(self.h, int(row0), int(nrows), _dp(out)), "get_gains_compact")
         return out
 
     def event_record(self, slot):

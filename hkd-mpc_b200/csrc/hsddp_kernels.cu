@@ -719,6 +719,15 @@ int hsddp_batch_get_array_rows(hsddp_batch* b, int which, int row0, int nrows, d
     return HSDDP_OK;
 }
 
+int hsddp_batch_get_gains_compact(hsddp_batch* b, int row0, int nrows, double* out) {
+    if (!b || !b->has_problems || !out || row0 < 0 || nrows <= 0 || row0 + nrows > b->bp.max_stages) return HSDDP_ERR_ARG;
+    CK(cudaSetDevice(b->device));
+    CK(cudaMemcpy2DAsync(out, (size_t)nrows * 288 * sizeof(double), b->bp.K + (size_t)row0 * 288, (size_t)b->bp.max_stages * 288 * sizeof(double),
+                         (size_t)nrows * 288 * sizeof(double), (size_t)b->bp.n_problems, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return HSDDP_OK;
+}
+
 int hsddp_batch_event_record(hsddp_batch* b, int slot) {
     if (!b || slot < 0 || slot >= 8) return HSDDP_ERR_ARG;
     CK(cudaSetDevice(b->device));

@@ -1,0 +1,146 @@
+// Header-only C++ shim over the C ABI (include/hsddp_b200.h) that keeps the reference's
+// solver surface for the one path this repository replaces:
+//
+//   MultiPhaseDDP<T>      HSDDPSolver/header/MultiPhaseDDP.h:18-122   (T = double only)
+//   HSDDP_OPTION          HSDDPSolver/common/HSDDP_CompoundTypes.h:18-60
+//   QuadReference         Reference/QuadReference.h:144-191           (load_top_level_data, initialize)
+//
+// Differences a maintainer must know about:
+//   * one solver object owns a BATCH of independent problems; every method acts on all of them and
+//     the bool-returning methods return one flag per problem;
+//   * phases are not SinglePhase objects with std::function callbacks (host callables cannot run on
+//     the device): a problem is (schedule, x0), where a schedule is the flattened result of
+//     HKDProblem::initialization for one reference window, and the HKD model / costs / reset map /
+//     constraints are the device-compiled ones;
+//   * results are copied out explicitly (get_Xbar, get_Ubar, get_K, ...), not read from Trajectory objects;
+//   * there is no CPU fallback: construction throws when no CUDA device is present.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "../../include/hsddp_b200.h"
+
+namespace hsddp_b200 {
+
+inline void check(int rc, const char* what) {
+    if (rc != HSDDP_OK) throw std::runtime_error(std::string(what) + " failed (" + std::to_string(rc) + "): " + hsddp_last_error());
+}
+
+// HSDDP_OPTION with the values solve() actually consumes from HKDMPC/settings/ddp_setting.info
+struct HSDDP_OPTION : hsddp_options {
+    HSDDP_OPTION() {
+        alpha = 0.1; gamma = 0.01; update_penalty = 5; update_relax = 1; update_regularization = 2; update_ReB = 1;
+        max_DDP_iter = 10; max_AL_iter = 5; cost_thresh = 1e-3; tconstr_thresh = 1e-3; pconstr_thresh = 1e-3;
+        dynamics_feas_thresh = 1e-3; merit_scale = 0.2; merit_offset = 1e2; AL_active = 1; ReB_active = 1; MS = 1; _pad = 0;
+    }
+};
+
+// Top-level reference table + per-window schedules (QuadReference + HKDProblem::initialization).
+class QuadReference {
+public:
+    QuadReference() = default;
+    ~QuadReference() { if (gait_) hkd_gait_destroy(gait_); }
+    QuadReference(const QuadReference&) = delete;
+    QuadReference& operator=(const QuadReference&) = delete;
+    void load_top_level_data(const std::string& fname) {
+        if (gait_) { hkd_gait_destroy(gait_); gait_ = nullptr; }
+        check(hkd_gait_load(fname.c_str(), &gait_), "hkd_gait_load");
+    }
+    int size() const { return hkd_gait_size(gait_); }
+    const hkd_gait* handle() const { return gait_; }
+private:
+    hkd_gait* gait_ = nullptr;
+};
+
+// RAII owner of one hsddp_schedule
+class Schedule {
+public:
+    Schedule(const QuadReference& ref, int window_start, float plan_duration) {
+        check(hkd_schedule_build(ref.handle(), window_start, plan_duration, &s_), "hkd_schedule_build");
+    }
+    ~Schedule() { hkd_schedule_free(&s_); }
+    Schedule(const Schedule&) = delete;
+    Schedule& operator=(const Schedule&) = delete;
+    const hsddp_schedule& get() const { return s_; }
+    std::vector<double> default_x0() const { std::vector<double> x(24); hkd_default_x0(&s_, x.data()); return x; }
+private:
+    hsddp_schedule s_{};
+};
+
+template <typename T>
+class MultiPhaseDDP;
+
+template <>
+class MultiPhaseDDP<double> {
+public:
+    explicit MultiPhaseDDP(int device = 0) { check(hsddp_batch_create(device, &b_), "hsddp_batch_create"); }
+    ~MultiPhaseDDP() { hsddp_batch_destroy(b_); }
+    MultiPhaseDDP(const MultiPhaseDDP&) = delete;
+    MultiPhaseDDP& operator=(const MultiPhaseDDP&) = delete;
+
+    // set_multiPhaseProblem: `schedule_id[i]` selects the schedule of problem i
+    void set_multiPhaseProblem(const std::vector<const Schedule*>& schedules, const std::vector<int32_t>& schedule_id,
+                               const hsddp_constraint_params* cparams = nullptr) {
+        std::vector<hsddp_schedule> flat;
+        for (const Schedule* s : schedules) flat.push_back(s->get());
+        check(hsddp_batch_set_problems(b_, (int)flat.size(), flat.data(), (int)schedule_id.size(), schedule_id.data(), cparams), "hsddp_batch_set_problems");
+        n_ = (int)schedule_id.size();
+        check(hsddp_batch_dims(b_, nullptr, &max_stages_, &max_nodes_), "hsddp_batch_dims");
+    }
+    void set_initial_condition(const std::vector<double>& x0) {
+        if ((int)x0.size() != 24 * n_) throw std::invalid_argument("x0 must hold 24 doubles per problem");
+        check(hsddp_batch_set_initial_condition(b_, x0.data()), "hsddp_batch_set_initial_condition");
+    }
+    void reset() { check(hsddp_batch_reset(b_), "hsddp_batch_reset"); }
+    void solve(HSDDP_OPTION option) { check(hsddp_batch_solve(b_, &option), "hsddp_batch_solve"); }
+
+    // step-level API (same names as the reference's public methods)
+    void linear_rollout(double eps, HSDDP_OPTION& o) { check(hsddp_batch_linear_rollout(b_, eps, &o), "linear_rollout"); }
+    std::vector<int32_t> hybrid_rollout(double eps, HSDDP_OPTION& o) { std::vector<int32_t> ok(n_); check(hsddp_batch_hybrid_rollout(b_, eps, &o, ok.data()), "hybrid_rollout"); return ok; }
+    std::vector<int32_t> line_search(HSDDP_OPTION& o) { std::vector<int32_t> ok(n_); check(hsddp_batch_forward_sweep(b_, &o, ok.data(), nullptr), "forward_sweep"); return ok; }
+    void compute_cost(const HSDDP_OPTION& o) { check(hsddp_batch_compute_cost(b_, &o), "compute_cost"); }
+    void LQ_approximation(HSDDP_OPTION& o) { check(hsddp_batch_lq_approximation(b_, &o), "lq_approximation"); }
+    std::vector<int32_t> backward_sweep(double regularization) { std::vector<int32_t> ok(n_); check(hsddp_batch_backward_sweep(b_, regularization, ok.data()), "backward_sweep"); return ok; }
+    std::vector<int32_t> backward_sweep_regularized(std::vector<double>& regularization, HSDDP_OPTION& o) {
+        std::vector<int32_t> ok(n_);
+        check(hsddp_batch_backward_sweep_regularized(b_, regularization.data(), &o, ok.data()), "backward_sweep_regularized");
+        return ok;
+    }
+    void update_nominal_trajectory() { check(hsddp_batch_update_nominal(b_), "update_nominal"); }
+    void update_AL_params(HSDDP_OPTION& o) { check(hsddp_batch_update_al_params(b_, &o), "update_al_params"); }
+    void update_REB_params(HSDDP_OPTION& o) { check(hsddp_batch_update_reb_params(b_, &o), "update_reb_params"); }
+
+    // results
+    std::vector<hsddp_info> get_info() { std::vector<hsddp_info> v(n_); check(hsddp_batch_get_info(b_, v.data()), "get_info"); return v; }
+    std::vector<double> get_actual_cost() { auto v = get_info(); std::vector<double> c(n_); for (int i = 0; i < n_; ++i) c[i] = v[i].cost; return c; }
+    std::vector<double> get_array(int which, size_t per_problem) { std::vector<double> v((size_t)n_ * per_problem); check(hsddp_batch_get_array(b_, which, v.data()), "get_array"); return v; }
+    std::vector<double> get_Xbar() { return get_array(HSDDP_ARR_XBAR, (size_t)max_nodes_ * 24); }
+    std::vector<double> get_Ubar() { return get_array(HSDDP_ARR_UBAR, (size_t)max_stages_ * 24); }
+    std::vector<double> get_K() { return get_array(HSDDP_ARR_K, (size_t)max_stages_ * 576); }
+    // get_solver_info: the four float history buffers of problem i (MultiPhaseDDP.cpp:532-541)
+    void get_solver_info(int i, std::vector<float>& cost, std::vector<float>& dyn_feas, std::vector<float>& eqn_feas, std::vector<float>& ineq_feas) {
+        std::vector<hsddp_iter_record> tr((size_t)n_ * HSDDP_TRACE_CAP);
+        check(hsddp_batch_get_trace(b_, tr.data()), "get_trace");
+        auto info = get_info();
+        cost.assign(1, (float)info[i].cost0); dyn_feas.assign(1, (float)info[i].feas0); eqn_feas.clear(); ineq_feas.clear();
+        for (int k = 0; k < info[i].n_iter && k < HSDDP_TRACE_CAP; ++k) {
+            const hsddp_iter_record& r = tr[(size_t)i * HSDDP_TRACE_CAP + k];
+            if (r.eps_accepted < 0) break;  // early exits do not append to the history (MultiPhaseDDP.cpp:340-343)
+            cost.push_back((float)r.cost_after); dyn_feas.push_back((float)r.feas_after);
+            eqn_feas.push_back((float)r.max_tconstr); ineq_feas.push_back((float)r.max_pconstr);
+        }
+    }
+    int n_problems() const { return n_; }
+    int max_stages() const { return max_stages_; }
+    int max_nodes() const { return max_nodes_; }
+    hsddp_batch* handle() { return b_; }
+
+private:
+    hsddp_batch* b_ = nullptr;
+    int n_ = 0;
+    int32_t max_stages_ = 0, max_nodes_ = 0;
+};
+
+}  // namespace hsddp_b200

@@ -215,6 +215,12 @@ int hsddp_batch_set_array(hsddp_batch* b, int which, const double* in);
  * MPC caller needs (first controls, states and feedback gains, HKDMPC/HKDMPC.cpp:245-275). */
 int hsddp_batch_get_array_rows(hsddp_batch* b, int which, int row0, int nrows, double* out);
 
+/* feedback gains in the solver's own compact layout, no host-side expansion: out is
+ * [n_problems][nrows][24][12] with out[..][j][c] = K(coupled control c of the stage, state j);
+ * coupled control c = 3*leg + i is GRF component i of a stance leg or joint-velocity command i of
+ * a swing leg; the 12 other controls of the stage have identically zero gain rows. */
+int hsddp_batch_get_gains_compact(hsddp_batch* b, int row0, int nrows, double* out);
+
 /* CUDA-event timing on the handle's stream (slots 0..7): record, then elapsed ms between two slots */
 int hsddp_batch_event_record(hsddp_batch* b, int slot);
 int hsddp_batch_event_elapsed_ms(hsddp_batch* b, int slot0, int slot1, float* ms);

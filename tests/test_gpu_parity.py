@@ -291,3 +291,42 @@ def test_full_size_config2_properties(pkg, orc, workloads):
     # oracle spot checks across the batch
     B.reset(); B.solve()
     _compare_solution(pkg, orc, w, B, [0, 1, 511, 1023], {})
+
+
+def _write_quad_reference_csv(npz_path, out_path, n_rows=120):
+    """Text form of a gait fixture in the reference's quad_reference.csv format (3 decimals, as
+    scripts/ReferenceGen/generate_reference.m writes it)."""
+    d = np.load(npz_path)
+    with open(out_path, "w") as f:
+        f.write("dt\n%4.3f\n" % float(d["dt"]))
+        for i in range(n_rows):
+            for key, name in (("body_state", "body_state "), ("qJ", "qJ"), ("foot_placements", "foot_placements"), ("grf", "grf")):
+                f.write(name + "\n" + "".join("%6.3f " % v for v in d[key][i]) + "\n")
+            f.write("torque\n" + "".join("%6.3f " % 0.0 for _ in range(12)) + "\n")
+            f.write("contact\n" + "".join("%d " % v for v in d["contact"][i]) + "\n")
+            f.write("status_dur\n" + "".join("%6.3f " % v for v in d["status_dur"][i]) + "\n")
+
+
+def test_cpp_shim_example_matches_oracle(pkg, orc, tmp_path):
+    """The C++ drop-in surface (MultiPhaseDDP<double>::solve via hkd-mpc_b200/host/MultiPhaseDDP.hpp),
+    fed through the text loader (QuadReference::load_top_level_data)."""
+    import subprocess
+    from conftest import ROOT
+    csv = str(tmp_path / "quad_reference.csv")
+    _write_quad_reference_csv(os.path.join(GOLDEN, "gait_trot.npz"), csv)
+    exe = str(tmp_path / "solve_trot")
+    libdir = os.path.dirname(pkg.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", os.path.join(ROOT, "examples", "solve_trot.cpp"), "-L" + libdir, "-lhsddp_b200",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    out = subprocess.run([exe, csv, "3"], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    assert len(out) == 3
+    T = _table(orc, "trot")
+    for i, line in enumerate(out):
+        tok = line.replace("=", " ").split()
+        status, iters, cost = int(tok[1]), int(tok[3]), float(tok[6])
+        P = orc.Problem(T, 0, 0.6)
+        x0 = P.x0
+        x0[3] += 0.001 * i
+        P.x0 = x0
+        s, _ = P.solve()
+        assert status == int(s["status"]) and iters == int(s["n_iter"]) and abs(cost - s["cost"]) < 1e-7 * abs(s["cost"])

@@ -88,3 +88,19 @@ def test_workload_generators(pkg, workloads):
     assert np.array_equal(w3b.x0, w3.x0[6:])
     # splitmix64 known answer (seed 0 -> 0xE220A8397B1DCDAF)
     assert workloads.splitmix64_uniform(0, 1)[0] == (0xE220A8397B1DCDAF >> 11) / 2.0 ** 53
+
+
+def test_cpp_shim_compiles_and_fails_loudly_without_gpu(pkg, tmp_path):
+    """The header-only C++ mirror of MultiPhaseDDP (hkd-mpc_b200/host/MultiPhaseDDP.hpp) builds against
+    the C ABI; on a box without a GPU the example must exit non-zero (no CPU fallback)."""
+    import subprocess
+    exe = str(tmp_path / "solve_trot")
+    libdir = os.path.dirname(pkg.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", os.path.join(ROOT, "examples", "solve_trot.cpp"), "-L" + libdir,
+                           "-lhsddp_b200", "-Wl,-rpath," + libdir, "-o", exe])
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the GPU run of the example is in test_gpu_parity.py")
+    ref = "/root/reference/Reference/Data/trot/quad_reference.csv"
+    r = subprocess.run([exe, ref if os.path.exists(ref) else "/nonexistent"], capture_output=True, text=True)
+    assert r.returncode != 0 and "error" in r.stderr
