@@ -36,12 +36,12 @@ constexpr double kHipX = 1.9000000000000000e-01, kHipY = 4.9000000000000002e-02;
 constexpr double kAbad = 6.2000000000000000e-02, kThigh = -2.0899999999999999e-01, kShank = -1.9500000000000001e-01;
 
 // Linearisation record of one stage, laid out as the Riccati kernel's tensor-core tiles read it:
-//   R[12][40] row-major:  columns 0..23  = rows 0..11 of A - I   (rows 3..5 hold dt at column 9..11, rows 9..11 zero)
+//   R[12][44] row-major (row stride 44 = 12 mod 16 doubles: conflict-free tensor-core fragment loads):  columns 0..23  = rows 0..11 of A - I   (rows 3..5 hold dt at column 9..11, rows 9..11 zero)
 //                         columns 24..35 = rows 0..11 of B_r, the 24x12 matrix of the COUPLED controls
 //                                          (reduced column c = 3*leg+j; only stance-leg columns have entries
-//                                          in these rows, all of them in rows 6..11); columns 36..39 padding
+//                                          in these rows, all of them in rows 6..11); columns 36..43 padding
 // Only the structural non-zeros are written; the rest of the record must be zero-initialised once.
-constexpr int kRld = 40;
+constexpr int kRld = 44;
 constexpr int kRSize = 12 * kRld;
 
 struct Trig {

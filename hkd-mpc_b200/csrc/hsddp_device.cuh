@@ -45,11 +45,14 @@ constexpr int MAXPH = HSDDP_MAX_PHASES;
 
 // per-stage LQ record (doubles), laid out exactly as the sweep's tensor-core tiles read it so that a
 // plain cp.async copy stages it into shared memory (see hkd_model.cuh: dynamics_partial_record)
-constexpr int LQ_R = 0;                           // [12][40] rows 0..11 of [A - I | B_r] (hkd::kRld = 40)
+constexpr int LQ_R = 0;                           // [12][44] rows 0..11 of [A - I | B_r] (hkd::kRld = 44)
 constexpr int LQ_LX = LQ_R + hkd::kRSize;         // [24]
 constexpr int LQ_LU = LQ_LX + 24;                 // [24]
 constexpr int LQ_LUU = LQ_LU + 24;                // [4][3][3] ReB Hessian blocks per leg (dt folded in)
-constexpr int LQ_STRIDE = 576;                    // 564 used
+constexpr int LQ_STRIDE = 616;                    // 612 used
+constexpr int ZS = 20;                            // row stride of Z = H B_r (16 columns used): 20 = 4 mod 16
+constexpr int TS = 28;                            // row stride (doubles) of the 24-wide shared-memory tiles: 28 = 12 mod 16
+                                                  // makes every m8n8k4 fragment load hit 32 distinct banks per half-warp
 // per-phase terminal record
 constexpr int TQ_PHIX = 0;   // [24]
 constexpr int TQ_HX = 24;    // [4][24] touchdown-constraint gradients, by leg
@@ -98,16 +101,18 @@ struct BatchPtrs {
     hsddp_iter_record* trace;                 // [P][HSDDP_TRACE_CAP]
     unsigned long long* counters;             // [0] = sum over problems of (backward sweeps x stages)
     int* work_counter;                        // dynamic problem queue of the persistent kernel
+    int* sm_slots;                            // [256] per-SM arrival counter: gives co-resident blocks distinct warp-role rotations
     hsddp_constraint_params cp;
 };
 
 // Shared-memory working set of one block.
+struct Smem;
 struct __align__(16) Smem {
     // --- sweep tiles; contiguous, reused as streaming buffers by the linear rollout ---
-    double H[576], Y[576], Z[576];
-    double Qux[384];           // Qux_r [16][24]
-    double Quu[288];           // Quu_r [12][24]
-    double KrS[288];           // K_r transposed [24][12] of the current stage
+    double H[24 * TS], Y[24 * TS];
+    double Z[24 * ZS];         // H B_r [24][ZS] (16 columns used); after P2 the same storage holds K_r^T [24][12]
+    double Qux[16 * TS];       // Qux_r [16][TS]
+    double Quu[12 * TS];       // Quu_r [12][TS]
     double rec[2][LQ_STRIDE];  // stage records, cp.async double buffer
     // --- vectors ---
     double dfc2[2][24];
@@ -125,6 +130,7 @@ struct __align__(16) Smem {
     unsigned long long* prof;
     unsigned long long profacc[16];
     int pid;
+    int rot;   // warp-role rotation of this block (0..3), see virtual_tid()
     int flag;
     int ibuf[4];
     double dbuf[8];
@@ -133,6 +139,18 @@ struct __align__(16) Smem {
 // ---------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------
+// Warp w of every block is scheduled on SM sub-partition w % 4.  The solver has serial roles
+// (Gauss-Jordan pivot columns, the linear-rollout recursion, thread-per-stage passes that fill only
+// the first two warps), so co-resident blocks would pile them onto the same scheduler.  Each block
+// therefore works with a ROTATED thread index: role r is played by hardware warp (r - rot) & 3.
+__device__ __forceinline__ int virtual_tid(const Smem& sm);
+__device__ inline void assign_rotation(int* sm_slots, int& rot_out) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    rot_out = atomicAdd(&sm_slots[smid & 255], 1) & 3;
+}
+__device__ __forceinline__ int virtual_tid(const Smem& sm) { return (int)((threadIdx.x + 32u * (unsigned)sm.rot) & (kThreads - 1)); }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -248,7 +266,7 @@ __device__ inline void resetmap_thread(const double* x, unsigned c, unsigned cn,
     }
 }
 
-// dense Px (HKDReset.h:78-136), column-major into P[576].  Jc: the foot Jacobians cached by the
+// dense Px (HKDReset.h:78-136), ROW-major into P[r * 24 + c].  Jc: the foot Jacobians cached by the
 // LQ approximation in the phase's terminal record ([4][3][6]: d/d eul, d/d qleg per leg).
 __device__ inline void resetmap_partial_block(const double* Jc_all, unsigned c, unsigned cn, double* P) {
     for (int e = threadIdx.x; e < 576; e += kThreads) P[e] = ((e % 24) == (e / 24)) ? 1.0 : 0.0;
@@ -263,9 +281,9 @@ __device__ inline void resetmap_partial_block(const double* Jc_all, unsigned c, 
             const double cmap = (r == 2) ? 0.0 : 1.0;
             P[row * 25] = 0.0;
             for (int cc = 0; cc < 3; ++cc) {
-                P[row + 24 * cc] = cmap * Jc[cc];                          // d/d eul
-                P[row + 24 * (3 + cc)] = cmap * ((r == cc) ? 1.0 : 0.0);   // d/d pos
-                P[row + 24 * (12 + 3 * l + cc)] = cmap * Jc[3 + cc];       // d/d qleg
+                P[row * 24 + cc] = cmap * Jc[cc];                          // d/d eul
+                P[row * 24 + 3 + cc] = cmap * ((r == cc) ? 1.0 : 0.0);     // d/d pos
+                P[row * 24 + 12 + 3 * l + cc] = cmap * Jc[3 + cc];         // d/d qleg
             }
         }
     }
@@ -281,10 +299,13 @@ __device__ inline void resetmap_partial_block(const double* Jc_all, unsigned c, 
 // ---------------------------------------------------------------------------
 __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
     const DevSchedule& sc = sm.sc;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = virtual_tid(sm), lane = tid & 31, warp = tid >> 5;
     const int N = sc.n_stages;
     PROF_DECL
-    double* wdx = sm.Y + 32 * warp;  // per-warp scratch
+    double* xs = sm.H;  // trial states of all nodes [n_nodes][24] (the sweep's tile storage is free here)
+    // (a0) trial states X = Xbar + eps dX for every node
+    for (int e = tid; e < sc.n_nodes * 24; e += kThreads) xs[e] = sm.Xbar[e] + eps * sm.dX[e];
+    __syncthreads();
     // (a) controls: U = (Ubar + eps dU) + K (X - Xbar), one warp per stage.  K is stored compactly as
     //     K_r^T [24][12] (only the coupled control of each leg has a non-zero gain row, see hsddp_sweep.cuh)
     for (int s = warp; s < N; s += kWarps) {
@@ -293,22 +314,17 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
         const int n = sc.node_off[ph] + k;
         const unsigned cm = sc.cmask[ph];
         if (lane < 24) {
-            const double xb = sm.Xbar[24 * n + lane];
-            const double x = xb + eps * sm.dX[24 * n + lane];
-            wdx[lane] = x - xb;
-        }
-        __syncwarp();
-        if (lane < 24) {
             const bool stance = (cm >> ((lane % 12) / 3)) & 1u;
             double acc = 0.0;
             if ((lane < 12) == stance) {
                 const double* KT = sm.K + 288 * (size_t)s + (lane % 12);  // KT[j][c]
+                const double* xv = xs + 24 * n;
+                const double* xb = sm.Xbar + 24 * n;
 #pragma unroll 8
-                for (int j = 0; j < 24; ++j) acc = fma(KT[12 * j], wdx[j], acc);
+                for (int j = 0; j < 24; ++j) acc = fma(KT[12 * j], xv[j] - xb[j], acc);
             }
             sm.U_t[24 * s + lane] = (sm.Ubar[24 * s + lane] + eps * sm.dU[24 * s + lane]) + acc;
         }
-        __syncwarp();
     }
     __syncthreads();
     PROF_MARK(sm, 0);
@@ -318,27 +334,22 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
         int ph, k;
         phase_of_stage(sc, s, ph, k);
         const int n = sc.node_off[ph] + k;
-        double x[24], u[24], xn[24];
-#pragma unroll
-        for (int j = 0; j < 24; ++j) { x[j] = sm.Xbar[24 * n + j] + eps * sm.dX[24 * n + j]; u[j] = sm.U_t[24 * s + j]; }
-        hkd::dynamics(x, u, sc.dt, sc.cmask[ph], xn);
+        double* xn = sm.Xsim_t + 24 * (n + 1);
+        hkd::dynamics(xs + 24 * n, sm.U_t + 24 * s, sc.dt, sc.cmask[ph], xn);
         double nrm2 = 0.0;
 #pragma unroll
-        for (int j = 0; j < 24; ++j) { nrm2 += xn[j] * xn[j]; sm.Xsim_t[24 * (n + 1) + j] = xn[j]; }
+        for (int j = 0; j < 24; ++j) nrm2 = fma(xn[j], xn[j], nrm2);
         if (sqrt(nrm2) > 1e6) first_bad = min(first_bad, s);
     }
-    if (tid < sc.n_phases) {
-        const int ph = tid;
-        double xi[24];
+    if (tid >= 64 && tid < 64 + sc.n_phases) {
+        const int ph = tid - 64;
+        double* xi = sm.Xsim_t + 24 * sc.node_off[ph];
         if (ph == 0) {
             for (int j = 0; j < 24; ++j) xi[j] = sm.x0[j];
         } else {
             const int ne = sc.node_off[ph - 1] + sc.horizon[ph - 1];
-            double xe[24];
-            for (int j = 0; j < 24; ++j) xe[j] = sm.Xbar[24 * ne + j] + eps * sm.dX[24 * ne + j];
-            resetmap_thread(xe, sc.cmask[ph - 1], sc.nmask[ph - 1], xi);
+            resetmap_thread(xs + 24 * ne, sc.cmask[ph - 1], sc.nmask[ph - 1], xi);
         }
-        for (int j = 0; j < 24; ++j) sm.Xsim_t[24 * sc.node_off[ph] + j] = xi[j];
     }
     // first diverged stage in the reference's sequential order
     const int bad = (int)block_reduce<1>(sm, (double)first_bad);
@@ -351,7 +362,7 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
         int ph, k;
         phase_of_node(sc, n, ph, k);
         if (ph < bad_ph || (ph == bad_ph && k <= bad_k)) {
-            const double x = sm.Xbar[e] + eps * sm.dX[e];
+            const double x = xs[e];
             sm.X[e] = x;
             if (ph < bad_ph) sm.Defect[e] = sm.Xsim_t[e] - x;  // compute_defect only after a complete phase
         }
@@ -381,8 +392,8 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
         const bool td = !((sc.cmask[ph] >> l) & 1u) && ((sc.nmask[ph] >> l) & 1u);
         if (td && ph < bad_ph) {
             const int ne = sc.node_off[ph] + sc.horizon[ph];
-            double xe[24], pf[3];
-            for (int j = 0; j < 24; ++j) xe[j] = sm.Xbar[24 * ne + j] + eps * sm.dX[24 * ne + j];
+            const double* xe = xs + 24 * ne;
+            double pf[3];
             hkd::foot_position(xe + 3, xe, xe + 12 + 3 * l, l, pf);
             sm.hcon[4 * ph + l] = pf[2] - 0.0;
             hmax = fabs(pf[2]);
@@ -413,7 +424,7 @@ __device__ inline void foot_rel_error(const double* x, const double* prel_r, dou
 
 __device__ inline void compute_cost_block(Smem& sm) {
     const DevSchedule& sc = sm.sc;
-    const int tid = threadIdx.x;
+    const int tid = virtual_tid(sm);
     PROF_DECL
     const int N = sc.n_stages;
     const double dt = sc.dt;
@@ -498,7 +509,7 @@ __device__ inline void compute_cost_block(Smem& sm) {
 // ---------------------------------------------------------------------------
 __device__ inline void lq_approximation_block(Smem& sm) {
     const DevSchedule& sc = sm.sc;
-    const int tid = threadIdx.x;
+    const int tid = virtual_tid(sm);
     PROF_DECL
     const int N = sc.n_stages;
     const double dt = sc.dt;
@@ -507,53 +518,63 @@ __device__ inline void lq_approximation_block(Smem& sm) {
         phase_of_stage(sc, s, ph, k);
         const int n = sc.node_off[ph] + k;
         const unsigned cm = sc.cmask[ph];
-        double x[24], u[24];
-#pragma unroll
-        for (int j = 0; j < 24; ++j) { x[j] = sm.X[24 * n + j]; u[j] = sm.U[24 * s + j]; }
+        const double* x = sm.X + 24 * n;
+        const double* u = sm.U + 24 * s;
         double* rec = sm.lqg + (size_t)s * LQ_STRIDE;
         hkd::dynamics_partial_record(x, u, dt, cm, rec + LQ_R);
         const double* xr = sm.xr + 24 * n;
         const double* ur = sm.ur + 24 * n;
-        double lx[24], lu[24];
+        double* lx = rec + LQ_LX;
+        double* lu = rec + LQ_LU;
 #pragma unroll
         for (int j = 0; j < 24; ++j) {
             lx[j] = (dt * weight_Q(j, cm)) * (x[j] - xr[j]);
             lu[j] = (dt * weight_R(j)) * (u[j] - ur[j]);
         }
-        double d[12];
-        foot_rel_error(x, sm.prel + 12 * n, d);
+        // foot-placement regulariser: pos rows accumulate over the legs in order, foot rows get one term each
+        {
+            double lp[3] = {lx[3], lx[4], lx[5]};
 #pragma unroll
-        for (int l = 0; l < 4; ++l) {
-            const double c = (double)((cm >> l) & 1u);
+            for (int l = 0; l < 4; ++l) {
+                const double c = (double)((cm >> l) & 1u);
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const double w = dt * c * weight_foot(l, j, cm);
-                lx[3 + j] += -(w * d[3 * l + j]);
-                lx[12 + 3 * l + j] += w * d[3 * l + j];
+                for (int j = 0; j < 3; ++j) {
+                    const double d = (x[12 + 3 * l + j] - x[3 + j]) - sm.prel[12 * n + 3 * l + j];
+                    const double w = dt * c * weight_foot(l, j, cm);
+                    lp[j] += -(w * d);
+                    lx[12 + 3 * l + j] += w * d;
+                }
             }
+            lx[3] = lp[0]; lx[4] = lp[1]; lx[5] = lp[2];
         }
         // ReB folding (compute_ReB_partials, ConstraintsBase.h:224-263); only gu is non-zero
-        double rows[5][3];
-        grf_rows(sm.cp.mu, rows);
+        const double mu = sm.cp.mu;
+#pragma unroll
         for (int l = 0; l < 4; ++l) {
             double hess[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, grad[3] = {0, 0, 0};
             if (sm.opt.ReB_active && ((cm >> l) & 1u)) {
+#pragma unroll
                 for (int r = 0; r < 5; ++r) {
+                    // friction-pyramid row r: (0,0,1), (-1,0,mu), (1,0,mu), (0,-1,mu), (0,1,mu)
+                    const double row[3] = {(r == 1) ? -1.0 : (r == 2) ? 1.0 : 0.0, (r == 3) ? -1.0 : (r == 4) ? 1.0 : 0.0, (r == 0) ? 1.0 : mu};
                     const double g = sm.gcon[20 * s + 5 * l + r];
                     const double eps_b = sm.reb[40 * s + 2 * (5 * l + r)], delta = sm.reb[40 * s + 2 * (5 * l + r) + 1];
                     double bd, bdd;
                     if (g > delta) { bd = -1.0 / g; bdd = 1.0 / (g * g); }
                     else { bd = (g - 2 * delta) / delta / delta; bdd = 1.0 / (delta * delta); }
-                    for (int a = 0; a < 3; ++a) grad[a] += eps_b * bd * rows[r][a];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) grad[a] += eps_b * bd * row[a];
+#pragma unroll
                     for (int a = 0; a < 3; ++a)
-                        for (int b = 0; b < 3; ++b) hess[3 * a + b] += eps_b * (bdd * rows[r][a] * rows[r][b]);
+#pragma unroll
+                        for (int b = 0; b < 3; ++b) hess[3 * a + b] += eps_b * (bdd * row[a] * row[b]);
                 }
             }
+#pragma unroll
             for (int a = 0; a < 3; ++a) lu[3 * l + a] += dt * grad[a];
+#pragma unroll
             for (int a = 0; a < 9; ++a) rec[LQ_LUU + 9 * l + a] = dt * hess[a];
         }
-#pragma unroll
-        for (int j = 0; j < 24; ++j) { rec[LQ_LX + j] = lx[j]; rec[LQ_LU + j] = lu[j]; }
     }
     if (tid < sc.n_phases) {
         const int ph = tid;

@@ -7,6 +7,7 @@
 // from a device-side queue so problems with few iterations retire early).
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -143,8 +144,9 @@ bad_solve:
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kThreads, 4) k_solve(BatchPtrs bp, hsddp_options opt, int cold_start) {
+__global__ void __launch_bounds__(kThreads, 6) k_solve(BatchPtrs bp, hsddp_options opt, int cold_start) {
     __shared__ Smem sm;
+    if (threadIdx.x == 0) assign_rotation(bp.sm_slots, sm.rot);
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) sm.ibuf[3] = atomicAdd(bp.work_counter, 1);
@@ -170,9 +172,10 @@ __global__ void __launch_bounds__(kThreads, 4) k_solve(BatchPtrs bp, hsddp_optio
 enum StepOp { OP_RESET = 0, OP_ROLLOUT, OP_COST, OP_LQ, OP_SWEEP, OP_SWEEP_REG, OP_LINEAR, OP_MERIT, OP_FORWARD, OP_NOMINAL, OP_AL, OP_REB };
 
 // step-level kernel: one block per problem, state round-trips through HBM
-__global__ void __launch_bounds__(kThreads, 4) k_step(BatchPtrs bp, hsddp_options opt, int op, double arg, double* darg, int* ok) {
+__global__ void __launch_bounds__(kThreads, 6) k_step(BatchPtrs bp, hsddp_options opt, int op, double arg, double* darg, int* ok) {
     __shared__ Smem sm;
     const int pid = blockIdx.x;
+    if (threadIdx.x == 0) assign_rotation(bp.sm_slots, sm.rot);
     bind_problem(sm, bp, pid);
     if (threadIdx.x == 0) sm.opt = opt;
     __syncthreads();
@@ -335,6 +338,10 @@ int hsddp_batch_create(int device, hsddp_batch** out) {
     b->n_sm = prop.multiProcessorCount;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b->blocks_per_sm, k_solve, kThreads, 0));
     if (b->blocks_per_sm < 1) b->blocks_per_sm = 1;
+    if (const char* e = getenv("HSDDP_BLOCKS_PER_SM")) {  // tuning / experiments only
+        const int v = atoi(e);
+        if (v >= 1 && v <= b->blocks_per_sm) b->blocks_per_sm = v;
+    }
     *out = b;
     return HSDDP_OK;
 }
@@ -441,6 +448,8 @@ int hsddp_batch_set_problems(hsddp_batch* b, int n_schedules, const hsddp_schedu
     if ((rc = dalloc(b, &bp.trace, P * HSDDP_TRACE_CAP))) return rc;
     if ((rc = dalloc(b, &bp.counters, (size_t)32))) return rc;
     if ((rc = dalloc(b, &bp.work_counter, (size_t)4))) return rc;
+    if ((rc = dalloc(b, &bp.sm_slots, (size_t)256))) return rc;
+    CK(cudaMemset(bp.sm_slots, 0, 256 * sizeof(int)));
     if ((rc = dalloc(b, &b->d_ok, P))) return rc;
     if ((rc = dalloc(b, &b->d_darg, P))) return rc;
     CK(cudaMemset(bp.x0, 0, P * 24 * sizeof(double)));

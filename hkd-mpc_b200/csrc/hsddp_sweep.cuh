@@ -79,9 +79,17 @@ __device__ __forceinline__ void prefetch_stage(Smem& sm, int buf, int s, int n1)
 // Returns false if a negative pivot was met (pivot 1 = a, pivot 2 = det / a), which for the caller
 // that runs Quu_r - 1e-9 I is the reference's LDLT(...).isPositive() verdict (Sylvester's law of
 // inertia).  After the call v = Quu_r^-1 * (original column).
-__device__ __forceinline__ bool gauss_jordan12(double (&v)[12], double* sbuf) {
+#ifdef HSDDP_PROFILE_GJ
+#define GJ_MARK(slot) do { if (threadIdx.x == 0) { const long long t1_ = clock64(); gjacc[slot] += (unsigned long long)(t1_ - gjt0); gjt0 = t1_; } } while (0)
+#else
+#define GJ_MARK(slot) do { } while (0)
+#endif
+__device__ __forceinline__ bool gauss_jordan12(double (&v)[12], double* sbuf, unsigned long long* gjacc = nullptr) {
     const int lane = threadIdx.x & 31;
     bool ok = true;
+#ifdef HSDDP_PROFILE_GJ
+    long long gjt0 = clock64();
+#endif
 #pragma unroll 1
     for (int step = 0; step < 6; ++step) {
         if ((lane >> 1) == step) {  // the two pivot columns (lanes 2*step, 2*step+1 < 12)
@@ -90,6 +98,7 @@ __device__ __forceinline__ bool gauss_jordan12(double (&v)[12], double* sbuf) {
             for (int r = 0; r < 12; r += 2) dst[r >> 1] = make_double2(v[r], v[r + 1]);
         }
         __syncwarp();
+        GJ_MARK(0);
         // pivot block P = [a b; c d] = [col0[0] col1[0]; col0[1] col1[1]] in the rotated frame
         const double2 pk = *reinterpret_cast<const double2*>(sbuf);
         const double2 pk1 = *reinterpret_cast<const double2*>(sbuf + 12);
@@ -98,6 +107,10 @@ __device__ __forceinline__ bool gauss_jordan12(double (&v)[12], double* sbuf) {
         const double rdet = 1.0 / det;
         const double t0 = (pk1.y * v[0] - pk1.x * v[1]) * rdet;
         const double t1 = (pk.x * v[1] - pk.y * v[0]) * rdet;
+#ifdef HSDDP_PROFILE_GJ
+        if (t1 == 1.2345e300) ok = false;  // force completion of the pivot math before the mark
+#endif
+        GJ_MARK(1);
 #pragma unroll
         for (int r = 2; r < 12; r += 2) {  // eliminate and rotate in one go
             const double2 a = *reinterpret_cast<const double2*>(sbuf + r);
@@ -107,7 +120,11 @@ __device__ __forceinline__ bool gauss_jordan12(double (&v)[12], double* sbuf) {
         }
         v[10] = t0;
         v[11] = t1;
+#ifdef HSDDP_PROFILE_GJ
+        if (v[0] == 1.2345e300) ok = false;
+#endif
         __syncwarp();
+        GJ_MARK(2);
     }
     return ok;
 }
@@ -120,7 +137,7 @@ __device__ __forceinline__ double lxx_tab(const double* d, const double* w, int 
     return 0.0;
 }
 __device__ inline void build_phase_tables(Smem& sm, unsigned cm, double dt) {
-    const int tid = threadIdx.x;
+    const int tid = virtual_tid(sm);
     if (tid < 24) {  // [0..11] running w, [12..23] terminal w
         const int q = tid % 12, l = q / 3, jj = q % 3;
         const double c = (double)((cm >> l) & 1u);
@@ -152,12 +169,12 @@ __device__ inline void build_phase_tables(Smem& sm, unsigned cm, double dt) {
 //   H [24][24] value Hessian (symmetric); between P2 and P4 its lower tiles hold Qxx
 //   Y [24][24] = H A ; Zr = sm.Z [24][16 used] = H B_r
 //   rec[buf]: R [12][40] = [A - I | B_r] rows 0..11, then lx | lu | luu blocks  (cp.async double buffer)
-//   QuxR = sm.Qux [16][24] ; QuuR = sm.Quu [12][24] ; KT = sm.KrS [24][12] (K_r transposed)
+//   QuxR = sm.Qux [16][24] ; QuuR = sm.Quu [12][24] ; KT = sm.Z [24][12] (K_r transposed)
 // Every phase of the stage is a short table-driven loop over 8x8 output tiles (3 DMMA each),
 // distributed round-robin over the 4 warps, so that the whole stage body stays i-cache resident.
 __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, double& dV1, double& dV2) {
     const DevSchedule& sc = sm.sc;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = virtual_tid(sm), warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const unsigned cm = sc.cmask[ph];
     const double dt = sc.dt;
@@ -176,7 +193,7 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
             const double wh = trec[TQ_WH + l];
             if (wh != 0.0) val += wh * (trec[TQ_HX + 24 * l + i] * trec[TQ_HX + 24 * l + j]);
         }
-        sm.H[e] += val;
+        sm.H[i * TS + j] += val;
     }
     cp_async_wait_all();
     __syncthreads();
@@ -199,30 +216,30 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                 const int i0 = 8 * (tile / 5), Jt = tile % 5;
                 double c2[2];
                 if (Jt < 3) {
-                    const double2 h2 = *reinterpret_cast<const double2*>(sm.H + (i0 + g) * 24 + 8 * Jt + 2 * t);
+                    const double2 h2 = *reinterpret_cast<const double2*>(sm.H + (i0 + g) * TS + 8 * Jt + 2 * t);
                     c2[0] = h2.x; c2[1] = h2.y;
                 } else { c2[0] = 0.0; c2[1] = 0.0; }
 #pragma unroll
-                for (int kk = 0; kk < 12; kk += 4) dmma884(c2, sm.H[(kk + t) * 24 + i0 + g], R[(kk + t) * hkd::kRld + 8 * Jt + g]);
+                for (int kk = 0; kk < 12; kk += 4) dmma884(c2, sm.H[(kk + t) * TS + i0 + g], R[(kk + t) * hkd::kRld + 8 * Jt + g]);
                 if (Jt < 3) {
-                    *reinterpret_cast<double2*>(sm.Y + (i0 + g) * 24 + 8 * Jt + 2 * t) = make_double2(c2[0], c2[1]);
+                    *reinterpret_cast<double2*>(sm.Y + (i0 + g) * TS + 8 * Jt + 2 * t) = make_double2(c2[0], c2[1]);
                 } else {
                     // swing columns of Z: H[:, 12+c] * dt
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         const int c = 8 * (Jt - 3) + 2 * t + q;
-                        if (c < 12) c2[q] = fma(sm.H[(i0 + g) * 24 + 12 + c], sm.swdt[c / 3], c2[q]);
+                        if (c < 12) c2[q] = fma(sm.H[(i0 + g) * TS + 12 + c], sm.swdt[c / 3], c2[q]);
                     }
-                    *reinterpret_cast<double2*>(sm.Z + (i0 + g) * 24 + 8 * (Jt - 3) + 2 * t) = make_double2(c2[0], c2[1]);
+                    *reinterpret_cast<double2*>(sm.Z + (i0 + g) * ZS + 8 * (Jt - 3) + 2 * t) = make_double2(c2[0], c2[1]);
                 }
             } else if (lane < 24) {  // Gn = G + H d   (Q10)
                 double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
                 for (int j = 0; j < 24; j += 4) {
-                    a0 = fma(sm.H[j * 24 + lane], dfc[j], a0);
-                    a1 = fma(sm.H[(j + 1) * 24 + lane], dfc[j + 1], a1);
-                    a2 = fma(sm.H[(j + 2) * 24 + lane], dfc[j + 2], a2);
-                    a3 = fma(sm.H[(j + 3) * 24 + lane], dfc[j + 3], a3);
+                    a0 = fma(sm.H[j * TS + lane], dfc[j], a0);
+                    a1 = fma(sm.H[(j + 1) * TS + lane], dfc[j + 1], a1);
+                    a2 = fma(sm.H[(j + 2) * TS + lane], dfc[j + 2], a2);
+                    a3 = fma(sm.H[(j + 3) * TS + lane], dfc[j + 3], a3);
                 }
                 sm.Gn[lane] = sm.G[lane] + ((a0 + a1) + (a2 + a3));
             }
@@ -237,23 +254,24 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
             else if (tile < 12) { ci = 24 + 8 * ((tile - 6) / 3); j0 = 8 * ((tile - 6) % 3); kind = 1; }
             else { ci = 24 + 8 * ((tile - 12) >> 1); j0 = 8 * ((tile - 12) & 1); kind = 2; }
             const double* M = (kind == 2) ? sm.Z : sm.Y;
+            const int ms = (kind == 2) ? ZS : TS;
             double c2[2] = {0.0, 0.0};
             if (kind == 0) {
                 const int i = ci + g, j = j0 + 2 * t;
-                const double2 y2 = *reinterpret_cast<const double2*>(sm.Y + i * 24 + j);
+                const double2 y2 = *reinterpret_cast<const double2*>(sm.Y + i * TS + j);
                 c2[0] = lxx_tab(sm.lxxd, sm.lxxw, i, j) + y2.x + ((i == j) ? reg : 0.0);
                 c2[1] = lxx_tab(sm.lxxd, sm.lxxw, i, j + 1) + y2.y + ((i == j + 1) ? reg : 0.0);
             }
 #pragma unroll
-            for (int kk = 0; kk < 12; kk += 4) dmma884(c2, R[(kk + t) * hkd::kRld + ci + g], M[(kk + t) * 24 + j0 + g]);
+            for (int kk = 0; kk < 12; kk += 4) dmma884(c2, R[(kk + t) * hkd::kRld + ci + g], M[(kk + t) * ms + j0 + g]);
             if (kind == 0) {
-                *reinterpret_cast<double2*>(sm.H + (ci + g) * 24 + j0 + 2 * t) = make_double2(c2[0], c2[1]);
+                *reinterpret_cast<double2*>(sm.H + (ci + g) * TS + j0 + 2 * t) = make_double2(c2[0], c2[1]);
             } else {
                 const int c = ci - 24 + g;  // reduced control row
                 if (c < 12) {
                     const bool swing = !((cm >> (c / 3)) & 1u);
                     if (swing) {  // (B_r^T M)[c][:] = dt * M[12+c][:]
-                        const double2 m2 = *reinterpret_cast<const double2*>(M + (12 + c) * 24 + j0 + 2 * t);
+                        const double2 m2 = *reinterpret_cast<const double2*>(M + (12 + c) * ms + j0 + 2 * t);
                         c2[0] = fma(sm.swdt[c / 3], m2.x, c2[0]);
                         c2[1] = fma(sm.swdt[c / 3], m2.y, c2[1]);
                     }
@@ -264,9 +282,9 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                             if (c == cc) c2[q] += dt * weight_R(act_index(c, cm)) + reg;
                             if (cc < 12 && c / 3 == cc / 3 && !swing) c2[q] += luu[9 * (c / 3) + 3 * (c % 3) + (cc % 3)];
                         }
-                        *reinterpret_cast<double2*>(sm.Quu + c * 24 + j0 + 2 * t) = make_double2(c2[0], c2[1]);
+                        *reinterpret_cast<double2*>(sm.Quu + c * TS + j0 + 2 * t) = make_double2(c2[0], c2[1]);
                     } else {
-                        *reinterpret_cast<double2*>(sm.Qux + c * 24 + j0 + 2 * t) = make_double2(c2[0], c2[1]);
+                        *reinterpret_cast<double2*>(sm.Qux + c * TS + j0 + 2 * t) = make_double2(c2[0], c2[1]);
                     }
                 }
             }
@@ -300,18 +318,18 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
 #pragma unroll
             for (int r = 0; r < 12; ++r) {
                 double val = (r == lane % 12) ? 1.0 : 0.0;  // harmless dummy column for idle lanes
-                if (is_piv) val = sm.Quu[r * 24 + lane] - ((r == lane) ? shift : 0.0);
-                else if (is_gain) val = sm.Qux[r * 24 + j];
+                if (is_piv) val = sm.Quu[r * TS + lane] - ((r == lane) ? shift : 0.0);
+                else if (is_gain) val = sm.Qux[r * TS + j];
                 else if (is_ff) val = sm.Qu[r];
                 col[r] = val;
             }
             PROF_MARK(sm, 13);
-            const bool ok = gauss_jordan12(col, sm.red + 32 * warp);
+            const bool ok = gauss_jordan12(col, sm.red + 32 * warp, sm.profacc + 10);
             PROF_MARK(sm, 14);
             if (warp == 2) {
                 if (lane == 0) sm.ibuf[0] = ok ? 1 : 0;
             } else if (is_gain) {  // gain column j: K_r[:, j] = -Quu_r^-1 Qux_r[:, j]  -> KT[j][0..11] (smem + HBM)
-                double2* ks = reinterpret_cast<double2*>(sm.KrS + 12 * j);
+                double2* ks = reinterpret_cast<double2*>(sm.Z + 12 * j);
                 double2* kg = reinterpret_cast<double2*>(sm.K + (size_t)s * 288 + 12 * j);
 #pragma unroll
                 for (int r = 0; r < 12; r += 2) {
@@ -355,11 +373,11 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                 const int i0 = 8 * I, j0 = 8 * J;
                 double c2[2];
                 {
-                    const double2 q2 = *reinterpret_cast<const double2*>(sm.H + (i0 + g) * 24 + j0 + 2 * t);
+                    const double2 q2 = *reinterpret_cast<const double2*>(sm.H + (i0 + g) * TS + j0 + 2 * t);
                     c2[0] = q2.x; c2[1] = q2.y;
                 }
 #pragma unroll
-                for (int kk = 0; kk < 12; kk += 4) dmma884(c2, sm.Qux[(kk + t) * 24 + i0 + g], sm.KrS[(j0 + g) * 12 + kk + t]);
+                for (int kk = 0; kk < 12; kk += 4) dmma884(c2, sm.Qux[(kk + t) * TS + i0 + g], sm.Z[(j0 + g) * 12 + kk + t]);
                 if (I == J) {
                     // symmetrise the diagonal tile: partner of (g, 2t+q') is (2t+q', g), held by lane 4*(2t+q') + g/2, slot g&1
                     const double p00 = __shfl_sync(0xffffffffu, c2[0], 4 * (2 * t) + (g >> 1));
@@ -369,14 +387,14 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                     c2[0] = 0.5 * (c2[0] + ((g & 1) ? p01 : p00));
                     c2[1] = 0.5 * (c2[1] + ((g & 1) ? p11 : p10));
                 } else {
-                    sm.H[(j0 + 2 * t) * 24 + i0 + g] = c2[0];
-                    sm.H[(j0 + 2 * t + 1) * 24 + i0 + g] = c2[1];
+                    sm.H[(j0 + 2 * t) * TS + i0 + g] = c2[0];
+                    sm.H[(j0 + 2 * t + 1) * TS + i0 + g] = c2[1];
                 }
-                *reinterpret_cast<double2*>(sm.H + (i0 + g) * 24 + j0 + 2 * t) = make_double2(c2[0], c2[1]);
+                *reinterpret_cast<double2*>(sm.H + (i0 + g) * TS + j0 + 2 * t) = make_double2(c2[0], c2[1]);
             } else if (tile == 7 && lane < 24) {
                 double acc = sm.Qx[lane];
 #pragma unroll
-                for (int r = 0; r < 12; ++r) acc = fma(sm.Qux[r * 24 + lane], sm.wu[r], acc);
+                for (int r = 0; r < 12; ++r) acc = fma(sm.Qux[r * TS + lane], sm.wu[r], acc);
                 sm.G[lane] = acc;
             }
         }
@@ -395,7 +413,7 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
         double acc = 0.0;
         if (tid < 24) {
 #pragma unroll
-            for (int j = 0; j < 24; ++j) acc = fma(sm.H[tid * 24 + j], sm.vtmp[j], acc);
+            for (int j = 0; j < 24; ++j) acc = fma(sm.H[j * TS + tid], sm.vtmp[j], acc);  // H symmetric: conflict-free column read
         }
         __syncthreads();
         if (tid < 24) sm.G[tid] += acc;
@@ -407,39 +425,40 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
 // MultiPhaseDDP::backward_sweep(regularization)
 __device__ inline bool backward_sweep_block(Smem& sm, double reg) {
     const DevSchedule& sc = sm.sc;
-    const int tid = threadIdx.x;
+    const int tid = virtual_tid(sm);
     PROF_DECL
     double dV1 = 0.0, dV2 = 0.0;
     bool success = true;
     for (int ph = sc.n_phases - 1; ph >= 0; --ph) {
         if (ph == sc.n_phases - 1) {
-            for (int e = tid; e < 576; e += kThreads) sm.H[e] = 0.0;
+            for (int e = tid; e < 24 * TS; e += kThreads) sm.H[e] = 0.0;
             if (tid < 24) sm.G[tid] = 0.0;
             __syncthreads();
         } else {
             // impact-aware step: G' = Px^T G0, H' = Px^T H0 Px at the phase's terminal state
             resetmap_partial_block(sm.tq + ph * TQ_STRIDE + TQ_JC, sc.cmask[ph], sc.nmask[ph], sm.Y);
-            const double* P = sm.Y;  // column-major P[r + 24 c]
-            for (int e = tid; e < 576; e += kThreads) {  // Z = P^T H  (row-major Z[i][j])
+            const double* P = sm.Y;  // row-major P[r * 24 + c]
+            double* T = sm.Qux;      // 24 x TS temporary spanning Qux|Quu (contiguous, free here)
+            for (int e = tid; e < 576; e += kThreads) {  // T = P^T H
                 const int i = e / 24, j = e % 24;
                 double acc = 0.0;
 #pragma unroll
-                for (int m = 0; m < 24; ++m) acc = fma(P[m + 24 * i], sm.H[m * 24 + j], acc);
-                sm.Z[e] = acc;
+                for (int m = 0; m < 24; ++m) acc = fma(P[m * 24 + i], sm.H[m * TS + j], acc);
+                T[i * TS + j] = acc;
             }
             if (tid < 24) {
                 double acc = 0.0;
 #pragma unroll
-                for (int m = 0; m < 24; ++m) acc = fma(P[m + 24 * tid], sm.G[m], acc);
+                for (int m = 0; m < 24; ++m) acc = fma(P[m * 24 + tid], sm.G[m], acc);
                 sm.vtmp[tid] = acc;
             }
             __syncthreads();
-            for (int e = tid; e < 576; e += kThreads) {  // H = Z P
+            for (int e = tid; e < 576; e += kThreads) {  // H = T P
                 const int i = e / 24, j = e % 24;
                 double acc = 0.0;
 #pragma unroll
-                for (int m = 0; m < 24; ++m) acc = fma(sm.Z[i * 24 + m], P[m + 24 * j], acc);
-                sm.H[e] = acc;
+                for (int m = 0; m < 24; ++m) acc = fma(T[i * TS + m], P[m * 24 + j], acc);
+                sm.H[i * TS + j] = acc;
             }
             if (tid < 24) sm.G[tid] = sm.vtmp[tid];
             __syncthreads();
@@ -454,7 +473,7 @@ __device__ inline bool backward_sweep_block(Smem& sm, double reg) {
         dV2 += d2;
     }
     if (success) {
-        for (int e = tid; e < 576; e += kThreads) sm.g0h0[24 + e] = sm.H[e];  // symmetric: row-major == column-major
+        for (int e = tid; e < 576; e += kThreads) sm.g0h0[24 + e] = sm.H[(e / 24) * TS + e % 24];  // symmetric: row-major == column-major
         if (tid < 24) sm.g0h0[tid] = sm.G[tid];
     }
     __syncthreads();
@@ -523,7 +542,7 @@ __device__ __forceinline__ void lr_prefetch(Smem& sm, double* buf, int s0, int s
 
 __device__ inline void linear_rollout_block(Smem& sm, double eps) {
     const DevSchedule& sc = sm.sc;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = virtual_tid(sm), lane = tid & 31;
     const double dt = sc.dt;
     const int N = sc.n_stages;
     double* scratch = sm.H;  // H, Y, Z, Qux, Quu, KrS, rec are contiguous and free outside the sweep

@@ -20,7 +20,7 @@ for _ in range(reps):
 prof = B.profile()
 if any(prof):
     names = ["rollout:U=K dx", "rollout:dynamics", "rollout:commit", "cost", "LQ approx", "sweep:phase init", "sweep:P1 Y,Z", "sweep:P2 Q",
-             "sweep:P3 GJ", "sweep:P4 H'", "sweep:Px transform", "linear:recursion", "linear:dV pass", "P3:load tableau", "P3:gauss-jordan", "P3:stores"]
+             "sweep:P3 GJ", "sweep:P4 H'", "GJ:publish cols (or Px)", "GJ:pivot math (or linear rec)", "GJ:eliminate (or dV pass)", "P3:load tableau", "P3:gauss-jordan", "P3:stores"]
     tot = sum(prof)
     for nm, v in zip(names, prof):
         print(f"  {nm:22s} {v:>14d} cyc  {100.0 * v / tot:5.1f}%")
