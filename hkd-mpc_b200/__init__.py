@@ -19,7 +19,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhsddp_b200.so")
+# HSDDP_LIB selects a development variant of the library (profiling builds); the default is the in-tree product build
+LIB_PATH = os.environ.get("HSDDP_LIB") or os.path.join(_HERE, "libhsddp_b200.so")
 
 MAX_PHASES = 16
 MAX_STAGES = 128
