@@ -314,6 +314,10 @@ class MultiPhaseDDPBatch:
         opt = opt or Options()
         _check(lib().hsddp_batch_solve_async(self.h, C.byref(opt)), "hsddp_batch_solve_async")
 
+    def set_solve_mode(self, mode):
+        """0 auto, 1 persistent kernel, 2 phased kernels (see include/hsddp_b200.h)."""
+        _check(lib().hsddp_batch_set_solve_mode(self.h, int(mode)), "hsddp_batch_set_solve_mode")
+
     def sync(self):
         _check(lib().hsddp_batch_sync(self.h), "hsddp_batch_sync")
 

@@ -48,12 +48,23 @@ struct Trig {
     double sy, cy, sp, cp, sr, cr;
 };
 
+#ifdef __CUDACC__
+// One out-of-line copy of the FP64 sincos / log expansions (argument reduction + slow path are ~200
+// instructions each): the solver kernel is instruction-cache bound when they are inlined at every call site.
+struct SinCos { double s, c; };
+static __device__ __noinline__ SinCos sincos_nl(double a) {
+    SinCos r;
+    sincos(a, &r.s, &r.c);
+    return r;
+}
+static __device__ __noinline__ double log_nl(double a) { return log(a); }
+#endif
+
 HKD_HD Trig trig_of(double yaw, double pitch, double roll) {
     Trig t;
 #ifdef __CUDA_ARCH__
-    sincos(yaw, &t.sy, &t.cy);
-    sincos(pitch, &t.sp, &t.cp);
-    sincos(roll, &t.sr, &t.cr);
+    const SinCos a = sincos_nl(yaw), b = sincos_nl(pitch), c = sincos_nl(roll);
+    t.sy = a.s; t.cy = a.c; t.sp = b.s; t.cp = b.c; t.sr = c.s; t.cr = c.c;
 #else
     t.sy = sin(yaw); t.cy = cos(yaw); t.sp = sin(pitch); t.cp = cos(pitch); t.sr = sin(roll); t.cr = cos(roll);
 #endif
@@ -224,7 +235,7 @@ HKD_HD void leg_kinematics(const double* q, int leg, double pb[3], double* dq) {
     const double l1 = kAbad * side;
     double s1, c1, s2, c2, s3, c3;
 #ifdef __CUDA_ARCH__
-    sincos(q[0], &s1, &c1); sincos(-q[1], &s2, &c2); sincos(-q[2], &s3, &c3);
+    { const SinCos a = sincos_nl(q[0]), b = sincos_nl(-q[1]), c = sincos_nl(-q[2]); s1 = a.s; c1 = a.c; s2 = b.s; c2 = b.c; s3 = c.s; c3 = c.c; }
 #else
     s1 = sin(q[0]); c1 = cos(q[0]); s2 = sin(-q[1]); c2 = cos(-q[1]); s3 = sin(-q[2]); c3 = cos(-q[2]);
 #endif

@@ -69,6 +69,8 @@ struct DevSchedule {
     unsigned nmask[MAXPH];  // contact after the phase
     long long ref_off;      // node offset of this schedule inside the concatenated reference arrays
     double dt;
+    unsigned char ph_of_stage[HSDDP_MAX_STAGES];           // filled on the host (hsddp_batch_set_problems)
+    unsigned char ph_of_node[HSDDP_MAX_STAGES + MAXPH];
 };
 
 // solver scalars of one problem (MultiPhaseDDP.h:92-104) + bookkeeping
@@ -77,6 +79,15 @@ struct SolverState {
     double max_tconstr_prev, max_pconstr_prev, max_tconstr, max_pconstr, merit_rho;
     double reg;
     int rollout_ok, sweep_ok;
+};
+
+// iteration-control state of one problem: the locals of MultiPhaseDDP::solve (MultiPhaseDDP.cpp:232-428),
+// kept in a struct so that solve() can be resumed phase by phase (one kernel per phase) or run in one go
+struct SolveCtl {
+    int iter, iter_ou, iter_in, n_sweeps, n_trials, status;
+    int active;  // 1 while the solve is running
+    int _pad;
+    double cost0, feas0;
 };
 
 struct BatchPtrs {
@@ -97,6 +108,10 @@ struct BatchPtrs {
     double* al;                               // [P][MAXPH][4][2]        (sigma, lambda)
     double* g0h0;                             // [P][600] value gradient / Hessian at the first node
     SolverState* state;                       // [P]
+    SolveCtl* ctl;                            // [P]
+    const int* active;                        // phased driver: problem indices of this round (nullptr: blockIdx.x)
+    int* next_active;                         // phased driver: problems still running after this round
+    int* next_count;
     hsddp_info* info;                         // [P]
     hsddp_iter_record* trace;                 // [P][HSDDP_TRACE_CAP]
     unsigned long long* counters;             // [0] = sum over problems of (backward sweeps x stages)
@@ -119,9 +134,11 @@ struct __align__(16) Smem {
     double G[24], Gn[24], Qx[24], Qu[24], wu[24], vtmp[24], vtmp2[24];
     double lxxd[24], lxxTd[24], lxxw[12], lxxTw[12];
     double swdt[4], cmv[4];    // per-phase constants (1-c_l) dt and (c_l/m) dt
+    double swc[16];            // (1-c_l) dt per reduced control column c = 3l+j, zero for c >= 12
     double red[kThreads];
     DevSchedule sc;
     SolverState st;
+    SolveCtl ctl;
     hsddp_constraint_params cp;
     hsddp_options opt;
     // per-problem base pointers
@@ -168,7 +185,7 @@ __device__ __forceinline__ double warp_max(double v) {
 }
 // block-wide reductions; result valid in every thread.  Contains barriers.
 template <int OP>  // 0 sum, 1 min, 2 max
-__device__ __forceinline__ double block_reduce(Smem& sm, double v) {
+__device__ __noinline__ double block_reduce(Smem& sm, double v) {
     v = (OP == 0) ? warp_sum(v) : (OP == 1) ? warp_min(v) : warp_max(v);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) sm.red[threadIdx.x >> 5] = v;
@@ -179,45 +196,41 @@ __device__ __forceinline__ double block_reduce(Smem& sm, double v) {
     return r;
 }
 
+// phase of a stage / node: byte tables built once per problem by bind_problem (sc lives in the block's Smem)
 __device__ __forceinline__ void phase_of_stage(const DevSchedule& sc, int s, int& ph, int& k) {
-    ph = 0;
-    while (ph + 1 < sc.n_phases && s >= sc.stage_off[ph + 1]) ++ph;
+    ph = sc.ph_of_stage[s];
     k = s - sc.stage_off[ph];
 }
 __device__ __forceinline__ void phase_of_node(const DevSchedule& sc, int n, int& ph, int& k) {
-    ph = 0;
-    while (ph + 1 < sc.n_phases && n >= sc.node_off[ph + 1]) ++ph;
+    ph = sc.ph_of_node[n];
     k = n - sc.node_off[ph];
 }
 
-// tracking weights (HKDCost.h:11-37)
+// tracking weights (HKDCost.h:11-37), table driven so that the cost / LQ passes can stay rolled
+// (the solver kernel is instruction-fetch bound; see tools/code_size.py)
+__constant__ double c_wQ[12] = {1, 4, 5, 1, 1, 30, .2, .2, .2, 4, 1, .5};
+__constant__ double c_wQfScale[24] = {1, 1, 2, 1, 1, 20, .3, .3, .3, 1, 3, 1, .01, .01, .01, .01, .01, .01, .01, .01, .01, .01, .01, .01};
 __device__ __forceinline__ double weight_Q(int j, unsigned cmask) {
-    switch (j) {
-        case 0: return 1; case 1: return 4; case 2: return 5; case 3: return 1; case 4: return 1; case 5: return 30;
-        case 6: case 7: case 8: return .2; case 9: return 4; case 10: return 1; case 11: return .5;
-        default: return .2 * (double)(1 - (int)((cmask >> ((j - 12) / 3)) & 1u));
-    }
+    return (j < 12) ? c_wQ[j] : .2 * (double)(1 - (int)((cmask >> ((j - 12) / 3)) & 1u));
 }
-__device__ __forceinline__ double weight_Qf(int j, unsigned cmask) {
-    double scale;
-    switch (j) {
-        case 2: scale = 2; break; case 5: scale = 20; break; case 6: case 7: case 8: scale = .3; break;
-        case 10: scale = 3; break; case 0: case 1: case 3: case 4: case 9: case 11: scale = 1; break;
-        default: scale = .01; break;
-    }
-    return (20 * scale) * weight_Q(j, cmask);
-}
+__device__ __forceinline__ double weight_Qf(int j, unsigned cmask) { return (20 * c_wQfScale[j]) * weight_Q(j, cmask); }
 __device__ __forceinline__ double weight_R(int j) { return j < 12 ? .2 : .1; }
 // foot-placement regulariser weight 20*diag(3c, c, 0) (HKDCost.h:56-69)
 __device__ __forceinline__ double weight_foot(int l, int j, unsigned cmask) {
     const double c = (double)((cmask >> l) & 1u);
     return ((j == 0) ? 3 * c : (j == 1) ? c : 0.0) * 20;
 }
+// GRF friction-pyramid rows (HKDConstraints.cpp:17-24): (0,0,1), (-1,0,mu), (1,0,mu), (0,-1,mu), (0,1,mu)
+__constant__ double c_grfxy[5][2] = {{0, 0}, {-1, 0}, {1, 0}, {0, -1}, {0, 1}};
 // GRF friction-pyramid rows (HKDConstraints.cpp:17-24)
 __device__ __forceinline__ void grf_rows(double mu, double rows[5][3]) {
     const double r[5][3] = {{0, 0, 1}, {-1, 0, mu}, {1, 0, mu}, {0, -1, mu}, {0, 1, mu}};
     for (int i = 0; i < 5; ++i) for (int j = 0; j < 3; ++j) rows[i][j] = r[i][j];
 }
+
+// single out-of-line copies of the leg kinematics (code size, see tools/code_size.py)
+__device__ __noinline__ void foot_position_nl(const double* x, int l, double* pf) { hkd::foot_position(x + 3, x, x + 12 + 3 * l, l, pf); }
+__device__ __noinline__ void foot_jacobian_nl(const double* x, int l, double* Jc) { hkd::foot_jacobian_compact(x, x + 12 + 3 * l, l, Jc); }
 
 __device__ inline void bind_problem(Smem& sm, const BatchPtrs& bp, int pid) {
     if (threadIdx.x == 0) {
@@ -238,6 +251,7 @@ __device__ inline void bind_problem(Smem& sm, const BatchPtrs& bp, int pid) {
         sm.prof = bp.counters + 8;
         sm.cp = bp.cp;
         sm.st = bp.state[pid];
+        sm.ctl = bp.ctl[pid];
     }
     const DevSchedule* src = bp.sched + bp.sched_id[pid];
     const int nw = (int)(sizeof(DevSchedule) / sizeof(int));
@@ -260,7 +274,7 @@ __device__ inline void resetmap_thread(const double* x, unsigned c, unsigned cn,
         if (cl && !nl) { xn[12 + 3 * l] = 0.0; xn[13 + 3 * l] = -0.8; xn[14 + 3 * l] = 1.7; }
         if (!cl && nl) {
             double pf[3];
-            hkd::foot_position(x + 3, x, x + 12 + 3 * l, l, pf);
+            foot_position_nl(x, l, pf);
             xn[12 + 3 * l] = 1.0 * pf[0]; xn[13 + 3 * l] = 1.0 * pf[1]; xn[14 + 3 * l] = 0.0 * pf[2];
         }
     }
@@ -394,7 +408,7 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
             const int ne = sc.node_off[ph] + sc.horizon[ph];
             const double* xe = xs + 24 * ne;
             double pf[3];
-            hkd::foot_position(xe + 3, xe, xe + 12 + 3 * l, l, pf);
+            foot_position_nl(xe, l, pf);
             sm.hcon[4 * ph + l] = pf[2] - 0.0;
             hmax = fabs(pf[2]);
         }
@@ -439,29 +453,32 @@ __device__ inline void compute_cost_block(Smem& sm) {
         const double* xr = sm.xr + 24 * n;
         const double* ur = sm.ur + 24 * n;
         double s1 = 0.0, s2 = 0.0;
-#pragma unroll
+#pragma unroll 4
         for (int j = 0; j < 24; ++j) { const double dx = x[j] - xr[j]; s1 += (0.5 * dx * weight_Q(j, cm)) * dx; }
-#pragma unroll
+#pragma unroll 4
         for (int j = 0; j < 24; ++j) { const double du = u[j] - ur[j]; s2 += (0.5 * du * weight_R(j)) * du; }
         double l = (s1 + s2) * dt;
-        double d[12];
-        foot_rel_error(x, sm.prel + 12 * n, d);
         double lf = 0.0;
+#pragma unroll 1
+        for (int ll = 0; ll < 4; ++ll) {
 #pragma unroll
-        for (int j = 0; j < 12; ++j) lf += (.5 * d[j] * weight_foot(j / 3, j % 3, cm)) * d[j];
+            for (int j = 0; j < 3; ++j) {
+                const double d = (x[12 + 3 * ll + j] - x[3 + j]) - sm.prel[12 * n + 3 * ll + j];
+                lf += (.5 * d * weight_foot(ll, j, cm)) * d;
+            }
+        }
         l += lf * dt;
         if (sm.opt.ReB_active && cm) {  // compute_ReB_cost, ConstraintsBase.h:204-222
             double reb_cost = 0.0;
-            for (int ll = 0; ll < 4; ++ll) {
-                if (!((cm >> ll) & 1u)) continue;
-                for (int r = 0; r < 5; ++r) {
-                    const double g = sm.gcon[20 * s + 5 * ll + r];
-                    const double eps_b = sm.reb[40 * s + 2 * (5 * ll + r)], delta = sm.reb[40 * s + 2 * (5 * ll + r) + 1];
-                    double barr;
-                    if (g > delta) barr = -log(g);
-                    else { const double z = (g - 2 * delta) / delta; barr = .5 * (z * z - 1); barr -= log(delta); }
-                    reb_cost += eps_b * barr;
-                }
+#pragma unroll 1
+            for (int e = 0; e < 20; ++e) {
+                if (!((cm >> (e / 5)) & 1u)) continue;
+                const double g = sm.gcon[20 * s + e];
+                const double eps_b = sm.reb[40 * s + 2 * e], delta = sm.reb[40 * s + 2 * e + 1];
+                double barr;
+                if (g > delta) barr = -hkd::log_nl(g);
+                else { const double z = (g - 2 * delta) / delta; barr = .5 * (z * z - 1); barr -= hkd::log_nl(delta); }
+                reb_cost += eps_b * barr;
             }
             l += dt * reb_cost;
         }
@@ -474,12 +491,15 @@ __device__ inline void compute_cost_block(Smem& sm) {
         const double* x = sm.X + 24 * n;
         const double* xr = sm.xr + 24 * n;
         double s1 = 0.0;
+#pragma unroll 1
         for (int j = 0; j < 24; ++j) { const double dx = x[j] - xr[j]; s1 += (dx * weight_Qf(j, cm)) * dx; }
         double Phi = 0.5 * s1;
-        double d[12];
-        foot_rel_error(x, sm.prel + 12 * n, d);
         double sf = 0.0;
-        for (int j = 0; j < 12; ++j) sf += (10 * d[j] * weight_foot(j / 3, j % 3, cm)) * d[j];
+#pragma unroll 1
+        for (int j = 0; j < 12; ++j) {
+            const double d = (x[12 + j] - x[3 + j % 3]) - sm.prel[12 * n + j];
+            sf += (10 * d * weight_foot(j / 3, j % 3, cm)) * d;
+        }
         Phi += sf;
         if (sm.opt.AL_active) {  // compute_AL_cost, ConstraintsBase.h:374-385
             double al_cost = 0.0;
@@ -526,37 +546,31 @@ __device__ inline void lq_approximation_block(Smem& sm) {
         const double* ur = sm.ur + 24 * n;
         double* lx = rec + LQ_LX;
         double* lu = rec + LQ_LU;
-#pragma unroll
-        for (int j = 0; j < 24; ++j) {
-            lx[j] = (dt * weight_Q(j, cm)) * (x[j] - xr[j]);
-            lu[j] = (dt * weight_R(j)) * (u[j] - ur[j]);
-        }
-        // foot-placement regulariser: pos rows accumulate over the legs in order, foot rows get one term each
-        {
-            double lp[3] = {lx[3], lx[4], lx[5]};
-#pragma unroll
-            for (int l = 0; l < 4; ++l) {
-                const double c = (double)((cm >> l) & 1u);
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const double d = (x[12 + 3 * l + j] - x[3 + j]) - sm.prel[12 * n + 3 * l + j];
-                    const double w = dt * c * weight_foot(l, j, cm);
-                    lp[j] += -(w * d);
-                    lx[12 + 3 * l + j] += w * d;
-                }
-            }
-            lx[3] = lp[0]; lx[4] = lp[1]; lx[5] = lp[2];
-        }
-        // ReB folding (compute_ReB_partials, ConstraintsBase.h:224-263); only gu is non-zero
         const double mu = sm.cp.mu;
-#pragma unroll
+#pragma unroll 4
+        for (int j = 0; j < 12; ++j) lx[j] = (dt * weight_Q(j, cm)) * (x[j] - xr[j]);
+#pragma unroll 4
+        for (int j = 12; j < 24; ++j) lu[j] = (dt * weight_R(j)) * (u[j] - ur[j]);
+        // foot-placement regulariser: pos rows accumulate over the legs in order, foot rows get one term each;
+        // ReB folding (compute_ReB_partials, ConstraintsBase.h:224-263; only gu is non-zero)
+        double lp[3] = {lx[3], lx[4], lx[5]};
+#pragma unroll 1
         for (int l = 0; l < 4; ++l) {
-            double hess[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, grad[3] = {0, 0, 0};
-            if (sm.opt.ReB_active && ((cm >> l) & 1u)) {
+            const bool stance = (cm >> l) & 1u;
+            const double c = (double)((cm >> l) & 1u);
 #pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int i = 12 + 3 * l + j;
+                const double d = (x[i] - x[3 + j]) - sm.prel[12 * n + 3 * l + j];
+                const double w = dt * c * weight_foot(l, j, cm);
+                lp[j] += -(w * d);
+                lx[i] = (dt * weight_Q(i, cm)) * (x[i] - xr[i]) + w * d;
+            }
+            double hess[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, grad[3] = {0, 0, 0};
+            if (sm.opt.ReB_active && stance) {
+#pragma unroll 1
                 for (int r = 0; r < 5; ++r) {
-                    // friction-pyramid row r: (0,0,1), (-1,0,mu), (1,0,mu), (0,-1,mu), (0,1,mu)
-                    const double row[3] = {(r == 1) ? -1.0 : (r == 2) ? 1.0 : 0.0, (r == 3) ? -1.0 : (r == 4) ? 1.0 : 0.0, (r == 0) ? 1.0 : mu};
+                    const double row[3] = {c_grfxy[r][0], c_grfxy[r][1], (r == 0) ? 1.0 : mu};
                     const double g = sm.gcon[20 * s + 5 * l + r];
                     const double eps_b = sm.reb[40 * s + 2 * (5 * l + r)], delta = sm.reb[40 * s + 2 * (5 * l + r) + 1];
                     double bd, bdd;
@@ -571,10 +585,11 @@ __device__ inline void lq_approximation_block(Smem& sm) {
                 }
             }
 #pragma unroll
-            for (int a = 0; a < 3; ++a) lu[3 * l + a] += dt * grad[a];
+            for (int a = 0; a < 3; ++a) lu[3 * l + a] = (dt * weight_R(3 * l + a)) * (u[3 * l + a] - ur[3 * l + a]) + dt * grad[a];
 #pragma unroll
             for (int a = 0; a < 9; ++a) rec[LQ_LUU + 9 * l + a] = dt * hess[a];
         }
+        lx[3] = lp[0]; lx[4] = lp[1]; lx[5] = lp[2];
     }
     if (tid < sc.n_phases) {
         const int ph = tid;
@@ -602,7 +617,7 @@ __device__ inline void lq_approximation_block(Smem& sm) {
             const bool td = !((cm >> l) & 1u) && ((sc.nmask[ph] >> l) & 1u);
             if (td) {  // reset-map Jacobian of a touchdown leg, cached for the sweep and the linear rollout
                 double Jc[18];
-                hkd::foot_jacobian_compact(x, x + 12 + 3 * l, l, Jc);
+                foot_jacobian_nl(x, l, Jc);
                 for (int c = 0; c < 18; ++c) rec[TQ_JC + 18 * l + c] = Jc[c];
             }
             if (td && sm.opt.AL_active) {

@@ -56,92 +56,165 @@ __device__ inline bool line_search_block(Smem& sm, double& eps_out, int& n_trial
     return success;
 }
 
-__device__ inline void solve_block(Smem& sm, const BatchPtrs& bp) {
+// ---------------------------------------------------------------------------
+// MultiPhaseDDP::solve (MultiPhaseDDP.cpp:232-428) as a resumable state machine.
+//   solve_begin_block      :257-260 + the head of the first outer iteration (:282-302)
+//   iter_prep_block        :306-319  compute_cost, LQ_approximation
+//   iter_sweep_block       :320-324  backward_sweep_regularized
+//   iter_forward_block     :326-409  linear rollout, merit, line search, termination tests, AL / ReB updates
+// k_solve runs them back to back for one problem (persistent blocks, small batches / latency);
+// k_phase runs ONE of them for every running problem (large batches: all co-resident blocks execute
+// the same code, which keeps the instruction cache hot).
+// ---------------------------------------------------------------------------
+__device__ inline void outer_start_block(Smem& sm) {  // :283-302
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sm.ctl.iter_ou++;
+        sm.ctl.iter_in = 0;
+        sm.st.max_tconstr_prev = sm.st.max_tconstr; sm.st.max_pconstr_prev = sm.st.max_pconstr; sm.st.reg = 0;
+    }
+    __syncthreads();
+}
+
+// end of an outer iteration (:383-413).  Leaves ctl.active = 0 when the solve is over.
+__device__ inline void outer_end_block(Smem& sm) {
+    const hsddp_options& opt = sm.opt;
+    for (;;) {
+        if (opt.AL_active) update_al_block(sm);
+        if (opt.ReB_active) update_reb_block(sm);
+        __syncthreads();
+        const SolverState& st = sm.st;
+        int status = -1;
+        if (st.max_tconstr < opt.tconstr_thresh && fabs(st.max_pconstr) < opt.pconstr_thresh && st.feas <= opt.dynamics_feas_thresh) status = HSDDP_STATUS_CONVERGED;
+        else if (fabs(st.max_tconstr - st.max_tconstr_prev) < 0.0001 && fabs(st.max_pconstr - st.max_pconstr_prev) < 0.0001 && st.feas <= opt.dynamics_feas_thresh) status = HSDDP_STATUS_STALLED;
+        else if (sm.ctl.iter_ou >= opt.max_AL_iter) status = HSDDP_STATUS_MAX_ITER;
+        __syncthreads();
+        if (status >= 0) {
+            if (threadIdx.x == 0) { sm.ctl.status = status; sm.ctl.active = 0; }
+            __syncthreads();
+            return;
+        }
+        outer_start_block(sm);
+        if (opt.max_DDP_iter > 0) return;  // (an empty inner loop falls straight through to the next outer end)
+    }
+}
+
+__device__ inline void solve_begin_block(Smem& sm) {
     const int tid = threadIdx.x;
-    const hsddp_options opt = sm.opt;
-    hsddp_iter_record* trace = bp.trace + (size_t)sm.pid * HSDDP_TRACE_CAP;
-    int iter = 0, iter_ou = 0, iter_in = 0, n_sweeps_total = 0, n_trials_total = 0;
-    int status = HSDDP_STATUS_MAX_ITER;
-    bool success = true;
+    __syncthreads();
     if (tid == 0) {
+        SolveCtl c = {};
+        c.status = HSDDP_STATUS_MAX_ITER; c.active = 1;
+        sm.ctl = c;
         sm.st.actual_cost = 0; sm.st.max_pconstr = 0; sm.st.max_pconstr_prev = 0; sm.st.max_tconstr = 0; sm.st.max_tconstr_prev = 0;
     }
     __syncthreads();
     hybrid_rollout_block(sm, 0.0);
     update_nominal_block(sm);
     compute_cost_block(sm);
-    const double cost0 = sm.st.actual_cost, feas0 = sm.st.feas;
+    if (tid == 0) { sm.ctl.cost0 = sm.st.actual_cost; sm.ctl.feas0 = sm.st.feas; }
+    __syncthreads();
+    if (sm.opt.max_AL_iter <= 0) {
+        if (tid == 0) sm.ctl.active = 0;
+        __syncthreads();
+        return;
+    }
+    outer_start_block(sm);
+    if (sm.opt.max_DDP_iter <= 0) outer_end_block(sm);
+}
 
-    while (iter_ou < opt.max_AL_iter) {
-        iter_ou++;
-        __syncthreads();
-        if (tid == 0) { sm.st.max_tconstr_prev = sm.st.max_tconstr; sm.st.max_pconstr_prev = sm.st.max_pconstr; sm.st.reg = 0; }
-        __syncthreads();
-        iter_in = 0;
-        while (iter_in < opt.max_DDP_iter) {
-            compute_cost_block(sm);
-            iter_in++; iter++;
+__device__ inline void iter_prep_block(Smem& sm, const BatchPtrs& bp) {
+    compute_cost_block(sm);
+    if (threadIdx.x == 0) {
+        sm.ctl.iter_in++; sm.ctl.iter++;
+        if (sm.ctl.iter <= HSDDP_TRACE_CAP) {
             hsddp_iter_record rec;
-            rec.outer = iter_ou; rec.inner = iter_in; rec.cost_before = sm.st.actual_cost; rec.feas_before = sm.st.feas;
+            rec.outer = sm.ctl.iter_ou; rec.inner = sm.ctl.iter_in; rec.cost_before = sm.st.actual_cost; rec.feas_before = sm.st.feas;
+            rec.reg_after = rec.n_sweeps = 0;
             rec.dV_1 = rec.dV_2 = rec.merit_rho = rec.eps_accepted = rec.n_trials = 0; rec._pad = 0;
             rec.cost_after = rec.feas_after = rec.max_tconstr = rec.max_pconstr = 0;
+            bp.trace[(size_t)sm.pid * HSDDP_TRACE_CAP + sm.ctl.iter - 1] = rec;
+        }
+    }
+    __syncthreads();
+    lq_approximation_block(sm);
+}
 
-            lq_approximation_block(sm);
-            int nsw = 0;
-            success = backward_sweep_regularized_block(sm, nsw);
-            n_sweeps_total += nsw;
+__device__ inline void iter_sweep_block(Smem& sm, const BatchPtrs& bp) {
+    int nsw = 0;
+    const bool success = backward_sweep_regularized_block(sm, nsw);
+    if (threadIdx.x == 0) {
+        sm.ctl.n_sweeps += nsw;
+        if (sm.ctl.iter <= HSDDP_TRACE_CAP) {
+            hsddp_iter_record& rec = bp.trace[(size_t)sm.pid * HSDDP_TRACE_CAP + sm.ctl.iter - 1];
             rec.n_sweeps = nsw; rec.reg_after = sm.st.reg;
-            if (!success) {
-                if (tid == 0 && iter <= HSDDP_TRACE_CAP) trace[iter - 1] = rec;
-                goto bad_solve;
-            }
-            if (opt.MS) linear_rollout_block(sm, 1.0);
-            prepare_merit_block(sm);
-            {
-                const double cost_prev = sm.st.actual_cost, merit_prev = sm.st.merit;
-                const double dV_abs = fabs(sm.st.dV_1 + 0.5 * sm.st.dV_2);
-                rec.dV_1 = sm.st.dV_1; rec.dV_2 = sm.st.dV_2; rec.merit_rho = sm.st.merit_rho;
-                if ((dV_abs < opt.cost_thresh) && (sm.st.feas <= opt.dynamics_feas_thresh)) {
-                    rec.eps_accepted = -1; rec.n_trials = 0;
-                    rec.cost_after = sm.st.actual_cost; rec.feas_after = sm.st.feas; rec.max_tconstr = sm.st.max_tconstr; rec.max_pconstr = sm.st.max_pconstr;
-                    if (tid == 0 && iter <= HSDDP_TRACE_CAP) trace[iter - 1] = rec;
-                    break;
-                }
-                double eps_acc = 0;
-                int ntr = 0;
-                if (line_search_block(sm, eps_acc, ntr)) {
-                    update_nominal_block(sm);
-                } else {  // Q2: only the scalars are restored
-                    __syncthreads();
-                    if (tid == 0) { sm.st.actual_cost = cost_prev; sm.st.merit = merit_prev; }
-                    __syncthreads();
-                }
-                n_trials_total += ntr;
-                rec.eps_accepted = eps_acc; rec.n_trials = ntr;
-                rec.cost_after = sm.st.actual_cost; rec.feas_after = sm.st.feas; rec.max_tconstr = sm.st.max_tconstr; rec.max_pconstr = sm.st.max_pconstr;
-                if (tid == 0 && iter <= HSDDP_TRACE_CAP) trace[iter - 1] = rec;
-                if ((fabs((cost_prev - sm.st.actual_cost) / cost_prev) < opt.cost_thresh) && (sm.st.feas <= opt.dynamics_feas_thresh)) break;
-            }
         }
-        if (opt.AL_active) update_al_block(sm);
-        if (opt.ReB_active) update_reb_block(sm);
-        {
-            const SolverState& st = sm.st;
-            if (st.max_tconstr < opt.tconstr_thresh && fabs(st.max_pconstr) < opt.pconstr_thresh && st.feas <= opt.dynamics_feas_thresh) { status = HSDDP_STATUS_CONVERGED; break; }
-            if (fabs(st.max_tconstr - st.max_tconstr_prev) < 0.0001 && fabs(st.max_pconstr - st.max_pconstr_prev) < 0.0001 && st.feas <= opt.dynamics_feas_thresh) { status = HSDDP_STATUS_STALLED; break; }
-        }
+        if (!success) { sm.ctl.status = HSDDP_STATUS_REG_OVERFLOW; sm.ctl.active = 0; }  // bad_solve (:321-324,421-427)
     }
-bad_solve:
-    if (!success) status = HSDDP_STATUS_REG_OVERFLOW;
     __syncthreads();
-    if (tid == 0) {
+}
+
+__device__ inline void iter_forward_block(Smem& sm, const BatchPtrs& bp) {
+    const int tid = threadIdx.x;
+    const hsddp_options& opt = sm.opt;
+    hsddp_iter_record* rec = (sm.ctl.iter <= HSDDP_TRACE_CAP) ? bp.trace + (size_t)sm.pid * HSDDP_TRACE_CAP + sm.ctl.iter - 1 : nullptr;
+    if (opt.MS) linear_rollout_block(sm, 1.0);
+    prepare_merit_block(sm);
+    const double cost_prev = sm.st.actual_cost, merit_prev = sm.st.merit;
+    const double dV_abs = fabs(sm.st.dV_1 + 0.5 * sm.st.dV_2);
+    bool leave_inner = false;
+    if (tid == 0 && rec) { rec->dV_1 = sm.st.dV_1; rec->dV_2 = sm.st.dV_2; rec->merit_rho = sm.st.merit_rho; }
+    if ((dV_abs < opt.cost_thresh) && (sm.st.feas <= opt.dynamics_feas_thresh)) {  // :340-343
+        if (tid == 0 && rec) {
+            rec->eps_accepted = -1; rec->n_trials = 0;
+            rec->cost_after = sm.st.actual_cost; rec->feas_after = sm.st.feas; rec->max_tconstr = sm.st.max_tconstr; rec->max_pconstr = sm.st.max_pconstr;
+        }
+        leave_inner = true;
+    } else {
+        double eps_acc = 0;
+        int ntr = 0;
+        if (line_search_block(sm, eps_acc, ntr)) {
+            update_nominal_block(sm);
+        } else {  // Q2: only the scalars are restored
+            __syncthreads();
+            if (tid == 0) { sm.st.actual_cost = cost_prev; sm.st.merit = merit_prev; }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            sm.ctl.n_trials += ntr;
+            if (rec) {
+                rec->eps_accepted = eps_acc; rec->n_trials = ntr;
+                rec->cost_after = sm.st.actual_cost; rec->feas_after = sm.st.feas; rec->max_tconstr = sm.st.max_tconstr; rec->max_pconstr = sm.st.max_pconstr;
+            }
+        }
+        if ((fabs((cost_prev - sm.st.actual_cost) / cost_prev) < opt.cost_thresh) && (sm.st.feas <= opt.dynamics_feas_thresh)) leave_inner = true;  // :358-359
+    }
+    __syncthreads();
+    if (leave_inner || sm.ctl.iter_in >= opt.max_DDP_iter) outer_end_block(sm);
+}
+
+__device__ inline void solve_finish_block(Smem& sm, const BatchPtrs& bp) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
         hsddp_info& info = bp.info[sm.pid];
-        info.status = status; info.n_iter = iter; info.n_outer = iter_ou; info.n_sweeps = n_sweeps_total; info.n_trials = n_trials_total; info._pad = 0;
+        const SolveCtl& c = sm.ctl;
+        info.status = c.status; info.n_iter = c.iter; info.n_outer = c.iter_ou; info.n_sweeps = c.n_sweeps; info.n_trials = c.n_trials; info._pad = 0;
         info.cost = sm.st.actual_cost; info.feas = sm.st.feas; info.max_tconstr = sm.st.max_tconstr; info.max_pconstr = sm.st.max_pconstr;
-        info.cost0 = cost0; info.feas0 = feas0;
-        atomicAdd(bp.counters, (unsigned long long)n_sweeps_total * (unsigned long long)sm.sc.n_stages);
+        info.cost0 = c.cost0; info.feas0 = c.feas0;
+        atomicAdd(bp.counters, (unsigned long long)c.n_sweeps * (unsigned long long)sm.sc.n_stages);
     }
     __syncthreads();
+}
+
+__device__ inline void solve_block(Smem& sm, const BatchPtrs& bp) {
+    solve_begin_block(sm);
+    while (sm.ctl.active) {
+        iter_prep_block(sm, bp);
+        iter_sweep_block(sm, bp);
+        if (!sm.ctl.active) break;
+        iter_forward_block(sm, bp);
+    }
+    solve_finish_block(sm, bp);
 }
 
 __global__ void __launch_bounds__(kThreads, 6) k_solve(BatchPtrs bp, hsddp_options opt, int cold_start) {
@@ -162,11 +235,45 @@ __global__ void __launch_bounds__(kThreads, 6) k_solve(BatchPtrs bp, hsddp_optio
         __syncthreads();
 #endif
         solve_block(sm, bp);
-        if (threadIdx.x == 0) bp.state[pid] = sm.st;
+        if (threadIdx.x == 0) { bp.state[pid] = sm.st; bp.ctl[pid] = sm.ctl; }
 #ifdef HSDDP_PROFILE
         if (threadIdx.x == 0) for (int i = 0; i < 16; ++i) atomicAdd(&sm.prof[i], sm.profacc[i]);
 #endif
     }
+}
+
+// One phase of solve() for every running problem: block b works on problem bp.active[b] (or b).
+enum SolvePhase { PH_BEGIN = 0, PH_PREP, PH_SWEEP, PH_FORWARD };
+template <int PH>
+__global__ void __launch_bounds__(kThreads, 6) k_phase(BatchPtrs bp, hsddp_options opt) {
+    __shared__ Smem sm;
+    const int pid = bp.active ? bp.active[blockIdx.x] : (int)blockIdx.x;
+    if (threadIdx.x == 0) assign_rotation(bp.sm_slots, sm.rot);
+    bind_problem(sm, bp, pid);
+    if (threadIdx.x == 0) sm.opt = opt;
+    __syncthreads();
+#ifdef HSDDP_PROFILE
+    if (threadIdx.x == 0) for (int i = 0; i < 16; ++i) sm.profacc[i] = 0;
+    __syncthreads();
+#endif
+    if (PH == PH_BEGIN) solve_begin_block(sm);
+    if (PH == PH_PREP) iter_prep_block(sm, bp);
+    if (PH == PH_SWEEP) iter_sweep_block(sm, bp);
+    if (PH == PH_FORWARD) {
+        if (sm.ctl.active) iter_forward_block(sm, bp);  // (a failed sweep already ended the solve)
+    }
+    __syncthreads();
+    if (PH == PH_BEGIN || PH == PH_FORWARD) {
+        if (sm.ctl.active) {
+            if (threadIdx.x == 0) bp.next_active[atomicAdd(bp.next_count, 1)] = pid;
+        } else {
+            solve_finish_block(sm, bp);
+        }
+    }
+    if (threadIdx.x == 0) { bp.state[pid] = sm.st; bp.ctl[pid] = sm.ctl; }
+#ifdef HSDDP_PROFILE
+    if (threadIdx.x == 0) for (int i = 0; i < 16; ++i) atomicAdd(&sm.prof[i], sm.profacc[i]);
+#endif
 }
 
 enum StepOp { OP_RESET = 0, OP_ROLLOUT, OP_COST, OP_LQ, OP_SWEEP, OP_SWEEP_REG, OP_LINEAR, OP_MERIT, OP_FORWARD, OP_NOMINAL, OP_AL, OP_REB };
@@ -268,6 +375,12 @@ struct hsddp_batch {
     float last_ms = 0.f;
     int* d_ok = nullptr;
     double* d_darg = nullptr;
+    // phased driver (one kernel per solve phase over the running problems)
+    int solve_mode = 0;            // 0 auto, 1 persistent k_solve, 2 phased k_phase<...>
+    int* d_active[2] = {nullptr, nullptr};
+    int* d_count = nullptr;
+    int* h_count = nullptr;        // pinned
+    int last_rounds = 0;
 };
 
 namespace {
@@ -342,6 +455,11 @@ int hsddp_batch_create(int device, hsddp_batch** out) {
         const int v = atoi(e);
         if (v >= 1 && v <= b->blocks_per_sm) b->blocks_per_sm = v;
     }
+    CK(cudaHostAlloc((void**)&b->h_count, 4 * sizeof(int), cudaHostAllocDefault));
+    if (const char* e = getenv("HSDDP_SOLVE_MODE")) {  // tuning / experiments only
+        const int v = atoi(e);
+        if (v >= 0 && v <= 2) b->solve_mode = v;
+    }
     *out = b;
     return HSDDP_OK;
 }
@@ -354,6 +472,7 @@ int hsddp_batch_destroy(hsddp_batch* b) {
     if (b->ev1) cudaEventDestroy(b->ev1);
     for (int i = 0; i < 8; ++i) if (b->slots[i]) cudaEventDestroy(b->slots[i]);
     if (b->stream) cudaStreamDestroy(b->stream);
+    if (b->h_count) cudaFreeHost(b->h_count);
     delete b;
     return HSDDP_OK;
 }
@@ -382,6 +501,8 @@ int hsddp_batch_set_problems(hsddp_batch* b, int n_schedules, const hsddp_schedu
             unsigned cm = 0, nm = 0;
             for (int l = 0; l < 4; ++l) { cm |= (s.contact[p][l] ? 1u : 0u) << l; nm |= (s.next_contact[p][l] ? 1u : 0u) << l; }
             d.cmask[p] = cm; d.nmask[p] = nm;
+            for (int k = 0; k < s.horizon[p] && so + k < HSDDP_MAX_STAGES; ++k) d.ph_of_stage[so + k] = (unsigned char)p;
+            for (int k = 0; k <= s.horizon[p] && no + k < HSDDP_MAX_STAGES + MAXPH; ++k) d.ph_of_node[no + k] = (unsigned char)p;
             no += s.horizon[p] + 1; so += s.horizon[p];
         }
         if (no != s.n_nodes || so != s.n_stages) { g_last_error = "schedule node/stage counts inconsistent"; return HSDDP_ERR_ARG; }
@@ -444,6 +565,11 @@ int hsddp_batch_set_problems(hsddp_batch* b, int n_schedules, const hsddp_schedu
     if ((rc = dalloc(b, &bp.al, P * MAXPH * 8))) return rc;
     if ((rc = dalloc(b, &bp.g0h0, P * 600))) return rc;
     if ((rc = dalloc(b, &bp.state, P))) return rc;
+    if ((rc = dalloc(b, &bp.ctl, P))) return rc;
+    if ((rc = dalloc(b, &b->d_active[0], P))) return rc;
+    if ((rc = dalloc(b, &b->d_active[1], P))) return rc;
+    if ((rc = dalloc(b, &b->d_count, (size_t)4))) return rc;
+    CK(cudaMemset(bp.ctl, 0, P * sizeof(SolveCtl)));
     if ((rc = dalloc(b, &bp.info, P))) return rc;
     if ((rc = dalloc(b, &bp.trace, P * HSDDP_TRACE_CAP))) return rc;
     if ((rc = dalloc(b, &bp.counters, (size_t)32))) return rc;
@@ -479,12 +605,56 @@ int hsddp_batch_reset(hsddp_batch* b) {
     return rc;
 }
 
+// Phased driver: every round advances all running problems by one DDP iteration with three launches
+// (prep, sweep, forward).  Blocks that are co-resident on an SM execute the same phase, so the instruction
+// cache holds one phase's code instead of six different ones; the host reads one counter per round.
+static int solve_phased(hsddp_batch* b, const hsddp_options& o) {
+    BatchPtrs bp = b->bp;
+    const int P = bp.n_problems;
+    CK(cudaEventRecord(b->ev0, b->stream));
+    CK(cudaMemsetAsync(b->d_count, 0, sizeof(int), b->stream));
+    bp.active = nullptr; bp.next_active = b->d_active[0]; bp.next_count = b->d_count;
+    k_phase<PH_BEGIN><<<P, kThreads, 0, b->stream>>>(bp, o);
+    CK(cudaGetLastError());
+    b->n_solve_launches++;
+    CK(cudaMemcpyAsync(b->h_count, b->d_count, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    int n_active = b->h_count[0], cur = 0, rounds = 0;
+    while (n_active > 0) {
+        bp.active = b->d_active[cur]; bp.next_active = b->d_active[cur ^ 1];
+        CK(cudaMemsetAsync(b->d_count, 0, sizeof(int), b->stream));
+        k_phase<PH_PREP><<<n_active, kThreads, 0, b->stream>>>(bp, o);
+        k_phase<PH_SWEEP><<<n_active, kThreads, 0, b->stream>>>(bp, o);
+        k_phase<PH_FORWARD><<<n_active, kThreads, 0, b->stream>>>(bp, o);
+        CK(cudaGetLastError());
+        b->n_solve_launches += 3;
+        CK(cudaMemcpyAsync(b->h_count, b->d_count, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+        n_active = b->h_count[0];
+        cur ^= 1;
+        if (++rounds > 100000) { g_last_error = "phased solve did not terminate"; return HSDDP_ERR_STATE; }
+    }
+    b->last_rounds = rounds;
+    CK(cudaEventRecord(b->ev1, b->stream));
+    return HSDDP_OK;
+}
+
+int hsddp_batch_set_solve_mode(hsddp_batch* b, int mode) {
+    if (!b || mode < 0 || mode > 2) return HSDDP_ERR_ARG;
+    b->solve_mode = mode;
+    return HSDDP_OK;
+}
+
 int hsddp_batch_solve_async(hsddp_batch* b, const hsddp_options* opt) {
     if (!b || !b->has_problems) { g_last_error = "no problems set"; return HSDDP_ERR_STATE; }
     int rc = check_opt(opt);
     if (rc) return rc;
     CK(cudaSetDevice(b->device));
     const hsddp_options o = opt ? *opt : default_options();
+    b->cold = false;
+    // auto: the phased driver pays one launch tail per phase and round, so it needs several waves of blocks
+    const bool phased = b->solve_mode == 2 || (b->solve_mode == 0 && b->bp.n_problems >= 4 * b->n_sm * b->blocks_per_sm);
+    if (phased) return solve_phased(b, o);
     CK(cudaMemsetAsync(b->bp.work_counter, 0, sizeof(int), b->stream));
     const int grid = std::min(b->bp.n_problems, b->n_sm * b->blocks_per_sm);
     CK(cudaEventRecord(b->ev0, b->stream));
@@ -492,7 +662,6 @@ int hsddp_batch_solve_async(hsddp_batch* b, const hsddp_options* opt) {
     CK(cudaGetLastError());
     b->n_solve_launches++;
     CK(cudaEventRecord(b->ev1, b->stream));
-    b->cold = false;
     return HSDDP_OK;
 }
 
