@@ -17,6 +17,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstddef>
 #include "../../include/hsddp_b200.h"
 #include "hkd_model.cuh"
 
@@ -51,6 +52,7 @@ constexpr int LQ_LU = LQ_LX + 24;                 // [24]
 constexpr int LQ_LUU = LQ_LU + 24;                // [4][3][3] ReB Hessian blocks per leg (dt folded in)
 constexpr int LQ_STRIDE = 616;                    // 612 used
 constexpr int ZS = 20;                            // row stride of Z = H B_r (16 columns used): 20 = 4 mod 16
+constexpr int kSweepDoubles = 2 * 24 * 28 + 24 * 20 + 16 * 28 + 12 * 28 + 2 * 616;  // H, Y, Z, Qux, Quu, rec: contiguous, free outside the sweep
 constexpr int TS = 28;                            // row stride (doubles) of the 24-wide shared-memory tiles: 28 = 12 mod 16
                                                   // makes every m8n8k4 fragment load hit 32 distinct banks per half-warp
 // per-phase terminal record
@@ -152,6 +154,8 @@ struct __align__(16) Smem {
     int ibuf[4];
     double dbuf[8];
 };
+
+static_assert(offsetof(Smem, dfc2) - offsetof(Smem, H) == sizeof(double) * kSweepDoubles, "kSweepDoubles must cover H..rec");
 
 // ---------------------------------------------------------------------------
 // small helpers
@@ -317,27 +321,53 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
     const int N = sc.n_stages;
     PROF_DECL
     double* xs = sm.H;  // trial states of all nodes [n_nodes][24] (the sweep's tile storage is free here)
-    // (a0) trial states X = Xbar + eps dX for every node
-    for (int e = tid; e < sc.n_nodes * 24; e += kThreads) xs[e] = sm.Xbar[e] + eps * sm.dX[e];
+    // (a0) trial states X = Xbar + eps dX for every node, and the deviations X - Xbar the feedback acts on
+    //      (kept in shared memory next to the states when both fit, else re-read from HBM)
+    const bool dev_in_smem = sc.n_nodes * 48 <= kSweepDoubles;
+    double* xd = xs + sc.n_nodes * 24;
+    for (int e = tid; e < sc.n_nodes * 24; e += kThreads) {
+        const double xb = sm.Xbar[e];
+        const double x = xb + eps * sm.dX[e];
+        xs[e] = x;
+        if (dev_in_smem) xd[e] = x - xb;
+    }
     __syncthreads();
     // (a) controls: U = (Ubar + eps dU) + K (X - Xbar), one warp per stage.  K is stored compactly as
-    //     K_r^T [24][12] (only the coupled control of each leg has a non-zero gain row, see hsddp_sweep.cuh)
-    for (int s = warp; s < N; s += kWarps) {
-        int ph, k;
-        phase_of_stage(sc, s, ph, k);
-        const int n = sc.node_off[ph] + k;
-        const unsigned cm = sc.cmask[ph];
-        if (lane < 24) {
-            const bool stance = (cm >> ((lane % 12) / 3)) & 1u;
-            double acc = 0.0;
-            if ((lane < 12) == stance) {
-                const double* KT = sm.K + 288 * (size_t)s + (lane % 12);  // KT[j][c]
-                const double* xv = xs + 24 * n;
-                const double* xb = sm.Xbar + 24 * n;
-#pragma unroll 8
-                for (int j = 0; j < 24; ++j) acc = fma(KT[12 * j], xv[j] - xb[j], acc);
+    //     K_r^T [24][12] (only the coupled control of each leg has a non-zero gain row, see hsddp_sweep.cuh).
+    //     Lane (p, q) = (lane & 7, lane >> 3) accumulates the control pair (2p, 2p+1) over the state
+    //     components j = q, q+4, ..: every load is a 16-byte piece of a 384-byte contiguous run of K.
+    {
+        const int p = lane & 7, q = lane >> 3;
+        const bool kact = p < 6;
+        for (int s = warp; s < N; s += kWarps) {
+            int ph, k;
+            phase_of_stage(sc, s, ph, k);
+            const int n = sc.node_off[ph] + k;
+            const unsigned cm = sc.cmask[ph];
+            const double2* K2 = reinterpret_cast<const double2*>(sm.K + 288 * (size_t)s) + p;
+            double2 kv[6];
+            double dv[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const int j = q + 4 * i;
+                kv[i] = kact ? K2[6 * j] : make_double2(0.0, 0.0);
+                dv[i] = dev_in_smem ? xd[24 * n + j] : xs[24 * n + j] - sm.Xbar[24 * n + j];
             }
-            sm.U_t[24 * s + lane] = (sm.Ubar[24 * s + lane] + eps * sm.dU[24 * s + lane]) + acc;
+            double ub = 0.0;
+            if (lane < 24) ub = sm.Ubar[24 * s + lane] + eps * sm.dU[24 * s + lane];
+            double ax = 0.0, ay = 0.0;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { ax = fma(kv[i].x, dv[i], ax); ay = fma(kv[i].y, dv[i], ay); }
+            ax += __shfl_xor_sync(0xffffffffu, ax, 8);  ay += __shfl_xor_sync(0xffffffffu, ay, 8);
+            ax += __shfl_xor_sync(0xffffffffu, ax, 16); ay += __shfl_xor_sync(0xffffffffu, ay, 16);
+            // control i = lane: coupled iff (i < 12) == stance(leg); its gain row is reduced index c = i % 12
+            const int c = lane % 12;
+            const double vx = __shfl_sync(0xffffffffu, ax, c >> 1), vy = __shfl_sync(0xffffffffu, ay, c >> 1);
+            if (lane < 24) {
+                const bool stance = (cm >> (c / 3)) & 1u;
+                const double acc = ((lane < 12) == stance) ? ((c & 1) ? vy : vx) : 0.0;
+                sm.U_t[24 * s + lane] = ub + acc;
+            }
         }
     }
     __syncthreads();

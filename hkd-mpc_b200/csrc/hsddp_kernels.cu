@@ -652,8 +652,7 @@ int hsddp_batch_solve_async(hsddp_batch* b, const hsddp_options* opt) {
     CK(cudaSetDevice(b->device));
     const hsddp_options o = opt ? *opt : default_options();
     b->cold = false;
-    // auto: the phased driver pays one launch tail per phase and round, so it needs several waves of blocks
-    const bool phased = b->solve_mode == 2 || (b->solve_mode == 0 && b->bp.n_problems >= 4 * b->n_sm * b->blocks_per_sm);
+    const bool phased = b->solve_mode == 2;  // auto = persistent: measured faster or equal at every batch size so far
     if (phased) return solve_phased(b, o);
     CK(cudaMemsetAsync(b->bp.work_counter, 0, sizeof(int), b->stream));
     const int grid = std::min(b->bp.n_problems, b->n_sm * b->blocks_per_sm);
