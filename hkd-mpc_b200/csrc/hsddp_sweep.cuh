@@ -165,187 +165,23 @@ __device__ inline void build_phase_tables(Smem& sm, unsigned cm, double dt) {
     __syncthreads();
 }
 
-// Per-lane base pointers of the tensor-core tiles of one stage.  Every fragment address in the stage
-// body is one of these plus a COMPILE-TIME offset: the tile loops are fully specialised per warp
-// (stage_p1/p2/p4<W>), so the per-tile index arithmetic of a table-driven loop disappears and the
-// 3..4 tiles of a warp are independent instruction streams the scheduler can interleave.
-struct StageLane {
-    const double* hA;   // H  + t*TS + g      a-operand (P1)
-    const double* hC;   // H  + g*TS + 2t     accumulator init / result, 8x8 tile element (g, 2t..2t+1)
-    double* hCw;
-    double* hT;         // H  + 2t*TS + g     mirrored store (P4)
-    const double* yB;   // Y  + t*TS + g      b-operand (P2)
-    double* yC;         // Y  + g*TS + 2t
-    const double* zB;   // Z  + t*ZS + g      b-operand (P2, Quu)
-    double* zC;         // Z  + g*ZS + 2t
-    const double* qA;   // Qux + t*TS + g     a-operand (P4)
-    const double* kB;   // KT (= Z) + g*12 + t  b-operand (P4)
-    const double* swc;  // swc + 2t            per-column swing factors (1-c_l) dt, zero for c >= 12
-    int g, t;
-};
-
-// non-volatile variant: lets the compiler interleave the independent tiles of a warp
-__device__ __forceinline__ void dmma884s(double (&c)[2], double a, double b) {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-        : "+d"(c[0]), "+d"(c[1])
-        : "d"(a), "d"(b));
-}
-
-// ---- P1: [Y | Z] = H [A | B_r], tile = 5*I + Jt (I row block of H, Jt column block of [A | B_r]) ----
-template <int TILE>
-__device__ __forceinline__ void p1_tile(const StageLane& L, const double* rB) {
-    constexpr int I = TILE / 5, Jt = TILE % 5;
-    double c2[2];
-    if (Jt < 3) {
-        const double2 h2 = *reinterpret_cast<const double2*>(L.hC + 8 * I * TS + 8 * Jt);
-        c2[0] = h2.x; c2[1] = h2.y;
-    } else { c2[0] = 0.0; c2[1] = 0.0; }
-#pragma unroll
-    for (int kk = 0; kk < 12; kk += 4) dmma884s(c2, L.hA[kk * TS + 8 * I], rB[kk * hkd::kRld + 8 * Jt]);
-    if (Jt < 3) {
-        *reinterpret_cast<double2*>(L.yC + 8 * I * TS + 8 * Jt) = make_double2(c2[0], c2[1]);
-    } else {
-        // swing columns of Z: H[:, 12+c] * (1-c_l) dt   (the factor is zero for stance legs and for the padding c >= 12)
-        const double2 h2 = *reinterpret_cast<const double2*>(L.hC + 8 * I * TS + 12 + 8 * (Jt - 3));
-        const double2 sw = *reinterpret_cast<const double2*>(L.swc + 8 * (Jt - 3));
-        c2[0] = fma(h2.x, sw.x, c2[0]);
-        c2[1] = fma(h2.y, sw.y, c2[1]);
-        *reinterpret_cast<double2*>(L.zC + 8 * I * ZS + 8 * (Jt - 3)) = make_double2(c2[0], c2[1]);
-    }
-}
-template <int W>
-__device__ __forceinline__ void stage_p1(Smem& sm, const StageLane& L, const double* rB, const double* dfc, int lane) {
-    p1_tile<W>(L, rB);
-    p1_tile<W + 4>(L, rB);
-    p1_tile<W + 8>(L, rB);
-    if (W < 3) p1_tile<(W < 3) ? W + 12 : 0>(L, rB);
-    else if (lane < 24) {  // Gn = G + H d   (Q10)
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-        for (int j = 0; j < 24; j += 4) {
-            a0 = fma(sm.H[j * TS + lane], dfc[j], a0);
-            a1 = fma(sm.H[(j + 1) * TS + lane], dfc[j + 1], a1);
-            a2 = fma(sm.H[(j + 2) * TS + lane], dfc[j + 2], a2);
-            a3 = fma(sm.H[(j + 3) * TS + lane], dfc[j + 3], a3);
-        }
-        sm.Gn[lane] = sm.G[lane] + ((a0 + a1) + (a2 + a3));
-    }
-}
-
-// ---- P2 ----
-// Qxx tile (I >= J), parked in H's lower tiles: lxx + Y + reg I + At^T Y
-template <int I, int J>
-__device__ __forceinline__ void p2_qxx(Smem& sm, const StageLane& L, const double* rA, double reg) {
-    const double2 y2 = *reinterpret_cast<const double2*>(L.yC + 8 * I * TS + 8 * J);
-    double c2[2] = {y2.x, y2.y};
-    const int g = L.g, t = L.t;
-    if (I == J) {  // diagonal of lxx (+ reg): element (g, 2t+q) is diagonal iff g == 2t+q
-        const double d = sm.lxxd[8 * I + g];
-        if (g == 2 * t) c2[0] = (d + y2.x) + reg;
-        if (g == 2 * t + 1) c2[1] = (d + y2.y) + reg;
-    } else if (J == 0 && I >= 1) {  // foot-regulariser coupling: row i = 8I+g >= 12, column 3 + (i-12)%3
-        const int i = 8 * I + g;
-        if (i >= 12) {
-            const int jc = 3 + (i - 12) % 3;
-            const double w = sm.lxxw[i - 12];
-            if (jc == 2 * t) c2[0] = -w + y2.x;
-            if (jc == 2 * t + 1) c2[1] = -w + y2.y;
-        }
-    }
-#pragma unroll
-    for (int kk = 0; kk < 12; kk += 4) dmma884s(c2, rA[kk * hkd::kRld + 8 * I], L.yB[kk * TS + 8 * J]);
-    *reinterpret_cast<double2*>(L.hCw + 8 * I * TS + 8 * J) = make_double2(c2[0], c2[1]);
-}
-// Qux_r tile: rows c = 8*Ci + g of B_r^T Y, columns 8J..8J+7
-template <int Ci, int J>
-__device__ __forceinline__ void p2_qux(Smem& sm, const StageLane& L, const double* rA, double swrow, int swoff) {
-    double c2[2] = {0.0, 0.0};
-#pragma unroll
-    for (int kk = 0; kk < 12; kk += 4) dmma884s(c2, rA[kk * hkd::kRld + 24 + 8 * Ci], L.yB[kk * TS + 8 * J]);
-    // swing rows: (B_r^T Y)[c][:] = (1-c_l) dt * Y[12+c][:]   (factor zero for stance rows; swoff clamps the padding rows)
-    const double2 m2 = *reinterpret_cast<const double2*>(sm.Y + swoff * TS + 8 * J + 2 * L.t);
-    if (swrow != 0.0) {
-        c2[0] = fma(swrow, m2.x, c2[0]);
-        c2[1] = fma(swrow, m2.y, c2[1]);
-    }
-    if (Ci == 0 || L.g < 4) *reinterpret_cast<double2*>(sm.Qux + (8 * Ci + L.g) * TS + 8 * J + 2 * L.t) = make_double2(c2[0], c2[1]);
-}
-// Quu_r tile: rows c = 8*Ci + g, columns cc = 8*Cj + 2t + q of luu_r + B_r^T Z
-template <int Ci, int Cj>
-__device__ __forceinline__ void p2_quu(Smem& sm, const StageLane& L, const double* rA, const double* luu, double swrow, int swoff,
-                                       double diag, int lo0, int lo1) {
-    double c2[2] = {0.0, 0.0};
-#pragma unroll
-    for (int kk = 0; kk < 12; kk += 4) dmma884s(c2, rA[kk * hkd::kRld + 24 + 8 * Ci], L.zB[kk * ZS + 8 * Cj]);
-    const double2 m2 = *reinterpret_cast<const double2*>(sm.Z + swoff * ZS + 8 * Cj + 2 * L.t);
-    if (swrow != 0.0) {
-        c2[0] = fma(swrow, m2.x, c2[0]);
-        c2[1] = fma(swrow, m2.y, c2[1]);
-    }
-    const int c = 8 * Ci + L.g;
-    if (Ci == Cj) {  // diagonal dt R + reg
-        if (L.g == 2 * L.t) c2[0] += diag;
-        if (L.g == 2 * L.t + 1) c2[1] += diag;
-    }
-    if (lo0 >= 0) c2[0] += luu[lo0];  // ReB Hessian block of a stance leg
-    if (lo1 >= 0) c2[1] += luu[lo1];
-    if (Ci == 0 || L.g < 4) *reinterpret_cast<double2*>(sm.Quu + c * TS + 8 * Cj + 2 * L.t) = make_double2(c2[0], c2[1]);
-}
-// per-phase, per-lane constants of the warp's Qux / Quu tiles (row c = 8*Ci + g)
-struct P2Lane {
-    double swrow[2];  // (1-c_l) dt of row c = g, 8+g (zero for stance rows and c >= 12)
-    int swoff[2];     // row 12+c of Y / Z, clamped into the tile
-    double diag;      // dt R(act) + reg of the warp's Quu tile row
-    int lo0, lo1;     // offsets into the stage's luu blocks for the warp's Quu tile element (g, 2t+q), or -1
-};
-template <int W>
-__device__ __forceinline__ void stage_p2(Smem& sm, const StageLane& L, const double* rA, const double* luu, const P2Lane& P, double reg) {
-    if (W == 0) { p2_qxx<0, 0>(sm, L, rA, reg); p2_qxx<2, 1>(sm, L, rA, reg); p2_qux<0, 2>(sm, L, rA, P.swrow[0], P.swoff[0]); p2_quu<0, 0>(sm, L, rA, luu, P.swrow[0], P.swoff[0], P.diag, P.lo0, P.lo1); }
-    if (W == 1) { p2_qxx<1, 0>(sm, L, rA, reg); p2_qxx<2, 2>(sm, L, rA, reg); p2_qux<1, 0>(sm, L, rA, P.swrow[1], P.swoff[1]); p2_quu<0, 1>(sm, L, rA, luu, P.swrow[0], P.swoff[0], P.diag, P.lo0, P.lo1); }
-    if (W == 2) { p2_qxx<1, 1>(sm, L, rA, reg); p2_qux<0, 0>(sm, L, rA, P.swrow[0], P.swoff[0]); p2_qux<1, 1>(sm, L, rA, P.swrow[1], P.swoff[1]); p2_quu<1, 0>(sm, L, rA, luu, P.swrow[1], P.swoff[1], P.diag, P.lo0, P.lo1); }
-    if (W == 3) { p2_qxx<2, 0>(sm, L, rA, reg); p2_qux<0, 1>(sm, L, rA, P.swrow[0], P.swoff[0]); p2_qux<1, 2>(sm, L, rA, P.swrow[1], P.swoff[1]); p2_quu<1, 1>(sm, L, rA, luu, P.swrow[1], P.swoff[1], P.diag, P.lo0, P.lo1); }
-}
-
-// ---- P4: H' = sym(Qxx) + Qux_r^T K_r, lower tile (I, J), mirrored into the upper triangle ----
-template <int I, int J>
-__device__ __forceinline__ void p4_tile(const StageLane& L) {
-    const double2 q2 = *reinterpret_cast<const double2*>(L.hC + 8 * I * TS + 8 * J);
-    double c2[2] = {q2.x, q2.y};
-#pragma unroll
-    for (int kk = 0; kk < 12; kk += 4) dmma884s(c2, L.qA[kk * TS + 8 * I], L.kB[8 * J * 12 + kk]);
-    if (I == J) {
-        // symmetrise the diagonal tile: partner of (g, 2t+q') is (2t+q', g), held by lane 4*(2t+q') + g/2, slot g&1
-        const int g = L.g, t = L.t;
-        const double p00 = __shfl_sync(0xffffffffu, c2[0], 4 * (2 * t) + (g >> 1));
-        const double p01 = __shfl_sync(0xffffffffu, c2[1], 4 * (2 * t) + (g >> 1));
-        const double p10 = __shfl_sync(0xffffffffu, c2[0], 4 * (2 * t + 1) + (g >> 1));
-        const double p11 = __shfl_sync(0xffffffffu, c2[1], 4 * (2 * t + 1) + (g >> 1));
-        c2[0] = 0.5 * (c2[0] + ((g & 1) ? p01 : p00));
-        c2[1] = 0.5 * (c2[1] + ((g & 1) ? p11 : p10));
-    } else {
-        L.hT[8 * J * TS + 8 * I] = c2[0];
-        L.hT[(8 * J + 1) * TS + 8 * I] = c2[1];
-    }
-    *reinterpret_cast<double2*>(L.hCw + 8 * I * TS + 8 * J) = make_double2(c2[0], c2[1]);
-}
-template <int W>
-__device__ __forceinline__ void stage_p4(Smem& sm, const StageLane& L, int lane) {
-    if (W == 0) { p4_tile<0, 0>(L); p4_tile<2, 1>(L); }
-    if (W == 1) { p4_tile<1, 0>(L); p4_tile<2, 2>(L); }
-    if (W == 2) { p4_tile<1, 1>(L); }
-    if (W == 3) {
-        p4_tile<2, 0>(L);
-        if (lane < 24) {  // G' = Qx + Qux_r^T dU_r
-            double a0 = sm.Qx[lane], a1 = 0.0;
-#pragma unroll
-            for (int r = 0; r < 12; r += 2) {
-                a0 = fma(sm.Qux[r * TS + lane], sm.wu[r], a0);
-                a1 = fma(sm.Qux[(r + 1) * TS + lane], sm.wu[r + 1], a1);
-            }
-            sm.G[lane] = a0 + a1;
-        }
-    }
-}
+// Tile descriptors of the stage body.  Every phase of a stage is a short ROLLED loop over 8x8 output tiles
+// (3 DMMA each) driven by these constant tables: tile `warp + 4 q` belongs to warp `warp`.  The loop bodies
+// hold no index arithmetic beyond adding the table offsets to per-lane base pointers, so the whole stage
+// stays small enough for the SM's instruction cache (the kernel is instruction-fetch sensitive:
+// a fully unrolled, per-warp specialised variant executes 30 % fewer instructions but runs slower, see
+// DESIGN.md §4 and tools/code_size.py).
+//   c_p1[tile] = {a: column of H (8 I), b: column of [A | B_r] (8 Jt), c: offset of the H / Y tile element,
+//                 z: offset of the Z tile element, -1 for a Y tile, -2: the Gn = G + H d vector job}
+//   c_p2[tile] = {a: column of R, b: column of Y / Z | kind << 16 | Ci << 20, cin: Y tile offset or -1, out: offset in H / Qux / Quu}
+//   c_p4[tile] = {a: column of Qux (8 I), b: 8 J * 12 into K_r^T, c: H tile offset, mirror offset (-1 diagonal tile, -2 idle, -3 the G' job)}
+__constant__ int4 c_p1[16] = {{0, 0, 0, -1}, {0, 8, 8, -1}, {0, 16, 16, -1}, {0, 24, 12, 0}, {0, 32, 20, 8}, {8, 0, 224, -1}, {8, 8, 232, -1}, {8, 16, 240, -1},
+                              {8, 24, 236, 160}, {8, 32, 244, 168}, {16, 0, 448, -1}, {16, 8, 456, -1}, {16, 16, 464, -1}, {16, 24, 460, 320}, {16, 32, 468, 328}, {0, 0, 0, -2}};
+__constant__ int4 c_p2[16] = {{0, 0, 0, 0}, {8, 0, 224, 224}, {8, 8, 232, 232}, {16, 0, 448, 448}, {16, 8, 456, 456}, {16, 16, 464, 464},
+                              {24, 65536, -1, 0}, {24, 65544, -1, 8}, {24, 65552, -1, 16}, {32, 1114112, -1, 224}, {32, 1114120, -1, 232}, {32, 1114128, -1, 240},
+                              {24, 131072, -1, 0}, {24, 131080, -1, 8}, {32, 1179648, -1, 224}, {32, 1179656, -1, 232}};
+__constant__ int4 c_p4[8] = {{0, 0, 0, -1}, {8, 0, 224, 8}, {8, 96, 232, -1}, {16, 0, 448, 16}, {16, 96, 456, 240}, {16, 192, 464, -1}, {0, 0, 0, -2}, {0, 0, 0, -3}};
+static_assert(TS == 28 && ZS == 20, "the tile descriptor tables are generated for TS = 28, ZS = 20");
 
 // One phase of the backward sweep.  On entry sm.G / sm.H hold Gprime / Hprime (zero for
 // the last phase).  Returns false if a stage failed the PD test.
@@ -368,29 +204,16 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
     PROF_DECL
     build_phase_tables(sm, cm, dt);
     prefetch_stage(sm, 0, sc.stage_off[ph] + Nph - 1, sc.node_off[ph] + Nph);
-    // per-lane tile bases and per-phase constants of the stage body
-    StageLane L;
-    L.g = g; L.t = t;
-    L.hA = sm.H + t * TS + g; L.hC = sm.H + g * TS + 2 * t; L.hCw = sm.H + g * TS + 2 * t; L.hT = sm.H + 2 * t * TS + g;
-    L.yB = sm.Y + t * TS + g; L.yC = sm.Y + g * TS + 2 * t;
-    L.zB = sm.Z + t * ZS + g; L.zC = sm.Z + g * ZS + 2 * t;
-    L.qA = sm.Qux + t * TS + g; L.kB = sm.Z + g * 12 + t;
-    L.swc = sm.swc + 2 * t;
-    P2Lane P2;
-#pragma unroll
-    for (int ci = 0; ci < 2; ++ci) {
-        const int c = 8 * ci + g;
-        P2.swrow[ci] = (c < 12) ? sm.swdt[c / 3] : 0.0;
-        P2.swoff[ci] = (c < 12) ? 12 + c : 23;
-    }
-    {
-        const int c = 8 * (warp >> 1) + g;  // row of the warp's Quu tile (Ci = warp >> 1, Cj = warp & 1)
-        const bool stance = (c < 12) && ((cm >> (c / 3)) & 1u);
-        P2.diag = (c < 12) ? dt * weight_R(act_index(c, cm)) + reg : 0.0;
-        const int cc0 = 8 * (warp & 1) + 2 * t;
-        P2.lo0 = (stance && cc0 < 12 && c / 3 == cc0 / 3) ? 9 * (c / 3) + 3 * (c % 3) + (cc0 % 3) : -1;
-        P2.lo1 = (stance && cc0 + 1 < 12 && c / 3 == (cc0 + 1) / 3) ? 9 * (c / 3) + 3 * (c % 3) + ((cc0 + 1) % 3) : -1;
-    }
+    // per-lane base pointers of the tile fragments: element (g, 2t..2t+1) of an accumulator tile, (t, g) of an operand tile
+    const double* hA = sm.H + t * TS + g;
+    double* hC = sm.H + g * TS + 2 * t;
+    double* hT = sm.H + 2 * t * TS + g;
+    double* yC = sm.Y + g * TS + 2 * t;
+    double* zC = sm.Z + g * ZS + 2 * t;
+    const double* qA = sm.Qux + t * TS + g;
+    const double* kB = sm.Z + g * 12 + t;
+    double* quxC = sm.Qux + g * TS + 2 * t;
+    double* quuC = sm.Quu + g * TS + 2 * t;
     // G[N] = Phix + Gprime ; H[N] = Phixx + Hprime
     if (tid < 24) sm.G[tid] += trec[TQ_PHIX + tid];
     for (int e = tid; e < 576; e += kThreads) {
@@ -418,25 +241,81 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
         const double* luu = sm.rec[buf] + LQ_LUU;
         const double* dfc = sm.dfc2[buf];
         // ---- P1: [Y | Z] = H [A | B_r] : 15 tiles (3 row blocks x 5 column blocks), Gn = G + H d ----
-        {
-            const double* rB = R + t * hkd::kRld + g;
-            switch (warp) {
-                case 0: stage_p1<0>(sm, L, rB, dfc, lane); break;
-                case 1: stage_p1<1>(sm, L, rB, dfc, lane); break;
-                case 2: stage_p1<2>(sm, L, rB, dfc, lane); break;
-                default: stage_p1<3>(sm, L, rB, dfc, lane); break;
+        const double* rB = R + t * hkd::kRld + g;  // operand element (t, g) of R; also the a-operand of P2
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            const int4 d = c_p1[warp + 4 * q];
+            if (d.w != -2) {
+                double c2[2] = {0.0, 0.0};
+                if (d.w < 0) { const double2 h2 = *reinterpret_cast<const double2*>(hC + d.z); c2[0] = h2.x; c2[1] = h2.y; }
+                const double* a = hA + d.x;
+                const double* b = rB + d.y;
+                dmma884(c2, a[0], b[0]);
+                dmma884(c2, a[4 * TS], b[4 * hkd::kRld]);
+                dmma884(c2, a[8 * TS], b[8 * hkd::kRld]);
+                if (d.w < 0) {
+                    *reinterpret_cast<double2*>(yC + d.z) = make_double2(c2[0], c2[1]);
+                } else {  // swing columns of Z: H[:, 12+c] * (1-c_l) dt (zero factor for stance legs and the padding c >= 12)
+                    const double2 h2 = *reinterpret_cast<const double2*>(hC + d.z);
+                    const double2 sw = *reinterpret_cast<const double2*>(sm.swc + 2 * t + d.y - 24);
+                    c2[0] = fma(h2.x, sw.x, c2[0]);
+                    c2[1] = fma(h2.y, sw.y, c2[1]);
+                    *reinterpret_cast<double2*>(zC + d.w) = make_double2(c2[0], c2[1]);
+                }
+            } else if (lane < 24) {  // Gn = G + H d   (Q10)
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+                for (int j = 0; j < 24; j += 4) {
+                    a0 = fma(sm.H[j * TS + lane], dfc[j], a0);
+                    a1 = fma(sm.H[(j + 1) * TS + lane], dfc[j + 1], a1);
+                    a2 = fma(sm.H[(j + 2) * TS + lane], dfc[j + 2], a2);
+                    a3 = fma(sm.H[(j + 3) * TS + lane], dfc[j + 3], a3);
+                }
+                sm.Gn[lane] = sm.G[lane] + ((a0 + a1) + (a2 + a3));
             }
         }
         __syncthreads();
         PROF_MARK(sm, 6);
         // ---- P2: 16 tiles C = [A | B_r]^T M :  6 x Qxx (lower, M = Y, parked in H) ; 6 x Qux_r (M = Y) ; 4 x Quu_r (M = Z) ----
-        {
-            const double* rA = R + t * hkd::kRld + g;
-            switch (warp) {
-                case 0: stage_p2<0>(sm, L, rA, luu, P2, reg); break;
-                case 1: stage_p2<1>(sm, L, rA, luu, P2, reg); break;
-                case 2: stage_p2<2>(sm, L, rA, luu, P2, reg); break;
-                default: stage_p2<3>(sm, L, rA, luu, P2, reg); break;
+        // (the sparse additive term of Qxx, lxx + reg I, is applied in P3 by the warp that is idle there)
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            const int4 d = c_p2[warp + 4 * q];
+            const int kind = (d.y >> 16) & 3, Ci = d.y >> 20, boff = d.y & 0xffff;
+            double c2[2] = {0.0, 0.0};
+            if (d.z >= 0) { const double2 y2 = *reinterpret_cast<const double2*>(yC + d.z); c2[0] = y2.x; c2[1] = y2.y; }
+            const double* a = rB + d.x;
+            const double* M = (kind == 2) ? sm.Z : sm.Y;
+            const int ms = (kind == 2) ? ZS : TS;
+            const double* b = M + t * ms + g + boff;
+            dmma884(c2, a[0], b[0]);
+            dmma884(c2, a[4 * hkd::kRld], b[4 * ms]);
+            dmma884(c2, a[8 * hkd::kRld], b[8 * ms]);
+            if (kind == 0) {
+                *reinterpret_cast<double2*>(hC + d.w) = make_double2(c2[0], c2[1]);
+            } else {
+                const int c = 8 * Ci + g;  // reduced control row
+                if (c < 12) {
+                    const double sw = sm.swc[c];
+                    if (sw != 0.0) {  // swing row: (B_r^T M)[c][:] = (1-c_l) dt * M[12+c][:]
+                        const double2 m2 = *reinterpret_cast<const double2*>(M + (12 + c) * ms + boff + 2 * t);
+                        c2[0] = fma(sw, m2.x, c2[0]);
+                        c2[1] = fma(sw, m2.y, c2[1]);
+                    }
+                    if (kind == 2) {  // + luu_r: dt R + reg on the diagonal, the ReB Hessian block of a stance leg
+                        const bool stance = sw == 0.0;
+                        const int cc = boff + 2 * t, l3 = 3 * (c / 3);
+                        const double diag = dt * (stance ? .2 : .1) + reg;  // weight_R(act_index(c, cm))
+                        if (c == cc) c2[0] += diag;
+                        if (c == cc + 1) c2[1] += diag;
+                        if (stance) {
+                            const double* lb = luu + 3 * c;  // luu[9 (c/3) + 3 (c%3) + k]
+                            if (cc >= l3 && cc < l3 + 3) c2[0] += lb[cc - l3];
+                            if (cc + 1 >= l3 && cc + 1 < l3 + 3) c2[1] += lb[cc + 1 - l3];
+                        }
+                    }
+                    *reinterpret_cast<double2*>(((kind == 2) ? quuC : quxC) + d.w) = make_double2(c2[0], c2[1]);
+                }
             }
         }
         if (warp == 3 && lane < 24) {  // Qx = lx + A^T Gn
@@ -465,13 +344,15 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
             const int j = (warp == 0) ? lane - 12 : lane + 8;  // Qux_r column of this lane (valid for lane >= 12, j < 24)
             const bool is_piv = lane < 12, is_gain = !is_piv && warp < 2 && j < 24, is_ff = (warp == 1 && lane == 16);
             const double shift = (warp == 2) ? 1e-9 : 0.0;  // Quu - 1e-9 I (Q7)
+            // column source: Quu_r[:, lane] (pivot lanes), Qux_r[:, j] (gain lanes), Qu_r (feed-forward lane);
+            // idle lanes carry a copy of a Quu_r column along (harmless, never stored)
+            const double* src = is_gain ? sm.Qux + j : is_ff ? sm.Qu : sm.Quu + (lane % 12);
+            const int stride = is_ff ? 1 : TS;
 #pragma unroll
-            for (int r = 0; r < 12; ++r) {
-                double val = (r == lane % 12) ? 1.0 : 0.0;  // harmless dummy column for idle lanes
-                if (is_piv) val = sm.Quu[r * TS + lane] - ((r == lane) ? shift : 0.0);
-                else if (is_gain) val = sm.Qux[r * TS + j];
-                else if (is_ff) val = sm.Qu[r];
-                col[r] = val;
+            for (int r = 0; r < 12; ++r) col[r] = src[r * stride];
+            if (shift != 0.0) {
+#pragma unroll
+                for (int r = 0; r < 12; ++r) if (r == lane) col[r] -= shift;
             }
             PROF_MARK(sm, 13);
             const bool ok = gauss_jordan12(col, sm.red + 32 * warp, sm.profacc + 10);
@@ -497,7 +378,13 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                 }
                 sm.dbuf[0] = dvk;
             }
-        } else if (lane < 16) {
+        } else {
+            // sparse additive part of Qxx (parked in H): lxx + reg I on the diagonal, the foot-regulariser coupling
+            // (12+c, 3 + c%3) of the lower triangle (P4 mirrors it)
+            if (lane < 24) sm.H[lane * (TS + 1)] = (sm.H[lane * (TS + 1)] + sm.lxxd[lane]) + reg;
+            if (lane < 12) sm.H[(12 + lane) * TS + 3 + lane % 3] -= sm.lxxw[lane];
+        }
+        if (warp == 3 && lane < 16) {
             // decoupled controls: Quu_ii = dt R_i + reg, Qu_i = lu_i, K row = 0
             double dv = 0.0;
             if (lane < 12) {
@@ -516,11 +403,39 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
         PROF_MARK(sm, 8);
         if (!sm.ibuf[0]) { cp_async_wait_all(); return false; }
         // ---- P4: H' = sym(Qxx) + Qux_r^T K_r (6 lower tiles, mirrored) ; G' = Qx + Qux_r^T dU_r ----
-        switch (warp) {
-            case 0: stage_p4<0>(sm, L, lane); break;
-            case 1: stage_p4<1>(sm, L, lane); break;
-            case 2: stage_p4<2>(sm, L, lane); break;
-            default: stage_p4<3>(sm, L, lane); break;
+#pragma unroll 1
+        for (int q = 0; q < 2; ++q) {
+            const int4 d = c_p4[warp + 4 * q];
+            if (d.w >= -1) {
+                const double2 q2 = *reinterpret_cast<const double2*>(hC + d.z);
+                double c2[2] = {q2.x, q2.y};
+                const double* a = qA + d.x;
+                const double* b = kB + d.y;
+                dmma884(c2, a[0], b[0]);
+                dmma884(c2, a[4 * TS], b[4]);
+                dmma884(c2, a[8 * TS], b[8]);
+                if (d.w < 0) {
+                    // symmetrise the diagonal tile: partner of (g, 2t+q') is (2t+q', g), held by lane 4*(2t+q') + g/2, slot g&1
+                    const double p00 = __shfl_sync(0xffffffffu, c2[0], 4 * (2 * t) + (g >> 1));
+                    const double p01 = __shfl_sync(0xffffffffu, c2[1], 4 * (2 * t) + (g >> 1));
+                    const double p10 = __shfl_sync(0xffffffffu, c2[0], 4 * (2 * t + 1) + (g >> 1));
+                    const double p11 = __shfl_sync(0xffffffffu, c2[1], 4 * (2 * t + 1) + (g >> 1));
+                    c2[0] = 0.5 * (c2[0] + ((g & 1) ? p01 : p00));
+                    c2[1] = 0.5 * (c2[1] + ((g & 1) ? p11 : p10));
+                } else {
+                    hT[d.w] = c2[0];
+                    hT[d.w + TS] = c2[1];
+                }
+                *reinterpret_cast<double2*>(hC + d.z) = make_double2(c2[0], c2[1]);
+            } else if (d.w == -3 && lane < 24) {  // G' = Qx + Qux_r^T dU_r
+                double a0 = sm.Qx[lane], a1 = 0.0;
+#pragma unroll
+                for (int r = 0; r < 12; r += 2) {
+                    a0 = fma(sm.Qux[r * TS + lane], sm.wu[r], a0);
+                    a1 = fma(sm.Qux[(r + 1) * TS + lane], sm.wu[r + 1], a1);
+                }
+                sm.G[lane] = a0 + a1;
+            }
         }
         const double dvk = sm.dbuf[0] + sm.dbuf[1];
         dV1 -= dvk;
