@@ -473,76 +473,57 @@ __device__ inline void compute_cost_block(Smem& sm) {
     const int N = sc.n_stages;
     const double dt = sc.dt;
     double csum = 0.0;
-    for (int s = tid; s < N; s += kThreads) {
+    // Every term of the running / terminal costs is a sum over (node or stage, component): the passes below walk
+    // those index spaces flat, so all 128 threads work and every global access is coalesced.
+    // (1) state tracking, (node, j): running 1/2 dt Q dx^2, terminal 1/2 Qf dx^2
+    for (int e = tid; e < sc.n_nodes * 24; e += kThreads) {
+        const int n = e / 24, j = e % 24;
+        const int ph = sc.ph_of_node[n];
+        const unsigned cm = sc.cmask[ph];
+        const bool terminal = (n - sc.node_off[ph]) == sc.horizon[ph];
+        const double dx = sm.X[e] - sm.xr[e];
+        csum += terminal ? 0.5 * ((dx * weight_Qf(j, cm)) * dx) : ((0.5 * dx * weight_Q(j, cm)) * dx) * dt;
+    }
+    // (2) control effort, (stage, j)
+    for (int e = tid; e < N * 24; e += kThreads) {
+        const int s = e / 24, j = e % 24;
         int ph, k;
         phase_of_stage(sc, s, ph, k);
-        const int n = sc.node_off[ph] + k;
-        const unsigned cm = sc.cmask[ph];
-        const double* x = sm.X + 24 * n;
-        const double* u = sm.U + 24 * s;
-        const double* xr = sm.xr + 24 * n;
-        const double* ur = sm.ur + 24 * n;
-        double s1 = 0.0, s2 = 0.0;
-#pragma unroll 4
-        for (int j = 0; j < 24; ++j) { const double dx = x[j] - xr[j]; s1 += (0.5 * dx * weight_Q(j, cm)) * dx; }
-#pragma unroll 4
-        for (int j = 0; j < 24; ++j) { const double du = u[j] - ur[j]; s2 += (0.5 * du * weight_R(j)) * du; }
-        double l = (s1 + s2) * dt;
-        double lf = 0.0;
-#pragma unroll 1
-        for (int ll = 0; ll < 4; ++ll) {
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const double d = (x[12 + 3 * ll + j] - x[3 + j]) - sm.prel[12 * n + 3 * ll + j];
-                lf += (.5 * d * weight_foot(ll, j, cm)) * d;
-            }
-        }
-        l += lf * dt;
-        if (sm.opt.ReB_active && cm) {  // compute_ReB_cost, ConstraintsBase.h:204-222
-            double reb_cost = 0.0;
-#pragma unroll 1
-            for (int e = 0; e < 20; ++e) {
-                if (!((cm >> (e / 5)) & 1u)) continue;
-                const double g = sm.gcon[20 * s + e];
-                const double eps_b = sm.reb[40 * s + 2 * e], delta = sm.reb[40 * s + 2 * e + 1];
-                double barr;
-                if (g > delta) barr = -hkd::log_nl(g);
-                else { const double z = (g - 2 * delta) / delta; barr = .5 * (z * z - 1); barr -= hkd::log_nl(delta); }
-                reb_cost += eps_b * barr;
-            }
-            l += dt * reb_cost;
-        }
-        csum += l;
+        const double du = sm.U[e] - sm.ur[24 * (sc.node_off[ph] + k) + j];
+        csum += ((0.5 * du * weight_R(j)) * du) * dt;
     }
-    if (tid < sc.n_phases) {  // terminal cost of each phase
-        const int ph = tid;
+    // (3) foot-placement regulariser, (node, leg component)
+    for (int e = tid; e < sc.n_nodes * 12; e += kThreads) {
+        const int n = e / 12, q = e % 12;
+        const int ph = sc.ph_of_node[n];
         const unsigned cm = sc.cmask[ph];
-        const int n = sc.node_off[ph] + sc.horizon[ph];
+        const bool terminal = (n - sc.node_off[ph]) == sc.horizon[ph];
         const double* x = sm.X + 24 * n;
-        const double* xr = sm.xr + 24 * n;
-        double s1 = 0.0;
-#pragma unroll 1
-        for (int j = 0; j < 24; ++j) { const double dx = x[j] - xr[j]; s1 += (dx * weight_Qf(j, cm)) * dx; }
-        double Phi = 0.5 * s1;
-        double sf = 0.0;
-#pragma unroll 1
-        for (int j = 0; j < 12; ++j) {
-            const double d = (x[12 + j] - x[3 + j % 3]) - sm.prel[12 * n + j];
-            sf += (10 * d * weight_foot(j / 3, j % 3, cm)) * d;
+        const double d = (x[12 + q] - x[3 + q % 3]) - sm.prel[e];
+        const double w = weight_foot(q / 3, q % 3, cm);
+        csum += terminal ? (10 * d * w) * d : ((.5 * d * w) * d) * dt;
+    }
+    // (4) relaxed-barrier terms of the GRF constraints, (stage, row)  (compute_ReB_cost, ConstraintsBase.h:204-222)
+    if (sm.opt.ReB_active) {
+        const double2* reb2 = reinterpret_cast<const double2*>(sm.reb);
+        for (int i = tid; i < N * 20; i += kThreads) {
+            const int s = i / 20, e = i % 20;
+            if (!((sc.cmask[sc.ph_of_stage[s]] >> (e / 5)) & 1u)) continue;
+            const double g = sm.gcon[i];
+            const double2 p = reb2[i];  // (eps, delta)
+            double barr;
+            if (g > p.y) barr = -hkd::log_nl(g);
+            else { const double z = (g - 2 * p.y) / p.y; barr = .5 * (z * z - 1); barr -= hkd::log_nl(p.y); }
+            csum += dt * (p.x * barr);
         }
-        Phi += sf;
-        if (sm.opt.AL_active) {  // compute_AL_cost, ConstraintsBase.h:374-385
-            double al_cost = 0.0;
-            for (int l = 0; l < 4; ++l) {
-                const bool td = !((cm >> l) & 1u) && ((sc.nmask[ph] >> l) & 1u);
-                if (!td) continue;
-                const double h = sm.hcon[4 * ph + l], sigma = sm.al[8 * ph + 2 * l], lambda = sm.al[8 * ph + 2 * l + 1];
-                al_cost += 0.5 * sigma * h * h;
-                al_cost += lambda * h;
-            }
-            Phi += al_cost;
+    }
+    // (5) augmented-Lagrangian terms of the touchdown constraints, (phase, leg)  (compute_AL_cost, ConstraintsBase.h:374-385)
+    if (sm.opt.AL_active && tid < sc.n_phases * 4) {
+        const int ph = tid >> 2, l = tid & 3;
+        if (!((sc.cmask[ph] >> l) & 1u) && ((sc.nmask[ph] >> l) & 1u)) {
+            const double h = sm.hcon[4 * ph + l], sigma = sm.al[8 * ph + 2 * l], lambda = sm.al[8 * ph + 2 * l + 1];
+            csum += 0.5 * sigma * h * h + lambda * h;
         }
-        csum += Phi;
     }
     double dsum = 0.0;
     for (int e = tid; e < sc.n_nodes * 24; e += kThreads) { const double d = sm.Defect[e]; dsum += d * d; }
@@ -563,7 +544,10 @@ __device__ inline void lq_approximation_block(Smem& sm) {
     PROF_DECL
     const int N = sc.n_stages;
     const double dt = sc.dt;
-    for (int s = tid; s < N; s += kThreads) {
+    // two threads per stage: half 0 the dynamics Jacobians and the ReB folding of legs {1,3},
+    // half 1 the cost gradients and the ReB folding of legs {0,2}
+    const int half = tid >> 6;
+    for (int s = tid & 63; s < N; s += 64) {
         int ph, k;
         phase_of_stage(sc, s, ph, k);
         const int n = sc.node_off[ph] + k;
@@ -571,36 +555,43 @@ __device__ inline void lq_approximation_block(Smem& sm) {
         const double* x = sm.X + 24 * n;
         const double* u = sm.U + 24 * s;
         double* rec = sm.lqg + (size_t)s * LQ_STRIDE;
-        hkd::dynamics_partial_record(x, u, dt, cm, rec + LQ_R);
         const double* xr = sm.xr + 24 * n;
         const double* ur = sm.ur + 24 * n;
         double* lx = rec + LQ_LX;
         double* lu = rec + LQ_LU;
         const double mu = sm.cp.mu;
+        if (half == 0) {
+            hkd::dynamics_partial_record(x, u, dt, cm, rec + LQ_R);
+        } else {
 #pragma unroll 4
-        for (int j = 0; j < 12; ++j) lx[j] = (dt * weight_Q(j, cm)) * (x[j] - xr[j]);
+            for (int j = 0; j < 12; ++j) lx[j] = (dt * weight_Q(j, cm)) * (x[j] - xr[j]);
 #pragma unroll 4
-        for (int j = 12; j < 24; ++j) lu[j] = (dt * weight_R(j)) * (u[j] - ur[j]);
-        // foot-placement regulariser: pos rows accumulate over the legs in order, foot rows get one term each;
-        // ReB folding (compute_ReB_partials, ConstraintsBase.h:224-263; only gu is non-zero)
-        double lp[3] = {lx[3], lx[4], lx[5]};
+            for (int j = 12; j < 24; ++j) lu[j] = (dt * weight_R(j)) * (u[j] - ur[j]);
+            // foot-placement regulariser: pos rows accumulate over the legs in order, foot rows get one term each
+            double lp[3] = {lx[3], lx[4], lx[5]};
 #pragma unroll 1
-        for (int l = 0; l < 4; ++l) {
-            const bool stance = (cm >> l) & 1u;
-            const double c = (double)((cm >> l) & 1u);
+            for (int l = 0; l < 4; ++l) {
+                const double c = (double)((cm >> l) & 1u);
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int i = 12 + 3 * l + j;
-                const double d = (x[i] - x[3 + j]) - sm.prel[12 * n + 3 * l + j];
-                const double w = dt * c * weight_foot(l, j, cm);
-                lp[j] += -(w * d);
-                lx[i] = (dt * weight_Q(i, cm)) * (x[i] - xr[i]) + w * d;
+                for (int j = 0; j < 3; ++j) {
+                    const int i = 12 + 3 * l + j;
+                    const double d = (x[i] - x[3 + j]) - sm.prel[12 * n + 3 * l + j];
+                    const double w = dt * c * weight_foot(l, j, cm);
+                    lp[j] += -(w * d);
+                    lx[i] = (dt * weight_Q(i, cm)) * (x[i] - xr[i]) + w * d;
+                }
             }
-            double hess[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, grad[3] = {0, 0, 0};
-            if (sm.opt.ReB_active && stance) {
+            lx[3] = lp[0]; lx[4] = lp[1]; lx[5] = lp[2];
+        }
+        // ReB folding (compute_ReB_partials, ConstraintsBase.h:224-263; only gu is non-zero)
 #pragma unroll 1
+        for (int l = 1 - half; l < 4; l += 2) {
+            double hess[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, grad[3] = {0, 0, 0};
+            if (sm.opt.ReB_active && ((cm >> l) & 1u)) {
+#pragma unroll
                 for (int r = 0; r < 5; ++r) {
-                    const double row[3] = {c_grfxy[r][0], c_grfxy[r][1], (r == 0) ? 1.0 : mu};
+                    // friction-pyramid row r: (0,0,1), (-1,0,mu), (1,0,mu), (0,-1,mu), (0,1,mu)
+                    const double row[3] = {(r == 1) ? -1.0 : (r == 2) ? 1.0 : 0.0, (r == 3) ? -1.0 : (r == 4) ? 1.0 : 0.0, (r == 0) ? 1.0 : mu};
                     const double g = sm.gcon[20 * s + 5 * l + r];
                     const double eps_b = sm.reb[40 * s + 2 * (5 * l + r)], delta = sm.reb[40 * s + 2 * (5 * l + r) + 1];
                     double bd, bdd;
@@ -619,7 +610,6 @@ __device__ inline void lq_approximation_block(Smem& sm) {
 #pragma unroll
             for (int a = 0; a < 9; ++a) rec[LQ_LUU + 9 * l + a] = dt * hess[a];
         }
-        lx[3] = lp[0]; lx[4] = lp[1]; lx[5] = lp[2];
     }
     if (tid < sc.n_phases) {
         const int ph = tid;
