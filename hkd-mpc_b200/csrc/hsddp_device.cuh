@@ -544,48 +544,58 @@ __device__ inline void lq_approximation_block(Smem& sm) {
     PROF_DECL
     const int N = sc.n_stages;
     const double dt = sc.dt;
-    // two threads per stage: half 0 the dynamics Jacobians and the ReB folding of legs {1,3},
-    // half 1 the cost gradients and the ReB folding of legs {0,2}
-    const int half = tid >> 6;
-    for (int s = tid & 63; s < N; s += 64) {
+    // (1) dynamics Jacobians, one thread per stage (the record rows are written in place)
+    for (int s = tid; s < N; s += kThreads) {
+        int ph, k;
+        phase_of_stage(sc, s, ph, k);
+        const int n = sc.node_off[ph] + k;
+        hkd::dynamics_partial_record(sm.X + 24 * n, sm.U + 24 * s, dt, sc.cmask[ph], sm.lqg + (size_t)s * LQ_STRIDE + LQ_R);
+    }
+    // (2) cost gradients, flat over (stage, component): lx (24) and the lu of the joint-velocity commands (12);
+    //     coalesced reads, 192-byte runs of writes.  Foot-placement regulariser: the position rows accumulate over
+    //     the legs in order, the foot rows get one term each.
+    for (int e = tid; e < N * 36; e += kThreads) {
+        const int s = e / 36, j = e % 36;
         int ph, k;
         phase_of_stage(sc, s, ph, k);
         const int n = sc.node_off[ph] + k;
         const unsigned cm = sc.cmask[ph];
-        const double* x = sm.X + 24 * n;
-        const double* u = sm.U + 24 * s;
         double* rec = sm.lqg + (size_t)s * LQ_STRIDE;
-        const double* xr = sm.xr + 24 * n;
-        const double* ur = sm.ur + 24 * n;
-        double* lx = rec + LQ_LX;
-        double* lu = rec + LQ_LU;
-        const double mu = sm.cp.mu;
-        if (half == 0) {
-            hkd::dynamics_partial_record(x, u, dt, cm, rec + LQ_R);
-        } else {
-#pragma unroll 4
-            for (int j = 0; j < 12; ++j) lx[j] = (dt * weight_Q(j, cm)) * (x[j] - xr[j]);
-#pragma unroll 4
-            for (int j = 12; j < 24; ++j) lu[j] = (dt * weight_R(j)) * (u[j] - ur[j]);
-            // foot-placement regulariser: pos rows accumulate over the legs in order, foot rows get one term each
-            double lp[3] = {lx[3], lx[4], lx[5]};
-#pragma unroll 1
+        if (j >= 24) {
+            const int i = j - 12;
+            rec[LQ_LU + i] = (dt * weight_R(i)) * (sm.U[24 * s + i] - sm.ur[24 * n + i]);
+            continue;
+        }
+        const double* x = sm.X + 24 * n;
+        double v = (dt * weight_Q(j, cm)) * (x[j] - sm.xr[24 * n + j]);
+        if (j >= 3 && j < 6) {
+#pragma unroll
             for (int l = 0; l < 4; ++l) {
                 const double c = (double)((cm >> l) & 1u);
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const int i = 12 + 3 * l + j;
-                    const double d = (x[i] - x[3 + j]) - sm.prel[12 * n + 3 * l + j];
-                    const double w = dt * c * weight_foot(l, j, cm);
-                    lp[j] += -(w * d);
-                    lx[i] = (dt * weight_Q(i, cm)) * (x[i] - xr[i]) + w * d;
-                }
+                const double d = (x[12 + 3 * l + j - 3] - x[j]) - sm.prel[12 * n + 3 * l + j - 3];
+                const double w = dt * c * weight_foot(l, j - 3, cm);
+                v += -(w * d);
             }
-            lx[3] = lp[0]; lx[4] = lp[1]; lx[5] = lp[2];
+        } else if (j >= 12) {
+            const int l = (j - 12) / 3, jj = (j - 12) % 3;
+            const double c = (double)((cm >> l) & 1u);
+            const double d = (x[j] - x[3 + jj]) - sm.prel[12 * n + j - 12];
+            const double w = dt * c * weight_foot(l, jj, cm);
+            v += w * d;
         }
-        // ReB folding (compute_ReB_partials, ConstraintsBase.h:224-263; only gu is non-zero)
-#pragma unroll 1
-        for (int l = 1 - half; l < 4; l += 2) {
+        rec[LQ_LX + j] = v;
+    }
+    // (3) GRF controls and the ReB folding, flat over (stage, leg)  (compute_ReB_partials, ConstraintsBase.h:224-263;
+    //     only gu is non-zero)
+    {
+        const double mu = sm.cp.mu;
+        for (int e = tid; e < N * 4; e += kThreads) {
+            const int s = e >> 2, l = e & 3;
+            int ph, k;
+            phase_of_stage(sc, s, ph, k);
+            const int n = sc.node_off[ph] + k;
+            const unsigned cm = sc.cmask[ph];
+            double* rec = sm.lqg + (size_t)s * LQ_STRIDE;
             double hess[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, grad[3] = {0, 0, 0};
             if (sm.opt.ReB_active && ((cm >> l) & 1u)) {
 #pragma unroll
@@ -606,7 +616,10 @@ __device__ inline void lq_approximation_block(Smem& sm) {
                 }
             }
 #pragma unroll
-            for (int a = 0; a < 3; ++a) lu[3 * l + a] = (dt * weight_R(3 * l + a)) * (u[3 * l + a] - ur[3 * l + a]) + dt * grad[a];
+            for (int a = 0; a < 3; ++a) {
+                const int i = 3 * l + a;
+                rec[LQ_LU + i] = (dt * weight_R(i)) * (sm.U[24 * s + i] - sm.ur[24 * n + i]) + dt * grad[a];
+            }
 #pragma unroll
             for (int a = 0; a < 9; ++a) rec[LQ_LUU + 9 * l + a] = dt * hess[a];
         }
