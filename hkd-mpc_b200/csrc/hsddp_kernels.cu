@@ -14,6 +14,11 @@
 #include "hsddp_device.cuh"
 #include "hsddp_sweep.cuh"
 
+// resident blocks per SM the kernels are compiled for (register budget = 65536 / (128 * HSDDP_MIN_BLOCKS))
+#ifndef HSDDP_MIN_BLOCKS
+#define HSDDP_MIN_BLOCKS 6
+#endif
+
 namespace hsddp {
 
 // ---------------------------------------------------------------------------
@@ -217,7 +222,7 @@ __device__ inline void solve_block(Smem& sm, const BatchPtrs& bp) {
     solve_finish_block(sm, bp);
 }
 
-__global__ void __launch_bounds__(kThreads, 6) k_solve(BatchPtrs bp, hsddp_options opt, int cold_start) {
+__global__ void __launch_bounds__(kThreads, HSDDP_MIN_BLOCKS) k_solve(BatchPtrs bp, hsddp_options opt, int cold_start) {
     __shared__ Smem sm;
     if (threadIdx.x == 0) assign_rotation(bp.sm_slots, sm.rot);
     for (;;) {
@@ -245,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, 6) k_solve(BatchPtrs bp, hsddp_optio
 // One phase of solve() for every running problem: block b works on problem bp.active[b] (or b).
 enum SolvePhase { PH_BEGIN = 0, PH_PREP, PH_SWEEP, PH_FORWARD };
 template <int PH>
-__global__ void __launch_bounds__(kThreads, 6) k_phase(BatchPtrs bp, hsddp_options opt) {
+__global__ void __launch_bounds__(kThreads, HSDDP_MIN_BLOCKS) k_phase(BatchPtrs bp, hsddp_options opt) {
     __shared__ Smem sm;
     const int pid = bp.active ? bp.active[blockIdx.x] : (int)blockIdx.x;
     if (threadIdx.x == 0) assign_rotation(bp.sm_slots, sm.rot);
@@ -279,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 6) k_phase(BatchPtrs bp, hsddp_optio
 enum StepOp { OP_RESET = 0, OP_ROLLOUT, OP_COST, OP_LQ, OP_SWEEP, OP_SWEEP_REG, OP_LINEAR, OP_MERIT, OP_FORWARD, OP_NOMINAL, OP_AL, OP_REB };
 
 // step-level kernel: one block per problem, state round-trips through HBM
-__global__ void __launch_bounds__(kThreads, 6) k_step(BatchPtrs bp, hsddp_options opt, int op, double arg, double* darg, int* ok) {
+__global__ void __launch_bounds__(kThreads, HSDDP_MIN_BLOCKS) k_step(BatchPtrs bp, hsddp_options opt, int op, double arg, double* darg, int* ok) {
     __shared__ Smem sm;
     const int pid = blockIdx.x;
     if (threadIdx.x == 0) assign_rotation(bp.sm_slots, sm.rot);

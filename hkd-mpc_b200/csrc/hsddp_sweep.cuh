@@ -214,17 +214,27 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
     const double* kB = sm.Z + g * 12 + t;
     double* quxC = sm.Qux + g * TS + 2 * t;
     double* quuC = sm.Quu + g * TS + 2 * t;
-    // G[N] = Phix + Gprime ; H[N] = Phixx + Hprime
-    if (tid < 24) sm.G[tid] += trec[TQ_PHIX + tid];
-    for (int e = tid; e < 576; e += kThreads) {
-        const int i = e / 24, j = e % 24;
-        double val = lxx_tab(sm.lxxTd, sm.lxxTw, i, j);
-#pragma unroll
+    // G[N] = Phix + Gprime ; H[N] = Phixx + Hprime.  Phixx is sparse: the diagonal, the foot-regulariser coupling
+    // (both triangles) and, per touchdown leg, the outer product of a 7-entry constraint gradient (AL term)
+    if (tid < 24) {
+        sm.G[tid] += trec[TQ_PHIX + tid];
+        sm.H[tid * (TS + 1)] += sm.lxxTd[tid];
+    } else if (tid < 48) {
+        const int c = tid - 24, q = c % 12, j3 = 3 + q % 3;
+        sm.H[(c < 12) ? (12 + q) * TS + j3 : j3 * TS + 12 + q] -= sm.lxxTw[q];
+    }
+    __syncthreads();
+    if (tid >= 64 && tid < 64 + 49) {
+        const int a = (tid - 64) / 7, b = (tid - 64) % 7;
+#pragma unroll 1
         for (int l = 0; l < 4; ++l) {
             const double wh = trec[TQ_WH + l];
-            if (wh != 0.0) val += wh * (trec[TQ_HX + 24 * l + i] * trec[TQ_HX + 24 * l + j]);
+            if (wh != 0.0) {
+                const int i = (a < 3) ? a : (a == 3) ? 5 : 12 + 3 * l + a - 4;
+                const int j = (b < 3) ? b : (b == 3) ? 5 : 12 + 3 * l + b - 4;
+                sm.H[i * TS + j] += wh * (trec[TQ_HX + 24 * l + i] * trec[TQ_HX + 24 * l + j]);
+            }
         }
-        sm.H[i * TS + j] += val;
     }
     cp_async_wait_all();
     __syncthreads();
@@ -337,70 +347,94 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
         }
         __syncthreads();
         PROF_MARK(sm, 7);
-        // ---- P3: Gauss-Jordan tableau (warps 0,1), shifted PD test (warp 2), inactive controls (warp 3) ----
-        if (warp < 3) {
-            double col[12];
-            // lanes 0..11: columns of Quu_r ; warp0 lanes 12..31: Qux_r columns 0..19 ; warp1 lanes 12..15: Qux_r 20..23, lane 16: Qu_r
-            const int j = (warp == 0) ? lane - 12 : lane + 8;  // Qux_r column of this lane (valid for lane >= 12, j < 24)
-            const bool is_piv = lane < 12, is_gain = !is_piv && warp < 2 && j < 24, is_ff = (warp == 1 && lane == 16);
-            const double shift = (warp == 2) ? 1e-9 : 0.0;  // Quu - 1e-9 I (Q7)
-            // column source: Quu_r[:, lane] (pivot lanes), Qux_r[:, j] (gain lanes), Qu_r (feed-forward lane);
-            // idle lanes carry a copy of a Quu_r column along (harmless, never stored)
-            const double* src = is_gain ? sm.Qux + j : is_ff ? sm.Qu : sm.Quu + (lane % 12);
-            const int stride = is_ff ? 1 : TS;
+        // ---- P3: Gauss-Jordan tableau (warps 0,1), sparse Qxx terms (warp 2), inactive controls (warp 3) ----
+        // PD verdict of the reference, LDLT(Quu - 1e-9 I).isPositive() (Q7), without a third elimination:
+        //   * a non-positive pivot of Quu_r itself          => Quu_r - 1e-9 I is not PD           (verdict false)
+        //   * all pivots positive and ||Quu_r^-1||_F < 5e8   => lambda_min(Quu_r) > 2e-9 > 1e-9    (verdict true)
+        //   * otherwise (never seen on the benchmark inputs) the shifted matrix is eliminated exactly in a second pass.
+        // Quu_r^-1 comes for free: twelve otherwise idle lanes of warp 1 carry the identity columns through the elimination.
+#pragma unroll 1
+        for (int pass = 0;; ++pass) {
+            if (warp < 2) {
+                double col[12];
+                // lanes 0..11: columns of Quu_r ; warp0 lanes 12..31: Qux_r columns 0..19 ;
+                // warp1 lanes 12..15: Qux_r 20..23, lane 16: Qu_r, lanes 17..28: identity columns
+                const int j = (warp == 0) ? lane - 12 : lane + 8;  // Qux_r column of this lane (valid for lane >= 12, j < 24)
+                const bool is_piv = lane < 12, is_gain = !is_piv && j < 24, is_ff = (warp == 1 && lane == 16);
+                const bool is_inv = (warp == 1 && lane >= 17 && lane < 29);
+                // idle lanes carry a copy of a Quu_r column along (harmless, never stored)
+                const double* src = is_gain ? sm.Qux + j : is_ff ? sm.Qu : sm.Quu + (lane % 12);
+                const int stride = is_ff ? 1 : TS;
 #pragma unroll
-            for (int r = 0; r < 12; ++r) col[r] = src[r * stride];
-            if (shift != 0.0) {
+                for (int r = 0; r < 12; ++r) col[r] = src[r * stride];
+                if (is_inv) {
 #pragma unroll
-                for (int r = 0; r < 12; ++r) if (r == lane) col[r] -= shift;
-            }
-            PROF_MARK(sm, 13);
-            const bool ok = gauss_jordan12(col, sm.red + 32 * warp, sm.profacc + 10);
-            PROF_MARK(sm, 14);
-            if (warp == 2) {
-                if (lane == 0) sm.ibuf[0] = ok ? 1 : 0;
-            } else if (is_gain) {  // gain column j: K_r[:, j] = -Quu_r^-1 Qux_r[:, j]  -> KT[j][0..11] (smem + HBM)
-                double2* ks = reinterpret_cast<double2*>(sm.Z + 12 * j);
-                double2* kg = reinterpret_cast<double2*>(sm.K + (size_t)s * 288 + 12 * j);
-#pragma unroll
-                for (int r = 0; r < 12; r += 2) {
-                    const double2 val = make_double2(-col[r], -col[r + 1]);
-                    ks[r >> 1] = val;
-                    kg[r >> 1] = val;
+                    for (int r = 0; r < 12; ++r) col[r] = (r == lane - 17) ? 1.0 : 0.0;
                 }
-            } else if (is_ff) {
-                double dvk = 0.0;
+                if (pass && is_piv) {  // exact pass: Quu - 1e-9 I
 #pragma unroll
-                for (int r = 0; r < 12; ++r) {
-                    sm.wu[r] = -col[r];                                   // dU_r
-                    sm.dU[24 * s + act_index(r, cm)] = -col[r];
-                    dvk = fma(sm.Qu[r], col[r], dvk);                     // -Qu^T dU
+                    for (int r = 0; r < 12; ++r) if (r == lane) col[r] -= 1e-9;
                 }
-                sm.dbuf[0] = dvk;
-            }
-        } else {
-            // sparse additive part of Qxx (parked in H): lxx + reg I on the diagonal, the foot-regulariser coupling
-            // (12+c, 3 + c%3) of the lower triangle (P4 mirrors it)
-            if (lane < 24) sm.H[lane * (TS + 1)] = (sm.H[lane * (TS + 1)] + sm.lxxd[lane]) + reg;
-            if (lane < 12) sm.H[(12 + lane) * TS + 3 + lane % 3] -= sm.lxxw[lane];
-        }
-        if (warp == 3 && lane < 16) {
-            // decoupled controls: Quu_ii = dt R_i + reg, Qu_i = lu_i, K row = 0
-            double dv = 0.0;
-            if (lane < 12) {
-                const int i = inact_index(lane, cm);
-                const double qu = luv[i];
-                const double du = -qu / (dt * weight_R(i) + reg);
-                sm.dU[24 * s + i] = du;
-                dv = -qu * du;
-            }
+                PROF_MARK(sm, 13);
+                const bool ok = gauss_jordan12(col, sm.red + 32 * warp, sm.profacc + 10);
+                PROF_MARK(sm, 14);
+                if (pass) {
+                    if (warp == 1 && lane == 0) sm.ibuf[0] = ok ? 1 : 0;
+                } else if (is_gain) {  // gain column j: K_r[:, j] = -Quu_r^-1 Qux_r[:, j]  -> KT[j][0..11] (smem + HBM)
+                    double2* ks = reinterpret_cast<double2*>(sm.Z + 12 * j);
+                    double2* kg = reinterpret_cast<double2*>(sm.K + (size_t)s * 288 + 12 * j);
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) dv += __shfl_xor_sync(0x0000ffffu, dv, o, 16);
-            if (lane == 0) sm.dbuf[1] = dv;
+                    for (int r = 0; r < 12; r += 2) {
+                        const double2 val = make_double2(-col[r], -col[r + 1]);
+                        ks[r >> 1] = val;
+                        kg[r >> 1] = val;
+                    }
+                } else if (is_ff) {
+                    double dvk = 0.0;
+#pragma unroll
+                    for (int r = 0; r < 12; ++r) {
+                        sm.wu[r] = -col[r];                                   // dU_r
+                        sm.dU[24 * s + act_index(r, cm)] = -col[r];
+                        dvk = fma(sm.Qu[r], col[r], dvk);                     // -Qu^T dU
+                    }
+                    sm.dbuf[0] = dvk;
+                }
+                if (!pass && warp == 1) {
+                    double f2 = 0.0;
+                    if (is_inv) {
+#pragma unroll
+                        for (int r = 0; r < 12; ++r) f2 = fma(col[r], col[r], f2);
+                    }
+                    f2 = warp_sum(f2);
+                    if (lane == 0) sm.ibuf[0] = !ok ? 0 : (f2 < 0.25e18) ? 1 : 2;
+                }
+            } else if (!pass) {
+                if (warp == 2) {
+                    // sparse additive part of Qxx (parked in H): lxx + reg I on the diagonal, the foot-regulariser coupling
+                    // (12+c, 3 + c%3) of the lower triangle (P4 mirrors it)
+                    if (lane < 24) sm.H[lane * (TS + 1)] = (sm.H[lane * (TS + 1)] + sm.lxxd[lane]) + reg;
+                    if (lane < 12) sm.H[(12 + lane) * TS + 3 + lane % 3] -= sm.lxxw[lane];
+                } else if (lane < 16) {
+                    // decoupled controls: Quu_ii = dt R_i + reg, Qu_i = lu_i, K row = 0
+                    double dv = 0.0;
+                    if (lane < 12) {
+                        const int i = inact_index(lane, cm);
+                        const double qu = luv[i];
+                        const double du = -qu / (dt * weight_R(i) + reg);
+                        sm.dU[24 * s + i] = du;
+                        dv = -qu * du;
+                    }
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) dv += __shfl_xor_sync(0x0000ffffu, dv, o, 16);
+                    if (lane == 0) sm.dbuf[1] = dv;
+                }
+            }
+            PROF_MARK(sm, 15);
+            __syncthreads();
+            PROF_MARK(sm, 8);
+            if (sm.ibuf[0] != 2) break;
+            __syncthreads();  // (everybody has read the verdict before warp 1 overwrites it in the exact pass)
         }
-        PROF_MARK(sm, 15);
-        __syncthreads();
-        PROF_MARK(sm, 8);
         if (!sm.ibuf[0]) { cp_async_wait_all(); return false; }
         // ---- P4: H' = sym(Qxx) + Qux_r^T K_r (6 lower tiles, mirrored) ; G' = Qx + Qux_r^T dU_r ----
 #pragma unroll 1
