@@ -222,8 +222,23 @@ __device__ inline void solve_block(Smem& sm, const BatchPtrs& bp) {
     solve_finish_block(sm, bp);
 }
 
+template <int MINB>
+__device__ __forceinline__ void solve_persistent(Smem& sm, const BatchPtrs& bp, const hsddp_options& opt, int cold_start);
+
+// throughput build: HSDDP_MIN_BLOCKS resident blocks per SM (80 registers / thread)
 __global__ void __launch_bounds__(kThreads, HSDDP_MIN_BLOCKS) k_solve(BatchPtrs bp, hsddp_options opt, int cold_start) {
     __shared__ Smem sm;
+    solve_persistent<0>(sm, bp, opt, cold_start);
+}
+// latency build: the same code compiled for two resident blocks (255 registers / thread: nothing spills, nothing is
+// rematerialised); used when the batch does not fill the GPU anyway (single-solve latency, MPC tick of one robot)
+__global__ void __launch_bounds__(kThreads, 2) k_solve_lat(BatchPtrs bp, hsddp_options opt, int cold_start) {
+    __shared__ Smem sm;
+    solve_persistent<1>(sm, bp, opt, cold_start);
+}
+
+template <int MINB>
+__device__ __forceinline__ void solve_persistent(Smem& sm, const BatchPtrs& bp, const hsddp_options& opt, int cold_start) {
     if (threadIdx.x == 0) assign_rotation(bp.sm_slots, sm.rot);
     for (;;) {
         __syncthreads();
@@ -660,9 +675,13 @@ int hsddp_batch_solve_async(hsddp_batch* b, const hsddp_options* opt) {
     const bool phased = b->solve_mode == 2;  // auto = persistent: measured faster or equal at every batch size so far
     if (phased) return solve_phased(b, o);
     CK(cudaMemsetAsync(b->bp.work_counter, 0, sizeof(int), b->stream));
-    const int grid = std::min(b->bp.n_problems, b->n_sm * b->blocks_per_sm);
     CK(cudaEventRecord(b->ev0, b->stream));
-    k_solve<<<grid, kThreads, 0, b->stream>>>(b->bp, o, 0);
+    if (b->bp.n_problems <= 2 * b->n_sm) {
+        k_solve_lat<<<b->bp.n_problems, kThreads, 0, b->stream>>>(b->bp, o, 0);
+    } else {
+        const int grid = std::min(b->bp.n_problems, b->n_sm * b->blocks_per_sm);
+        k_solve<<<grid, kThreads, 0, b->stream>>>(b->bp, o, 0);
+    }
     CK(cudaGetLastError());
     b->n_solve_launches++;
     CK(cudaEventRecord(b->ev1, b->stream));

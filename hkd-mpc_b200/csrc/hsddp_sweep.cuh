@@ -79,6 +79,10 @@ __device__ __forceinline__ void prefetch_stage(Smem& sm, int buf, int s, int n1)
 // Returns false if a negative pivot was met (pivot 1 = a, pivot 2 = det / a), which for the caller
 // that runs Quu_r - 1e-9 I is the reference's LDLT(...).isPositive() verdict (Sylvester's law of
 // inertia).  After the call v = Quu_r^-1 * (original column).
+#ifndef HSDDP_GJ_UNROLL
+#define HSDDP_GJ_UNROLL 1
+#endif
+constexpr int kGjUnroll = HSDDP_GJ_UNROLL;
 #ifdef HSDDP_PROFILE_GJ
 #define GJ_MARK(slot) do { if (threadIdx.x == 0) { const long long t1_ = clock64(); gjacc[slot] += (unsigned long long)(t1_ - gjt0); gjt0 = t1_; } } while (0)
 #else
@@ -90,7 +94,7 @@ __device__ __forceinline__ bool gauss_jordan12(double (&v)[12], double* sbuf, un
 #ifdef HSDDP_PROFILE_GJ
     long long gjt0 = clock64();
 #endif
-#pragma unroll 1
+#pragma unroll kGjUnroll
     for (int step = 0; step < 6; ++step) {
         if ((lane >> 1) == step) {  // the two pivot columns (lanes 2*step, 2*step+1 < 12)
             double2* dst = reinterpret_cast<double2*>(sbuf + 12 * (lane & 1));
