@@ -249,6 +249,28 @@ def main():
     e2e_ms = max(B.event_elapsed_ms(4, 5), e2e_wall_ms)
     e2e_ms = sh.max_over_ranks(e2e_ms, dev)
 
+    # ---- single-solve latency (BASELINE.json: "single-solve p50 latency"): batch = 1, config 1, 101 cold solves ----
+    latency = None
+    if rank == 0:
+        w1 = wl.config1(pkg, args.plan)
+        B1 = pkg.MultiPhaseDDPBatch(local_rank)
+        B1.set_problems(w1.schedules, w1.schedule_id)
+        B1.set_initial_condition(w1.x0)
+        dev_ms, wall_ms = [], []
+        for rep in range(104):
+            t1 = time.perf_counter()
+            B1.reset()
+            B1.solve(opt)
+            i1 = B1.info()
+            t2 = time.perf_counter()
+            if rep >= 3:
+                dev_ms.append(B1.last_solve_ms()); wall_ms.append((t2 - t1) * 1e3)
+        latency = {"p50_ms": float(np.median(dev_ms)), "p50_wall_ms": float(np.median(wall_ms)), "p99_ms": float(np.percentile(dev_ms, 99)),
+                   "reps": len(dev_ms), "iterations": int(i1["n_iter"][0]),
+                   "what": "one cold Mini Cheetah trot solve (config 1), batch 1: p50_ms = solve kernel on the device (CUDA events), "
+                           "p50_wall_ms = host wall clock of reset + solve + info read-back"}
+        del B1
+
     # ---- statistics (the only inter-GPU traffic: a few numbers per rank) ----
     per_launch_sweep_stages = (cnt1["sweep_stages"] - cnt["sweep_stages"])
     g = sh.gather_stats(sh.local_stats(info, per_launch_sweep_stages), dev)
@@ -273,6 +295,14 @@ def main():
         except Exception:
             hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
         hbm_ach = bytes_launch / (kernel_ms * 1e-3) / 1e9
+        # DRAM bytes of one k_solve launch from the committed ncu --set full capture of this workload (profiles/)
+        traffic, traffic_src = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "k_solve_traffic.json")))
+            if tr.get("config") == args.config and int(tr.get("problems", 0)) == w.n and abs(tr.get("plan", 0.6) - args.plan) < 1e-9:
+                traffic, traffic_src = float(tr["dram_bytes_read"]) + float(tr["dram_bytes_write"]), tr.get("source")
+        except Exception:
+            pass
         line = {
             "metric": "batched HS-DDP solves/sec", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -287,12 +317,14 @@ def main():
                     "ms_per_step": e2e_ms / args.steps,
                     "what": "set_initial_condition(x0 from pinned host) + reset + solve + copy-out to pinned host of info and the first 8 states, controls and (compact 24x12) gains of every problem"},
             "roofline": {"bound": "tensor", "pipe": "FP64 (DFMA / DMMA m8n8k4)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": "k_solve", "kernel_ms": kernel_ms,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "traffic_source": traffic_src, "kernel": "k_solve", "kernel_ms": kernel_ms,
                          "flop_per_launch": flop_launch,
                          "peak_source": "measured in this run by hsddp_fp64_peak_tflops: DFMA %.1f, DMMA %.1f TFLOP/s "
                                         "(MEASURED_PEAKS.json has no FP64 entry)" % (peak_dfma, peak_dmma),
                          "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                                  "bytes_per_launch": bytes_launch, "peak_source": hbm_src}},
+            "latency": latency,
             "convergence": {k: float(v) for k, v in tot.items()},
             "clocks": clocks,
         }

@@ -175,6 +175,32 @@ def test_config3_mixed_gaits_ragged_schedules(pkg, orc, workloads):
     print("config3 ill-posed-for-parity:", ill)
 
 
+def test_solve_modes_agree(pkg, orc, workloads):
+    """The kernel-per-phase driver (solve mode 2), the persistent kernel (mode 1, throughput build: the batch is
+    larger than 2 x 148) and the latency build of the persistent kernel (batch of 3) run the same device
+    functions.  They are separate compilations (the compiler contracts and schedules FMAs differently), so their
+    results agree to rounding, not bitwise: each mode meets the oracle bar, and the modes agree with each other
+    to 1e-9 on every problem whose iteration count coincides (all but the rounding-chaotic ones)."""
+    w = workloads.config3(pkg, 330)
+    out = {}
+    for mode in (1, 2):
+        B = _batch_for(pkg, w)
+        B.set_solve_mode(mode)
+        B.solve()
+        out[mode] = (B.info().copy(), B.get("Xbar").copy(), B.get("Ubar").copy(), B.get("K").copy())
+        _compare_solution(pkg, orc, w, B, range(0, 12), {}, max_ill_posed=2)
+    i1, i2 = out[1][0], out[2][0]
+    same = (i1["n_iter"] == i2["n_iter"]) & (i1["status"] == i2["status"])
+    assert same.mean() > 0.95, same.mean()
+    for a, b in zip(out[1][1:], out[2][1:]):
+        for i in np.nonzero(same)[0]:
+            assert rel_err(a[i], b[i]) < RTOL, i
+    w3 = workloads.config3(pkg, 3)
+    B3 = _batch_for(pkg, w3)
+    B3.solve()
+    _compare_solution(pkg, orc, w3, B3, range(3), {}, max_ill_posed=1)
+
+
 def test_config4_long_flight_phase(pkg, orc, workloads):
     w = workloads.config4(pkg, 12)
     assert any(max(s.horizon) >= 30 for s in w.schedules)
