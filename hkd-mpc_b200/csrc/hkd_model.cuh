@@ -35,14 +35,39 @@ constexpr double kJxx = 3.6415571589736352e+01, kJyy = 4.1234427331951844e+00, k
 constexpr double kHipX = 1.9000000000000000e-01, kHipY = 4.9000000000000002e-02;
 constexpr double kAbad = 6.2000000000000000e-02, kThigh = -2.0899999999999999e-01, kShank = -1.9500000000000001e-01;
 
-// Linearisation record of one stage, laid out as the Riccati kernel's tensor-core tiles read it:
-//   R[12][44] row-major (row stride 44 = 12 mod 16 doubles: conflict-free tensor-core fragment loads):  columns 0..23  = rows 0..11 of A - I   (rows 3..5 hold dt at column 9..11, rows 9..11 zero)
-//                         columns 24..35 = rows 0..11 of B_r, the 24x12 matrix of the COUPLED controls
-//                                          (reduced column c = 3*leg+j; only stance-leg columns have entries
-//                                          in these rows, all of them in rows 6..11); columns 36..43 padding
-// Only the structural non-zeros are written; the rest of the record must be zero-initialised once.
+// Linearisation record of one stage.  In HBM it is COMPACT: only the 111 structurally non-zero, state-dependent
+// entries of rows 0..11 of [A - I | B_r] are stored (B_r = the 24x12 matrix of the COUPLED controls, reduced column
+// c = 3*leg+j; only stance-leg columns have entries in these rows).  Order of the compact record Rc[112]:
+//     [ 0.. 3]  row 0 (yaw rate)    columns {1,2,7,8}
+//     [ 4.. 6]  row 1 (pitch rate)  columns {2,7,8}
+//     [ 7..11]  row 2 (roll rate)   columns {1,2,6,7,8}
+//     [12+29a ..] rows 6+a (angular acceleration), a = 0..2:  +0..8 columns 0..8 ; +9+2l+k column 12+3l+k (foot x,y of leg l) ;
+//                 +17+c column 24+c of the dense tile = B_r column c
+//     [99+4j+l]  row 9+j, B_r column 3l+j  ((c_l / m) dt)
+//     [111]      padding
+// The rows 3..5 of A - I hold the constant dt at columns 9..11 and are not stored.
+// In shared memory the Riccati kernel works on the dense tile R[12][44] (row stride 44 = 12 mod 16 doubles:
+// conflict-free tensor-core fragment loads; columns 0..23 = A - I, 24..35 = B_r, 36..43 zero padding); the compact
+// entries are scattered into it by cp.async (cr_dense_pos), everything else in the tile stays zero.
 constexpr int kRld = 44;
 constexpr int kRSize = 12 * kRld;
+constexpr int kCrNnz = 111;
+constexpr int kCrSize = 112;
+HKD_HD int cr_w(int a, int q) { return 12 + 29 * a + q; }            // row 6+a: q = column (0..8), 9+2l+k (foot), 17+c (B_r)
+HKD_HD int cr_v(int j, int l) { return 99 + 4 * j + l; }             // row 9+j, B_r column 3l+j
+// position of compact entry i inside the dense tile R[12][kRld]
+HKD_HD int cr_dense_pos(int i) {
+    if (i < 4) return (i < 2) ? 1 + i : 5 + i;                        // row 0: 1,2,7,8
+    if (i < 7) return kRld + ((i == 4) ? 2 : 3 + i - 1);              // row 1: 2,7,8   (i=5 -> 7, i=6 -> 8)
+    if (i < 12) return 2 * kRld + ((i < 9) ? i - 6 : i - 3);          // row 2: 1,2,6,7,8  (i=7->1, 8->2, 9->6, 10->7, 11->8)
+    if (i < 99) {
+        const int a = (i - 12) / 29, q = (i - 12) % 29;
+        const int col = (q < 9) ? q : (q < 17) ? 12 + 3 * ((q - 9) / 2) + (q - 9) % 2 : 24 + (q - 17);
+        return (6 + a) * kRld + col;
+    }
+    const int j = (i - 99) / 4, l = (i - 99) % 4;
+    return (9 + j) * kRld + 24 + 3 * l + j;
+}
 
 struct Trig {
     double sy, cy, sp, cp, sr, cr;
@@ -129,8 +154,8 @@ HKD_HD void dynamics(const double* x, const double* u, double dt, unsigned cmask
     }
 }
 
-// Analytic linearisation (HKD::Model::dynamics_partial) written straight into a stage record.
-HKD_HD void dynamics_partial_record(const double* x, const double* u, double dt, unsigned cmask, double* R40) {
+// Analytic linearisation (HKD::Model::dynamics_partial) written straight into a COMPACT stage record Rc[kCrSize] (layout above).
+HKD_HD void dynamics_partial_record(const double* x, const double* u, double dt, unsigned cmask, double* Rc) {
     const Trig t = trig_of(x[0], x[1], x[2]);
     const double wx = x[6], wy = x[7], wz = x[8];
     const double s1 = t.sr * wy + t.cr * wz;
@@ -138,20 +163,19 @@ HKD_HD void dynamics_partial_record(const double* x, const double* u, double dt,
     const double icp = 1.0 / t.cp;
     const double tp = t.sp * icp;
     // Euler-rate rows 0..2
-    R40[0 * kRld + 1] = dt * (s1 * t.sp * icp * icp);
-    R40[0 * kRld + 2] = dt * (s2 * icp);
-    R40[0 * kRld + 7] = dt * (t.sr * icp);
-    R40[0 * kRld + 8] = dt * (t.cr * icp);
-    R40[1 * kRld + 2] = dt * (-s1);
-    R40[1 * kRld + 7] = dt * t.cr;
-    R40[1 * kRld + 8] = dt * (-t.sr);
-    R40[2 * kRld + 1] = dt * (s1 * icp * icp);
-    R40[2 * kRld + 2] = dt * (tp * s2);
-    R40[2 * kRld + 6] = dt;
-    R40[2 * kRld + 7] = dt * (tp * t.sr);
-    R40[2 * kRld + 8] = dt * (tp * t.cr);
-    // position rows 3..5
-    R40[3 * kRld + 9] = dt; R40[4 * kRld + 10] = dt; R40[5 * kRld + 11] = dt;
+    Rc[0] = dt * (s1 * t.sp * icp * icp);
+    Rc[1] = dt * (s2 * icp);
+    Rc[2] = dt * (t.sr * icp);
+    Rc[3] = dt * (t.cr * icp);
+    Rc[4] = dt * (-s1);
+    Rc[5] = dt * t.cr;
+    Rc[6] = dt * (-t.sr);
+    Rc[7] = dt * (s1 * icp * icp);
+    Rc[8] = dt * (tp * s2);
+    Rc[9] = dt;
+    Rc[10] = dt * (tp * t.sr);
+    Rc[11] = dt * (tp * t.cr);
+    // position rows 3..5 hold the constant dt at columns 9..11: not stored
     // angular-acceleration rows 6..8: M = dt * Jinv * R^T
     double R[9], F[3], tw[3];
     rotation(t, R);
@@ -170,7 +194,7 @@ HKD_HD void dynamics_partial_record(const double* x, const double* u, double dt,
                           -t.cp,        -t.sp * t.sr,       -t.sp * t.cr};
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        double* row = R40 + (6 + a) * kRld;
+        double* row = Rc + cr_w(a, 0);
         row[0] = jd[a] * (-R[3 + a] * tw[0] + R[a] * tw[1]);
         row[1] = jd[a] * (dP[a] * tw[0] + dP[3 + a] * tw[1] + dP[6 + a] * tw[2]);
         // position columns: tau_world depends on p through r_l = foot - p  ->  column j = M (F x e_j)
@@ -178,19 +202,19 @@ HKD_HD void dynamics_partial_record(const double* x, const double* u, double dt,
         row[4] = -M[3 * a + 0] * F[2] + M[3 * a + 2] * F[0];
         row[5] = M[3 * a + 0] * F[1] - M[3 * a + 1] * F[0];
     }
-    R40[6 * kRld + 2] = 0.0;
-    R40[7 * kRld + 2] = jd[1] * rt2;
-    R40[8 * kRld + 2] = jd[2] * (-rt1);
+    Rc[cr_w(0, 2)] = 0.0;
+    Rc[cr_w(1, 2)] = jd[1] * rt2;
+    Rc[cr_w(2, 2)] = jd[2] * (-rt1);
     // gyroscopic block
-    R40[6 * kRld + 6] = 0.0;
-    R40[6 * kRld + 7] = jd[0] * (kIyy - kIzz) * wz;
-    R40[6 * kRld + 8] = jd[0] * (kIyy - kIzz) * wy;
-    R40[7 * kRld + 6] = jd[1] * (kIzz - kIxx) * wz;
-    R40[7 * kRld + 7] = 0.0;
-    R40[7 * kRld + 8] = jd[1] * (kIzz - kIxx) * wx;
-    R40[8 * kRld + 6] = jd[2] * (kIxx - kIyy) * wy;
-    R40[8 * kRld + 7] = jd[2] * (kIxx - kIyy) * wx;
-    R40[8 * kRld + 8] = 0.0;
+    Rc[cr_w(0, 6)] = 0.0;
+    Rc[cr_w(0, 7)] = jd[0] * (kIyy - kIzz) * wz;
+    Rc[cr_w(0, 8)] = jd[0] * (kIyy - kIzz) * wy;
+    Rc[cr_w(1, 6)] = jd[1] * (kIzz - kIxx) * wz;
+    Rc[cr_w(1, 7)] = 0.0;
+    Rc[cr_w(1, 8)] = jd[1] * (kIzz - kIxx) * wx;
+    Rc[cr_w(2, 6)] = jd[2] * (kIxx - kIyy) * wy;
+    Rc[cr_w(2, 7)] = jd[2] * (kIxx - kIyy) * wx;
+    Rc[cr_w(2, 8)] = 0.0;
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
         const bool stance = (cmask >> l) & 1u;
@@ -200,32 +224,31 @@ HKD_HD void dynamics_partial_record(const double* x, const double* u, double dt,
         for (int a = 0; a < 3; ++a) {
             const double m0 = M[3 * a], m1 = M[3 * a + 1], m2 = M[3 * a + 2];
             // foot x,y columns: M (e_j x f) ; force columns: M (r x e_j)   (zero for a swing leg)
-            R40[(6 + a) * kRld + 12 + 3 * l] = stance ? (-m1 * fz + m2 * fy) : 0.0;
-            R40[(6 + a) * kRld + 13 + 3 * l] = stance ? (m0 * fz - m2 * fx) : 0.0;
-            R40[(6 + a) * kRld + 24 + 3 * l + 0] = stance ? (m1 * rz - m2 * ry) : 0.0;
-            R40[(6 + a) * kRld + 24 + 3 * l + 1] = stance ? (-m0 * rz + m2 * rx) : 0.0;
-            R40[(6 + a) * kRld + 24 + 3 * l + 2] = stance ? (m0 * ry - m1 * rx) : 0.0;
+            Rc[cr_w(a, 9 + 2 * l)] = stance ? (-m1 * fz + m2 * fy) : 0.0;
+            Rc[cr_w(a, 10 + 2 * l)] = stance ? (m0 * fz - m2 * fx) : 0.0;
+            Rc[cr_w(a, 17 + 3 * l + 0)] = stance ? (m1 * rz - m2 * ry) : 0.0;
+            Rc[cr_w(a, 17 + 3 * l + 1)] = stance ? (-m0 * rz + m2 * rx) : 0.0;
+            Rc[cr_w(a, 17 + 3 * l + 2)] = stance ? (m0 * ry - m1 * rx) : 0.0;
         }
         // linear acceleration rows 9..11: (c/m) dt on the leg's own force component
 #pragma unroll
-        for (int j = 0; j < 3; ++j) R40[(9 + j) * kRld + 24 + 3 * l + j] = stance ? (1.0 / kMass) * dt : 0.0;
+        for (int j = 0; j < 3; ++j) Rc[cr_v(j, l)] = stance ? (1.0 / kMass) * dt : 0.0;
     }
 }
 
-// expand a stage record to the dense column-major A, B of the reference
-HKD_HD void expand_AB(const double* R40, double dt, unsigned cmask, double* A, double* B) {
+// expand a compact stage record to the dense column-major A, B of the reference
+HKD_HD void expand_AB(const double* Rc, double dt, unsigned cmask, double* A, double* B) {
     for (int i = 0; i < 576; ++i) { A[i] = 0.0; B[i] = 0.0; }
     for (int i = 0; i < 24; ++i) A[i * 25] = 1.0;
-    for (int r = 0; r < 12; ++r)
-        for (int c = 0; c < 24; ++c) A[r + 24 * c] += R40[r * kRld + c];
-    for (int l = 0; l < 4; ++l) {
-        const bool stance = (cmask >> l) & 1u;
-        for (int j = 0; j < 3; ++j) {
-            const int c = 3 * l + j;
-            if (stance) { for (int k = 0; k < 12; ++k) B[k + 24 * c] = R40[k * kRld + 24 + c]; }
-            else B[(12 + c) + 24 * (12 + c)] = dt;
-        }
+    for (int j = 0; j < 3; ++j) A[(3 + j) + 24 * (9 + j)] += dt;
+    for (int i = 0; i < kCrNnz; ++i) {
+        const int pos = cr_dense_pos(i), r = pos / kRld, c = pos % kRld;
+        if (c < 24) A[r + 24 * c] += Rc[i];
+        else if ((cmask >> ((c - 24) / 3)) & 1u) B[r + 24 * (c - 24)] = Rc[i];
     }
+    for (int l = 0; l < 4; ++l)
+        if (!((cmask >> l) & 1u))
+            for (int j = 0; j < 3; ++j) B[(12 + 3 * l + j) + 24 * (12 + 3 * l + j)] = dt;
 }
 
 // leg kinematics in the body frame and its joint Jacobian dq[3*i+j] = d pb_i / d q_j

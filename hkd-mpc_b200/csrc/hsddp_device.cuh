@@ -44,12 +44,19 @@ constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
 constexpr int MAXPH = HSDDP_MAX_PHASES;
 
-// per-stage LQ record (doubles), laid out exactly as the sweep's tensor-core tiles read it so that a
-// plain cp.async copy stages it into shared memory (see hkd_model.cuh: dynamics_partial_record)
+// per-stage LQ record.  In HBM (BatchPtrs::lq) it is compact, CR_STRIDE doubles: the 111 structural entries of
+// [A - I | B_r] (hkd_model.cuh), then lx, lu and the ReB Hessian blocks.  In shared memory (Smem::rec) the sweep
+// works on the dense tile R[12][44] followed by the same three vectors (LQ_* offsets); cp.async scatters the compact
+// entries into the dense tile (8-byte copies) and copies the vectors (16-byte copies).
+constexpr int CR_R = 0;                           // [112] compact [A - I | B_r] entries (hkd::kCrSize)
+constexpr int CR_LX = CR_R + hkd::kCrSize;        // [24]
+constexpr int CR_LU = CR_LX + 24;                 // [24]
+constexpr int CR_LUU = CR_LU + 24;                // [4][3][3] ReB Hessian blocks per leg (dt folded in)
+constexpr int CR_STRIDE = 200;                    // 196 used; 1600 bytes, 16-byte aligned
 constexpr int LQ_R = 0;                           // [12][44] rows 0..11 of [A - I | B_r] (hkd::kRld = 44)
 constexpr int LQ_LX = LQ_R + hkd::kRSize;         // [24]
 constexpr int LQ_LU = LQ_LX + 24;                 // [24]
-constexpr int LQ_LUU = LQ_LU + 24;                // [4][3][3] ReB Hessian blocks per leg (dt folded in)
+constexpr int LQ_LUU = LQ_LU + 24;                // [4][3][3]
 constexpr int LQ_STRIDE = 616;                    // 612 used
 constexpr int ZS = 20;                            // row stride of Z = H B_r (16 columns used): 20 = 4 mod 16
 constexpr int kSweepDoubles = 2 * 24 * 28 + 24 * 20 + 16 * 28 + 12 * 28 + 2 * 616;  // H, Y, Z, Qux, Quu, rec: contiguous, free outside the sweep
@@ -102,7 +109,7 @@ struct BatchPtrs {
     double *Xbar, *X, *Xsim_t, *Defect, *dX;  // [P][max_nodes][24]
     double *Ubar, *U, *U_t, *dU;              // [P][max_stages][24]
     double* K;                                // [P][max_stages][24][12] compact gains, transposed: KT[j][c] = K_r[c][j] (c <-> coupled control of leg c/3)
-    double* lq;                               // [P][max_stages][LQ_STRIDE]
+    double* lq;                               // [P][max_stages][CR_STRIDE] compact stage records
     double* tq;                               // [P][MAXPH][TQ_STRIDE]
     double* gcon;                             // [P][max_stages][20]
     double* reb;                              // [P][max_stages][20][2]  (eps, delta)
@@ -244,7 +251,7 @@ __device__ inline void bind_problem(Smem& sm, const BatchPtrs& bp, int pid) {
         sm.Defect = bp.Defect + pid * sn; sm.dX = bp.dX + pid * sn;
         sm.Ubar = bp.Ubar + pid * ss; sm.U = bp.U + pid * ss; sm.U_t = bp.U_t + pid * ss; sm.dU = bp.dU + pid * ss;
         sm.K = bp.K + (size_t)pid * bp.max_stages * 288;
-        sm.lqg = bp.lq + (size_t)pid * bp.max_stages * LQ_STRIDE;
+        sm.lqg = bp.lq + (size_t)pid * bp.max_stages * CR_STRIDE;
         sm.tq = bp.tq + (size_t)pid * MAXPH * TQ_STRIDE;
         sm.gcon = bp.gcon + (size_t)pid * bp.max_stages * 20;
         sm.reb = bp.reb + (size_t)pid * bp.max_stages * 40;
@@ -549,7 +556,7 @@ __device__ inline void lq_approximation_block(Smem& sm) {
         int ph, k;
         phase_of_stage(sc, s, ph, k);
         const int n = sc.node_off[ph] + k;
-        hkd::dynamics_partial_record(sm.X + 24 * n, sm.U + 24 * s, dt, sc.cmask[ph], sm.lqg + (size_t)s * LQ_STRIDE + LQ_R);
+        hkd::dynamics_partial_record(sm.X + 24 * n, sm.U + 24 * s, dt, sc.cmask[ph], sm.lqg + (size_t)s * CR_STRIDE + CR_R);
     }
     // (2) cost gradients, flat over (stage, component): lx (24) and the lu of the joint-velocity commands (12);
     //     coalesced reads, 192-byte runs of writes.  Foot-placement regulariser: the position rows accumulate over
@@ -560,10 +567,10 @@ __device__ inline void lq_approximation_block(Smem& sm) {
         phase_of_stage(sc, s, ph, k);
         const int n = sc.node_off[ph] + k;
         const unsigned cm = sc.cmask[ph];
-        double* rec = sm.lqg + (size_t)s * LQ_STRIDE;
+        double* rec = sm.lqg + (size_t)s * CR_STRIDE;
         if (j >= 24) {
             const int i = j - 12;
-            rec[LQ_LU + i] = (dt * weight_R(i)) * (sm.U[24 * s + i] - sm.ur[24 * n + i]);
+            rec[CR_LU + i] = (dt * weight_R(i)) * (sm.U[24 * s + i] - sm.ur[24 * n + i]);
             continue;
         }
         const double* x = sm.X + 24 * n;
@@ -583,7 +590,7 @@ __device__ inline void lq_approximation_block(Smem& sm) {
             const double w = dt * c * weight_foot(l, jj, cm);
             v += w * d;
         }
-        rec[LQ_LX + j] = v;
+        rec[CR_LX + j] = v;
     }
     // (3) GRF controls and the ReB folding, flat over (stage, leg)  (compute_ReB_partials, ConstraintsBase.h:224-263;
     //     only gu is non-zero)
@@ -595,7 +602,7 @@ __device__ inline void lq_approximation_block(Smem& sm) {
             phase_of_stage(sc, s, ph, k);
             const int n = sc.node_off[ph] + k;
             const unsigned cm = sc.cmask[ph];
-            double* rec = sm.lqg + (size_t)s * LQ_STRIDE;
+            double* rec = sm.lqg + (size_t)s * CR_STRIDE;
             double hess[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, grad[3] = {0, 0, 0};
             if (sm.opt.ReB_active && ((cm >> l) & 1u)) {
 #pragma unroll
@@ -618,10 +625,10 @@ __device__ inline void lq_approximation_block(Smem& sm) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 const int i = 3 * l + a;
-                rec[LQ_LU + i] = (dt * weight_R(i)) * (sm.U[24 * s + i] - sm.ur[24 * n + i]) + dt * grad[a];
+                rec[CR_LU + i] = (dt * weight_R(i)) * (sm.U[24 * s + i] - sm.ur[24 * n + i]) + dt * grad[a];
             }
 #pragma unroll
-            for (int a = 0; a < 9; ++a) rec[LQ_LUU + 9 * l + a] = dt * hess[a];
+            for (int a = 0; a < 9; ++a) rec[CR_LUU + 9 * l + a] = dt * hess[a];
         }
     }
     if (tid < sc.n_phases) {

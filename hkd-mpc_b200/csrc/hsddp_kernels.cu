@@ -577,7 +577,7 @@ int hsddp_batch_set_problems(hsddp_batch* b, int n_schedules, const hsddp_schedu
     if ((rc = dalloc(b, &bp.U_t, P * SS))) return rc;
     if ((rc = dalloc(b, &bp.dU, P * SS))) return rc;
     if ((rc = dalloc(b, &bp.K, P * max_stages * 288))) return rc;
-    if ((rc = dalloc(b, &bp.lq, P * max_stages * LQ_STRIDE))) return rc;
+    if ((rc = dalloc(b, &bp.lq, P * max_stages * CR_STRIDE))) return rc;
     if ((rc = dalloc(b, &bp.tq, P * MAXPH * TQ_STRIDE))) return rc;
     if ((rc = dalloc(b, &bp.gcon, P * max_stages * 20))) return rc;
     if ((rc = dalloc(b, &bp.reb, P * max_stages * 40))) return rc;
@@ -604,7 +604,7 @@ int hsddp_batch_set_problems(hsddp_batch* b, int n_schedules, const hsddp_schedu
     CK(cudaMemset(bp.state, 0, P * sizeof(SolverState)));
     CK(cudaMemset(bp.counters, 0, 32 * sizeof(unsigned long long)));
     CK(cudaMemset(bp.tq, 0, P * MAXPH * TQ_STRIDE * sizeof(double)));
-    CK(cudaMemset(bp.lq, 0, P * max_stages * LQ_STRIDE * sizeof(double)));
+    CK(cudaMemset(bp.lq, 0, P * max_stages * CR_STRIDE * sizeof(double)));
     CK(cudaMemset(bp.g0h0, 0, P * 600 * sizeof(double)));
     b->has_problems = true;
     return hsddp_batch_reset(b);
@@ -827,7 +827,7 @@ int hsddp_batch_get_array(hsddp_batch* b, int which, double* out) {
     if (which == HSDDP_ARR_A || which == HSDDP_ARR_B || which == HSDDP_ARR_LX || which == HSDDP_ARR_LU ||
         which == HSDDP_ARR_LUU || which == HSDDP_ARR_LXX) {
         // dense views reconstructed on the host from the compact LQ records
-        std::vector<double> lq(P * bp.max_stages * LQ_STRIDE);
+        std::vector<double> lq(P * bp.max_stages * CR_STRIDE);
         CK(cudaMemcpy(lq.data(), bp.lq, lq.size() * sizeof(double), cudaMemcpyDeviceToHost));
         const bool vec = (which == HSDDP_ARR_LX || which == HSDDP_ARR_LU);
         const size_t per = (size_t)bp.max_stages * (vec ? 24 : 576);
@@ -837,20 +837,20 @@ int hsddp_batch_get_array(hsddp_batch* b, int which, double* out) {
             for (int ph = 0; ph < sc.n_phases; ++ph)
                 for (int k = 0; k < sc.horizon[ph]; ++k) {
                     const int s = sc.stage_off[ph] + k;
-                    const double* rec = &lq[(p * bp.max_stages + s) * LQ_STRIDE];
+                    const double* rec = &lq[(p * bp.max_stages + s) * CR_STRIDE];
                     double* o = out + p * per + (size_t)s * (vec ? 24 : 576);
                     const unsigned cm = sc.cmask[ph];
-                    if (which == HSDDP_ARR_LX) std::memcpy(o, rec + LQ_LX, 24 * sizeof(double));
-                    else if (which == HSDDP_ARR_LU) std::memcpy(o, rec + LQ_LU, 24 * sizeof(double));
+                    if (which == HSDDP_ARR_LX) std::memcpy(o, rec + CR_LX, 24 * sizeof(double));
+                    else if (which == HSDDP_ARR_LU) std::memcpy(o, rec + CR_LU, 24 * sizeof(double));
                     else if (which == HSDDP_ARR_A || which == HSDDP_ARR_B) {
                         double A[576], B[576];
-                        hkd::expand_AB(rec + LQ_R, sc.dt, cm, A, B);
+                        hkd::expand_AB(rec + CR_R, sc.dt, cm, A, B);
                         std::memcpy(o, which == HSDDP_ARR_A ? A : B, 576 * sizeof(double));
                     } else if (which == HSDDP_ARR_LUU) {
                         for (int i = 0; i < 24; ++i) o[i * 25] = sc.dt * (i < 12 ? .2 : .1);
                         for (int l = 0; l < 4; ++l)
                             for (int a = 0; a < 3; ++a)
-                                for (int c = 0; c < 3; ++c) o[(3 * l + a) + 24 * (3 * l + c)] += rec[LQ_LUU + 9 * l + 3 * a + c];
+                                for (int c = 0; c < 3; ++c) o[(3 * l + a) + 24 * (3 * l + c)] += rec[CR_LUU + 9 * l + 3 * a + c];
                     } else {  // LXX: dt*Q + foot regulariser block (HKDCost.cpp:36-37)
                         const double q[12] = {1, 4, 5, 1, 1, 30, .2, .2, .2, 4, 1, .5};
                         for (int i = 0; i < 24; ++i) {

@@ -62,13 +62,31 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// stage record (LQ_STRIDE doubles) and the defect of the stage's successor node -> buffer `buf`
-__device__ __forceinline__ void prefetch_stage(Smem& sm, int buf, int s, int n1) {
-    const char* src = reinterpret_cast<const char*>(sm.lqg + (size_t)s * LQ_STRIDE);
-    char* dst = reinterpret_cast<char*>(sm.rec[buf]);
-    for (int c = threadIdx.x; c < LQ_STRIDE / 2; c += kThreads) cp_async16(dst + 16 * c, src + 16 * c);
-    if (threadIdx.x < 12) cp_async16(reinterpret_cast<char*>(sm.dfc2[buf]) + 16 * threadIdx.x,
-                                     reinterpret_cast<const char*>(sm.Defect + 24 * n1) + 16 * threadIdx.x);
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc));
+}
+
+// compact stage record (CR_STRIDE doubles in HBM) -> dense record buffer `buf`, and the defect of the stage's
+// successor node.  Thread i < 111 scatters compact entry i to its place in the dense tile (`rpos` = that thread's
+// hkd::cr_dense_pos(i), computed once per phase); the three vectors follow as 16-byte copies.  The rest of the
+// tile is zero (zero_stage_buffers) and is never written.
+__device__ __forceinline__ void prefetch_stage(Smem& sm, int buf, int s, int n1, int rpos) {
+    const double* src = sm.lqg + (size_t)s * CR_STRIDE;
+    double* dst = sm.rec[buf];
+    if (threadIdx.x < hkd::kCrNnz) cp_async8(dst + LQ_R + rpos, src + CR_R + threadIdx.x);
+    if (threadIdx.x < 42) cp_async16(dst + LQ_LX + 2 * threadIdx.x, src + CR_LX + 2 * threadIdx.x);
+    else if (threadIdx.x >= 64 && threadIdx.x < 76)
+        cp_async16(reinterpret_cast<char*>(sm.dfc2[buf]) + 16 * (threadIdx.x - 64), reinterpret_cast<const char*>(sm.Defect + 24 * n1) + 16 * (threadIdx.x - 64));
+}
+// dense tiles of both record buffers: zero, plus the constant dt of rows 3..5 of A - I.  Called once per sweep
+// (the storage is shared with the rollouts).
+__device__ inline void zero_stage_buffers(Smem& sm) {
+    for (int e = threadIdx.x; e < 2 * hkd::kRSize; e += kThreads) {
+        const int b = e / hkd::kRSize, i = e % hkd::kRSize, r = i / hkd::kRld, c = i % hkd::kRld;
+        sm.rec[b][LQ_R + i] = (r >= 3 && r < 6 && c == 6 + r) ? sm.sc.dt : 0.0;
+    }
+    __syncthreads();
 }
 
 // Block Gauss-Jordan with 2x2 pivot blocks on 12 rows, one tableau column per lane (v[0..11]).
@@ -207,7 +225,8 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
     const double* trec = sm.tq + ph * TQ_STRIDE;
     PROF_DECL
     build_phase_tables(sm, cm, dt);
-    prefetch_stage(sm, 0, sc.stage_off[ph] + Nph - 1, sc.node_off[ph] + Nph);
+    const int rpos = hkd::cr_dense_pos(min((int)threadIdx.x, hkd::kCrNnz - 1));
+    prefetch_stage(sm, 0, sc.stage_off[ph] + Nph - 1, sc.node_off[ph] + Nph, rpos);
     // per-lane base pointers of the tile fragments: element (g, 2t..2t+1) of an accumulator tile, (t, g) of an operand tile
     const double* hA = sm.H + t * TS + g;
     double* hC = sm.H + g * TS + 2 * t;
@@ -248,7 +267,7 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
     for (int k = Nph - 1; k >= 0; --k) {
         const int s = sc.stage_off[ph] + k;
         const int buf = (Nph - 1 - k) & 1;
-        if (k > 0) prefetch_stage(sm, buf ^ 1, s - 1, sc.node_off[ph] + k);
+        if (k > 0) prefetch_stage(sm, buf ^ 1, s - 1, sc.node_off[ph] + k, rpos);
         const double* R = sm.rec[buf] + LQ_R;     // [12][40]: cols 0..23 A - I, cols 24..39 B_r
         const double* lxv = sm.rec[buf] + LQ_LX;
         const double* luv = sm.rec[buf] + LQ_LU;
@@ -506,6 +525,7 @@ __device__ inline bool backward_sweep_block(Smem& sm, double reg) {
     PROF_DECL
     double dV1 = 0.0, dV2 = 0.0;
     bool success = true;
+    zero_stage_buffers(sm);
     for (int ph = sc.n_phases - 1; ph >= 0; --ph) {
         if (ph == sc.n_phases - 1) {
             for (int e = tid; e < 24 * TS; e += kThreads) sm.H[e] = 0.0;
@@ -587,9 +607,13 @@ __device__ inline bool backward_sweep_regularized_block(Smem& sm, int& n_sweeps)
 // cost change (dV_1, dV_2) does not feed back into the recursion, so it is accumulated
 // afterwards by all threads in parallel.
 // ---------------------------------------------------------------------------
-constexpr int LR_SLOT = 516;   // doubles per stage slot: KT 288 | A rows {0,1,2,6,7,8} 144 | B_r rows {6,7,8} 36 | defect 24 | dU 24
-constexpr int LR_CHUNK = 3;    // stages per chunk (2 chunks resident: 2*3*516 = 3096 doubles of the sweep's tile storage)
-constexpr int LR_UNITS = 258;  // 16-byte units per slot
+constexpr int LR_SLOT = 436;   // doubles per stage slot: KT 288 | compact record entries 0..99 (rows 0..2, 6..8 of [A - I | B_r]) 100 | defect 24 | dU 24
+#ifndef HSDDP_LR_CHUNK
+#define HSDDP_LR_CHUNK 4
+#endif
+constexpr int LR_CHUNK = HSDDP_LR_CHUNK;    // stages per chunk (2 chunks resident: 2*4*436 = 3488 doubles of the sweep's tile storage)
+constexpr int LR_UNITS = 218;  // 16-byte units per slot
+static_assert(2 * LR_CHUNK * LR_SLOT <= kSweepDoubles, "linear-rollout ring does not fit the sweep's tile storage");
 
 __device__ __forceinline__ int node_of_stage(const DevSchedule& sc, int s) {
     int ph, k;
@@ -602,17 +626,11 @@ __device__ __forceinline__ void lr_prefetch(Smem& sm, double* buf, int s0, int s
     for (int e = threadIdx.x; e < total; e += kThreads) {
         const int si = e / LR_UNITS, u = e % LR_UNITS;
         const int s = s0 + si;
-        const double* R = sm.lqg + (size_t)s * LQ_STRIDE + LQ_R;
         const double* src;
         if (u < 144) src = sm.K + (size_t)s * 288 + 2 * u;
-        else if (u < 216) {  // six dense rows of A - I, 12 units each
-            const int q = (u - 144) / 12, o = (u - 144) % 12;
-            src = R + (q < 3 ? q : q + 3) * hkd::kRld + 2 * o;
-        } else if (u < 234) {  // rows 6..8 of B_r, 6 units each
-            const int q = (u - 216) / 6, o = (u - 216) % 6;
-            src = R + (6 + q) * hkd::kRld + 24 + 2 * o;
-        } else if (u < 246) src = sm.Defect + 24 * (node_of_stage(sm.sc, s) + 1) + 2 * (u - 234);
-        else src = sm.dU + 24 * s + 2 * (u - 246);
+        else if (u < 194) src = sm.lqg + (size_t)s * CR_STRIDE + CR_R + 2 * (u - 144);
+        else if (u < 206) src = sm.Defect + 24 * (node_of_stage(sm.sc, s) + 1) + 2 * (u - 194);
+        else src = sm.dU + 24 * s + 2 * (u - 206);
         cp_async16(buf + si * LR_SLOT + 2 * u, src);
     }
 }
@@ -677,11 +695,9 @@ __device__ inline void linear_rollout_block(Smem& sm, double eps) {
                 }
                 const double* slot = buf + (s - c0) * LR_SLOT;
                 const double* KT = slot;
-                const double* A0 = slot + 288;   // rows 0..2 of A - I
-                const double* A6 = slot + 360;   // rows 6..8
-                const double* B6 = slot + 432;   // rows 6..8 of B_r, [3][12]
-                const double* dfn = slot + 468;
-                const double* dUs = slot + 492;
+                const double* Rc = slot + 288;   // compact entries of rows 0..2 and 6..8 of [A - I | B_r] (hkd_model.cuh)
+                const double* dfn = slot + 388;
+                const double* dUs = slot + 412;
                 // du = eps dU + K dx : lanes 0..11 the coupled controls, lanes 12..23 the decoupled ones
                 if (lane < 12) {
                     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -703,24 +719,29 @@ __device__ inline void linear_rollout_block(Smem& sm, double eps) {
                 __syncwarp();
                 if (lane < 24) {
                     double acc = dx;
-                    if (lane < 3 || (lane >= 6 && lane < 9)) {
-                        const double* Ar = (lane < 3) ? (A0 + 24 * lane) : (A6 + 24 * (lane - 6));
-                        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                    if (lane == 0) {         // yaw rate: columns {1,2,7,8}
+                        acc += (fma(Rc[0], sdx[1], Rc[1] * sdx[2])) + (fma(Rc[2], sdx[7], Rc[3] * sdx[8]));
+                    } else if (lane == 1) {  // pitch rate: columns {2,7,8}
+                        acc += fma(Rc[4], sdx[2], fma(Rc[5], sdx[7], Rc[6] * sdx[8]));
+                    } else if (lane == 2) {  // roll rate: columns {1,2,6,7,8}
+                        acc += (fma(Rc[7], sdx[1], Rc[8] * sdx[2])) + fma(Rc[9], sdx[6], fma(Rc[10], sdx[7], Rc[11] * sdx[8]));
+                    } else if (lane >= 6 && lane < 9) {  // angular acceleration rows: 9 body columns, 8 foot columns, 12 B_r columns
+                        const double* W = Rc + 12 + 29 * (lane - 6);
+                        double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0;
 #pragma unroll
-                        for (int j = 0; j < 24; j += 4) {
-                            a0 = fma(Ar[j], sdx[j], a0);
-                            a1 = fma(Ar[j + 1], sdx[j + 1], a1);
-                            a2 = fma(Ar[j + 2], sdx[j + 2], a2);
-                            a3 = fma(Ar[j + 3], sdx[j + 3], a3);
+                        for (int q = 0; q < 9; q += 3) {
+                            a0 = fma(W[q], sdx[q], a0);
+                            a1 = fma(W[q + 1], sdx[q + 1], a1);
+                            a2 = fma(W[q + 2], sdx[q + 2], a2);
                         }
-                        acc += (a0 + a1) + (a2 + a3);
-                        if (lane >= 6) {
-                            const double* Br = B6 + 12 * (lane - 6);
-                            double b0 = 0.0, b1 = 0.0;
 #pragma unroll
-                            for (int c = 0; c < 12; c += 2) { b0 = fma(Br[c], sdu[c], b0); b1 = fma(Br[c + 1], sdu[c + 1], b1); }
-                            acc += b0 + b1;
+                        for (int l = 0; l < 4; ++l) {
+                            a0 = fma(W[9 + 2 * l], sdx[12 + 3 * l], a0);
+                            a1 = fma(W[10 + 2 * l], sdx[13 + 3 * l], a1);
                         }
+#pragma unroll
+                        for (int c = 0; c < 12; c += 2) { b0 = fma(W[17 + c], sdu[c], b0); b1 = fma(W[18 + c], sdu[c + 1], b1); }
+                        acc += ((a0 + a1) + a2) + (b0 + b1);
                     } else if (lane < 6) {
                         acc = fma(dt, sdx[lane + 6], acc);
                     } else if (lane < 12) {
@@ -751,11 +772,11 @@ __device__ inline void linear_rollout_block(Smem& sm, double eps) {
         phase_of_stage(sc, s, p, k);
         const unsigned cm = sc.cmask[p];
         const int n = sc.node_off[p] + k;
-        const double* rec = sm.lqg + (size_t)s * LQ_STRIDE;
+        const double* rec = sm.lqg + (size_t)s * CR_STRIDE;
         const double* dxv = sm.dX + 24 * n;
         const double* duv = sm.U_t + 24 * s;
         const double dxi = dxv[i], dui = duv[i];
-        dV1 += rec[LQ_LX + i] * dxi + rec[LQ_LU + i] * dui;
+        dV1 += rec[CR_LX + i] * dxi + rec[CR_LU + i] * dui;
         // (lxx dx)_i
         double qdx = (dt * weight_Q(i, cm)) * dxi;
         if (i >= 3 && i < 6) {
@@ -776,7 +797,7 @@ __device__ inline void linear_rollout_block(Smem& sm, double eps) {
         if (i < 12) {
             const int l = i / 3, a = i % 3;
 #pragma unroll
-            for (int b = 0; b < 3; ++b) rdu += rec[LQ_LUU + 9 * l + 3 * a + b] * duv[3 * l + b];
+            for (int b = 0; b < 3; ++b) rdu += rec[CR_LUU + 9 * l + 3 * a + b] * duv[3 * l + b];
         }
         dV2 += dui * rdu;
     }

@@ -223,7 +223,7 @@ void hkd_model_dynamics(const double x[24], const double u[24], double dt, const
 }
 
 void hkd_model_dynamics_partial(const double x[24], const double u[24], double dt, const int32_t contact[4], double A[576], double B[576]) {
-    double R40[hkd::kRSize] = {0};
+    double R40[hkd::kCrSize] = {0};
     const unsigned m = mask_of(contact);
     hkd::dynamics_partial_record(x, u, dt, m, R40);
     hkd::expand_AB(R40, dt, m, A, B);
