@@ -89,6 +89,11 @@ INFO_DTYPE = np.dtype([("status", "i4"), ("n_iter", "i4"), ("n_outer", "i4"), ("
 TRACE_COLS = ["outer", "inner", "cost_before", "feas_before", "reg_after", "n_sweeps", "dV_1", "dV_2", "merit_rho",
               "eps_accepted", "n_trials", "cost_after", "feas_after", "max_tconstr", "max_pconstr", "pad"]
 
+CMD_MAX_STEPS = 10
+CMD_DTYPE = np.dtype([("N_mpcsteps", "i4"), ("foot_found", "i4", (4,)), ("contacts", "i4", (CMD_MAX_STEPS, 4)),
+                      ("hkd_controls", "f4", (CMD_MAX_STEPS, 24)), ("des_body_state", "f4", (CMD_MAX_STEPS, 12)),
+                      ("feedback", "f4", (CMD_MAX_STEPS, 12, 12)), ("foot_placement", "f4", (12,)), ("_pad", "i4")])
+
 _lib = None
 
 
@@ -149,6 +154,8 @@ def lib():
         L.hsddp_fp64_peak_tflops.argtypes = [C.c_int, C.c_int, dp]
         L.hsddp_batch_get_array_rows.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp]
         L.hsddp_batch_get_gains_compact.argtypes = [vp, C.c_int, C.c_int, dp]
+        L.hsddp_batch_get_mpc_command.argtypes = [vp, C.c_int, vp]
+        L.hsddp_batch_set_solve_mode.argtypes = [vp, C.c_int]
         L.hsddp_batch_event_record.argtypes = [vp, C.c_int]
         L.hsddp_batch_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
         L.hsddp_batch_get_counters.argtypes = [vp, C.POINTER(C.c_ulonglong)]
@@ -408,6 +415,13 @@ class MultiPhaseDDPBatch:
         if out is None:
             out = np.zeros((self.n, nrows, 24, 12))
         _check(lib().hsddp_batch_get_gains_compact(self.h, int(row0), int(nrows), _dp(out)), "get_gains_compact")
+        return out
+
+    def mpc_command(self, n_steps=8, out=None):
+        """hkd_command_lcmt payload of every problem (HKDMPC.cpp:207-298), packed on the device."""
+        if out is None:
+            out = np.zeros(self.n, dtype=CMD_DTYPE)
+        _check(lib().hsddp_batch_get_mpc_command(self.h, int(n_steps), out.ctypes.data_as(C.c_void_p)), "get_mpc_command")
         return out
 
     def event_record(self, slot):

@@ -338,6 +338,57 @@ __global__ void __launch_bounds__(kThreads, HSDDP_MIN_BLOCKS) k_step(BatchPtrs b
     if (threadIdx.x == 0) { bp.state[pid] = sm.st; if (ok) ok[pid] = okv; }
 }
 
+// HKDMPCSolver::publish_mpc_cmd + update_foot_placement (HKDMPC/HKDMPC.cpp:207-298): one block per problem packs the
+// command record.  Stage k of the command = stage s of phase i, walked with the reference's (k, s, i) loop.
+__global__ void k_command(BatchPtrs bp, int n_steps, hsddp_mpc_command* out) {
+    const int pid = blockIdx.x;
+    const DevSchedule& sc = bp.sched[bp.sched_id[pid]];
+    hsddp_mpc_command& cmd = out[pid];
+    __shared__ int s_stage[HSDDP_CMD_MAX_STEPS], s_node[HSDDP_CMD_MAX_STEPS], s_phase[HSDDP_CMD_MAX_STEPS];
+    if (threadIdx.x == 0) {
+        int s = 0, i = 0;
+        for (int k = 0; k < n_steps; ++k) {
+            if (s >= sc.horizon[i]) { s = 0; i++; }
+            if (i >= sc.n_phases) { i = sc.n_phases - 1; s = sc.horizon[i] - 1; }  // (horizon shorter than the command: repeat the last stage)
+            s_stage[k] = sc.stage_off[i] + s; s_node[k] = sc.node_off[i] + s; s_phase[k] = i;
+            s++;
+        }
+        cmd.N_mpcsteps = n_steps; cmd._pad = 0;
+    }
+    __syncthreads();
+    const double* Xbar = bp.Xbar + (size_t)pid * bp.max_nodes * 24;
+    const double* Ubar = bp.Ubar + (size_t)pid * bp.max_stages * 24;
+    const double* K = bp.K + (size_t)pid * bp.max_stages * 288;
+    for (int e = threadIdx.x; e < HSDDP_CMD_MAX_STEPS * 24; e += blockDim.x) {
+        const int k = e / 24, j = e % 24;
+        cmd.hkd_controls[k][j] = (k < n_steps) ? (float)Ubar[24 * s_stage[k] + j] : 0.f;
+        if (j < 12) cmd.des_body_state[k][j] = (k < n_steps) ? (float)Xbar[24 * s_node[k] + j] : 0.f;
+        if (j < 4) cmd.contacts[k][j] = (k < n_steps) ? (int)((sc.cmask[s_phase[k]] >> j) & 1u) : 0;
+    }
+    for (int e = threadIdx.x; e < HSDDP_CMD_MAX_STEPS * 144; e += blockDim.x) {
+        const int k = e / 144, m = (e % 144) / 12, n = e % 12;
+        float v = 0.f;
+        // K(m, n), m < 12: GRF component m; non-zero only for a stance leg, where it is the coupled control m
+        if (k < n_steps && ((sc.cmask[s_phase[k]] >> (m / 3)) & 1u)) v = (float)K[288 * (size_t)s_stage[k] + 12 * n + m];
+        cmd.feedback[k][m][n] = v;
+    }
+    if (threadIdx.x < 4) {
+        const int l = threadIdx.x;
+        int found = 0;
+        float pf[3] = {0.f, 0.f, 0.f};
+        for (int i = 0; i < sc.n_phases - 1 && !found; ++i) {
+            if (!((sc.cmask[i] >> l) & 1u) && ((sc.cmask[i + 1] >> l) & 1u)) {
+                const double* q = Xbar + 24 * sc.node_off[i + 1] + 12 + 3 * l;
+                pf[0] = (float)q[0]; pf[1] = (float)q[1]; pf[2] = (float)q[2];
+                found = 1;
+            }
+            if (i >= 4) break;
+        }
+        cmd.foot_found[l] = found;
+        cmd.foot_placement[3 * l] = pf[0]; cmd.foot_placement[3 * l + 1] = pf[1]; cmd.foot_placement[3 * l + 2] = pf[2];
+    }
+}
+
 // FP64 throughput probes (roofline denominators measured on the box)
 __global__ void k_dfma_probe(double* out, int iters) {
     double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -401,6 +452,7 @@ struct hsddp_batch {
     int* d_count = nullptr;
     int* h_count = nullptr;        // pinned
     int last_rounds = 0;
+    hsddp_mpc_command* d_cmd = nullptr;  // lives in `allocs` (freed with the problem set)
 };
 
 namespace {
@@ -417,6 +469,7 @@ int dalloc(hsddp_batch* b, T** p, size_t n) {
 void free_problem_allocs(hsddp_batch* b) {
     for (void* p : b->allocs) cudaFree(p);
     b->allocs.clear();
+    b->d_cmd = nullptr;
     b->has_problems = false;
 }
 
@@ -925,6 +978,24 @@ int hsddp_batch_get_gains_compact(hsddp_batch* b, int row0, int nrows, double* o
     CK(cudaSetDevice(b->device));
     CK(cudaMemcpy2DAsync(out, (size_t)nrows * 288 * sizeof(double), b->bp.K + (size_t)row0 * 288, (size_t)b->bp.max_stages * 288 * sizeof(double),
                          (size_t)nrows * 288 * sizeof(double), (size_t)b->bp.n_problems, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return HSDDP_OK;
+}
+
+int hsddp_batch_get_mpc_command(hsddp_batch* b, int n_steps, hsddp_mpc_command* out) {
+    if (!b || !b->has_problems || !out || n_steps < 1 || n_steps > HSDDP_CMD_MAX_STEPS) return HSDDP_ERR_ARG;
+    CK(cudaSetDevice(b->device));
+    const size_t bytes = sizeof(hsddp_mpc_command) * (size_t)b->bp.n_problems;
+    if (!b->d_cmd) {
+        void* q = nullptr;
+        CK(cudaMalloc(&q, bytes));
+        b->allocs.push_back(q);
+        b->d_cmd = (hsddp_mpc_command*)q;
+    }
+    k_command<<<b->bp.n_problems, 128, 0, b->stream>>>(b->bp, n_steps, b->d_cmd);
+    CK(cudaGetLastError());
+    b->n_step_launches++;
+    CK(cudaMemcpyAsync(out, b->d_cmd, bytes, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
     return HSDDP_OK;
 }

@@ -227,6 +227,29 @@ int hsddp_batch_get_array_rows(hsddp_batch* b, int which, int row0, int nrows, d
  * a swing leg; the 12 other controls of the stage have identically zero gain rows. */
 int hsddp_batch_get_gains_compact(hsddp_batch* b, int row0, int nrows, double* out);
 
+/* What leaves the GPU after an MPC solve: the payload of the hkd_command LCM message, lcmtypes/hkd_command_lcmt.lcm, as
+ * HKDMPCSolver::publish_mpc_cmd (HKDMPC/HKDMPC.cpp:243-298) and update_foot_placement (:207-240) fill it, packed on
+ * the device into one record per problem (single-precision like the LCM message) and copied out in one transfer.
+ *   hkd_controls[k], des_body_state[k], feedback[k] : Ubar, Xbar[0:12] and K(0:12, 0:12) of the k-th stage of the
+ *       horizon, walking the phases exactly as publish_mpc_cmd does; contacts[k] = contact flags of that phase
+ *   foot_placement[3l..3l+2] : qdummy of leg l at the first node of the first phase (among the first five phase
+ *       boundaries) where the leg goes swing -> stance; foot_found[l] = 0 if there is none (the reference then keeps
+ *       its previous value).
+ * mpc_times / statusTimes / solve_time of the LCM message are host-side bookkeeping, not solver outputs. */
+#define HSDDP_CMD_MAX_STEPS 10
+typedef struct hsddp_mpc_command {
+    int32_t N_mpcsteps;
+    int32_t foot_found[4];
+    int32_t contacts[HSDDP_CMD_MAX_STEPS][4];
+    float hkd_controls[HSDDP_CMD_MAX_STEPS][24];
+    float des_body_state[HSDDP_CMD_MAX_STEPS][12];
+    float feedback[HSDDP_CMD_MAX_STEPS][12][12];
+    float foot_placement[12];
+    int32_t _pad;
+} hsddp_mpc_command;
+/* n_steps = nsteps_between_mpc + 7 (8 in the reference), at most HSDDP_CMD_MAX_STEPS; out: [n_problems] on the host */
+int hsddp_batch_get_mpc_command(hsddp_batch* b, int n_steps, hsddp_mpc_command* out);
+
 /* CUDA-event timing on the handle's stream (slots 0..7): record, then elapsed ms between two slots */
 int hsddp_batch_event_record(hsddp_batch* b, int slot);
 int hsddp_batch_event_elapsed_ms(hsddp_batch* b, int slot0, int slot1, float* ms);

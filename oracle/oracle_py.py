@@ -288,3 +288,35 @@ def batch_solve(tables, k0, x0, plan=0.6, model=None, opts=None, cparams=None, n
 
 def hardware_concurrency():
     return lib().orc_hardware_concurrency()
+
+
+def mpc_command(P, n_steps=8):
+    """HKDMPCSolver::publish_mpc_cmd + update_foot_placement (HKDMPC/HKDMPC.cpp:207-298) restated on the oracle's
+    trajectories: returns dict(hkd_controls [n,24], des_body_state [n,12], feedback [n,12,12], contacts [n,4],
+    foot_placement [12], foot_found [4]) in float32 like the LCM message."""
+    Xbar, Ubar, K = P.get("Xbar"), P.get("Ubar"), P.get("K")  # K: [stages, 24, 24] with K[s][i, j] = dense gain
+    node_off, stage_off, no, so = [], [], 0, 0
+    for ph in P.phases:
+        node_off.append(no); stage_off.append(so)
+        no += ph["horizon"] + 1; so += ph["horizon"]
+    out = dict(hkd_controls=np.zeros((n_steps, 24), np.float32), des_body_state=np.zeros((n_steps, 12), np.float32),
+               feedback=np.zeros((n_steps, 12, 12), np.float32), contacts=np.zeros((n_steps, 4), np.int32),
+               foot_placement=np.zeros(12, np.float32), foot_found=np.zeros(4, np.int32))
+    k = s = i = 0
+    while k < n_steps:
+        if s >= P.phases[i]["horizon"]:
+            s = 0; i += 1
+        out["hkd_controls"][k] = Ubar[stage_off[i] + s]
+        out["des_body_state"][k] = Xbar[node_off[i] + s][:12]
+        out["feedback"][k] = K[stage_off[i] + s][:12, :12]
+        out["contacts"][k] = P.phases[i]["contact"]
+        s += 1; k += 1
+    for i in range(P.n_phases - 1):
+        c, cn = P.phases[i]["contact"], P.phases[i + 1]["contact"]
+        for l in range(4):
+            if not out["foot_found"][l] and c[l] == 0 and cn[l] == 1:
+                out["foot_placement"][3 * l:3 * l + 3] = Xbar[node_off[i + 1]][12 + 3 * l:15 + 3 * l]
+                out["foot_found"][l] = 1
+        if i >= 4:
+            break
+    return out

@@ -201,6 +201,31 @@ def test_solve_modes_agree(pkg, orc, workloads):
     _compare_solution(pkg, orc, w3, B3, range(3), {}, max_ill_posed=1)
 
 
+def test_mpc_command_extraction(pkg, orc, workloads):
+    """What leaves the GPU after a solve (hkd_command_lcmt payload, HKDMPC.cpp:207-298): packed on the device,
+    compared with the restated publish_mpc_cmd / update_foot_placement applied to the oracle's trajectories."""
+    w = workloads.config3(pkg, 9)
+    B = _batch_for(pkg, w)
+    B.solve()
+    cmd = B.mpc_command(8)
+    tables = {}
+    checked = 0
+    for i in range(w.n):
+        P, s, otr, well_posed, sens = _oracle_pair(orc, w, i, tables)
+        if not well_posed:
+            continue
+        ref = orc.mpc_command(P, 8)
+        assert cmd["N_mpcsteps"][i] == 8
+        assert np.array_equal(cmd["contacts"][i, :8], ref["contacts"]) and np.array_equal(cmd["foot_found"][i], ref["foot_found"])
+        for name in ("hkd_controls", "des_body_state", "feedback"):
+            a, b = cmd[name][i, :8].astype(np.float64), ref[name].astype(np.float64)
+            assert np.abs(a - b).max() <= 2e-7 * max(1.0, np.abs(b).max()), (i, name)   # float32 payload
+            assert not np.any(cmd[name][i, 8:])
+        assert np.abs(cmd["foot_placement"][i] - ref["foot_placement"]).max() <= 2e-7
+        checked += 1
+    assert checked >= 6
+
+
 def test_config4_long_flight_phase(pkg, orc, workloads):
     w = workloads.config4(pkg, 12)
     assert any(max(s.horizon) >= 30 for s in w.schedules)

@@ -22,6 +22,8 @@ def test_struct_layouts_match_the_header(pkg):
     assert C.sizeof(pkg.Info) == 6 * 4 + 6 * 8
     assert pkg.INFO_DTYPE.itemsize == C.sizeof(pkg.Info)
     assert C.sizeof(pkg.ScheduleStruct) == 656 + 8 + 4 * 8
+    # hsddp_mpc_command: 1 + 4 + 40 ints, 240 + 120 + 1440 + 12 floats, 1 pad int
+    assert pkg.CMD_DTYPE.itemsize == 4 * (1 + 4 + 40 + 240 + 120 + 1440 + 12 + 1)
 
 
 def test_no_gpu_means_loud_failure(pkg):
