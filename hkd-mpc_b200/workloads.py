@@ -100,7 +100,7 @@ def config3(pkg, n=16384, plan=0.6, first=0):
     for j in range(n):
         i = first + j
         g = GAITS[i % 3]
-        k0 = (7 * (i // 3)) % (sizes[g] - 63)
+        k0 = (7 * (i // 3)) % (sizes[g] - (int(round(plan / 0.01)) + 3))  # (n_samples - 63 for the 0.6 s horizon of SURVEY.md §8d)
         entries.append((g, k0, "reference"))
     w = _build_indexed(pkg, f"config3: {n} mixed-gait problems (trot/bound/pronk)", entries, plan, first)
     return w
