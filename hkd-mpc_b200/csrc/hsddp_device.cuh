@@ -370,26 +370,34 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
             // control i = lane: coupled iff (i < 12) == stance(leg); its gain row is reduced index c = i % 12
             const int c = lane % 12;
             const double vx = __shfl_sync(0xffffffffu, ax, c >> 1), vy = __shfl_sync(0xffffffffu, ay, c >> 1);
+            __syncwarp();  // (every lane has read its state deviations: the slot is reused for the trial control)
             if (lane < 24) {
                 const bool stance = (cm >> (c / 3)) & 1u;
                 const double acc = ((lane < 12) == stance) ? ((c & 1) ? vy : vx) : 0.0;
                 sm.U_t[24 * s + lane] = ub + acc;
+                if (dev_in_smem) xd[24 * n + lane] = ub + acc;
             }
         }
     }
     __syncthreads();
     PROF_MARK(sm, 0);
-    // (b) dynamics, one thread per stage; phase-initial simulated states
+    // (b) dynamics, one thread per stage; phase-initial simulated states.  With the shared-memory staging the stage's
+    //     slot of `xd` holds its trial control on entry and its simulated successor state on exit (the strided
+    //     per-thread accesses stay on chip); otherwise both go through HBM.
     int first_bad = 0x7fffffff;
     for (int s = tid; s < N; s += kThreads) {
         int ph, k;
         phase_of_stage(sc, s, ph, k);
         const int n = sc.node_off[ph] + k;
-        double* xn = sm.Xsim_t + 24 * (n + 1);
-        hkd::dynamics(xs + 24 * n, sm.U_t + 24 * s, sc.dt, sc.cmask[ph], xn);
+        double* slot = dev_in_smem ? xd + 24 * n : sm.Xsim_t + 24 * (n + 1);
+        const double* usrc = dev_in_smem ? slot : sm.U_t + 24 * s;
+        double ul[24];
+#pragma unroll
+        for (int j = 0; j < 24; ++j) ul[j] = usrc[j];
+        hkd::dynamics(xs + 24 * n, ul, sc.dt, sc.cmask[ph], slot);
         double nrm2 = 0.0;
 #pragma unroll
-        for (int j = 0; j < 24; ++j) nrm2 = fma(xn[j], xn[j], nrm2);
+        for (int j = 0; j < 24; ++j) nrm2 = fma(slot[j], slot[j], nrm2);
         if (sqrt(nrm2) > 1e6) first_bad = min(first_bad, s);
     }
     if (tid >= 64 && tid < 64 + sc.n_phases) {
@@ -415,7 +423,10 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
         if (ph < bad_ph || (ph == bad_ph && k <= bad_k)) {
             const double x = xs[e];
             sm.X[e] = x;
-            if (ph < bad_ph) sm.Defect[e] = sm.Xsim_t[e] - x;  // compute_defect only after a complete phase
+            if (ph < bad_ph) {  // compute_defect only after a complete phase
+                const double xsim = (dev_in_smem && k > 0) ? xd[e - 24] : sm.Xsim_t[e];
+                sm.Defect[e] = xsim - x;
+            }
         }
     }
     double gmin = 0.0;
