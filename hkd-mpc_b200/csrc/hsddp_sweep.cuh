@@ -18,7 +18,7 @@
 // One stage:
 //     Y = H A            Z = H B_r                              (DMMA m8n8k4, K = 12 / 8)
 //     Qxx = lxx + A^T Y  Qux_r = B_r^T Y   Quu_r = luu_r + B_r^T Z    Qx, Qu_r   (DMMA + fix-ups)
-//     block Gauss-Jordan (2x2 pivots) on the register tableau [Quu_r | Qux_r | Qu_r] (lane = column) -> -K_r, -dU_r
+//     block Gauss-Jordan (2x2 pivots, six steps) on the register tableau [Quu_r | Qux_r | Qu_r | I] (lane = column) -> -K_r, -dU_r
 //     PD verdict = no negative pivot of Quu_r - 1e-9 I (third warp, concurrently; Q7)
 //     H' = sym(Qxx) + Qux_r^T K_r      G' = Qx + Qux_r^T dU_r   (DMMA, accumulators kept in registers)
 #pragma once
@@ -147,6 +147,47 @@ __device__ __forceinline__ bool gauss_jordan12(double (&v)[12], double* sbuf, un
 #endif
         __syncwarp();
         GJ_MARK(2);
+    }
+    return ok;
+}
+
+// Same elimination with 3x3 pivot blocks: four sequential steps instead of six (the chain of publish -> barrier ->
+// load -> invert -> eliminate is what a stage waits for, so fewer, fatter steps win).  The pivot block is inverted
+// with its adjugate; its leading minors p00, p00 p11 - p01 p10 and det are the signs of the three scalar pivots
+// (Sylvester), so the verdict is the same "no non-positive pivot".  `sbuf`: 36 doubles per warp.
+// Columns rotate by three per step; four steps rotate by 12 = identity.
+__device__ __forceinline__ bool gauss_jordan12_b3(double (&v)[12], double* sbuf) {
+    const int lane = threadIdx.x & 31;
+    bool ok = true;
+#pragma unroll 1
+    for (int step = 0; step < 4; ++step) {
+        const int pl = lane - 3 * step;
+        if (pl >= 0 && pl < 3) {  // the three pivot columns (lanes 3*step .. 3*step+2 < 12)
+            double2* dst = reinterpret_cast<double2*>(sbuf + 12 * pl);
+#pragma unroll
+            for (int r = 0; r < 12; r += 2) dst[r >> 1] = make_double2(v[r], v[r + 1]);
+        }
+        __syncwarp();
+        // pivot block P[i][j] = column j, row i (rotated frame: rows 0..2)
+        const double2 a01 = *reinterpret_cast<const double2*>(sbuf);        // p00 p10
+        const double2 b01 = *reinterpret_cast<const double2*>(sbuf + 12);   // p01 p11
+        const double2 c01 = *reinterpret_cast<const double2*>(sbuf + 24);   // p02 p12
+        const double p20 = sbuf[2], p21 = sbuf[14], p22 = sbuf[26];
+        const double p00 = a01.x, p10 = a01.y, p01 = b01.x, p11 = b01.y, p02 = c01.x, p12 = c01.y;
+        const double c00 = p11 * p22 - p12 * p21, c01_ = p02 * p21 - p01 * p22, c02 = p01 * p12 - p02 * p11;
+        const double c10 = p12 * p20 - p10 * p22, c11 = p00 * p22 - p02 * p20, c12 = p02 * p10 - p00 * p12;
+        const double c20 = p10 * p21 - p11 * p20, c21 = p01 * p20 - p00 * p21, c22 = p00 * p11 - p01 * p10;
+        const double det = fma(p00, c00, fma(p01, c10, p02 * c20));
+        if (!(p00 > 0.0) || !(c22 > 0.0) || !(det > 0.0)) ok = false;
+        const double rdet = 1.0 / det;
+        const double t0 = fma(c00, v[0], fma(c01_, v[1], c02 * v[2])) * rdet;
+        const double t1 = fma(c10, v[0], fma(c11, v[1], c12 * v[2])) * rdet;
+        const double t2 = fma(c20, v[0], fma(c21, v[1], c22 * v[2])) * rdet;
+#pragma unroll
+        for (int r = 3; r < 12; ++r)  // eliminate and rotate in one go
+            v[r - 3] = fma(-sbuf[24 + r], t2, fma(-sbuf[12 + r], t1, fma(-sbuf[r], t0, v[r])));
+        v[9] = t0; v[10] = t1; v[11] = t2;
+        __syncwarp();
     }
     return ok;
 }
@@ -399,7 +440,12 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                     for (int r = 0; r < 12; ++r) if (r == lane) col[r] -= 1e-9;
                 }
                 PROF_MARK(sm, 13);
-                const bool ok = gauss_jordan12(col, sm.red + 32 * warp, sm.profacc + 10);
+                #ifdef HSDDP_GJ_BLOCK3  // four 3x3 steps: 16 % less latency alone (tools/microbench/gj3.cu), but more FP64 instructions:
+                        // single-solve latency 6.05 -> 5.9 ms, throughput unchanged to slightly worse -> off by default
+                const bool ok = gauss_jordan12_b3(col, sm.red + 40 * warp);
+#else
+                const bool ok = gauss_jordan12(col, sm.red + 40 * warp, sm.profacc + 10);
+#endif
                 PROF_MARK(sm, 14);
                 if (pass) {
                     if (warp == 1 && lane == 0) sm.ibuf[0] = ok ? 1 : 0;
