@@ -155,6 +155,9 @@ def lib():
         L.hsddp_batch_get_array_rows.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp]
         L.hsddp_batch_get_gains_compact.argtypes = [vp, C.c_int, C.c_int, dp]
         L.hsddp_batch_get_mpc_command.argtypes = [vp, C.c_int, vp]
+        L.hsddp_batch_set_problems_from_gaits.argtypes = [vp, C.c_int, ip, C.POINTER(C.c_float), dp, dp, dp, dp, ip, C.c_int, ip, ip, C.c_float, C.c_int, ip,
+                                                          C.POINTER(ConstraintParams)]
+        L.hsddp_batch_get_schedule.argtypes = [vp, C.c_int, ip, ip, ip, ip, dp, dp, dp, dp]
         L.hsddp_batch_set_solve_mode.argtypes = [vp, C.c_int]
         L.hsddp_batch_event_record.argtypes = [vp, C.c_int]
         L.hsddp_batch_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
@@ -236,6 +239,7 @@ class QuadReference:
             self._keep = [np.ascontiguousarray(d[k], np.float32) for k in ("body_state", "qJ", "foot_placements", "grf")]
             contact = np.ascontiguousarray(d["contact"], np.int32)
             self._keep.append(contact)
+            self.dt = float(d["dt"])
             _check(lib().hkd_gait_create(contact.shape[0], C.c_float(float(d["dt"])), *[_fp(a) for a in self._keep[:4]],
                                          _ip(contact), C.byref(h)), "hkd_gait_create")
         self.handle = h
@@ -305,6 +309,34 @@ class MultiPhaseDDPBatch:
         ms, mn, n = C.c_int32(), C.c_int32(), C.c_int32()
         lib().hsddp_batch_dims(self.h, C.byref(n), C.byref(ms), C.byref(mn))
         self.max_stages, self.max_nodes = ms.value, mn.value
+
+    def set_problems_from_gaits(self, refs, sched_gait, sched_window, plan_duration, schedule_id, cparams=None):
+        """Reference ingestion on the device: the gait tables `refs` (QuadReference objects created
+        from arrays) go to HBM once, and a kernel builds the schedule of every (gait, window start) pair."""
+        rows = np.array([r.n for r in refs], np.int32)
+        dts = np.array([r.dt for r in refs], np.float32)
+        cat = [np.ascontiguousarray(np.concatenate([np.asarray(r._keep[k], np.float64).reshape(-1, 12) for r in refs])) for k in range(4)]
+        contact = np.ascontiguousarray(np.concatenate([r._keep[4].reshape(-1, 4) for r in refs]), np.int32)
+        sg = np.ascontiguousarray(sched_gait, np.int32); sw = np.ascontiguousarray(sched_window, np.int32)
+        sid = np.ascontiguousarray(schedule_id, np.int32)
+        cp = cparams or ConstraintParams()
+        _check(lib().hsddp_batch_set_problems_from_gaits(self.h, len(refs), _ip(rows), dts.ctypes.data_as(C.POINTER(C.c_float)), *[_dp(a) for a in cat],
+                                                        _ip(contact), len(sg), _ip(sg), _ip(sw), C.c_float(plan_duration), len(sid), _ip(sid),
+                                                        C.byref(cp)), "hsddp_batch_set_problems_from_gaits")
+        n, ms, mn = C.c_int32(), C.c_int32(), C.c_int32()
+        lib().hsddp_batch_dims(self.h, C.byref(n), C.byref(ms), C.byref(mn))
+        self.n, self.max_stages, self.max_nodes = n.value, ms.value, mn.value
+
+    def device_schedule(self, i):
+        """Schedule i as the device holds it (phase table + reference rows)."""
+        nph = C.c_int32()
+        hz = np.zeros(MAX_PHASES, np.int32); c = np.zeros((MAX_PHASES, 4), np.int32); cn = np.zeros((MAX_PHASES, 4), np.int32)
+        mn = self.max_nodes
+        xr, ur, pr, xi = np.zeros((mn, 24)), np.zeros((mn, 24)), np.zeros((mn, 12)), np.zeros((mn, 24))
+        _check(lib().hsddp_batch_get_schedule(self.h, int(i), C.byref(nph), _ip(hz), _ip(c), _ip(cn), _dp(xr), _dp(ur), _dp(pr), _dp(xi)), "get_schedule")
+        P = nph.value
+        nn = int(hz[:P].sum()) + P
+        return dict(n_phases=P, horizon=hz[:P].tolist(), contact=c[:P].tolist(), next_contact=cn[:P].tolist(), xr=xr[:nn], ur=ur[:nn], prel_r=pr[:nn], xinit=xi[:nn])
 
     def set_initial_condition(self, x0):
         x0 = np.ascontiguousarray(x0, np.float64).reshape(self.n, 24)

@@ -389,6 +389,143 @@ __global__ void k_command(BatchPtrs bp, int n_steps, hsddp_mpc_command* out) {
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// N2: reference ingestion on the device.  The gait library (QuadReference::tp_data of every gait, already parsed
+// through stof) is resident in HBM; one kernel builds, for every (gait, window start), what QuadReference::initialize
+// + HKDProblem::initialization produce: the phase table (HKDProblem.cpp:26-68), the contact after each phase
+// (:268-299, Q17) and the per-node reference rows the cost callbacks and the initial guess see (HKDReference.cpp:8-57,
+// HKDProblem.cpp:84-90).  The host builder (host/hkd_problem.cpp: hkd_schedule_build) is restated here with the
+// SAME float arithmetic — every float / double product-sum that the host rounds twice is written with
+// __fmul_rn / __fadd_rn / __dmul_rn / __dadd_rn so that the compiler cannot contract it — and the two are compared
+// bit for bit in tests/test_gpu_parity.py::test_device_schedule_builder_bit_exact.
+// ---------------------------------------------------------------------------
+struct GaitLib {
+    const double *body_state, *qJ, *foot, *grf;  // concatenated over gaits, [row][12]
+    const int* contact;                          // [row][4]
+    const int* row_off;                          // first row of gait g
+    const int* n_rows;                           // rows of gait g
+    const float* dt;                             // sample period of gait g
+};
+
+__device__ __forceinline__ bool approx_eq_f(float a, float b) { return fabsf(__fsub_rn(a, b)) <= 1e-6f; }
+__device__ __forceinline__ bool approx_leq_f(float a, float b) { return a < b || approx_eq_f(a, b); }
+__device__ __forceinline__ bool approx_geq_f(float a, float b) { return a > b || approx_eq_f(a, b); }
+// QuadReference::get_a_reference_ptr_at_t index rule (QuadReference.cpp:65-80), float arithmetic
+__device__ __forceinline__ int ref_index_at(float t, float dt, int sz) {
+    int k = (int)floorf(__fdiv_rn(t, dt));
+    const float rem = __fsub_rn(t, __fmul_rn((float)k, dt));
+    if ((double)rem > __dmul_rn(0.5, (double)dt)) k++;
+    if (k > sz) k = sz;
+    return k;
+}
+
+// pass 1: phase tables, one thread per schedule.  status[i] != 0 marks an unusable window.
+__global__ void k_build_phase_tables(GaitLib lib, int n_sched, const int* sched_gait, const int* sched_window, float plan, int node_stride,
+                                     DevSchedule* out, int* status) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sched) return;
+    const int gi = sched_gait[i], k0 = sched_window[i];
+    const float dtg = lib.dt[gi];
+    const int sz = (int)roundf(__fdiv_rn(plan, dtg)) + 1;
+    DevSchedule d;
+    memset(&d, 0, sizeof d);
+    int st = 0;
+    if (k0 < 0 || k0 + sz >= lib.n_rows[gi]) st = 1;
+    const int* contact = lib.contact + 4 * (size_t)(lib.row_off[gi] + k0);
+    const float dt_sim = 0.01f, dt_mpc = 0.01f;
+    int n_phases = 0, so = 0, no = 0;
+    if (!st) {
+        int cprev[4], ccur[4];
+        float phase_start = 0.f, t = 0.f;
+        { const int* c = contact + 4 * ref_index_at(t, dtg, sz); for (int l = 0; l < 4; ++l) cprev[l] = c[l]; }
+        while (approx_leq_f(t, plan)) {
+            { const int* c = contact + 4 * ref_index_at(t, dtg, sz); for (int l = 0; l < 4; ++l) ccur[l] = c[l]; }
+            bool change = false;
+            for (int l = 0; l < 4; ++l) change = change || (ccur[l] != cprev[l]);
+            if (change || approx_geq_f(t, plan)) {
+                if (n_phases >= MAXPH) { st = 2; break; }
+                const int hz = (int)roundf(__fdiv_rn(__fsub_rn(t, phase_start), dt_sim));
+                if (hz < 1 || so + hz > HSDDP_MAX_STAGES) { st = 2; break; }
+                d.horizon[n_phases] = hz; d.node_off[n_phases] = no; d.stage_off[n_phases] = so;
+                unsigned cm = 0;
+                for (int l = 0; l < 4; ++l) cm |= (cprev[l] ? 1u : 0u) << l;
+                d.cmask[n_phases] = cm;
+                // phase start time, kept as float bits in nmask until the table is complete
+                d.nmask[n_phases] = __float_as_uint(phase_start);
+                for (int k = 0; k < hz; ++k) d.ph_of_stage[so + k] = (unsigned char)n_phases;
+                for (int k = 0; k <= hz; ++k) d.ph_of_node[no + k] = (unsigned char)n_phases;
+                no += hz + 1; so += hz;
+                ++n_phases;
+                for (int l = 0; l < 4; ++l) cprev[l] = ccur[l];
+                phase_start = t;
+            }
+            t = __fadd_rn(t, dt_sim);
+        }
+    }
+    if (!st && (n_phases < 1 || no > node_stride)) st = 2;
+    d.n_phases = n_phases; d.n_stages = so; d.n_nodes = no; d.dt = (double)dt_sim;
+    d.ref_off = (long long)i * node_stride;
+    out[i] = d;
+    status[i] = st;
+    (void)dt_mpc;
+}
+
+// pass 2: reference rows, one thread per (schedule, node); also turns the start times parked in nmask into the
+// contact-after-phase masks (thread of node 0 of each schedule, after every node of that schedule has read them —
+// so the start times are first copied to shared memory by the whole block).
+__global__ void k_build_reference_rows(GaitLib lib, int n_sched, const int* sched_gait, const int* sched_window, float plan, int node_stride,
+                                       DevSchedule* scheds, const int* status, double* xr, double* ur, double* prel, double* xinit) {
+    const int i = blockIdx.x;
+    if (i >= n_sched || status[i]) return;
+    __shared__ float start_time[MAXPH];
+    DevSchedule& d = scheds[i];
+    const int n_phases = d.n_phases;
+    if (threadIdx.x < n_phases) start_time[threadIdx.x] = __uint_as_float(d.nmask[threadIdx.x]);
+    __syncthreads();
+    const int gi = sched_gait[i], k0 = sched_window[i];
+    const float dtg = lib.dt[gi];
+    const int sz = (int)roundf(__fdiv_rn(plan, dtg)) + 1;
+    const size_t row0 = (size_t)(lib.row_off[gi] + k0);
+    const float dt_sim = 0.01f, dt_mpc = 0.01f;
+    for (int n = threadIdx.x; n < d.n_nodes; n += blockDim.x) {
+        const int ph = d.ph_of_node[n], k = n - d.node_off[ph];
+        const size_t node = (size_t)d.ref_off + n;
+        // time seen by the cost callbacks: float(t_offset + k*dt), dt widened to double (SinglePhase.cpp:243,254)
+        const float t_offset = __fsub_rn(start_time[ph], start_time[0]);
+        const float tc = (float)__dadd_rn((double)t_offset, __dmul_rn((double)k, d.dt));
+        const int kc = ref_index_at(tc, dtg, sz);
+        // time used for the initial guess: float(phase_start + k*dt_sim), all float (HKDProblem.cpp:86-90)
+        const float ti = __fadd_rn(start_time[ph], __fmul_rn((float)k, dt_sim));
+        const int ki = ref_index_at(ti, dtg, sz);
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {  // HKDReference.cpp:33-56 (Q12): foot placement if the SAMPLE's contact flag is set, else joint angle
+            const size_t r = row0 + (pass ? ki : kc);
+            double* x = (pass ? xinit : xr) + 24 * node;
+            for (int j = 0; j < 12; ++j) x[j] = lib.body_state[12 * r + j];
+            for (int l = 0; l < 4; ++l)
+                for (int j = 0; j < 3; ++j)
+                    x[12 + 3 * l + j] = (lib.contact[4 * r + l] > 0) ? lib.foot[12 * r + 3 * l + j] : lib.qJ[12 * r + 3 * l + j];
+        }
+        const size_t r = row0 + kc;
+        for (int j = 0; j < 12; ++j) { ur[24 * node + j] = lib.grf[12 * r + j]; ur[24 * node + 12 + j] = 0.0; }  // qJd is never loaded: zeros
+        for (int l = 0; l < 4; ++l)
+            for (int j = 0; j < 3; ++j) prel[12 * node + 3 * l + j] = lib.foot[12 * r + 3 * l + j] - lib.body_state[12 * r + 3 + j];
+    }
+    __syncthreads();
+    if (threadIdx.x < n_phases) {  // contact after each phase (reset map / touchdown wiring), HKDProblem.cpp:268-299, Q17
+        const int p = threadIdx.x;
+        unsigned nm;
+        if (p < n_phases - 1) nm = d.cmask[p + 1];
+        else {
+            const int* c = lib.contact + 4 * (row0 + ref_index_at(__fadd_rn(plan, dt_mpc), dtg, sz));
+            nm = 0;
+            for (int l = 0; l < 4; ++l) nm |= (c[l] ? 1u : 0u) << l;
+        }
+        d.nmask[p] = nm;
+    }
+}
+
 // FP64 throughput probes (roofline denominators measured on the box)
 __global__ void k_dfma_probe(double* out, int iters) {
     double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -550,6 +687,54 @@ int hsddp_batch_destroy(hsddp_batch* b) {
     return HSDDP_OK;
 }
 
+// per-problem workspace; bp.n_problems / max_stages / max_nodes are set by the caller
+static int alloc_workspace(hsddp_batch* b, int n_problems, int max_stages, int max_nodes) {
+    BatchPtrs& bp = b->bp;
+    int rc;
+    const size_t P = (size_t)n_problems, SN = (size_t)max_nodes * 24, SS = (size_t)max_stages * 24;
+    if ((rc = dalloc(b, &bp.x0, P * 24))) return rc;
+    if ((rc = dalloc(b, &bp.Xbar, P * SN))) return rc;
+    if ((rc = dalloc(b, &bp.X, P * SN))) return rc;
+    if ((rc = dalloc(b, &bp.Xsim_t, P * SN))) return rc;
+    if ((rc = dalloc(b, &bp.Defect, P * SN))) return rc;
+    if ((rc = dalloc(b, &bp.dX, P * SN))) return rc;
+    if ((rc = dalloc(b, &bp.Ubar, P * SS))) return rc;
+    if ((rc = dalloc(b, &bp.U, P * SS))) return rc;
+    if ((rc = dalloc(b, &bp.U_t, P * SS))) return rc;
+    if ((rc = dalloc(b, &bp.dU, P * SS))) return rc;
+    if ((rc = dalloc(b, &bp.K, P * max_stages * 288))) return rc;
+    if ((rc = dalloc(b, &bp.lq, P * max_stages * CR_STRIDE))) return rc;
+    if ((rc = dalloc(b, &bp.tq, P * MAXPH * TQ_STRIDE))) return rc;
+    if ((rc = dalloc(b, &bp.gcon, P * max_stages * 20))) return rc;
+    if ((rc = dalloc(b, &bp.reb, P * max_stages * 40))) return rc;
+    if ((rc = dalloc(b, &bp.hcon, P * MAXPH * 4))) return rc;
+    if ((rc = dalloc(b, &bp.al, P * MAXPH * 8))) return rc;
+    if ((rc = dalloc(b, &bp.g0h0, P * 600))) return rc;
+    if ((rc = dalloc(b, &bp.state, P))) return rc;
+    if ((rc = dalloc(b, &bp.ctl, P))) return rc;
+    if ((rc = dalloc(b, &b->d_active[0], P))) return rc;
+    if ((rc = dalloc(b, &b->d_active[1], P))) return rc;
+    if ((rc = dalloc(b, &b->d_count, (size_t)4))) return rc;
+    CK(cudaMemset(bp.ctl, 0, P * sizeof(SolveCtl)));
+    if ((rc = dalloc(b, &bp.info, P))) return rc;
+    if ((rc = dalloc(b, &bp.trace, P * HSDDP_TRACE_CAP))) return rc;
+    if ((rc = dalloc(b, &bp.counters, (size_t)32))) return rc;
+    if ((rc = dalloc(b, &bp.work_counter, (size_t)4))) return rc;
+    if ((rc = dalloc(b, &bp.sm_slots, (size_t)256))) return rc;
+    CK(cudaMemset(bp.sm_slots, 0, 256 * sizeof(int)));
+    if ((rc = dalloc(b, &b->d_ok, P))) return rc;
+    if ((rc = dalloc(b, &b->d_darg, P))) return rc;
+    CK(cudaMemset(bp.x0, 0, P * 24 * sizeof(double)));
+    CK(cudaMemset(bp.info, 0, P * sizeof(hsddp_info)));
+    CK(cudaMemset(bp.trace, 0, P * HSDDP_TRACE_CAP * sizeof(hsddp_iter_record)));
+    CK(cudaMemset(bp.state, 0, P * sizeof(SolverState)));
+    CK(cudaMemset(bp.counters, 0, 32 * sizeof(unsigned long long)));
+    CK(cudaMemset(bp.tq, 0, P * MAXPH * TQ_STRIDE * sizeof(double)));
+    CK(cudaMemset(bp.lq, 0, P * max_stages * CR_STRIDE * sizeof(double)));
+    CK(cudaMemset(bp.g0h0, 0, P * 600 * sizeof(double)));
+    return HSDDP_OK;
+}
+
 int hsddp_batch_set_problems(hsddp_batch* b, int n_schedules, const hsddp_schedule* schedules, int n_problems,
                              const int32_t* schedule_id, const hsddp_constraint_params* cparams) {
     if (!b || n_schedules <= 0 || !schedules || n_problems <= 0 || !schedule_id) return HSDDP_ERR_ARG;
@@ -618,49 +803,103 @@ int hsddp_batch_set_problems(hsddp_batch* b, int n_schedules, const hsddp_schedu
     CK(cudaMemcpy(d_xinit, xinit.data(), xinit.size() * sizeof(double), cudaMemcpyHostToDevice));
     bp.sched = d_sched; bp.sched_id = d_sid; bp.xr = d_xr; bp.ur = d_ur; bp.prel = d_prel; bp.xinit = d_xinit;
 
-    const size_t P = (size_t)n_problems, SN = (size_t)max_nodes * 24, SS = (size_t)max_stages * 24;
-    if ((rc = dalloc(b, &bp.x0, P * 24))) return rc;
-    if ((rc = dalloc(b, &bp.Xbar, P * SN))) return rc;
-    if ((rc = dalloc(b, &bp.X, P * SN))) return rc;
-    if ((rc = dalloc(b, &bp.Xsim_t, P * SN))) return rc;
-    if ((rc = dalloc(b, &bp.Defect, P * SN))) return rc;
-    if ((rc = dalloc(b, &bp.dX, P * SN))) return rc;
-    if ((rc = dalloc(b, &bp.Ubar, P * SS))) return rc;
-    if ((rc = dalloc(b, &bp.U, P * SS))) return rc;
-    if ((rc = dalloc(b, &bp.U_t, P * SS))) return rc;
-    if ((rc = dalloc(b, &bp.dU, P * SS))) return rc;
-    if ((rc = dalloc(b, &bp.K, P * max_stages * 288))) return rc;
-    if ((rc = dalloc(b, &bp.lq, P * max_stages * CR_STRIDE))) return rc;
-    if ((rc = dalloc(b, &bp.tq, P * MAXPH * TQ_STRIDE))) return rc;
-    if ((rc = dalloc(b, &bp.gcon, P * max_stages * 20))) return rc;
-    if ((rc = dalloc(b, &bp.reb, P * max_stages * 40))) return rc;
-    if ((rc = dalloc(b, &bp.hcon, P * MAXPH * 4))) return rc;
-    if ((rc = dalloc(b, &bp.al, P * MAXPH * 8))) return rc;
-    if ((rc = dalloc(b, &bp.g0h0, P * 600))) return rc;
-    if ((rc = dalloc(b, &bp.state, P))) return rc;
-    if ((rc = dalloc(b, &bp.ctl, P))) return rc;
-    if ((rc = dalloc(b, &b->d_active[0], P))) return rc;
-    if ((rc = dalloc(b, &b->d_active[1], P))) return rc;
-    if ((rc = dalloc(b, &b->d_count, (size_t)4))) return rc;
-    CK(cudaMemset(bp.ctl, 0, P * sizeof(SolveCtl)));
-    if ((rc = dalloc(b, &bp.info, P))) return rc;
-    if ((rc = dalloc(b, &bp.trace, P * HSDDP_TRACE_CAP))) return rc;
-    if ((rc = dalloc(b, &bp.counters, (size_t)32))) return rc;
-    if ((rc = dalloc(b, &bp.work_counter, (size_t)4))) return rc;
-    if ((rc = dalloc(b, &bp.sm_slots, (size_t)256))) return rc;
-    CK(cudaMemset(bp.sm_slots, 0, 256 * sizeof(int)));
-    if ((rc = dalloc(b, &b->d_ok, P))) return rc;
-    if ((rc = dalloc(b, &b->d_darg, P))) return rc;
-    CK(cudaMemset(bp.x0, 0, P * 24 * sizeof(double)));
-    CK(cudaMemset(bp.info, 0, P * sizeof(hsddp_info)));
-    CK(cudaMemset(bp.trace, 0, P * HSDDP_TRACE_CAP * sizeof(hsddp_iter_record)));
-    CK(cudaMemset(bp.state, 0, P * sizeof(SolverState)));
-    CK(cudaMemset(bp.counters, 0, 32 * sizeof(unsigned long long)));
-    CK(cudaMemset(bp.tq, 0, P * MAXPH * TQ_STRIDE * sizeof(double)));
-    CK(cudaMemset(bp.lq, 0, P * max_stages * CR_STRIDE * sizeof(double)));
-    CK(cudaMemset(bp.g0h0, 0, P * 600 * sizeof(double)));
+    if ((rc = alloc_workspace(b, n_problems, max_stages, max_nodes))) return rc;
     b->has_problems = true;
     return hsddp_batch_reset(b);
+}
+
+
+int hsddp_batch_set_problems_from_gaits(hsddp_batch* b, int n_gaits, const int32_t* gait_rows, const float* gait_dt,
+                                        const double* body_state, const double* qJ, const double* foot_placements, const double* grf,
+                                        const int32_t* contact, int n_schedules, const int32_t* sched_gait, const int32_t* sched_window,
+                                        float plan_duration, int n_problems, const int32_t* schedule_id, const hsddp_constraint_params* cparams) {
+    if (!b || n_gaits <= 0 || !gait_rows || !gait_dt || !body_state || !qJ || !foot_placements || !grf || !contact || n_schedules <= 0 ||
+        !sched_gait || !sched_window || n_problems <= 0 || !schedule_id || !(plan_duration > 0.f))
+        return HSDDP_ERR_ARG;
+    CK(cudaSetDevice(b->device));
+    free_problem_allocs(b);
+    std::vector<int> row_off(n_gaits);
+    size_t rows = 0;
+    for (int g = 0; g < n_gaits; ++g) { row_off[g] = (int)rows; rows += (size_t)gait_rows[g]; }
+    for (int i = 0; i < n_schedules; ++i)
+        if (sched_gait[i] < 0 || sched_gait[i] >= n_gaits) { g_last_error = "sched_gait out of range"; return HSDDP_ERR_ARG; }
+    for (int i = 0; i < n_problems; ++i)
+        if (schedule_id[i] < 0 || schedule_id[i] >= n_schedules) { g_last_error = "schedule_id out of range"; return HSDDP_ERR_ARG; }
+    // gait library -> HBM
+    double *d_bs, *d_qj, *d_ft, *d_grf; int *d_ct, *d_ro, *d_nr, *d_sg, *d_sw, *d_status; float* d_dt;
+    int rc;
+    if ((rc = dalloc(b, &d_bs, rows * 12)) || (rc = dalloc(b, &d_qj, rows * 12)) || (rc = dalloc(b, &d_ft, rows * 12)) || (rc = dalloc(b, &d_grf, rows * 12)) ||
+        (rc = dalloc(b, &d_ct, rows * 4)) || (rc = dalloc(b, &d_ro, (size_t)n_gaits)) || (rc = dalloc(b, &d_nr, (size_t)n_gaits)) || (rc = dalloc(b, &d_dt, (size_t)n_gaits)) ||
+        (rc = dalloc(b, &d_sg, (size_t)n_schedules)) || (rc = dalloc(b, &d_sw, (size_t)n_schedules)) || (rc = dalloc(b, &d_status, (size_t)n_schedules)))
+        return rc;
+    CK(cudaMemcpy(d_bs, body_state, rows * 12 * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_qj, qJ, rows * 12 * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_ft, foot_placements, rows * 12 * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_grf, grf, rows * 12 * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_ct, contact, rows * 4 * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_ro, row_off.data(), n_gaits * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_nr, gait_rows, n_gaits * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_dt, gait_dt, n_gaits * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_sg, sched_gait, n_schedules * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_sw, sched_window, n_schedules * sizeof(int), cudaMemcpyHostToDevice));
+    GaitLib lib{d_bs, d_qj, d_ft, d_grf, d_ct, d_ro, d_nr, d_dt};
+
+    BatchPtrs& bp = b->bp;
+    std::memset(&bp, 0, sizeof bp);
+    if (cparams) bp.cp = *cparams;
+    else { bp.cp.grf_delta = 0.1; bp.cp.grf_delta_min = 0.1; bp.cp.grf_eps = 0.1; bp.cp.td_sigma = 50; bp.cp.td_sigma_max = 1e4; bp.cp.td_lambda = 0; bp.cp.mu = 0.7; }
+    const int node_stride = std::min(HSDDP_MAX_STAGES, (int)std::lround(plan_duration / 0.01f) + 1) + MAXPH;
+    DevSchedule* d_sched; int* d_sid; double *d_xr, *d_ur, *d_prel, *d_xinit;
+    const size_t total_nodes = (size_t)n_schedules * node_stride;
+    if ((rc = dalloc(b, &d_sched, (size_t)n_schedules)) || (rc = dalloc(b, &d_sid, (size_t)n_problems)) || (rc = dalloc(b, &d_xr, total_nodes * 24)) ||
+        (rc = dalloc(b, &d_ur, total_nodes * 24)) || (rc = dalloc(b, &d_prel, total_nodes * 12)) || (rc = dalloc(b, &d_xinit, total_nodes * 24)))
+        return rc;
+    CK(cudaMemcpy(d_sid, schedule_id, sizeof(int) * n_problems, cudaMemcpyHostToDevice));
+    k_build_phase_tables<<<(n_schedules + 127) / 128, 128, 0, b->stream>>>(lib, n_schedules, d_sg, d_sw, plan_duration, node_stride, d_sched, d_status);
+    k_build_reference_rows<<<n_schedules, 128, 0, b->stream>>>(lib, n_schedules, d_sg, d_sw, plan_duration, node_stride, d_sched, d_status, d_xr, d_ur, d_prel, d_xinit);
+    CK(cudaGetLastError());
+    b->n_step_launches += 2;
+    // the host keeps the phase tables too (dense gain / Jacobian getters, workspace sizing)
+    b->h_sched.assign(n_schedules, DevSchedule{});
+    std::vector<int> status(n_schedules);
+    CK(cudaMemcpyAsync(b->h_sched.data(), d_sched, sizeof(DevSchedule) * n_schedules, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaMemcpyAsync(status.data(), d_status, sizeof(int) * n_schedules, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    int max_stages = 0, max_nodes = 0;
+    for (int i = 0; i < n_schedules; ++i) {
+        if (status[i]) { g_last_error = status[i] == 1 ? "window does not fit the gait table" : "schedule exceeds HSDDP_MAX_PHASES / HSDDP_MAX_STAGES"; free_problem_allocs(b); return status[i] == 1 ? HSDDP_ERR_ARG : HSDDP_ERR_UNSUPPORTED; }
+        max_stages = std::max(max_stages, b->h_sched[i].n_stages);
+        max_nodes = std::max(max_nodes, b->h_sched[i].n_nodes);
+    }
+    b->h_sched_id.assign(schedule_id, schedule_id + n_problems);
+    bp.n_problems = n_problems; bp.max_stages = max_stages; bp.max_nodes = max_nodes;
+    bp.sched = d_sched; bp.sched_id = d_sid; bp.xr = d_xr; bp.ur = d_ur; bp.prel = d_prel; bp.xinit = d_xinit;
+    if ((rc = alloc_workspace(b, n_problems, max_stages, max_nodes))) return rc;
+    b->has_problems = true;
+    return hsddp_batch_reset(b);
+}
+
+/* device-built schedule i back on the host (tests): phase table + reference rows, row counts as in hsddp_schedule */
+int hsddp_batch_get_schedule(hsddp_batch* b, int i, int32_t* n_phases, int32_t* horizon, int32_t* contact, int32_t* next_contact,
+                             double* xr, double* ur, double* prel_r, double* xinit) {
+    if (!b || !b->has_problems || i < 0 || i >= (int)b->h_sched.size()) return HSDDP_ERR_ARG;
+    CK(cudaSetDevice(b->device));
+    DevSchedule d;
+    CK(cudaMemcpy(&d, b->bp.sched + i, sizeof d, cudaMemcpyDeviceToHost));
+    if (n_phases) *n_phases = d.n_phases;
+    for (int p = 0; p < d.n_phases; ++p) {
+        if (horizon) horizon[p] = d.horizon[p];
+        for (int l = 0; l < 4; ++l) {
+            if (contact) contact[4 * p + l] = (d.cmask[p] >> l) & 1u;
+            if (next_contact) next_contact[4 * p + l] = (d.nmask[p] >> l) & 1u;
+        }
+    }
+    const size_t o = (size_t)d.ref_off, nn = (size_t)d.n_nodes;
+    if (xr) CK(cudaMemcpy(xr, b->bp.xr + o * 24, nn * 24 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (ur) CK(cudaMemcpy(ur, b->bp.ur + o * 24, nn * 24 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (prel_r) CK(cudaMemcpy(prel_r, b->bp.prel + o * 12, nn * 12 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (xinit) CK(cudaMemcpy(xinit, b->bp.xinit + o * 24, nn * 24 * sizeof(double), cudaMemcpyDeviceToHost));
+    return HSDDP_OK;
 }
 
 int hsddp_batch_set_initial_condition(hsddp_batch* b, const double* x0) {

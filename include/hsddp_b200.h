@@ -146,6 +146,19 @@ const char* hsddp_last_error(void);
 int hsddp_batch_set_problems(hsddp_batch* b, int n_schedules, const hsddp_schedule* schedules, int n_problems,
                              const int32_t* schedule_id, const hsddp_constraint_params* cparams);
 /* MultiPhaseDDP::set_initial_condition (MultiPhaseDDP.h:37): x0 is [n_problems][24] on the host */
+/* Reference ingestion on the device.  The gait library — QuadReference::tp_data of n_gaits
+ * reference files, every value already passed through stof (Reference/QuadReference.cpp:129-285), rows of all gaits
+ * concatenated — is copied to HBM once; a kernel then does, for every schedule i = (sched_gait[i], sched_window[i]),
+ * what QuadReference::initialize (QuadReference.cpp:6-26) and HKDProblem::initialization (HKDProblem.cpp:15-111,
+ * 225-310) do on the host: phase split with the reference's float time arithmetic, contact after each phase, and the
+ * per-node reference rows.  Bit-identical to hkd_schedule_build + hsddp_batch_set_problems. */
+int hsddp_batch_set_problems_from_gaits(hsddp_batch* b, int n_gaits, const int32_t* gait_rows, const float* gait_dt,
+                                        const double* body_state, const double* qJ, const double* foot_placements, const double* grf,
+                                        const int32_t* contact, int n_schedules, const int32_t* sched_gait, const int32_t* sched_window,
+                                        float plan_duration, int n_problems, const int32_t* schedule_id, const hsddp_constraint_params* cparams);
+/* schedule i as the device holds it (n_phases; horizon [phases]; contact, next_contact [phases][4]; reference rows) */
+int hsddp_batch_get_schedule(hsddp_batch* b, int i, int32_t* n_phases, int32_t* horizon, int32_t* contact, int32_t* next_contact,
+                             double* xr, double* ur, double* prel_r, double* xinit);
 int hsddp_batch_set_initial_condition(hsddp_batch* b, const double* x0);
 /* re-arm the cold-start guess and the ReB/AL parameters without re-uploading schedules */
 int hsddp_batch_reset(hsddp_batch* b);

@@ -226,6 +226,38 @@ def test_mpc_command_extraction(pkg, orc, workloads):
     assert checked >= 6
 
 
+def test_device_schedule_builder_bit_exact(pkg, orc, workloads):
+    """Reference ingestion on the device (N2): schedules built by the kernel from the HBM-resident gait library are
+    bit-identical to the host builder's (phase tables and every reference row), for all three gaits, several windows
+    and horizons; and a solve on them gives bit-identical results to a solve on host-built schedules."""
+    refs = {g: pkg.QuadReference(workloads.gait_path(g)) for g in workloads.GAITS}
+    order = list(workloads.GAITS)
+    for plan in (0.25, 0.5, 0.6, 1.0):
+        sg, sw, host = [], [], []
+        for gi, g in enumerate(order):
+            for k0 in (0, 1, 7, 50, 101, 233, 250, refs[g].n - int(round(plan / 0.01)) - 3):
+                sg.append(gi); sw.append(k0); host.append(pkg.Schedule(refs[g], k0, plan))
+        B = pkg.MultiPhaseDDPBatch(0)
+        B.set_problems_from_gaits([refs[g] for g in order], sg, sw, plan, np.arange(len(sg)))
+        for i, S in enumerate(host):
+            d = B.device_schedule(i)
+            assert d["n_phases"] == S.n_phases and d["horizon"] == S.horizon, (plan, i)
+            assert d["contact"] == S.contact and d["next_contact"] == S.next_contact, (plan, i)
+            for name in ("xr", "ur", "prel_r", "xinit"):
+                assert d[name].tobytes() == S.array(name).tobytes(), (plan, i, name)
+    # same solve either way
+    w = workloads.config3(pkg, 24)
+    Bh = _batch_for(pkg, w)
+    Bh.solve()
+    Bd = pkg.MultiPhaseDDPBatch(0)
+    Bd.set_problems_from_gaits([refs[g] for g in order], [order.index(g) for g, _ in w.keys], [k for _, k in w.keys], w.plan, w.schedule_id)
+    Bd.set_initial_condition(w.x0)
+    Bd.solve()
+    assert Bd.info().tobytes() == Bh.info().tobytes()
+    S = min(Bd.get("Xbar").shape[1], Bh.get("Xbar").shape[1])
+    assert np.array_equal(Bd.get("Xbar")[:, :S], Bh.get("Xbar")[:, :S]) and np.array_equal(Bd.get("K"), Bh.get("K"))
+
+
 def test_config4_long_flight_phase(pkg, orc, workloads):
     w = workloads.config4(pkg, 12)
     assert any(max(s.horizon) >= 30 for s in w.schedules)
