@@ -199,7 +199,9 @@ template <int OP>  // 0 sum, 1 min, 2 max
 __device__ __noinline__ double block_reduce(Smem& sm, double v) {
     v = (OP == 0) ? warp_sum(v) : (OP == 1) ? warp_min(v) : warp_max(v);
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) sm.red[threadIdx.x >> 5] = v;
+    // partials are indexed by the ROLE of the warp, not by the hardware warp: the warp-role rotation of a block depends
+    // on arrival order, and the result must not (bitwise run-to-run determinism)
+    if ((threadIdx.x & 31) == 0) sm.red[virtual_tid(sm) >> 5] = v;
     __syncthreads();
     double r = sm.red[0];
 #pragma unroll

@@ -376,6 +376,41 @@ def test_full_size_config2_properties(pkg, orc, workloads):
     _compare_solution(pkg, orc, w, B, [0, 1, 511, 1023], {})
 
 
+def test_full_size_config3_properties(pkg, orc, workloads):
+    """16,384 mixed-gait problems (BASELINE configs[2], the bench workload): size-independent properties.
+    Determinism, independence of the shard a problem is solved in (the multi-GPU claim: index sharding with no
+    data-path collective changes nothing), sane termination records, and a command record that is a view of the
+    trajectories."""
+    n = 16384
+    w = workloads.config3(pkg, n)
+    B = _batch_for(pkg, w)
+    B.solve()
+    info = B.info().copy()
+    assert np.all(np.isin(info["status"], (0, 1, 2, 3))) and np.all(info["n_iter"] >= 1) and np.all(info["n_iter"] <= 50)
+    assert np.all(info["n_sweeps"] >= info["n_iter"]) and np.all(info["n_trials"] <= 4 * info["n_iter"])
+    done = info["status"] <= 1
+    assert done.mean() > 0.8 and np.all(info["feas"][done] <= 1e-3) and np.all(np.isfinite(info["cost"]))
+    Ub = B.get_rows("Ubar", 0, 8)
+    Xb = B.get_rows("Xbar", 0, 8)
+    assert np.isfinite(Ub).all() and np.isfinite(Xb).all()
+    B.reset(); B.solve()
+    assert B.info().tobytes() == info.tobytes() and np.array_equal(B.get_rows("Ubar", 0, 8), Ub)
+    # rank r of an 8-way index sharding solves problems [2048 r, 2048 (r+1)) alone: same bits as inside the big batch
+    for r in (0, 5):
+        ws = workloads.config3(pkg, 2048, first=2048 * r)
+        Bs = _batch_for(pkg, ws)
+        Bs.solve()
+        assert Bs.info().tobytes() == info[2048 * r:2048 * (r + 1)].tobytes()
+        assert np.array_equal(Bs.get_rows("Ubar", 0, 8), Ub[2048 * r:2048 * (r + 1)])
+    # the command record of a problem is (float32 of) its first stages: phase 0 is at least 8 stages long for most windows
+    cmd = B.mpc_command(8)
+    first_len = np.array([w.schedules[s].horizon[0] for s in w.schedule_id])
+    sel = np.nonzero(first_len >= 8)[0][:2000]
+    assert len(sel) > 100
+    assert np.array_equal(cmd["hkd_controls"][sel, :8], Ub[sel].astype(np.float32))
+    assert np.array_equal(cmd["des_body_state"][sel, :8], Xb[sel][:, :, :12].astype(np.float32))
+
+
 def _write_quad_reference_csv(npz_path, out_path, n_rows=120):
     """Text form of a gait fixture in the reference's quad_reference.csv format (3 decimals, as
     scripts/ReferenceGen/generate_reference.m writes it)."""
