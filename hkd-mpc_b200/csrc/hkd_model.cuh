@@ -155,85 +155,97 @@ HKD_HD void dynamics(const double* x, const double* u, double dt, unsigned cmask
 }
 
 // Analytic linearisation (HKD::Model::dynamics_partial) written straight into a COMPACT stage record Rc[kCrSize] (layout above).
-HKD_HD void dynamics_partial_record(const double* x, const double* u, double dt, unsigned cmask, double* Rc) {
+// PARTS bit 0: the Euler-rate rows and the body columns (0..8) of the angular-acceleration rows;
+// PARTS bit 1: the per-leg columns (foot x,y and B_r) of the angular-acceleration rows and the linear-acceleration rows.
+// The two halves write disjoint entries, so two threads can share one stage (lq_approximation_block).
+template <int PARTS>
+HKD_HD void dynamics_partial_parts(const double* x, const double* u, double dt, unsigned cmask, double* Rc) {
     const Trig t = trig_of(x[0], x[1], x[2]);
-    const double wx = x[6], wy = x[7], wz = x[8];
-    const double s1 = t.sr * wy + t.cr * wz;
-    const double s2 = t.cr * wy - t.sr * wz;
-    const double icp = 1.0 / t.cp;
-    const double tp = t.sp * icp;
-    // Euler-rate rows 0..2
-    Rc[0] = dt * (s1 * t.sp * icp * icp);
-    Rc[1] = dt * (s2 * icp);
-    Rc[2] = dt * (t.sr * icp);
-    Rc[3] = dt * (t.cr * icp);
-    Rc[4] = dt * (-s1);
-    Rc[5] = dt * t.cr;
-    Rc[6] = dt * (-t.sr);
-    Rc[7] = dt * (s1 * icp * icp);
-    Rc[8] = dt * (tp * s2);
-    Rc[9] = dt;
-    Rc[10] = dt * (tp * t.sr);
-    Rc[11] = dt * (tp * t.cr);
-    // position rows 3..5 hold the constant dt at columns 9..11: not stored
-    // angular-acceleration rows 6..8: M = dt * Jinv * R^T
-    double R[9], F[3], tw[3];
+    double R[9];
     rotation(t, R);
-    wrench(x, u, cmask, F, tw);
     const double jd[3] = {dt * kJxx, dt * kJyy, dt * kJzz};
-    double M[9];
+    double M[9];  // M = dt * Jinv * R^T
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int i = 0; i < 3; ++i) M[3 * a + i] = jd[a] * R[3 * i + a];
-    // d/d yaw:  (dR/dyaw)^T tau = -R[1][:] tau0 + R[0][:] tau1 ; d/d roll: (0, (R^T tau)_2, -(R^T tau)_1)
-    const double rt1 = R[1] * tw[0] + R[4] * tw[1] + R[7] * tw[2];
-    const double rt2 = R[2] * tw[0] + R[5] * tw[1] + R[8] * tw[2];
-    const double dP[9] = {-t.cy * t.sp, t.cy * t.cp * t.sr, t.cy * t.cp * t.cr,
-                          -t.sy * t.sp, t.sy * t.cp * t.sr, t.sy * t.cp * t.cr,
-                          -t.cp,        -t.sp * t.sr,       -t.sp * t.cr};
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        double* row = Rc + cr_w(a, 0);
-        row[0] = jd[a] * (-R[3 + a] * tw[0] + R[a] * tw[1]);
-        row[1] = jd[a] * (dP[a] * tw[0] + dP[3 + a] * tw[1] + dP[6 + a] * tw[2]);
-        // position columns: tau_world depends on p through r_l = foot - p  ->  column j = M (F x e_j)
-        row[3] = M[3 * a + 1] * F[2] - M[3 * a + 2] * F[1];
-        row[4] = -M[3 * a + 0] * F[2] + M[3 * a + 2] * F[0];
-        row[5] = M[3 * a + 0] * F[1] - M[3 * a + 1] * F[0];
-    }
-    Rc[cr_w(0, 2)] = 0.0;
-    Rc[cr_w(1, 2)] = jd[1] * rt2;
-    Rc[cr_w(2, 2)] = jd[2] * (-rt1);
-    // gyroscopic block
-    Rc[cr_w(0, 6)] = 0.0;
-    Rc[cr_w(0, 7)] = jd[0] * (kIyy - kIzz) * wz;
-    Rc[cr_w(0, 8)] = jd[0] * (kIyy - kIzz) * wy;
-    Rc[cr_w(1, 6)] = jd[1] * (kIzz - kIxx) * wz;
-    Rc[cr_w(1, 7)] = 0.0;
-    Rc[cr_w(1, 8)] = jd[1] * (kIzz - kIxx) * wx;
-    Rc[cr_w(2, 6)] = jd[2] * (kIxx - kIyy) * wy;
-    Rc[cr_w(2, 7)] = jd[2] * (kIxx - kIyy) * wx;
-    Rc[cr_w(2, 8)] = 0.0;
-#pragma unroll
-    for (int l = 0; l < 4; ++l) {
-        const bool stance = (cmask >> l) & 1u;
-        const double rx = x[12 + 3 * l] - x[3], ry = x[13 + 3 * l] - x[4], rz = -x[5];
-        const double fx = u[3 * l], fy = u[3 * l + 1], fz = u[3 * l + 2];
+    if (PARTS & 1) {
+        const double wx = x[6], wy = x[7], wz = x[8];
+        const double s1 = t.sr * wy + t.cr * wz;
+        const double s2 = t.cr * wy - t.sr * wz;
+        const double icp = 1.0 / t.cp;
+        const double tp = t.sp * icp;
+        // Euler-rate rows 0..2
+        Rc[0] = dt * (s1 * t.sp * icp * icp);
+        Rc[1] = dt * (s2 * icp);
+        Rc[2] = dt * (t.sr * icp);
+        Rc[3] = dt * (t.cr * icp);
+        Rc[4] = dt * (-s1);
+        Rc[5] = dt * t.cr;
+        Rc[6] = dt * (-t.sr);
+        Rc[7] = dt * (s1 * icp * icp);
+        Rc[8] = dt * (tp * s2);
+        Rc[9] = dt;
+        Rc[10] = dt * (tp * t.sr);
+        Rc[11] = dt * (tp * t.cr);
+        // position rows 3..5 hold the constant dt at columns 9..11: not stored
+        // angular-acceleration rows 6..8, body columns
+        double F[3], tw[3];
+        wrench(x, u, cmask, F, tw);
+        // d/d yaw:  (dR/dyaw)^T tau = -R[1][:] tau0 + R[0][:] tau1 ; d/d roll: (0, (R^T tau)_2, -(R^T tau)_1)
+        const double rt1 = R[1] * tw[0] + R[4] * tw[1] + R[7] * tw[2];
+        const double rt2 = R[2] * tw[0] + R[5] * tw[1] + R[8] * tw[2];
+        const double dP[9] = {-t.cy * t.sp, t.cy * t.cp * t.sr, t.cy * t.cp * t.cr,
+                              -t.sy * t.sp, t.sy * t.cp * t.sr, t.sy * t.cp * t.cr,
+                              -t.cp,        -t.sp * t.sr,       -t.sp * t.cr};
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            const double m0 = M[3 * a], m1 = M[3 * a + 1], m2 = M[3 * a + 2];
-            // foot x,y columns: M (e_j x f) ; force columns: M (r x e_j)   (zero for a swing leg)
-            Rc[cr_w(a, 9 + 2 * l)] = stance ? (-m1 * fz + m2 * fy) : 0.0;
-            Rc[cr_w(a, 10 + 2 * l)] = stance ? (m0 * fz - m2 * fx) : 0.0;
-            Rc[cr_w(a, 17 + 3 * l + 0)] = stance ? (m1 * rz - m2 * ry) : 0.0;
-            Rc[cr_w(a, 17 + 3 * l + 1)] = stance ? (-m0 * rz + m2 * rx) : 0.0;
-            Rc[cr_w(a, 17 + 3 * l + 2)] = stance ? (m0 * ry - m1 * rx) : 0.0;
+            double* row = Rc + cr_w(a, 0);
+            row[0] = jd[a] * (-R[3 + a] * tw[0] + R[a] * tw[1]);
+            row[1] = jd[a] * (dP[a] * tw[0] + dP[3 + a] * tw[1] + dP[6 + a] * tw[2]);
+            // position columns: tau_world depends on p through r_l = foot - p  ->  column j = M (F x e_j)
+            row[3] = M[3 * a + 1] * F[2] - M[3 * a + 2] * F[1];
+            row[4] = -M[3 * a + 0] * F[2] + M[3 * a + 2] * F[0];
+            row[5] = M[3 * a + 0] * F[1] - M[3 * a + 1] * F[0];
         }
-        // linear acceleration rows 9..11: (c/m) dt on the leg's own force component
-#pragma unroll
-        for (int j = 0; j < 3; ++j) Rc[cr_v(j, l)] = stance ? (1.0 / kMass) * dt : 0.0;
+        Rc[cr_w(0, 2)] = 0.0;
+        Rc[cr_w(1, 2)] = jd[1] * rt2;
+        Rc[cr_w(2, 2)] = jd[2] * (-rt1);
+        // gyroscopic block
+        Rc[cr_w(0, 6)] = 0.0;
+        Rc[cr_w(0, 7)] = jd[0] * (kIyy - kIzz) * wz;
+        Rc[cr_w(0, 8)] = jd[0] * (kIyy - kIzz) * wy;
+        Rc[cr_w(1, 6)] = jd[1] * (kIzz - kIxx) * wz;
+        Rc[cr_w(1, 7)] = 0.0;
+        Rc[cr_w(1, 8)] = jd[1] * (kIzz - kIxx) * wx;
+        Rc[cr_w(2, 6)] = jd[2] * (kIxx - kIyy) * wy;
+        Rc[cr_w(2, 7)] = jd[2] * (kIxx - kIyy) * wx;
+        Rc[cr_w(2, 8)] = 0.0;
     }
+    if (PARTS & 2) {
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const bool stance = (cmask >> l) & 1u;
+            const double rx = x[12 + 3 * l] - x[3], ry = x[13 + 3 * l] - x[4], rz = -x[5];
+            const double fx = u[3 * l], fy = u[3 * l + 1], fz = u[3 * l + 2];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const double m0 = M[3 * a], m1 = M[3 * a + 1], m2 = M[3 * a + 2];
+                // foot x,y columns: M (e_j x f) ; force columns: M (r x e_j)   (zero for a swing leg)
+                Rc[cr_w(a, 9 + 2 * l)] = stance ? (-m1 * fz + m2 * fy) : 0.0;
+                Rc[cr_w(a, 10 + 2 * l)] = stance ? (m0 * fz - m2 * fx) : 0.0;
+                Rc[cr_w(a, 17 + 3 * l + 0)] = stance ? (m1 * rz - m2 * ry) : 0.0;
+                Rc[cr_w(a, 17 + 3 * l + 1)] = stance ? (-m0 * rz + m2 * rx) : 0.0;
+                Rc[cr_w(a, 17 + 3 * l + 2)] = stance ? (m0 * ry - m1 * rx) : 0.0;
+            }
+            // linear acceleration rows 9..11: (c/m) dt on the leg's own force component
+#pragma unroll
+            for (int j = 0; j < 3; ++j) Rc[cr_v(j, l)] = stance ? (1.0 / kMass) * dt : 0.0;
+        }
+    }
+}
+HKD_HD void dynamics_partial_record(const double* x, const double* u, double dt, unsigned cmask, double* Rc) {
+    dynamics_partial_parts<3>(x, u, dt, cmask, Rc);
 }
 
 // expand a compact stage record to the dense column-major A, B of the reference

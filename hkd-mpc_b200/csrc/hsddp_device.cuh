@@ -163,6 +163,7 @@ struct __align__(16) Smem {
 };
 
 static_assert(offsetof(Smem, dfc2) - offsetof(Smem, H) == sizeof(double) * kSweepDoubles, "kSweepDoubles must cover H..rec");
+static_assert(32 * 113 <= kSweepDoubles, "LQ staging buffer does not fit");
 
 // ---------------------------------------------------------------------------
 // small helpers
@@ -564,12 +565,29 @@ __device__ inline void lq_approximation_block(Smem& sm) {
     PROF_DECL
     const int N = sc.n_stages;
     const double dt = sc.dt;
-    // (1) dynamics Jacobians, one thread per stage (the record rows are written in place)
-    for (int s = tid; s < N; s += kThreads) {
-        int ph, k;
-        phase_of_stage(sc, s, ph, k);
-        const int n = sc.node_off[ph] + k;
-        hkd::dynamics_partial_record(sm.X + 24 * n, sm.U + 24 * s, dt, sc.cmask[ph], sm.lqg + (size_t)s * CR_STRIDE + CR_R);
+    // (1) dynamics Jacobians.  Two threads share a stage (disjoint halves of the record, hkd_model.cuh) and write its
+    //     compact record into shared memory (row stride 113 doubles: the per-thread rows do not collide on banks);
+    //     after each pass of 32 stages all threads copy the rows out with coalesced stores.
+    {
+        double* stg = sm.H;  // the sweep's tile storage is free here (kSweepDoubles >= 32 * 113)
+        for (int s0 = 0; s0 < N; s0 += 32) {
+            const int s = s0 + (tid & 31);
+            if (tid < 64 && s < N) {
+                int ph, k;
+                phase_of_stage(sc, s, ph, k);
+                const int n = sc.node_off[ph] + k;
+                double* row = stg + 113 * (tid & 31);
+                if (tid < 32) hkd::dynamics_partial_parts<1>(sm.X + 24 * n, sm.U + 24 * s, dt, sc.cmask[ph], row);
+                else hkd::dynamics_partial_parts<2>(sm.X + 24 * n, sm.U + 24 * s, dt, sc.cmask[ph], row);
+            }
+            __syncthreads();
+            const int ns = min(32, N - s0);
+            for (int e = tid; e < ns * hkd::kCrNnz; e += kThreads) {
+                const int r = e / hkd::kCrNnz, i = e % hkd::kCrNnz;
+                sm.lqg[(size_t)(s0 + r) * CR_STRIDE + CR_R + i] = stg[113 * r + i];
+            }
+            __syncthreads();
+        }
     }
     // (2) cost gradients, flat over (stage, component): lx (24) and the lu of the joint-velocity commands (12);
     //     coalesced reads, 192-byte runs of writes.  Foot-placement regulariser: the position rows accumulate over
