@@ -228,22 +228,20 @@ __device__ inline void build_phase_tables(Smem& sm, unsigned cm, double dt) {
     __syncthreads();
 }
 
-// Tile descriptors of the stage body.  Every phase of a stage is a short ROLLED loop over 8x8 output tiles
-// (3 DMMA each) driven by these constant tables: tile `warp + 4 q` belongs to warp `warp`.  The loop bodies
-// hold no index arithmetic beyond adding the table offsets to per-lane base pointers, so the whole stage
-// stays small enough for the SM's instruction cache (the kernel is instruction-fetch sensitive:
-// a fully unrolled, per-warp specialised variant executes 30 % fewer instructions but runs slower, see
-// DESIGN.md §4 and tools/code_size.py).
-//   c_p1[tile] = {a: column of H (8 I), b: column of [A | B_r] (8 Jt), c: offset of the H / Y tile element,
-//                 z: offset of the Z tile element, -1 for a Y tile, -2: the Gn = G + H d vector job}
-//   c_p2[tile] = {a: column of R, b: column of Y / Z | kind << 16 | Ci << 20, cin: Y tile offset or -1, out: offset in H / Qux / Quu}
-//   c_p4[tile] = {a: column of Qux (8 I), b: 8 J * 12 into K_r^T, c: H tile offset, mirror offset (-1 diagonal tile, -2 idle, -3 the G' job)}
-__constant__ int4 c_p1[16] = {{0, 0, 0, -1}, {0, 8, 8, -1}, {0, 16, 16, -1}, {0, 24, 12, 0}, {0, 32, 20, 8}, {8, 0, 224, -1}, {8, 8, 232, -1}, {8, 16, 240, -1},
-                              {8, 24, 236, 160}, {8, 32, 244, 168}, {16, 0, 448, -1}, {16, 8, 456, -1}, {16, 16, 464, -1}, {16, 24, 460, 320}, {16, 32, 468, 328}, {0, 0, 0, -2}};
-__constant__ int4 c_p2[16] = {{0, 0, 0, 0}, {8, 0, 224, 224}, {8, 8, 232, 232}, {16, 0, 448, 448}, {16, 8, 456, 456}, {16, 16, 464, 464},
-                              {24, 65536, -1, 0}, {24, 65544, -1, 8}, {24, 65552, -1, 16}, {32, 1114112, -1, 224}, {32, 1114120, -1, 232}, {32, 1114128, -1, 240},
-                              {24, 131072, -1, 0}, {24, 131080, -1, 8}, {32, 1179648, -1, 224}, {32, 1179656, -1, 232}};
-__constant__ int4 c_p4[8] = {{0, 0, 0, -1}, {8, 0, 224, 8}, {8, 96, 232, -1}, {16, 0, 448, 16}, {16, 96, 456, 240}, {16, 192, 464, -1}, {0, 0, 0, -2}, {0, 0, 0, -3}};
+// Tile descriptors of the stage body.  Every phase of a stage is a set of short ROLLED loops over 8x8 output tiles
+// (3 DMMA each), one loop per KIND of tile, driven by these constant tables.  A loop body holds no index arithmetic
+// beyond adding the table offsets to per-lane base pointers and no branches on the kind of tile, and the whole stage
+// stays small enough for the SM's instruction cache (the kernel is instruction-fetch sensitive: a fully unrolled,
+// per-warp specialised variant executes 30 % fewer instructions but runs slower inside k_solve, see DESIGN.md §4.0
+// and tools/code_size.py).  Tiles of one kind are dealt round-robin to the warps so that every warp gets four
+// tiles per phase (P1, P2) and the vector jobs (Gn, Qx, Qu_r, G') go to the warps with the lightest tiles.
+__constant__ int4 c_y[9] = {{0, 0, 0, 0}, {0, 8, 8, 0}, {0, 16, 16, 0}, {8, 0, 224, 0}, {8, 8, 232, 0}, {8, 16, 240, 0}, {16, 0, 448, 0}, {16, 8, 456, 0}, {16, 16, 464, 0}};      // P1 Y tiles: {8 I, 8 Jt, H / Y tile offset, -}
+__constant__ int4 c_z[6] = {{0, 24, 12, 0}, {0, 32, 20, 8}, {8, 24, 236, 160}, {8, 32, 244, 168}, {16, 24, 460, 320}, {16, 32, 468, 328}};   // P1 Z tiles: {8 I, column of R, offset of H[:, 12 + 8 Jz], Z tile offset}
+__constant__ int4 c_xx[6] = {{0, 0, 0, 0}, {8, 0, 224, 0}, {8, 8, 232, 0}, {16, 0, 448, 0}, {16, 8, 456, 0}, {16, 16, 464, 0}};  // P2 Qxx (lower): {column of R, column of Y, Y / H tile offset, -}
+__constant__ int4 c_ux[6] = {{24, 0, 0, 0}, {24, 8, 8, 0}, {24, 16, 16, 0}, {32, 0, 224, 1}, {32, 8, 232, 1}, {32, 16, 240, 1}};  // P2 Qux_r: {column of R, column of Y, Qux tile offset, Ci}
+__constant__ int4 c_uu[4] = {{24, 0, 0, 0}, {24, 8, 8, 0}, {32, 0, 224, 1}, {32, 8, 232, 1}};  // P2 Quu_r: {column of R, column of Z, Quu tile offset, Ci}
+__constant__ int4 c_4d[3] = {{0, 0, 0, 0}, {8, 96, 232, 0}, {16, 192, 464, 0}};  // P4 diagonal tiles: {column of Qux, 8 I * 12 into K_r^T, H tile offset, -}
+__constant__ int4 c_4o[3] = {{16, 96, 456, 240}, {8, 0, 224, 8}, {16, 0, 448, 16}};  // P4 off-diagonal tiles (2,1), (1,0), (2,0): {.., .., H tile offset, mirror offset}
 static_assert(TS == 28 && ZS == 20, "the tile descriptor tables are generated for TS = 28, ZS = 20");
 
 // One phase of the backward sweep.  On entry sm.G / sm.H hold Gprime / Hprime (zero for
@@ -314,82 +312,116 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
         const double* luv = sm.rec[buf] + LQ_LU;
         const double* luu = sm.rec[buf] + LQ_LUU;
         const double* dfc = sm.dfc2[buf];
-        // ---- P1: [Y | Z] = H [A | B_r] : 15 tiles (3 row blocks x 5 column blocks), Gn = G + H d ----
+        // ---- P1: [Y | Z] = H [A | B_r] : 9 Y tiles + 6 Z tiles, Gn = G + H d ----
         const double* rB = R + t * hkd::kRld + g;  // operand element (t, g) of R; also the a-operand of P2
 #pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-            const int4 d = c_p1[warp + 4 * q];
-            if (d.w != -2) {
+        for (int q = warp; q < 9; q += 4) {  // Y = H + H At : warps get 3, 2, 2, 2 tiles
+            const int4 d = c_y[q];
+            const double2 h2 = *reinterpret_cast<const double2*>(hC + d.z);
+            double c2[2] = {h2.x, h2.y};
+            const double* a = hA + d.x;
+            const double* b = rB + d.y;
+            dmma884(c2, a[0], b[0]);
+            dmma884(c2, a[4 * TS], b[4 * hkd::kRld]);
+            dmma884(c2, a[8 * TS], b[8 * hkd::kRld]);
+            *reinterpret_cast<double2*>(yC + d.z) = make_double2(c2[0], c2[1]);
+        }
+        {
+            // Z = H B_r : warps get 1, 2, 2, 1 tiles (tiles 0 | 1,2 | 3,4 | 5)
+            const int z0 = (0x5310 >> (4 * warp)) & 15, z1 = z0 + ((0x1221 >> (4 * warp)) & 15);
+#pragma unroll 1
+            for (int q = z0; q < z1; ++q) {
+                const int4 d = c_z[q];
                 double c2[2] = {0.0, 0.0};
-                if (d.w < 0) { const double2 h2 = *reinterpret_cast<const double2*>(hC + d.z); c2[0] = h2.x; c2[1] = h2.y; }
                 const double* a = hA + d.x;
                 const double* b = rB + d.y;
                 dmma884(c2, a[0], b[0]);
                 dmma884(c2, a[4 * TS], b[4 * hkd::kRld]);
                 dmma884(c2, a[8 * TS], b[8 * hkd::kRld]);
-                if (d.w < 0) {
-                    *reinterpret_cast<double2*>(yC + d.z) = make_double2(c2[0], c2[1]);
-                } else {  // swing columns of Z: H[:, 12+c] * (1-c_l) dt (zero factor for stance legs and the padding c >= 12)
-                    const double2 h2 = *reinterpret_cast<const double2*>(hC + d.z);
-                    const double2 sw = *reinterpret_cast<const double2*>(sm.swc + 2 * t + d.y - 24);
-                    c2[0] = fma(h2.x, sw.x, c2[0]);
-                    c2[1] = fma(h2.y, sw.y, c2[1]);
-                    *reinterpret_cast<double2*>(zC + d.w) = make_double2(c2[0], c2[1]);
-                }
-            } else if (lane < 24) {  // Gn = G + H d   (Q10)
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-                for (int j = 0; j < 24; j += 4) {
-                    a0 = fma(sm.H[j * TS + lane], dfc[j], a0);
-                    a1 = fma(sm.H[(j + 1) * TS + lane], dfc[j + 1], a1);
-                    a2 = fma(sm.H[(j + 2) * TS + lane], dfc[j + 2], a2);
-                    a3 = fma(sm.H[(j + 3) * TS + lane], dfc[j + 3], a3);
-                }
-                sm.Gn[lane] = sm.G[lane] + ((a0 + a1) + (a2 + a3));
+                // swing columns of Z: H[:, 12+c] * (1-c_l) dt (zero factor for stance legs and the padding c >= 12)
+                const double2 h2 = *reinterpret_cast<const double2*>(hC + d.z);
+                const double2 sw = *reinterpret_cast<const double2*>(sm.swc + 2 * t + d.y - 24);
+                c2[0] = fma(h2.x, sw.x, c2[0]);
+                c2[1] = fma(h2.y, sw.y, c2[1]);
+                *reinterpret_cast<double2*>(zC + d.w) = make_double2(c2[0], c2[1]);
             }
+        }
+        if (warp == 3 && lane < 24) {  // Gn = G + H d   (Q10)
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 24; j += 4) {
+                a0 = fma(sm.H[j * TS + lane], dfc[j], a0);
+                a1 = fma(sm.H[(j + 1) * TS + lane], dfc[j + 1], a1);
+                a2 = fma(sm.H[(j + 2) * TS + lane], dfc[j + 2], a2);
+                a3 = fma(sm.H[(j + 3) * TS + lane], dfc[j + 3], a3);
+            }
+            sm.Gn[lane] = sm.G[lane] + ((a0 + a1) + (a2 + a3));
         }
         __syncthreads();
         PROF_MARK(sm, 6);
-        // ---- P2: 16 tiles C = [A | B_r]^T M :  6 x Qxx (lower, M = Y, parked in H) ; 6 x Qux_r (M = Y) ; 4 x Quu_r (M = Z) ----
+        // ---- P2: C = [A | B_r]^T M :  6 x Qxx (lower, M = Y, parked in H) ; 6 x Qux_r (M = Y) ; 4 x Quu_r (M = Z) ----
         // (the sparse additive term of Qxx, lxx + reg I, is applied in P3 by the warp that is idle there)
+        const double* yB = sm.Y + t * TS + g;
 #pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-            const int4 d = c_p2[warp + 4 * q];
-            const int kind = (d.y >> 16) & 3, Ci = d.y >> 20, boff = d.y & 0xffff;
-            double c2[2] = {0.0, 0.0};
-            if (d.z >= 0) { const double2 y2 = *reinterpret_cast<const double2*>(yC + d.z); c2[0] = y2.x; c2[1] = y2.y; }
+        for (int q = warp; q < 6; q += 4) {  // Qxx = Y + At^T Y : warps 0, 1 two tiles, warps 2, 3 one
+            const int4 d = c_xx[q];
+            const double2 y2 = *reinterpret_cast<const double2*>(yC + d.z);
+            double c2[2] = {y2.x, y2.y};
             const double* a = rB + d.x;
-            const double* M = (kind == 2) ? sm.Z : sm.Y;
-            const int ms = (kind == 2) ? ZS : TS;
-            const double* b = M + t * ms + g + boff;
+            const double* b = yB + d.y;
             dmma884(c2, a[0], b[0]);
-            dmma884(c2, a[4 * hkd::kRld], b[4 * ms]);
-            dmma884(c2, a[8 * hkd::kRld], b[8 * ms]);
-            if (kind == 0) {
-                *reinterpret_cast<double2*>(hC + d.w) = make_double2(c2[0], c2[1]);
-            } else {
-                const int c = 8 * Ci + g;  // reduced control row
-                if (c < 12) {
-                    const double sw = sm.swc[c];
-                    if (sw != 0.0) {  // swing row: (B_r^T M)[c][:] = (1-c_l) dt * M[12+c][:]
-                        const double2 m2 = *reinterpret_cast<const double2*>(M + (12 + c) * ms + boff + 2 * t);
-                        c2[0] = fma(sw, m2.x, c2[0]);
-                        c2[1] = fma(sw, m2.y, c2[1]);
-                    }
-                    if (kind == 2) {  // + luu_r: dt R + reg on the diagonal, the ReB Hessian block of a stance leg
-                        const bool stance = sw == 0.0;
-                        const int cc = boff + 2 * t, l3 = 3 * (c / 3);
-                        const double diag = dt * (stance ? .2 : .1) + reg;  // weight_R(act_index(c, cm))
-                        if (c == cc) c2[0] += diag;
-                        if (c == cc + 1) c2[1] += diag;
-                        if (stance) {
-                            const double* lb = luu + 3 * c;  // luu[9 (c/3) + 3 (c%3) + k]
-                            if (cc >= l3 && cc < l3 + 3) c2[0] += lb[cc - l3];
-                            if (cc + 1 >= l3 && cc + 1 < l3 + 3) c2[1] += lb[cc + 1 - l3];
-                        }
-                    }
-                    *reinterpret_cast<double2*>(((kind == 2) ? quuC : quxC) + d.w) = make_double2(c2[0], c2[1]);
+            dmma884(c2, a[4 * hkd::kRld], b[4 * TS]);
+            dmma884(c2, a[8 * hkd::kRld], b[8 * TS]);
+            *reinterpret_cast<double2*>(hC + d.z) = make_double2(c2[0], c2[1]);
+        }
+#pragma unroll 1
+        for (int q = (warp + 2) & 3; q < 6; q += 4) {  // Qux_r = B_r^T Y : warps 2, 3 two tiles, warps 0, 1 one
+            const int4 d = c_ux[q];
+            double c2[2] = {0.0, 0.0};
+            const double* a = rB + d.x;
+            const double* b = yB + d.y;
+            dmma884(c2, a[0], b[0]);
+            dmma884(c2, a[4 * hkd::kRld], b[4 * TS]);
+            dmma884(c2, a[8 * hkd::kRld], b[8 * TS]);
+            const int c = 8 * d.w + g;  // reduced control row
+            if (c < 12) {
+                const double sw = sm.swc[c];
+                if (sw != 0.0) {  // swing row: (B_r^T Y)[c][:] = (1-c_l) dt * Y[12+c][:]
+                    const double2 m2 = *reinterpret_cast<const double2*>(sm.Y + (12 + c) * TS + d.y + 2 * t);
+                    c2[0] = fma(sw, m2.x, c2[0]);
+                    c2[1] = fma(sw, m2.y, c2[1]);
                 }
+                *reinterpret_cast<double2*>(quxC + d.z) = make_double2(c2[0], c2[1]);
+            }
+        }
+        {   // Quu_r = luu_r + B_r^T Z : one tile per warp
+            const int4 d = c_uu[warp];
+            double c2[2] = {0.0, 0.0};
+            const double* a = rB + d.x;
+            const double* b = sm.Z + t * ZS + g + d.y;
+            dmma884(c2, a[0], b[0]);
+            dmma884(c2, a[4 * hkd::kRld], b[4 * ZS]);
+            dmma884(c2, a[8 * hkd::kRld], b[8 * ZS]);
+            const int c = 8 * d.w + g;  // reduced control row
+            if (c < 12) {
+                const double sw = sm.swc[c];
+                if (sw != 0.0) {  // swing row: (B_r^T Z)[c][:] = (1-c_l) dt * Z[12+c][:]
+                    const double2 m2 = *reinterpret_cast<const double2*>(sm.Z + (12 + c) * ZS + d.y + 2 * t);
+                    c2[0] = fma(sw, m2.x, c2[0]);
+                    c2[1] = fma(sw, m2.y, c2[1]);
+                }
+                // + luu_r: dt R + reg on the diagonal, the ReB Hessian block of a stance leg
+                const bool stance = sw == 0.0;
+                const int cc = d.y + 2 * t, l3 = 3 * (c / 3);
+                const double diag = dt * (stance ? .2 : .1) + reg;  // weight_R(act_index(c, cm))
+                if (c == cc) c2[0] += diag;
+                if (c == cc + 1) c2[1] += diag;
+                if (stance) {
+                    const double* lb = luu + 3 * c;  // luu[9 (c/3) + 3 (c%3) + k]
+                    if (cc >= l3 && cc < l3 + 3) c2[0] += lb[cc - l3];
+                    if (cc + 1 >= l3 && cc + 1 < l3 + 3) c2[1] += lb[cc + 1 - l3];
+                }
+                *reinterpret_cast<double2*>(quuC + d.z) = make_double2(c2[0], c2[1]);
             }
         }
         if (warp == 3 && lane < 24) {  // Qx = lx + A^T Gn
@@ -506,10 +538,9 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
         }
         if (!sm.ibuf[0]) { cp_async_wait_all(); return false; }
         // ---- P4: H' = sym(Qxx) + Qux_r^T K_r (6 lower tiles, mirrored) ; G' = Qx + Qux_r^T dU_r ----
-#pragma unroll 1
-        for (int q = 0; q < 2; ++q) {
-            const int4 d = c_p4[warp + 4 * q];
-            if (d.w >= -1) {
+        if (warp < 3) {  // warp w: diagonal tile (w, w) and one off-diagonal tile
+            {
+                const int4 d = c_4d[warp];
                 const double2 q2 = *reinterpret_cast<const double2*>(hC + d.z);
                 double c2[2] = {q2.x, q2.y};
                 const double* a = qA + d.x;
@@ -517,28 +548,36 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                 dmma884(c2, a[0], b[0]);
                 dmma884(c2, a[4 * TS], b[4]);
                 dmma884(c2, a[8 * TS], b[8]);
-                if (d.w < 0) {
-                    // symmetrise the diagonal tile: partner of (g, 2t+q') is (2t+q', g), held by lane 4*(2t+q') + g/2, slot g&1
-                    const double p00 = __shfl_sync(0xffffffffu, c2[0], 4 * (2 * t) + (g >> 1));
-                    const double p01 = __shfl_sync(0xffffffffu, c2[1], 4 * (2 * t) + (g >> 1));
-                    const double p10 = __shfl_sync(0xffffffffu, c2[0], 4 * (2 * t + 1) + (g >> 1));
-                    const double p11 = __shfl_sync(0xffffffffu, c2[1], 4 * (2 * t + 1) + (g >> 1));
-                    c2[0] = 0.5 * (c2[0] + ((g & 1) ? p01 : p00));
-                    c2[1] = 0.5 * (c2[1] + ((g & 1) ? p11 : p10));
-                } else {
-                    hT[d.w] = c2[0];
-                    hT[d.w + TS] = c2[1];
-                }
+                // symmetrise the diagonal tile: partner of (g, 2t+q') is (2t+q', g), held by lane 4*(2t+q') + g/2, slot g&1
+                const double p00 = __shfl_sync(0xffffffffu, c2[0], 4 * (2 * t) + (g >> 1));
+                const double p01 = __shfl_sync(0xffffffffu, c2[1], 4 * (2 * t) + (g >> 1));
+                const double p10 = __shfl_sync(0xffffffffu, c2[0], 4 * (2 * t + 1) + (g >> 1));
+                const double p11 = __shfl_sync(0xffffffffu, c2[1], 4 * (2 * t + 1) + (g >> 1));
+                c2[0] = 0.5 * (c2[0] + ((g & 1) ? p01 : p00));
+                c2[1] = 0.5 * (c2[1] + ((g & 1) ? p11 : p10));
                 *reinterpret_cast<double2*>(hC + d.z) = make_double2(c2[0], c2[1]);
-            } else if (d.w == -3 && lane < 24) {  // G' = Qx + Qux_r^T dU_r
-                double a0 = sm.Qx[lane], a1 = 0.0;
-#pragma unroll
-                for (int r = 0; r < 12; r += 2) {
-                    a0 = fma(sm.Qux[r * TS + lane], sm.wu[r], a0);
-                    a1 = fma(sm.Qux[(r + 1) * TS + lane], sm.wu[r + 1], a1);
-                }
-                sm.G[lane] = a0 + a1;
             }
+            {
+                const int4 d = c_4o[warp];
+                const double2 q2 = *reinterpret_cast<const double2*>(hC + d.z);
+                double c2[2] = {q2.x, q2.y};
+                const double* a = qA + d.x;
+                const double* b = kB + d.y;
+                dmma884(c2, a[0], b[0]);
+                dmma884(c2, a[4 * TS], b[4]);
+                dmma884(c2, a[8 * TS], b[8]);
+                hT[d.w] = c2[0];
+                hT[d.w + TS] = c2[1];
+                *reinterpret_cast<double2*>(hC + d.z) = make_double2(c2[0], c2[1]);
+            }
+        } else if (lane < 24) {  // G' = Qx + Qux_r^T dU_r
+            double a0 = sm.Qx[lane], a1 = 0.0;
+#pragma unroll
+            for (int r = 0; r < 12; r += 2) {
+                a0 = fma(sm.Qux[r * TS + lane], sm.wu[r], a0);
+                a1 = fma(sm.Qux[(r + 1) * TS + lane], sm.wu[r + 1], a1);
+            }
+            sm.G[lane] = a0 + a1;
         }
         const double dvk = sm.dbuf[0] + sm.dbuf[1];
         dV1 -= dvk;
