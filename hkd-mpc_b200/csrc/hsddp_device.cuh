@@ -294,24 +294,24 @@ __device__ inline void resetmap_thread(const double* x, unsigned c, unsigned cn,
     }
 }
 
-// dense Px (HKDReset.h:78-136), ROW-major into P[r * 24 + c].  Jc: the foot Jacobians cached by the
-// LQ approximation in the phase's terminal record ([4][3][6]: d/d eul, d/d qleg per leg).
-__device__ inline void resetmap_partial_block(const double* Jc_all, unsigned c, unsigned cn, double* P) {
-    for (int e = threadIdx.x; e < 576; e += kThreads) P[e] = ((e % 24) == (e / 24)) ? 1.0 : 0.0;
+// dense Px (HKDReset.h:78-136), ROW-major into P[r * S + c] (S = row stride in doubles).  Jc: the foot Jacobians cached
+// by the LQ approximation in the phase's terminal record ([4][3][6]: d/d eul, d/d qleg per leg).
+__device__ inline void resetmap_partial_block(const double* Jc_all, unsigned c, unsigned cn, double* P, int S) {
+    for (int e = threadIdx.x; e < 576; e += kThreads) P[(e / 24) * S + e % 24] = ((e % 24) == (e / 24)) ? 1.0 : 0.0;
     __syncthreads();
     if (threadIdx.x < 12) {
         const int l = threadIdx.x / 3, r = threadIdx.x % 3;
         const bool cl = (c >> l) & 1u, nl = (cn >> l) & 1u;
         const int row = 12 + 3 * l + r;
-        if (cl && !nl) P[row * 25] = 0.0;
+        if (cl && !nl) P[row * (S + 1)] = 0.0;
         if (!cl && nl) {
             const double* Jc = Jc_all + 18 * l + 6 * r;
             const double cmap = (r == 2) ? 0.0 : 1.0;
-            P[row * 25] = 0.0;
+            P[row * (S + 1)] = 0.0;
             for (int cc = 0; cc < 3; ++cc) {
-                P[row * 24 + cc] = cmap * Jc[cc];                          // d/d eul
-                P[row * 24 + 3 + cc] = cmap * ((r == cc) ? 1.0 : 0.0);     // d/d pos
-                P[row * 24 + 12 + 3 * l + cc] = cmap * Jc[3 + cc];         // d/d qleg
+                P[row * S + cc] = cmap * Jc[cc];                          // d/d eul
+                P[row * S + 3 + cc] = cmap * ((r == cc) ? 1.0 : 0.0);     // d/d pos
+                P[row * S + 12 + 3 * l + cc] = cmap * Jc[3 + cc];         // d/d qleg
             }
         }
     }

@@ -617,30 +617,35 @@ __device__ inline bool backward_sweep_block(Smem& sm, double reg) {
             if (tid < 24) sm.G[tid] = 0.0;
             __syncthreads();
         } else {
-            // impact-aware step: G' = Px^T G0, H' = Px^T H0 Px at the phase's terminal state
-            resetmap_partial_block(sm.tq + ph * TQ_STRIDE + TQ_JC, sc.cmask[ph], sc.nmask[ph], sm.Y);
-            const double* P = sm.Y;  // row-major P[r * 24 + c]
-            double* T = sm.Qux;      // 24 x TS temporary spanning Qux|Quu (contiguous, free here)
-            for (int e = tid; e < 576; e += kThreads) {  // T = P^T H
-                const int i = e / 24, j = e % 24;
-                double acc = 0.0;
+            // impact-aware step: G' = Px^T G0, H' = Px^T H0 Px at the phase's terminal state.  Both products are
+            // C = A^T B with A, B stored row (= k) major, i.e. the tile shape of P1: W = H^T P (= H P, H is symmetric),
+            // then H' = P^T W; 9 tiles x 6 DMMA each, dealt round-robin to the warps.
+            resetmap_partial_block(sm.tq + ph * TQ_STRIDE + TQ_JC, sc.cmask[ph], sc.nmask[ph], sm.Y, TS);
+            const double* P = sm.Y;  // row-major P[r * TS + c]
+            double* W = sm.Qux;      // 24 x TS temporary spanning Qux|Quu (contiguous, free here)
+            const int lane = tid & 31, wrp = tid >> 5, g = lane >> 2, t = lane & 3;
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                const double* A = (pass ? P : sm.H) + t * TS + g;
+                const double* B = (pass ? W : P) + t * TS + g;
+                double* Cm = (pass ? sm.H : W) + g * TS + 2 * t;
+#pragma unroll 1
+                for (int q = wrp; q < 9; q += 4) {
+                    const int4 d = c_y[q];
+                    double c2[2] = {0.0, 0.0};
+                    const double* a = A + d.x;
+                    const double* b = B + d.y;
 #pragma unroll
-                for (int m = 0; m < 24; ++m) acc = fma(P[m * 24 + i], sm.H[m * TS + j], acc);
-                T[i * TS + j] = acc;
-            }
-            if (tid < 24) {
-                double acc = 0.0;
+                    for (int kk = 0; kk < 24; kk += 4) dmma884(c2, a[kk * TS], b[kk * TS]);
+                    *reinterpret_cast<double2*>(Cm + d.z) = make_double2(c2[0], c2[1]);
+                }
+                if (!pass && tid < 24) {
+                    double acc = 0.0;
 #pragma unroll
-                for (int m = 0; m < 24; ++m) acc = fma(P[m * 24 + tid], sm.G[m], acc);
-                sm.vtmp[tid] = acc;
-            }
-            __syncthreads();
-            for (int e = tid; e < 576; e += kThreads) {  // H = T P
-                const int i = e / 24, j = e % 24;
-                double acc = 0.0;
-#pragma unroll
-                for (int m = 0; m < 24; ++m) acc = fma(T[i * TS + m], P[m * 24 + j], acc);
-                sm.H[i * TS + j] = acc;
+                    for (int m = 0; m < 24; ++m) acc = fma(P[m * TS + tid], sm.G[m], acc);
+                    sm.vtmp[tid] = acc;
+                }
+                __syncthreads();
             }
             if (tid < 24) sm.G[tid] = sm.vtmp[tid];
             __syncthreads();
