@@ -235,9 +235,9 @@ __device__ inline void build_phase_tables(Smem& sm, unsigned cm, double dt) {
 // per-warp specialised variant executes 30 % fewer instructions but runs slower inside k_solve, see DESIGN.md §4.0
 // and tools/code_size.py).  Tiles of one kind are dealt round-robin to the warps so that every warp gets four
 // tiles per phase (P1, P2) and the vector jobs (Gn, Qx, Qu_r, G') go to the warps with the lightest tiles.
-__constant__ int4 c_y[9] = {{0, 0, 0, 0}, {0, 8, 8, 0}, {0, 16, 16, 0}, {8, 0, 224, 0}, {8, 8, 232, 0}, {8, 16, 240, 0}, {16, 0, 448, 0}, {16, 8, 456, 0}, {16, 16, 464, 0}};      // P1 Y tiles: {8 I, 8 Jt, H / Y tile offset, -}
-__constant__ int4 c_z[6] = {{0, 24, 12, 0}, {0, 32, 20, 8}, {8, 24, 236, 160}, {8, 32, 244, 168}, {16, 24, 460, 320}, {16, 32, 468, 328}};   // P1 Z tiles: {8 I, column of R, offset of H[:, 12 + 8 Jz], Z tile offset}
-__constant__ int4 c_xx[6] = {{0, 0, 0, 0}, {8, 0, 224, 0}, {8, 8, 232, 0}, {16, 0, 448, 0}, {16, 8, 456, 0}, {16, 16, 464, 0}};  // P2 Qxx (lower): {column of R, column of Y, Y / H tile offset, -}
+__constant__ int4 c_y[9] = {{0, 0, 0, 0}, {8, 0, 224, 0}, {16, 0, 448, 0}, {0, 8, 8, 0}, {8, 8, 232, 0}, {16, 8, 456, 0}, {0, 16, 16, 0}, {8, 16, 240, 0}, {16, 16, 464, 0}};      // P1 Y tiles: {8 I, 8 Jt, H / Y tile offset, -}
+__constant__ int4 c_z[6] = {{0, 24, 12, 0}, {8, 24, 236, 160}, {16, 24, 460, 320}, {0, 32, 20, 8}, {8, 32, 244, 168}, {16, 32, 468, 328}};   // P1 Z tiles: {8 I, column of R, offset of H[:, 12 + 8 Jz], Z tile offset}
+__constant__ int4 c_xx[6] = {{0, 0, 0, 0}, {8, 0, 224, 0}, {16, 0, 448, 0}, {8, 8, 232, 0}, {16, 8, 456, 0}, {16, 16, 464, 0}};  // P2 Qxx (lower): {column of R, column of Y, Y / H tile offset, -}
 __constant__ int4 c_ux[6] = {{24, 0, 0, 0}, {24, 8, 8, 0}, {24, 16, 16, 0}, {32, 0, 224, 1}, {32, 8, 232, 1}, {32, 16, 240, 1}};  // P2 Qux_r: {column of R, column of Y, Qux tile offset, Ci}
 __constant__ int4 c_uu[4] = {{24, 0, 0, 0}, {24, 8, 8, 0}, {32, 0, 224, 1}, {32, 8, 232, 1}};  // P2 Quu_r: {column of R, column of Z, Quu tile offset, Ci}
 __constant__ int4 c_4d[3] = {{0, 0, 0, 0}, {8, 96, 232, 0}, {16, 192, 464, 0}};  // P4 diagonal tiles: {column of Qux, 8 I * 12 into K_r^T, H tile offset, -}
@@ -314,33 +314,37 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
         const double* dfc = sm.dfc2[buf];
         // ---- P1: [Y | Z] = H [A | B_r] : 9 Y tiles + 6 Z tiles, Gn = G + H d ----
         const double* rB = R + t * hkd::kRld + g;  // operand element (t, g) of R; also the a-operand of P2
+        if (warp < 3) {  // Y = H + H At : warp w owns column block w; its three row blocks share the b operand
+            const double* b = rB + 8 * warp;
+            const double b0 = b[0], b1 = b[4 * hkd::kRld], b2 = b[8 * hkd::kRld];
 #pragma unroll 1
-        for (int q = warp; q < 9; q += 4) {  // Y = H + H At : warps get 3, 2, 2, 2 tiles
-            const int4 d = c_y[q];
-            const double2 h2 = *reinterpret_cast<const double2*>(hC + d.z);
-            double c2[2] = {h2.x, h2.y};
-            const double* a = hA + d.x;
-            const double* b = rB + d.y;
-            dmma884(c2, a[0], b[0]);
-            dmma884(c2, a[4 * TS], b[4 * hkd::kRld]);
-            dmma884(c2, a[8 * TS], b[8 * hkd::kRld]);
-            *reinterpret_cast<double2*>(yC + d.z) = make_double2(c2[0], c2[1]);
+            for (int q = 3 * warp; q < 3 * warp + 3; ++q) {
+                const int4 d = c_y[q];
+                const double2 h2 = *reinterpret_cast<const double2*>(hC + d.z);
+                double c2[2] = {h2.x, h2.y};
+                const double* a = hA + d.x;
+                dmma884(c2, a[0], b0);
+                dmma884(c2, a[4 * TS], b1);
+                dmma884(c2, a[8 * TS], b2);
+                *reinterpret_cast<double2*>(yC + d.z) = make_double2(c2[0], c2[1]);
+            }
         }
         {
-            // Z = H B_r : warps get 1, 2, 2, 1 tiles (tiles 0 | 1,2 | 3,4 | 5)
-            const int z0 = (0x5310 >> (4 * warp)) & 15, z1 = z0 + ((0x1221 >> (4 * warp)) & 15);
+            // Z = H B_r : warp 3 the three row blocks of column block 0 (shared b operand), warps 0..2 one tile of column block 1
+            const int z0 = (warp == 3) ? 0 : 3 + warp, z1 = (warp == 3) ? 3 : z0 + 1;
+            const double* b = rB + ((warp == 3) ? 24 : 32);
+            const double b0 = b[0], b1 = b[4 * hkd::kRld], b2 = b[8 * hkd::kRld];
+            const double2 sw = *reinterpret_cast<const double2*>(sm.swc + 2 * t + ((warp == 3) ? 0 : 8));
 #pragma unroll 1
             for (int q = z0; q < z1; ++q) {
                 const int4 d = c_z[q];
                 double c2[2] = {0.0, 0.0};
                 const double* a = hA + d.x;
-                const double* b = rB + d.y;
-                dmma884(c2, a[0], b[0]);
-                dmma884(c2, a[4 * TS], b[4 * hkd::kRld]);
-                dmma884(c2, a[8 * TS], b[8 * hkd::kRld]);
+                dmma884(c2, a[0], b0);
+                dmma884(c2, a[4 * TS], b1);
+                dmma884(c2, a[8 * TS], b2);
                 // swing columns of Z: H[:, 12+c] * (1-c_l) dt (zero factor for stance legs and the padding c >= 12)
                 const double2 h2 = *reinterpret_cast<const double2*>(hC + d.z);
-                const double2 sw = *reinterpret_cast<const double2*>(sm.swc + 2 * t + d.y - 24);
                 c2[0] = fma(h2.x, sw.x, c2[0]);
                 c2[1] = fma(h2.y, sw.y, c2[1]);
                 *reinterpret_cast<double2*>(zC + d.w) = make_double2(c2[0], c2[1]);
@@ -362,36 +366,43 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
         // ---- P2: C = [A | B_r]^T M :  6 x Qxx (lower, M = Y, parked in H) ; 6 x Qux_r (M = Y) ; 4 x Quu_r (M = Z) ----
         // (the sparse additive term of Qxx, lxx + reg I, is applied in P3 by the warp that is idle there)
         const double* yB = sm.Y + t * TS + g;
+        if (warp < 2) {  // Qxx = Y + At^T Y : warp 0 column block 0 (shared b operand), warp 1 tiles (1,1), (2,1), (2,2)
+            int pa = -1, pb = -1;
+            double a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
 #pragma unroll 1
-        for (int q = warp; q < 6; q += 4) {  // Qxx = Y + At^T Y : warps 0, 1 two tiles, warps 2, 3 one
-            const int4 d = c_xx[q];
-            const double2 y2 = *reinterpret_cast<const double2*>(yC + d.z);
-            double c2[2] = {y2.x, y2.y};
-            const double* a = rB + d.x;
-            const double* b = yB + d.y;
-            dmma884(c2, a[0], b[0]);
-            dmma884(c2, a[4 * hkd::kRld], b[4 * TS]);
-            dmma884(c2, a[8 * hkd::kRld], b[8 * TS]);
-            *reinterpret_cast<double2*>(hC + d.z) = make_double2(c2[0], c2[1]);
-        }
+            for (int q = 3 * warp; q < 3 * warp + 3; ++q) {
+                const int4 d = c_xx[q];
+                const double2 y2 = *reinterpret_cast<const double2*>(yC + d.z);
+                double c2[2] = {y2.x, y2.y};
+                if (d.x != pa) { const double* a = rB + d.x; a0 = a[0]; a1 = a[4 * hkd::kRld]; a2 = a[8 * hkd::kRld]; pa = d.x; }
+                if (d.y != pb) { const double* b = yB + d.y; b0 = b[0]; b1 = b[4 * TS]; b2 = b[8 * TS]; pb = d.y; }
+                dmma884(c2, a0, b0);
+                dmma884(c2, a1, b1);
+                dmma884(c2, a2, b2);
+                *reinterpret_cast<double2*>(hC + d.z) = make_double2(c2[0], c2[1]);
+            }
+        } else {  // Qux_r = B_r^T Y : warp 2 rows 0..7, warp 3 rows 8..11; the three column blocks share the a operand
+            const int Ci = warp - 2;
+            const double* a = rB + 24 + 8 * Ci;
+            const double a0 = a[0], a1 = a[4 * hkd::kRld], a2 = a[8 * hkd::kRld];
+            const int c = 8 * Ci + g;  // reduced control row
+            const double sw = (c < 12) ? sm.swc[c] : 0.0;
 #pragma unroll 1
-        for (int q = (warp + 2) & 3; q < 6; q += 4) {  // Qux_r = B_r^T Y : warps 2, 3 two tiles, warps 0, 1 one
-            const int4 d = c_ux[q];
-            double c2[2] = {0.0, 0.0};
-            const double* a = rB + d.x;
-            const double* b = yB + d.y;
-            dmma884(c2, a[0], b[0]);
-            dmma884(c2, a[4 * hkd::kRld], b[4 * TS]);
-            dmma884(c2, a[8 * hkd::kRld], b[8 * TS]);
-            const int c = 8 * d.w + g;  // reduced control row
-            if (c < 12) {
-                const double sw = sm.swc[c];
-                if (sw != 0.0) {  // swing row: (B_r^T Y)[c][:] = (1-c_l) dt * Y[12+c][:]
-                    const double2 m2 = *reinterpret_cast<const double2*>(sm.Y + (12 + c) * TS + d.y + 2 * t);
-                    c2[0] = fma(sw, m2.x, c2[0]);
-                    c2[1] = fma(sw, m2.y, c2[1]);
+            for (int q = 3 * Ci; q < 3 * Ci + 3; ++q) {
+                const int4 d = c_ux[q];
+                double c2[2] = {0.0, 0.0};
+                const double* b = yB + d.y;
+                dmma884(c2, a0, b[0]);
+                dmma884(c2, a1, b[4 * TS]);
+                dmma884(c2, a2, b[8 * TS]);
+                if (c < 12) {
+                    if (sw != 0.0) {  // swing row: (B_r^T Y)[c][:] = (1-c_l) dt * Y[12+c][:]
+                        const double2 m2 = *reinterpret_cast<const double2*>(sm.Y + (12 + c) * TS + d.y + 2 * t);
+                        c2[0] = fma(sw, m2.x, c2[0]);
+                        c2[1] = fma(sw, m2.y, c2[1]);
+                    }
+                    *reinterpret_cast<double2*>(quxC + d.z) = make_double2(c2[0], c2[1]);
                 }
-                *reinterpret_cast<double2*>(quxC + d.z) = make_double2(c2[0], c2[1]);
             }
         }
         {   // Quu_r = luu_r + B_r^T Z : one tile per warp
