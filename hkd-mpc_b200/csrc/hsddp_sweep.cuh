@@ -722,17 +722,20 @@ __device__ __forceinline__ int node_of_stage(const DevSchedule& sc, int s) {
     return sc.node_off[ph] + k;
 }
 
-__device__ __forceinline__ void lr_prefetch(Smem& sm, double* buf, int s0, int s1) {
-    const int total = (s1 - s0) * LR_UNITS;
-    for (int e = threadIdx.x; e < total; e += kThreads) {
-        const int si = e / LR_UNITS, u = e % LR_UNITS;
+// Streams the stages [s0, s1) into ring slots.  Issued by the warps that do NOT run the recursion (roles 1..3,
+// `ptid` = 0..95 among them): the address arithmetic of the copies would otherwise sit on the recursion's critical path.
+__device__ __forceinline__ void lr_prefetch(Smem& sm, double* buf, int s0, int s1, int ptid) {
+    for (int si = 0; si < s1 - s0; ++si) {
         const int s = s0 + si;
-        const double* src;
-        if (u < 144) src = sm.K + (size_t)s * 288 + 2 * u;
-        else if (u < 194) src = sm.lqg + (size_t)s * CR_STRIDE + CR_R + 2 * (u - 144);
-        else if (u < 206) src = sm.Defect + 24 * (node_of_stage(sm.sc, s) + 1) + 2 * (u - 194);
-        else src = sm.dU + 24 * s + 2 * (u - 206);
-        cp_async16(buf + si * LR_SLOT + 2 * u, src);
+        double* slot = buf + si * LR_SLOT;
+        const double* srcK = sm.K + (size_t)s * 288;
+        const double* srcR = sm.lqg + (size_t)s * CR_STRIDE + CR_R;
+        const double* srcD = sm.Defect + 24 * (node_of_stage(sm.sc, s) + 1);
+        const double* srcU = sm.dU + 24 * s;
+        for (int u = ptid; u < LR_UNITS; u += 96) {
+            const double* src = (u < 144) ? srcK + 2 * u : (u < 194) ? srcR + 2 * (u - 144) : (u < 206) ? srcD + 2 * (u - 194) : srcU + 2 * (u - 206);
+            cp_async16(slot + 2 * u, src);
+        }
     }
 }
 
@@ -746,7 +749,7 @@ __device__ inline void linear_rollout_block(Smem& sm, double eps) {
     double* sdu = sm.vtmp2;  // coupled controls du_r[0..11]
     PROF_DECL
     __syncthreads();
-    lr_prefetch(sm, scratch, 0, min(LR_CHUNK, N));
+    if (tid >= 32) lr_prefetch(sm, scratch, 0, min(LR_CHUNK, N), tid - 32);
     cp_async_wait_all();
     __syncthreads();
     int ph = 0;
@@ -755,7 +758,7 @@ __device__ inline void linear_rollout_block(Smem& sm, double eps) {
         const int c1 = min(c0 + LR_CHUNK, N);
         double* buf = scratch + ((c0 / LR_CHUNK) & 1) * (LR_CHUNK * LR_SLOT);
         double* nbuf = scratch + (((c0 / LR_CHUNK) & 1) ^ 1) * (LR_CHUNK * LR_SLOT);
-        if (c1 < N) lr_prefetch(sm, nbuf, c1, min(c1 + LR_CHUNK, N));
+        if (c1 < N && tid >= 32) lr_prefetch(sm, nbuf, c1, min(c1 + LR_CHUNK, N), tid - 32);
         if (tid < 32) {
             for (int s = c0; s < c1; ++s) {
                 while (ph + 1 < sc.n_phases && s >= sc.stage_off[ph + 1]) ++ph;
