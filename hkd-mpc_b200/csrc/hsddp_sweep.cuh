@@ -739,6 +739,43 @@ __device__ __forceinline__ void lr_prefetch(Smem& sm, double* buf, int s0, int s
     }
 }
 
+// expected cost change of one (stage, component): lx dx + lu du and dx' lxx dx + du' luu du (SinglePhase.cpp:165-172)
+__device__ __forceinline__ void lr_dv_elem(Smem& sm, double dt, int s, int i, double& dV1, double& dV2) {
+    const DevSchedule& sc = sm.sc;
+    int p, k;
+    phase_of_stage(sc, s, p, k);
+    const unsigned cm = sc.cmask[p];
+    const int n = sc.node_off[p] + k;
+    const double* rec = sm.lqg + (size_t)s * CR_STRIDE;
+    const double* dxv = sm.dX + 24 * n;
+    const double* duv = sm.U_t + 24 * s;
+    const double dxi = dxv[i], dui = duv[i];
+    dV1 += rec[CR_LX + i] * dxi + rec[CR_LU + i] * dui;
+    // (lxx dx)_i
+    double qdx = (dt * weight_Q(i, cm)) * dxi;
+    if (i >= 3 && i < 6) {
+        for (int l = 0; l < 4; ++l) {
+            const double c = (double)((cm >> l) & 1u);
+            const double w = (dt * c * weight_foot(l, i - 3, cm)) * c;
+            qdx += w * dxi - w * dxv[12 + 3 * l + i - 3];
+        }
+    } else if (i >= 12) {
+        const int l = (i - 12) / 3, jj = (i - 12) % 3;
+        const double c = (double)((cm >> l) & 1u);
+        const double w = (dt * c * weight_foot(l, jj, cm)) * c;
+        qdx += w * dxi - w * dxv[3 + jj];
+    }
+    dV2 += dxi * qdx;
+    // (luu du)_i
+    double rdu = (dt * weight_R(i)) * dui;
+    if (i < 12) {
+        const int l = i / 3, a = i % 3;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) rdu += rec[CR_LUU + 9 * l + 3 * a + b] * duv[3 * l + b];
+    }
+    dV2 += dui * rdu;
+}
+
 __device__ inline void linear_rollout_block(Smem& sm, double eps) {
     const DevSchedule& sc = sm.sc;
     const int tid = virtual_tid(sm), lane = tid & 31;
@@ -754,11 +791,18 @@ __device__ inline void linear_rollout_block(Smem& sm, double eps) {
     __syncthreads();
     int ph = 0;
     double dx = 0.0;
+    double dV1 = 0.0, dV2 = 0.0;   // expected cost change: the three warps that do not run the recursion accumulate the
+    int last_c0 = 0;               // terms of the chunk that has just been finished while warp 0 works on the next one
     for (int c0 = 0; c0 < N; c0 += LR_CHUNK) {
+        last_c0 = c0;
         const int c1 = min(c0 + LR_CHUNK, N);
         double* buf = scratch + ((c0 / LR_CHUNK) & 1) * (LR_CHUNK * LR_SLOT);
         double* nbuf = scratch + (((c0 / LR_CHUNK) & 1) ^ 1) * (LR_CHUNK * LR_SLOT);
-        if (c1 < N && tid >= 32) lr_prefetch(sm, nbuf, c1, min(c1 + LR_CHUNK, N), tid - 32);
+        if (tid >= 32) {
+            if (c1 < N) lr_prefetch(sm, nbuf, c1, min(c1 + LR_CHUNK, N), tid - 32);
+            if (c0 > 0)
+                for (int e = (c0 - LR_CHUNK) * 24 + tid - 32; e < c0 * 24; e += 96) lr_dv_elem(sm, dt, e / 24, e % 24, dV1, dV2);
+        }
         if (tid < 32) {
             for (int s = c0; s < c1; ++s) {
                 while (ph + 1 < sc.n_phases && s >= sc.stage_off[ph + 1]) ++ph;
@@ -868,43 +912,8 @@ __device__ inline void linear_rollout_block(Smem& sm, double eps) {
         __syncthreads();
     }
     PROF_MARK(sm, 11);
-    // ---- expected cost change, all threads ----
-    double dV1 = 0.0, dV2 = 0.0;
-    for (int e = tid; e < N * 24; e += kThreads) {
-        const int s = e / 24, i = e % 24;
-        int p, k;
-        phase_of_stage(sc, s, p, k);
-        const unsigned cm = sc.cmask[p];
-        const int n = sc.node_off[p] + k;
-        const double* rec = sm.lqg + (size_t)s * CR_STRIDE;
-        const double* dxv = sm.dX + 24 * n;
-        const double* duv = sm.U_t + 24 * s;
-        const double dxi = dxv[i], dui = duv[i];
-        dV1 += rec[CR_LX + i] * dxi + rec[CR_LU + i] * dui;
-        // (lxx dx)_i
-        double qdx = (dt * weight_Q(i, cm)) * dxi;
-        if (i >= 3 && i < 6) {
-            for (int l = 0; l < 4; ++l) {
-                const double c = (double)((cm >> l) & 1u);
-                const double w = (dt * c * weight_foot(l, i - 3, cm)) * c;
-                qdx += w * dxi - w * dxv[12 + 3 * l + i - 3];
-            }
-        } else if (i >= 12) {
-            const int l = (i - 12) / 3, jj = (i - 12) % 3;
-            const double c = (double)((cm >> l) & 1u);
-            const double w = (dt * c * weight_foot(l, jj, cm)) * c;
-            qdx += w * dxi - w * dxv[3 + jj];
-        }
-        dV2 += dxi * qdx;
-        // (luu du)_i
-        double rdu = (dt * weight_R(i)) * dui;
-        if (i < 12) {
-            const int l = i / 3, a = i % 3;
-#pragma unroll
-            for (int b = 0; b < 3; ++b) rdu += rec[CR_LUU + 9 * l + 3 * a + b] * duv[3 * l + b];
-        }
-        dV2 += dui * rdu;
-    }
+    // ---- expected cost change: what is left (last chunk, terminal terms), all threads ----
+    for (int e = last_c0 * 24 + tid; e < N * 24; e += kThreads) lr_dv_elem(sm, dt, e / 24, e % 24, dV1, dV2);  // stages of the last chunk
     for (int e = tid; e < sc.n_phases * 24; e += kThreads) {  // terminal terms
         const int p = e / 24, i = e % 24;
         const unsigned cm = sc.cmask[p];
