@@ -964,7 +964,10 @@ int hsddp_batch_solve_async(hsddp_batch* b, const hsddp_options* opt) {
     CK(cudaSetDevice(b->device));
     const hsddp_options o = opt ? *opt : default_options();
     b->cold = false;
-    const bool phased = b->solve_mode == 2;  // auto = persistent: measured faster or equal at every batch size so far
+    // auto: the persistent kernel up to ~20 waves of blocks; beyond that the phased driver, whose launch tails no longer
+    // matter and whose phase-homogeneous kernels keep the instruction cache hot (measured: equal at 16,384 problems,
+    // 7 % faster at 65,536; slower below -- DESIGN.md §4)
+    const bool phased = b->solve_mode == 2 || (b->solve_mode == 0 && b->bp.n_problems >= 24 * b->n_sm * b->blocks_per_sm);
     if (phased) return solve_phased(b, o);
     CK(cudaMemsetAsync(b->bp.work_counter, 0, sizeof(int), b->stream));
     CK(cudaEventRecord(b->ev0, b->stream));
