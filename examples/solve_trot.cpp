@@ -26,6 +26,10 @@ int main(int argc, char** argv) {
         solver.solve(ddp_options);
         for (const hsddp_info& info : solver.get_info())
             std::printf("status %d  iterations %d  total cost = %.8f  dynamics infeasibility = %.3e\n", info.status, info.n_iter, info.cost, info.feas);
+        // what the reference publishes on "mpc_command" (HKDMPC.cpp:243-298)
+        const std::vector<hsddp_mpc_command> cmd = solver.get_mpc_command(8);
+        std::printf("command of problem 0: %d steps, first GRF z of leg 0 = %.4f N, feedback[0][2][5] = %.4f\n", cmd[0].N_mpcsteps,
+                    cmd[0].hkd_controls[0][2], cmd[0].feedback[0][2][5]);
     } catch (const std::exception& e) {
         std::fprintf(stderr, "error: %s\n", e.what());
         return 1;

@@ -132,6 +132,15 @@ public:
             eqn_feas.push_back((float)r.max_tconstr); ineq_feas.push_back((float)r.max_pconstr);
         }
     }
+    // what HKDMPCSolver::publish_mpc_cmd + update_foot_placement ship to the robot (HKDMPC/HKDMPC.cpp:207-298):
+    // packed on the device, one record per problem
+    std::vector<hsddp_mpc_command> get_mpc_command(int n_steps = 8) {
+        std::vector<hsddp_mpc_command> v(n_);
+        check(hsddp_batch_get_mpc_command(b_, n_steps, v.data()), "get_mpc_command");
+        return v;
+    }
+    // 0 auto, 1 persistent kernel, 2 one kernel per solve phase (include/hsddp_b200.h)
+    void set_solve_mode(int mode) { check(hsddp_batch_set_solve_mode(b_, mode), "set_solve_mode"); }
     int n_problems() const { return n_; }
     int max_stages() const { return max_stages_; }
     int max_nodes() const { return max_nodes_; }

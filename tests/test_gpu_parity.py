@@ -437,9 +437,9 @@ def test_cpp_shim_example_matches_oracle(pkg, orc, tmp_path):
     subprocess.check_call(["g++", "-std=c++17", os.path.join(ROOT, "examples", "solve_trot.cpp"), "-L" + libdir, "-lhsddp_b200",
                            "-Wl,-rpath," + libdir, "-o", exe])
     out = subprocess.run([exe, csv, "3"], capture_output=True, text=True, check=True).stdout.strip().splitlines()
-    assert len(out) == 3
+    assert len(out) == 4 and out[3].startswith("command of problem 0: 8 steps")
     T = _table(orc, "trot")
-    for i, line in enumerate(out):
+    for i, line in enumerate(out[:3]):
         tok = line.replace("=", " ").split()
         status, iters, cost = int(tok[1]), int(tok[3]), float(tok[6])
         P = orc.Problem(T, 0, 0.6)
@@ -448,3 +448,8 @@ def test_cpp_shim_example_matches_oracle(pkg, orc, tmp_path):
         P.x0 = x0
         s, _ = P.solve()
         assert status == int(s["status"]) and iters == int(s["n_iter"]) and abs(cost - s["cost"]) < 1e-7 * abs(s["cost"])
+        if i == 0:  # the command line of the example: first GRF z of leg 0 and one feedback entry
+            ref = orc.mpc_command(P, 8)
+            tok = out[3].replace("=", " ").replace(",", " ").split()
+            fz, fb = float(tok[tok.index("N") - 1]), float(tok[-1])
+            assert abs(fz - ref["hkd_controls"][0, 2]) < 1e-3 and abs(fb - ref["feedback"][0, 2, 5]) < 1e-3
