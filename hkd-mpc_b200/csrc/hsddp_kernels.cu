@@ -975,6 +975,7 @@ int hsddp_batch_solve_async(hsddp_batch* b, const hsddp_options* opt) {
         k_solve_lat<<<b->bp.n_problems, kThreads, 0, b->stream>>>(b->bp, o, 0);
     } else {
         const int grid = std::min(b->bp.n_problems, b->n_sm * b->blocks_per_sm);
+        if (getenv("HSDDP_DEBUG")) std::fprintf(stderr, "[hsddp] k_solve grid %d (%d SMs x %d blocks), %d problems\n", grid, b->n_sm, b->blocks_per_sm, b->bp.n_problems);
         k_solve<<<grid, kThreads, 0, b->stream>>>(b->bp, o, 0);
     }
     CK(cudaGetLastError());
