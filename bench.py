@@ -315,8 +315,10 @@ def main():
                     "ms_per_step": e2e_ms / args.steps,
                     "what": "set_initial_condition(x0 from pinned host) + reset + solve + copy-out to pinned host of the result record and the MPC command of every problem (hkd_command_lcmt payload: 8 controls, body states, 12x12 feedback blocks, foot placements; HKDMPC.cpp:207-298)"},
             "roofline": {"bound": "tensor", "pipe": "FP64 (DFMA / DMMA m8n8k4)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
-                         "traffic_source": traffic_src, "kernel": "k_solve", "kernel_ms": kernel_ms,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per solve (dram__bytes_read.sum + dram__bytes_write.sum over its launches)",
+                         "traffic_source": traffic_src,
+                         "kernel": "one solve of the batch = the k_phase<begin|prep|sweep|forward> launches of the phased driver (k_solve when the persistent kernel is selected); the backward-sweep kernel is 56 % of it (profiles/)",
+                         "kernel_ms": kernel_ms,
                          "flop_per_launch": flop_launch,
                          "peak_source": "measured in this run by hsddp_fp64_peak_tflops: DFMA %.1f, DMMA %.1f TFLOP/s "
                                         "(MEASURED_PEAKS.json has no FP64 entry)" % (peak_dfma, peak_dmma),

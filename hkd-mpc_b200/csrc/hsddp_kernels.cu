@@ -589,6 +589,11 @@ struct hsddp_batch {
     int* d_count = nullptr;
     int* h_count = nullptr;        // pinned
     int last_rounds = 0;
+    static constexpr int kMaxGroups = 8;
+    int phased_groups = 4;         // index ranges driven concurrently on their own streams (2: +3 %, 4: +4.5 %, 8: no more)
+    cudaStream_t gstream[kMaxGroups] = {};
+    cudaEvent_t gevent[kMaxGroups] = {};
+    cudaEvent_t ev_fork = nullptr;
     hsddp_mpc_command* d_cmd = nullptr;  // lives in `allocs` (freed with the problem set)
 };
 
@@ -665,7 +670,12 @@ int hsddp_batch_create(int device, hsddp_batch** out) {
         const int v = atoi(e);
         if (v >= 1 && v <= b->blocks_per_sm) b->blocks_per_sm = v;
     }
-    CK(cudaHostAlloc((void**)&b->h_count, 4 * sizeof(int), cudaHostAllocDefault));
+    CK(cudaHostAlloc((void**)&b->h_count, hsddp_batch::kMaxGroups * sizeof(int), cudaHostAllocDefault));
+    CK(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+    if (const char* e = getenv("HSDDP_PHASED_GROUPS")) {  // tuning / experiments only
+        const int v = atoi(e);
+        if (v >= 1 && v <= hsddp_batch::kMaxGroups) b->phased_groups = v;
+    }
     if (const char* e = getenv("HSDDP_SOLVE_MODE")) {  // tuning / experiments only
         const int v = atoi(e);
         if (v >= 0 && v <= 2) b->solve_mode = v;
@@ -683,6 +693,11 @@ int hsddp_batch_destroy(hsddp_batch* b) {
     for (int i = 0; i < 8; ++i) if (b->slots[i]) cudaEventDestroy(b->slots[i]);
     if (b->stream) cudaStreamDestroy(b->stream);
     if (b->h_count) cudaFreeHost(b->h_count);
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+    for (int g = 0; g < hsddp_batch::kMaxGroups; ++g) {
+        if (b->gevent[g]) cudaEventDestroy(b->gevent[g]);
+        if (b->gstream[g]) cudaStreamDestroy(b->gstream[g]);
+    }
     delete b;
     return HSDDP_OK;
 }
@@ -714,7 +729,7 @@ static int alloc_workspace(hsddp_batch* b, int n_problems, int max_stages, int m
     if ((rc = dalloc(b, &bp.ctl, P))) return rc;
     if ((rc = dalloc(b, &b->d_active[0], P))) return rc;
     if ((rc = dalloc(b, &b->d_active[1], P))) return rc;
-    if ((rc = dalloc(b, &b->d_count, (size_t)4))) return rc;
+    if ((rc = dalloc(b, &b->d_count, (size_t)hsddp_batch::kMaxGroups))) return rc;
     CK(cudaMemset(bp.ctl, 0, P * sizeof(SolveCtl)));
     if ((rc = dalloc(b, &bp.info, P))) return rc;
     if ((rc = dalloc(b, &bp.trace, P * HSDDP_TRACE_CAP))) return rc;
@@ -920,33 +935,69 @@ int hsddp_batch_reset(hsddp_batch* b) {
 // Phased driver: every round advances all running problems by one DDP iteration with three launches
 // (prep, sweep, forward).  Blocks that are co-resident on an SM execute the same phase, so the instruction
 // cache holds one phase's code instead of six different ones; the host reads one counter per round.
+// The batch is split into `groups` index ranges, each driven round by round on its own stream: the launch tail of
+// one group's kernel (its last, partially filled wave of blocks) overlaps with the other groups' kernels.
+__global__ void k_iota(int* a, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = i;
+}
+
 static int solve_phased(hsddp_batch* b, const hsddp_options& o) {
-    BatchPtrs bp = b->bp;
-    const int P = bp.n_problems;
+    const int P = b->bp.n_problems;
+    int G = b->phased_groups;
+    if (P < 2 * 4096) G = 1;  // small batches: nothing to overlap with
+    G = std::max(1, std::min(G, hsddp_batch::kMaxGroups));
+    for (int g = 0; g < G; ++g) {
+        if (!b->gstream[g]) {
+            CK(cudaStreamCreateWithFlags(&b->gstream[g], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&b->gevent[g], cudaEventDisableTiming));
+        }
+    }
     CK(cudaEventRecord(b->ev0, b->stream));
-    CK(cudaMemsetAsync(b->d_count, 0, sizeof(int), b->stream));
-    bp.active = nullptr; bp.next_active = b->d_active[0]; bp.next_count = b->d_count;
-    k_phase<PH_BEGIN><<<P, kThreads, 0, b->stream>>>(bp, o);
-    CK(cudaGetLastError());
-    b->n_solve_launches++;
-    CK(cudaMemcpyAsync(b->h_count, b->d_count, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
-    CK(cudaStreamSynchronize(b->stream));
-    int n_active = b->h_count[0], cur = 0, rounds = 0;
-    while (n_active > 0) {
-        bp.active = b->d_active[cur]; bp.next_active = b->d_active[cur ^ 1];
-        CK(cudaMemsetAsync(b->d_count, 0, sizeof(int), b->stream));
-        k_phase<PH_PREP><<<n_active, kThreads, 0, b->stream>>>(bp, o);
-        k_phase<PH_SWEEP><<<n_active, kThreads, 0, b->stream>>>(bp, o);
-        k_phase<PH_FORWARD><<<n_active, kThreads, 0, b->stream>>>(bp, o);
+    CK(cudaMemsetAsync(b->d_count, 0, hsddp_batch::kMaxGroups * sizeof(int), b->stream));
+    k_iota<<<(P + 255) / 256, 256, 0, b->stream>>>(b->d_active[0], P);
+    CK(cudaEventRecord(b->ev_fork, b->stream));
+    int off[hsddp_batch::kMaxGroups + 1], n_active[hsddp_batch::kMaxGroups], cur[hsddp_batch::kMaxGroups];
+    for (int g = 0; g <= G; ++g) off[g] = (int)((long long)P * g / G);
+    BatchPtrs bp[hsddp_batch::kMaxGroups];
+    // round 0: begin (initial rollout, first outer iteration set-up) over every problem of the group
+    for (int g = 0; g < G; ++g) {
+        CK(cudaStreamWaitEvent(b->gstream[g], b->ev_fork, 0));
+        bp[g] = b->bp;
+        bp[g].active = b->d_active[0] + off[g]; bp[g].next_active = b->d_active[1] + off[g]; bp[g].next_count = b->d_count + g;
+        k_phase<PH_BEGIN><<<off[g + 1] - off[g], kThreads, 0, b->gstream[g]>>>(bp[g], o);
         CK(cudaGetLastError());
-        b->n_solve_launches += 3;
-        CK(cudaMemcpyAsync(b->h_count, b->d_count, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
-        CK(cudaStreamSynchronize(b->stream));
-        n_active = b->h_count[0];
-        cur ^= 1;
+        b->n_solve_launches++;
+        CK(cudaMemcpyAsync(b->h_count + g, b->d_count + g, sizeof(int), cudaMemcpyDeviceToHost, b->gstream[g]));
+        cur[g] = 1;
+    }
+    for (int g = 0; g < G; ++g) { CK(cudaStreamSynchronize(b->gstream[g])); n_active[g] = b->h_count[g]; }
+    int rounds = 0;
+    for (;;) {
+        bool any = false;
+        for (int g = 0; g < G; ++g) {
+            if (n_active[g] <= 0) continue;
+            any = true;
+            bp[g].active = b->d_active[cur[g]] + off[g]; bp[g].next_active = b->d_active[cur[g] ^ 1] + off[g];
+            CK(cudaMemsetAsync(b->d_count + g, 0, sizeof(int), b->gstream[g]));
+            k_phase<PH_PREP><<<n_active[g], kThreads, 0, b->gstream[g]>>>(bp[g], o);
+            k_phase<PH_SWEEP><<<n_active[g], kThreads, 0, b->gstream[g]>>>(bp[g], o);
+            k_phase<PH_FORWARD><<<n_active[g], kThreads, 0, b->gstream[g]>>>(bp[g], o);
+            CK(cudaGetLastError());
+            b->n_solve_launches += 3;
+            CK(cudaMemcpyAsync(b->h_count + g, b->d_count + g, sizeof(int), cudaMemcpyDeviceToHost, b->gstream[g]));
+            cur[g] ^= 1;
+        }
+        if (!any) break;
+        for (int g = 0; g < G; ++g)
+            if (n_active[g] > 0) { CK(cudaStreamSynchronize(b->gstream[g])); n_active[g] = b->h_count[g]; }
         if (++rounds > 100000) { g_last_error = "phased solve did not terminate"; return HSDDP_ERR_STATE; }
     }
     b->last_rounds = rounds;
+    for (int g = 0; g < G; ++g) {  // join: the handle's stream continues after every group
+        CK(cudaEventRecord(b->gevent[g], b->gstream[g]));
+        CK(cudaStreamWaitEvent(b->stream, b->gevent[g], 0));
+    }
     CK(cudaEventRecord(b->ev1, b->stream));
     return HSDDP_OK;
 }
@@ -964,10 +1015,11 @@ int hsddp_batch_solve_async(hsddp_batch* b, const hsddp_options* opt) {
     CK(cudaSetDevice(b->device));
     const hsddp_options o = opt ? *opt : default_options();
     b->cold = false;
-    // auto: the persistent kernel up to ~20 waves of blocks; beyond that the phased driver, whose launch tails no longer
-    // matter and whose phase-homogeneous kernels keep the instruction cache hot (measured: equal at 16,384 problems,
-    // 7 % faster at 65,536; slower below -- DESIGN.md §4)
-    const bool phased = b->solve_mode == 2 || (b->solve_mode == 0 && b->bp.n_problems >= 24 * b->n_sm * b->blocks_per_sm);
+    // auto: the persistent kernel up to ~12 waves of blocks; beyond that the phased driver, whose phase-homogeneous
+    // kernels keep the instruction cache hot and whose launch tails are hidden by driving four index ranges on their
+    // own streams (measured on config 3: 8,192 problems 233 vs 230 ms, 12,288: 323 vs 337, 16,384: 426 vs 455,
+    // 65,536: 1,535 vs 1,694 -- DESIGN.md §4)
+    const bool phased = b->solve_mode == 2 || (b->solve_mode == 0 && b->bp.n_problems >= 12 * b->n_sm * b->blocks_per_sm);
     if (phased) return solve_phased(b, o);
     CK(cudaMemsetAsync(b->bp.work_counter, 0, sizeof(int), b->stream));
     CK(cudaEventRecord(b->ev0, b->stream));

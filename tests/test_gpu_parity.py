@@ -376,14 +376,17 @@ def test_full_size_config2_properties(pkg, orc, workloads):
     _compare_solution(pkg, orc, w, B, [0, 1, 511, 1023], {})
 
 
-def test_full_size_config3_properties(pkg, orc, workloads):
-    """16,384 mixed-gait problems (BASELINE configs[2], the bench workload): size-independent properties.
+@pytest.mark.parametrize("mode", [1, 2])
+def test_full_size_config3_properties(pkg, orc, workloads, mode):
+    """16,384 mixed-gait problems (BASELINE configs[2], the bench workload): size-independent properties, for the
+    persistent kernel (mode 1) and the phased multi-stream driver (mode 2, what `auto` picks at this size).
     Determinism, independence of the shard a problem is solved in (the multi-GPU claim: index sharding with no
     data-path collective changes nothing), sane termination records, and a command record that is a view of the
     trajectories."""
     n = 16384
     w = workloads.config3(pkg, n)
     B = _batch_for(pkg, w)
+    B.set_solve_mode(mode)
     B.solve()
     info = B.info().copy()
     assert np.all(np.isin(info["status"], (0, 1, 2, 3))) and np.all(info["n_iter"] >= 1) and np.all(info["n_iter"] <= 50)
@@ -399,6 +402,7 @@ def test_full_size_config3_properties(pkg, orc, workloads):
     for r in (0, 5):
         ws = workloads.config3(pkg, 2048, first=2048 * r)
         Bs = _batch_for(pkg, ws)
+        Bs.set_solve_mode(mode)
         Bs.solve()
         assert Bs.info().tobytes() == info[2048 * r:2048 * (r + 1)].tobytes()
         assert np.array_equal(Bs.get_rows("Ubar", 0, 8), Ub[2048 * r:2048 * (r + 1)])
@@ -409,6 +413,16 @@ def test_full_size_config3_properties(pkg, orc, workloads):
     assert len(sel) > 100
     assert np.array_equal(cmd["hkd_controls"][sel, :8], Ub[sel].astype(np.float32))
     assert np.array_equal(cmd["des_body_state"][sel, :8], Xb[sel][:, :, :12].astype(np.float32))
+    if mode == 2:  # the two drivers agree to rounding on the well-conditioned problems (separate compilations)
+        B1 = _batch_for(pkg, w)
+        B1.set_solve_mode(1)
+        B1.solve()
+        i1 = B1.info()
+        same = (i1["n_iter"] == info["n_iter"]) & (i1["status"] == info["status"])
+        assert same.mean() > 0.97, same.mean()
+        U1 = B1.get_rows("Ubar", 0, 8)
+        err = np.abs(U1[same] - Ub[same]).reshape(same.sum(), -1).max(axis=1) / np.maximum(1.0, np.abs(Ub[same]).reshape(same.sum(), -1).max(axis=1))
+        assert np.quantile(err, 0.99) < 1e-9, np.quantile(err, [0.5, 0.99, 1.0])
 
 
 def _write_quad_reference_csv(npz_path, out_path, n_rows=120):

@@ -1,3 +1,4 @@
-for n in 4096 8192 16384; do for m in 1 2; do HSDDP_SOLVE_MODE=$m python tools/profile_case.py $n config3 2 | tail -1 | sed "s/^/mode $m: /"; done; done
-for m in 1 2; do HSDDP_SOLVE_MODE=$m python tools/profile_case.py 65536 config3 1 | sed "s/^/mode $m: /"; done
-python -m pytest tests -m gpu -x -q -k "solve_modes" 2>&1 | tail -2
+for g in 4 6 8; do HSDDP_PHASED_GROUPS=$g HSDDP_SOLVE_MODE=2 python tools/profile_case.py 16384 config3 2 | tail -1 | sed "s/^/phased groups $g: /"; done
+for g in 4 8; do HSDDP_PHASED_GROUPS=$g HSDDP_SOLVE_MODE=2 python tools/profile_case.py 12288 config3 2 | tail -1 | sed "s/^/phased groups $g: /"; done
+HSDDP_SOLVE_MODE=1 python tools/profile_case.py 12288 config3 2 | tail -1 | sed "s/^/persistent: /"
+for g in 8; do HSDDP_PHASED_GROUPS=$g HSDDP_SOLVE_MODE=2 python tools/profile_case.py 65536 config3 1 | tail -1 | sed "s/^/phased groups $g: /"; done
