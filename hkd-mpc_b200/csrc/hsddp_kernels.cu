@@ -264,8 +264,18 @@ __device__ __forceinline__ void solve_persistent(Smem& sm, const BatchPtrs& bp, 
 
 // One phase of solve() for every running problem: block b works on problem bp.active[b] (or b).
 enum SolvePhase { PH_BEGIN = 0, PH_PREP, PH_SWEEP, PH_FORWARD };
+// Register budgets of the per-phase kernels (resident blocks per SM they are compiled for).  Measured on 16,384
+// config-3 problems: the backward-sweep kernel, bound by shared-memory wavefronts, is best at 5 blocks (102
+// registers, nothing spills in the stage loop): 418 ms against 427 (6 blocks) and 438 (4); the prep and forward
+// kernels are best at 6.
+#ifndef HSDDP_MINB_SWEEP
+#define HSDDP_MINB_SWEEP 5
+#endif
+#ifndef HSDDP_MINB_OTHER
+#define HSDDP_MINB_OTHER 6
+#endif
 template <int PH>
-__global__ void __launch_bounds__(kThreads, HSDDP_MIN_BLOCKS) k_phase(BatchPtrs bp, hsddp_options opt) {
+__global__ void __launch_bounds__(kThreads, PH == 2 ? HSDDP_MINB_SWEEP : HSDDP_MINB_OTHER) k_phase(BatchPtrs bp, hsddp_options opt) {
     __shared__ Smem sm;
     const int pid = bp.active ? bp.active[blockIdx.x] : (int)blockIdx.x;
     if (threadIdx.x == 0) assign_rotation(bp.sm_slots, sm.rot);
