@@ -174,7 +174,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # keep NCCL's version banner off stdout (rank 0 prints ONE JSON line); HSDDP_NCCL_DEBUG overrides
+        os.environ["NCCL_DEBUG"] = os.environ.get("HSDDP_NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     w = build_workload(pkg, wl, args, rank, world)
