@@ -265,10 +265,18 @@ def main():
             t2 = time.perf_counter()
             if rep >= 3:
                 dev_ms.append(B1.last_solve_ms()); wall_ms.append((t2 - t1) * 1e3)
+        # the MPC tick of the reference: warm re-solve from the previous solution with 2 AL x 1 DDP iterations (HKDMPC.cpp:102-103)
+        tick_opt = pkg.Options(max_AL_iter=2, max_DDP_iter=1)
+        tick_ms = []
+        for rep in range(104):
+            B1.solve(tick_opt)
+            if rep >= 3:
+                tick_ms.append(B1.last_solve_ms())
         latency = {"p50_ms": float(np.median(dev_ms)), "p50_wall_ms": float(np.median(wall_ms)), "p99_ms": float(np.percentile(dev_ms, 99)),
+                   "mpc_tick_p50_ms": float(np.median(tick_ms)),
                    "reps": len(dev_ms), "iterations": int(i1["n_iter"][0]),
                    "what": "one cold Mini Cheetah trot solve (config 1), batch 1: p50_ms = solve kernel on the device (CUDA events), "
-                           "p50_wall_ms = host wall clock of reset + solve + info read-back"}
+                           "p50_wall_ms = host wall clock of reset + solve + info read-back; mpc_tick_p50_ms = warm re-solve with 2 AL x 1 DDP iterations (the reference's MPC update, HKDMPC.cpp:102-103), device time"}
         del B1
 
     # ---- statistics (the only inter-GPU traffic: a few numbers per rank) ----
