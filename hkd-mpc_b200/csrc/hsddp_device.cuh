@@ -142,7 +142,7 @@ struct __align__(16) Smem {
     double dfc2[2][24];
     double G[24], Gn[24], Qx[24], Qu[24], wu[24], vtmp[24], vtmp2[24];
     double lxxd[24], lxxTd[24], lxxw[12], lxxTw[12];
-    double swdt[4], cmv[4];    // per-phase constants (1-c_l) dt and (c_l/m) dt
+    double swdt[4];            // per-phase constants (1-c_l) dt
     double swc[16];            // (1-c_l) dt per reduced control column c = 3l+j, zero for c >= 12
     double red[kThreads];
     DevSchedule sc;
@@ -234,14 +234,6 @@ __device__ __forceinline__ double weight_foot(int l, int j, unsigned cmask) {
     const double c = (double)((cmask >> l) & 1u);
     return ((j == 0) ? 3 * c : (j == 1) ? c : 0.0) * 20;
 }
-// GRF friction-pyramid rows (HKDConstraints.cpp:17-24): (0,0,1), (-1,0,mu), (1,0,mu), (0,-1,mu), (0,1,mu)
-__constant__ double c_grfxy[5][2] = {{0, 0}, {-1, 0}, {1, 0}, {0, -1}, {0, 1}};
-// GRF friction-pyramid rows (HKDConstraints.cpp:17-24)
-__device__ __forceinline__ void grf_rows(double mu, double rows[5][3]) {
-    const double r[5][3] = {{0, 0, 1}, {-1, 0, mu}, {1, 0, mu}, {0, -1, mu}, {0, 1, mu}};
-    for (int i = 0; i < 5; ++i) for (int j = 0; j < 3; ++j) rows[i][j] = r[i][j];
-}
-
 // single out-of-line copies of the leg kinematics (code size, see tools/code_size.py)
 __device__ __noinline__ void foot_position_nl(const double* x, int l, double* pf) { hkd::foot_position(x + 3, x, x + 12 + 3 * l, l, pf); }
 __device__ __noinline__ void foot_jacobian_nl(const double* x, int l, double* Jc) { hkd::foot_jacobian_compact(x, x + 12 + 3 * l, l, Jc); }
@@ -705,24 +697,6 @@ __device__ inline void lq_approximation_block(Smem& sm) {
     }
     __syncthreads();
     PROF_MARK(sm, 4);
-}
-
-// running-cost Hessian lxx(i,j) of a phase: dt*Q on the diagonal + the foot regulariser block
-__device__ __forceinline__ double lxx_entry(int i, int j, unsigned cm, double scale_track, double scale_foot, bool terminal) {
-    double v = 0.0;
-    if (i == j) v = terminal ? weight_Qf(i, cm) : scale_track * weight_Q(i, cm);
-    // foot block: rows/cols {3,4,5} and {12+3l+jj}
-    if (i >= 3 && i < 6) {
-        const int jj = i - 3;
-        if (j == i) { for (int l = 0; l < 4; ++l) { const double c = (double)((cm >> l) & 1u); v += (scale_foot * c * weight_foot(l, jj, cm)) * c; } }
-        else if (j >= 12 && (j - 12) % 3 == jj) { const int l = (j - 12) / 3; const double c = (double)((cm >> l) & 1u); v += -((scale_foot * c * weight_foot(l, jj, cm)) * c); }
-    } else if (i >= 12) {
-        const int l = (i - 12) / 3, jj = (i - 12) % 3;
-        const double c = (double)((cm >> l) & 1u);
-        if (j == i) v += (scale_foot * c * weight_foot(l, jj, cm)) * c;
-        else if (j == 3 + jj) v += -((scale_foot * c * weight_foot(l, jj, cm)) * c);
-    }
-    return v;
 }
 
 // ---------------------------------------------------------------------------

@@ -600,7 +600,7 @@ struct hsddp_batch {
     int* h_count = nullptr;        // pinned
     int last_rounds = 0;
     static constexpr int kMaxGroups = 8;
-    int phased_groups = 4;         // index ranges driven concurrently on their own streams (2: +3 %, 4: +4.5 %, 8: no more)
+    int phased_groups = 8;         // index ranges driven concurrently on their own streams (config 3, 16,384 problems: 2: 408 ms, 4: 401, 8: 397)
     cudaStream_t gstream[kMaxGroups] = {};
     cudaEvent_t gevent[kMaxGroups] = {};
     cudaEvent_t ev_fork = nullptr;
@@ -955,7 +955,7 @@ __global__ void k_iota(int* a, int n) {
 static int solve_phased(hsddp_batch* b, const hsddp_options& o) {
     const int P = b->bp.n_problems;
     int G = b->phased_groups;
-    if (P < 2 * 4096) G = 1;  // small batches: nothing to overlap with
+    G = std::min(G, std::max(1, P / 1024));  // keep at least ~1.5 waves of blocks per group
     G = std::max(1, std::min(G, hsddp_batch::kMaxGroups));
     for (int g = 0; g < G; ++g) {
         if (!b->gstream[g]) {
@@ -981,13 +981,18 @@ static int solve_phased(hsddp_batch* b, const hsddp_options& o) {
         CK(cudaMemcpyAsync(b->h_count + g, b->d_count + g, sizeof(int), cudaMemcpyDeviceToHost, b->gstream[g]));
         cur[g] = 1;
     }
-    for (int g = 0; g < G; ++g) { CK(cudaStreamSynchronize(b->gstream[g])); n_active[g] = b->h_count[g]; }
-    int rounds = 0;
-    for (;;) {
-        bool any = false;
+    // Rounds are pipelined per group: the host waits for ONE group's survivor count and queues that group's next
+    // round at once, while the other groups' rounds are still queued or running, so no launch tail leaves the GPU idle.
+    int rounds = 0, alive = G, group_rounds[hsddp_batch::kMaxGroups] = {};
+    bool done[hsddp_batch::kMaxGroups] = {};
+    const bool dbg = getenv("HSDDP_DEBUG") != nullptr;
+    while (alive > 0) {
         for (int g = 0; g < G; ++g) {
-            if (n_active[g] <= 0) continue;
-            any = true;
+            if (done[g]) continue;
+            CK(cudaStreamSynchronize(b->gstream[g]));
+            n_active[g] = b->h_count[g];
+            if (dbg) std::fprintf(stderr, "[hsddp] group %d round %d: %d active\n", g, group_rounds[g], n_active[g]);
+            if (n_active[g] <= 0) { done[g] = true; --alive; continue; }
             bp[g].active = b->d_active[cur[g]] + off[g]; bp[g].next_active = b->d_active[cur[g] ^ 1] + off[g];
             CK(cudaMemsetAsync(b->d_count + g, 0, sizeof(int), b->gstream[g]));
             k_phase<PH_PREP><<<n_active[g], kThreads, 0, b->gstream[g]>>>(bp[g], o);
@@ -997,11 +1002,9 @@ static int solve_phased(hsddp_batch* b, const hsddp_options& o) {
             b->n_solve_launches += 3;
             CK(cudaMemcpyAsync(b->h_count + g, b->d_count + g, sizeof(int), cudaMemcpyDeviceToHost, b->gstream[g]));
             cur[g] ^= 1;
+            rounds = std::max(rounds, ++group_rounds[g]);
+            if (group_rounds[g] > 100000) { g_last_error = "phased solve did not terminate"; return HSDDP_ERR_STATE; }
         }
-        if (!any) break;
-        for (int g = 0; g < G; ++g)
-            if (n_active[g] > 0) { CK(cudaStreamSynchronize(b->gstream[g])); n_active[g] = b->h_count[g]; }
-        if (++rounds > 100000) { g_last_error = "phased solve did not terminate"; return HSDDP_ERR_STATE; }
     }
     b->last_rounds = rounds;
     for (int g = 0; g < G; ++g) {  // join: the handle's stream continues after every group
@@ -1025,11 +1028,12 @@ int hsddp_batch_solve_async(hsddp_batch* b, const hsddp_options* opt) {
     CK(cudaSetDevice(b->device));
     const hsddp_options o = opt ? *opt : default_options();
     b->cold = false;
-    // auto: the persistent kernel up to ~12 waves of blocks; beyond that the phased driver, whose phase-homogeneous
-    // kernels keep the instruction cache hot and whose launch tails are hidden by driving four index ranges on their
-    // own streams (measured on config 3: 8,192 problems 233 vs 230 ms, 12,288: 323 vs 337, 16,384: 426 vs 455,
-    // 65,536: 1,535 vs 1,694 -- DESIGN.md §4)
-    const bool phased = b->solve_mode == 2 || (b->solve_mode == 0 && b->bp.n_problems >= 12 * b->n_sm * b->blocks_per_sm);
+    // auto: the persistent kernel up to ~4.5 waves of blocks; beyond that the phased driver, whose phase-homogeneous
+    // kernels keep the instruction cache hot and whose launch tails are hidden by driving up to eight index ranges on
+    // their own streams, each re-queued as soon as its survivor count is known (measured on config 3, persistent vs
+    // phased: 2,048 problems 77 vs 83 ms, 4,096: 126 vs 123, 8,192: 232 vs 212, 12,288: 335 vs 303, 16,384: 455 vs 396
+    // -- DESIGN.md §4)
+    const bool phased = b->solve_mode == 2 || (b->solve_mode == 0 && 2 * b->bp.n_problems >= 9 * b->n_sm * b->blocks_per_sm);
     if (phased) return solve_phased(b, o);
     CK(cudaMemsetAsync(b->bp.work_counter, 0, sizeof(int), b->stream));
     CK(cudaEventRecord(b->ev0, b->stream));

@@ -19,28 +19,13 @@
 //     Y = H A            Z = H B_r                              (DMMA m8n8k4, K = 12 / 8)
 //     Qxx = lxx + A^T Y  Qux_r = B_r^T Y   Quu_r = luu_r + B_r^T Z    Qx, Qu_r   (DMMA + fix-ups)
 //     block Gauss-Jordan (2x2 pivots, six steps) on the register tableau [Quu_r | Qux_r | Qu_r | I] (lane = column) -> -K_r, -dU_r
-//     PD verdict = no negative pivot of Quu_r - 1e-9 I (third warp, concurrently; Q7)
+//     PD verdict (Q7, chol(Quu - 1e-9 I)): a non-positive pivot block of Quu_r => not PD; all pivots positive and
+//     ||Quu_r^-1||_F^2 < 0.25e18 (so lambda_min > 2e-9) => PD; otherwise an exact second pass on Quu_r - 1e-9 I
 //     H' = sym(Qxx) + Qux_r^T K_r      G' = Qx + Qux_r^T dU_r   (DMMA, accumulators kept in registers)
 #pragma once
 #include "hsddp_device.cuh"
 
 namespace hsddp {
-
-struct PhaseConst {
-    double cm[4];    // (c_l / m) dt   : B(9+j, 3l+j)
-    double swdt[4];  // (1 - c_l) dt   : B(12+3l+j, 12+3l+j)
-};
-
-__device__ __forceinline__ PhaseConst phase_const(unsigned cmask, double dt) {
-    PhaseConst pc;
-#pragma unroll
-    for (int l = 0; l < 4; ++l) {
-        const double c = (double)((cmask >> l) & 1u);
-        pc.cm[l] = (c / hkd::kMass) * dt;
-        pc.swdt[l] = (1.0 - c) * dt;
-    }
-    return pc;
-}
 
 // full control index of reduced index c
 __device__ __forceinline__ int act_index(int c, unsigned cmask) { return ((cmask >> (c / 3)) & 1u) ? c : 12 + c; }
@@ -192,13 +177,6 @@ __device__ __forceinline__ bool gauss_jordan12_b3(double (&v)[12], double* sbuf)
     return ok;
 }
 
-// running / terminal cost Hessian of a phase in table form: lxx(i,j) = [i==j] d[i] - coupling w
-__device__ __forceinline__ double lxx_tab(const double* d, const double* w, int i, int j) {
-    if (i == j) return d[i];
-    if (i >= 3 && i < 6 && j >= 12 && (j - 12) % 3 == i - 3) return -w[j - 12];
-    if (i >= 12 && j == 3 + (i - 12) % 3) return -w[i - 12];
-    return 0.0;
-}
 __device__ inline void build_phase_tables(Smem& sm, unsigned cm, double dt) {
     const int tid = virtual_tid(sm);
     if (tid < 24) {  // [0..11] running w, [12..23] terminal w
@@ -209,7 +187,6 @@ __device__ inline void build_phase_tables(Smem& sm, unsigned cm, double dt) {
     } else if (tid < 28) {
         const int l = tid - 24;
         const double c = (double)((cm >> l) & 1u);
-        sm.cmv[l] = (c / hkd::kMass) * dt;
         sm.swdt[l] = (1.0 - c) * dt;
     } else if (tid < 44) {  // per reduced control column: (1-c_l) dt, zero padding for c >= 12
         const int c = tid - 28;
