@@ -58,10 +58,19 @@ constexpr int LQ_LX = LQ_R + hkd::kRSize;         // [24]
 constexpr int LQ_LU = LQ_LX + 24;                 // [24]
 constexpr int LQ_LUU = LQ_LU + 24;                // [4][3][3]
 constexpr int LQ_STRIDE = 616;                    // 612 used
-constexpr int ZS = 20;                            // row stride of Z = H B_r (16 columns used): 20 = 4 mod 16
-constexpr int kSweepDoubles = 2 * 24 * 28 + 24 * 20 + 16 * 28 + 12 * 28 + 2 * 616;  // H, Y, Z, Qux, Quu, rec: contiguous, free outside the sweep
-constexpr int TS = 28;                            // row stride (doubles) of the 24-wide shared-memory tiles: 28 = 12 mod 16
-                                                  // makes every m8n8k4 fragment load hit 32 distinct banks per half-warp
+// Row offsets of the shared-memory tiles of the sweep.  Rows are laid out in PAIRS: row r of a 24-wide tile starts at
+// ro(r) = 24 r + 4 (r / 2) doubles, i.e. the start residues mod 16 doubles cycle through 0, 8, 4, 12.  That makes both
+// fragment access patterns of the FP64 m8n8k4 MMA free of bank conflicts (no uniform row stride can: the 8-byte operand
+// loads need stride = 4 or 12 mod 16, the 16-byte accumulator loads/stores need 8 mod 16):
+//   * operand loads: rows t, t+4, t+8.. x eight consecutive columns, one half-warp = 4 rows with residues {0, 8, 4, 12}
+//   * accumulator tiles: rows g x column pairs, one quarter-warp = rows 2q, 2q+1, whose starts differ by 24 = 8 mod 16
+// ro() is additive over multiples of two rows: ro(r + 2m) = ro(r) + 52 m.  zo() is the same idea for the 16-wide Z.
+__host__ __device__ constexpr int ro(int r) { return 26 * r - 2 * (r & 1); }
+__host__ __device__ constexpr int zo(int r) { return 22 * r + 2 * (r & 1); }
+constexpr int RO4 = ro(4), RO8 = ro(8), ZO4 = zo(4), ZO8 = zo(8);
+constexpr int kQuuPad = 4;                        // Quu starts 4 mod 16 doubles after Qux: the Gauss-Jordan column loads
+                                                  // (12 Quu columns + Qux columns in one half-warp) then hit distinct banks
+constexpr int kSweepDoubles = 2 * ro(24) + zo(24) + ro(16) + kQuuPad + ro(12) + 2 * 616;  // H, Y, Z, Qux, Quu, rec: contiguous, free outside the sweep
 // per-phase terminal record
 constexpr int TQ_PHIX = 0;   // [24]
 constexpr int TQ_HX = 24;    // [4][24] touchdown-constraint gradients, by leg
@@ -133,10 +142,10 @@ struct BatchPtrs {
 struct Smem;
 struct __align__(16) Smem {
     // --- sweep tiles; contiguous, reused as streaming buffers by the linear rollout ---
-    double H[24 * TS], Y[24 * TS];
-    double Z[24 * ZS];         // H B_r [24][ZS] (16 columns used); after P2 the same storage holds K_r^T [24][12]
-    double Qux[16 * TS];       // Qux_r [16][TS]
-    double Quu[12 * TS];       // Quu_r [12][TS]
+    double H[ro(24)], Y[ro(24)];  // [24][24], row r at ro(r)
+    double Z[zo(24)];             // H B_r [24][16], row r at zo(r); after P2 the same storage holds K_r^T [24][12]
+    double Qux[ro(16) + kQuuPad]; // Qux_r [16][24], row r at ro(r)
+    double Quu[ro(12)];           // Quu_r [12][24], row r at ro(r)
     double rec[2][LQ_STRIDE];  // stage records, cp.async double buffer
     // --- vectors ---
     double dfc2[2][24];
@@ -288,22 +297,23 @@ __device__ inline void resetmap_thread(const double* x, unsigned c, unsigned cn,
 
 // dense Px (HKDReset.h:78-136), ROW-major into P[r * S + c] (S = row stride in doubles).  Jc: the foot Jacobians cached
 // by the LQ approximation in the phase's terminal record ([4][3][6]: d/d eul, d/d qleg per leg).
-__device__ inline void resetmap_partial_block(const double* Jc_all, unsigned c, unsigned cn, double* P, int S) {
-    for (int e = threadIdx.x; e < 576; e += kThreads) P[(e / 24) * S + e % 24] = ((e % 24) == (e / 24)) ? 1.0 : 0.0;
+__device__ inline void resetmap_partial_block(const double* Jc_all, unsigned c, unsigned cn, double* P) {
+    for (int e = threadIdx.x; e < 576; e += kThreads) P[ro(e / 24) + e % 24] = ((e % 24) == (e / 24)) ? 1.0 : 0.0;
     __syncthreads();
     if (threadIdx.x < 12) {
         const int l = threadIdx.x / 3, r = threadIdx.x % 3;
         const bool cl = (c >> l) & 1u, nl = (cn >> l) & 1u;
         const int row = 12 + 3 * l + r;
-        if (cl && !nl) P[row * (S + 1)] = 0.0;
+        double* Prow = P + ro(row);
+        if (cl && !nl) Prow[row] = 0.0;
         if (!cl && nl) {
             const double* Jc = Jc_all + 18 * l + 6 * r;
             const double cmap = (r == 2) ? 0.0 : 1.0;
-            P[row * (S + 1)] = 0.0;
+            Prow[row] = 0.0;
             for (int cc = 0; cc < 3; ++cc) {
-                P[row * S + cc] = cmap * Jc[cc];                          // d/d eul
-                P[row * S + 3 + cc] = cmap * ((r == cc) ? 1.0 : 0.0);     // d/d pos
-                P[row * S + 12 + 3 * l + cc] = cmap * Jc[3 + cc];         // d/d qleg
+                Prow[cc] = cmap * Jc[cc];                          // d/d eul
+                Prow[3 + cc] = cmap * ((r == cc) ? 1.0 : 0.0);     // d/d pos
+                Prow[12 + 3 * l + cc] = cmap * Jc[3 + cc];         // d/d qleg
             }
         }
     }

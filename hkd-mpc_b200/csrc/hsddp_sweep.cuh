@@ -212,19 +212,20 @@ __device__ inline void build_phase_tables(Smem& sm, unsigned cm, double dt) {
 // per-warp specialised variant executes 30 % fewer instructions but runs slower inside k_solve, see DESIGN.md §4.0
 // and tools/code_size.py).  Tiles of one kind are dealt round-robin to the warps so that every warp gets four
 // tiles per phase (P1, P2) and the vector jobs (Gn, Qx, Qu_r, G') go to the warps with the lightest tiles.
-__constant__ int4 c_y[9] = {{0, 0, 0, 0}, {8, 0, 224, 0}, {16, 0, 448, 0}, {0, 8, 8, 0}, {8, 8, 232, 0}, {16, 8, 456, 0}, {0, 16, 16, 0}, {8, 16, 240, 0}, {16, 16, 464, 0}};      // P1 Y tiles: {8 I, 8 Jt, H / Y tile offset, -}
-__constant__ int4 c_z[6] = {{0, 24, 12, 0}, {8, 24, 236, 160}, {16, 24, 460, 320}, {0, 32, 20, 8}, {8, 32, 244, 168}, {16, 32, 468, 328}};   // P1 Z tiles: {8 I, column of R, offset of H[:, 12 + 8 Jz], Z tile offset}
-__constant__ int4 c_xx[6] = {{0, 0, 0, 0}, {8, 0, 224, 0}, {16, 0, 448, 0}, {8, 8, 232, 0}, {16, 8, 456, 0}, {16, 16, 464, 0}};  // P2 Qxx (lower): {column of R, column of Y, Y / H tile offset, -}
-__constant__ int4 c_ux[6] = {{24, 0, 0, 0}, {24, 8, 8, 0}, {24, 16, 16, 0}, {32, 0, 224, 1}, {32, 8, 232, 1}, {32, 16, 240, 1}};  // P2 Qux_r: {column of R, column of Y, Qux tile offset, Ci}
-__constant__ int4 c_uu[4] = {{24, 0, 0, 0}, {24, 8, 8, 0}, {32, 0, 224, 1}, {32, 8, 232, 1}};  // P2 Quu_r: {column of R, column of Z, Quu tile offset, Ci}
-__constant__ int4 c_4d[3] = {{0, 0, 0, 0}, {8, 96, 232, 0}, {16, 192, 464, 0}};  // P4 diagonal tiles: {column of Qux, 8 I * 12 into K_r^T, H tile offset, -}
-__constant__ int4 c_4o[3] = {{16, 96, 456, 240}, {8, 0, 224, 8}, {16, 0, 448, 16}};  // P4 off-diagonal tiles (2,1), (1,0), (2,0): {.., .., H tile offset, mirror offset}
-static_assert(TS == 28 && ZS == 20, "the tile descriptor tables are generated for TS = 28, ZS = 20");
+__constant__ int4 c_y[9] = {{0, 0, 0, 0}, {8, 0, 208, 0}, {16, 0, 416, 0}, {0, 8, 8, 0}, {8, 8, 216, 0}, {16, 8, 424, 0}, {0, 16, 16, 0}, {8, 16, 224, 0}, {16, 16, 432, 0}};  // P1 Y tiles: {8 I, 8 Jt, H / Y tile offset ro(8 I) + 8 J, -}
+__constant__ int4 c_z[6] = {{0, 24, 12, 0}, {8, 24, 220, 176}, {16, 24, 428, 352}, {0, 32, 20, 8}, {8, 32, 228, 184}, {16, 32, 436, 360}};  // P1 Z tiles: {8 I, column of R, offset of H[8 I][12 + 8 Jz], Z tile offset zo(8 I) + 8 Jz}
+__constant__ int4 c_xx[6] = {{0, 0, 0, 0}, {8, 0, 208, 0}, {16, 0, 416, 0}, {8, 8, 216, 0}, {16, 8, 424, 0}, {16, 16, 432, 0}};  // P2 Qxx (lower): {column of R, column of Y, Y / H tile offset, -}
+__constant__ int4 c_ux[6] = {{24, 0, 0, 0}, {24, 8, 8, 0}, {24, 16, 16, 0}, {32, 0, 208, 1}, {32, 8, 216, 1}, {32, 16, 224, 1}};  // P2 Qux_r: {column of R, column of Y, Qux tile offset, Ci}
+__constant__ int4 c_uu[4] = {{24, 0, 0, 0}, {24, 8, 8, 0}, {32, 0, 208, 1}, {32, 8, 216, 1}};  // P2 Quu_r: {column of R, column of Z, Quu tile offset, Ci}
+__constant__ int4 c_4d[3] = {{0, 0, 0, 0}, {8, 96, 216, 0}, {16, 192, 432, 0}};  // P4 diagonal tiles: {column of Qux, 8 I * 12 into K_r^T, H tile offset, -}
+__constant__ int4 c_4o[3] = {{16, 96, 424, 224}, {8, 0, 208, 8}, {16, 0, 416, 16}};  // P4 off-diagonal tiles (2,1), (1,0), (2,0): {.., .., H tile offset, mirror offset ro(8 J) + 8 I}
+static_assert(RO8 == 208 && ZO8 == 176, "the tile descriptor tables are generated for ro(8) = 208, zo(8) = 176");
 
 // One phase of the backward sweep.  On entry sm.G / sm.H hold Gprime / Hprime (zero for
 // the last phase).  Returns false if a stage failed the PD test.
 //
-// Shared-memory tiles (row stride 24 doubles unless noted):
+// Shared-memory tiles:
+//   (rows of the 24-wide tiles start at ro(r), rows of Z at zo(r): the conflict-free pair layout of hsddp_device.cuh)
 //   H [24][24] value Hessian (symmetric); between P2 and P4 its lower tiles hold Qxx
 //   Y [24][24] = H A ; Zr = sm.Z [24][16 used] = H B_r
 //   rec[buf]: R [12][40] = [A - I | B_r] rows 0..11, then lx | lu | luu blocks  (cp.async double buffer)
@@ -244,23 +245,23 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
     const int rpos = hkd::cr_dense_pos(min((int)threadIdx.x, hkd::kCrNnz - 1));
     prefetch_stage(sm, 0, sc.stage_off[ph] + Nph - 1, sc.node_off[ph] + Nph, rpos);
     // per-lane base pointers of the tile fragments: element (g, 2t..2t+1) of an accumulator tile, (t, g) of an operand tile
-    const double* hA = sm.H + t * TS + g;
-    double* hC = sm.H + g * TS + 2 * t;
-    double* hT = sm.H + 2 * t * TS + g;
-    double* yC = sm.Y + g * TS + 2 * t;
-    double* zC = sm.Z + g * ZS + 2 * t;
-    const double* qA = sm.Qux + t * TS + g;
+    const double* hA = sm.H + ro(t) + g;
+    double* hC = sm.H + ro(g) + 2 * t;
+    double* hT = sm.H + ro(2 * t) + g;
+    double* yC = sm.Y + ro(g) + 2 * t;
+    double* zC = sm.Z + zo(g) + 2 * t;
+    const double* qA = sm.Qux + ro(t) + g;
     const double* kB = sm.Z + g * 12 + t;
-    double* quxC = sm.Qux + g * TS + 2 * t;
-    double* quuC = sm.Quu + g * TS + 2 * t;
+    double* quxC = sm.Qux + ro(g) + 2 * t;
+    double* quuC = sm.Quu + ro(g) + 2 * t;
     // G[N] = Phix + Gprime ; H[N] = Phixx + Hprime.  Phixx is sparse: the diagonal, the foot-regulariser coupling
     // (both triangles) and, per touchdown leg, the outer product of a 7-entry constraint gradient (AL term)
     if (tid < 24) {
         sm.G[tid] += trec[TQ_PHIX + tid];
-        sm.H[tid * (TS + 1)] += sm.lxxTd[tid];
+        sm.H[ro(tid) + tid] += sm.lxxTd[tid];
     } else if (tid < 48) {
         const int c = tid - 24, q = c % 12, j3 = 3 + q % 3;
-        sm.H[(c < 12) ? (12 + q) * TS + j3 : j3 * TS + 12 + q] -= sm.lxxTw[q];
+        sm.H[(c < 12) ? ro(12 + q) + j3 : ro(j3) + 12 + q] -= sm.lxxTw[q];
     }
     __syncthreads();
     if (tid >= 64 && tid < 64 + 49) {
@@ -271,7 +272,7 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
             if (wh != 0.0) {
                 const int i = (a < 3) ? a : (a == 3) ? 5 : 12 + 3 * l + a - 4;
                 const int j = (b < 3) ? b : (b == 3) ? 5 : 12 + 3 * l + b - 4;
-                sm.H[i * TS + j] += wh * (trec[TQ_HX + 24 * l + i] * trec[TQ_HX + 24 * l + j]);
+                sm.H[ro(i) + j] += wh * (trec[TQ_HX + 24 * l + i] * trec[TQ_HX + 24 * l + j]);
             }
         }
     }
@@ -301,8 +302,8 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                 double c2[2] = {h2.x, h2.y};
                 const double* a = hA + d.x;
                 dmma884(c2, a[0], b0);
-                dmma884(c2, a[4 * TS], b1);
-                dmma884(c2, a[8 * TS], b2);
+                dmma884(c2, a[RO4], b1);
+                dmma884(c2, a[RO8], b2);
                 *reinterpret_cast<double2*>(yC + d.z) = make_double2(c2[0], c2[1]);
             }
         }
@@ -318,8 +319,8 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                 double c2[2] = {0.0, 0.0};
                 const double* a = hA + d.x;
                 dmma884(c2, a[0], b0);
-                dmma884(c2, a[4 * TS], b1);
-                dmma884(c2, a[8 * TS], b2);
+                dmma884(c2, a[RO4], b1);
+                dmma884(c2, a[RO8], b2);
                 // swing columns of Z: H[:, 12+c] * (1-c_l) dt (zero factor for stance legs and the padding c >= 12)
                 const double2 h2 = *reinterpret_cast<const double2*>(hC + d.z);
                 c2[0] = fma(h2.x, sw.x, c2[0]);
@@ -331,10 +332,10 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
             for (int j = 0; j < 24; j += 4) {
-                a0 = fma(sm.H[j * TS + lane], dfc[j], a0);
-                a1 = fma(sm.H[(j + 1) * TS + lane], dfc[j + 1], a1);
-                a2 = fma(sm.H[(j + 2) * TS + lane], dfc[j + 2], a2);
-                a3 = fma(sm.H[(j + 3) * TS + lane], dfc[j + 3], a3);
+                a0 = fma(sm.H[ro(j) + lane], dfc[j], a0);
+                a1 = fma(sm.H[ro(j + 1) + lane], dfc[j + 1], a1);
+                a2 = fma(sm.H[ro(j + 2) + lane], dfc[j + 2], a2);
+                a3 = fma(sm.H[ro(j + 3) + lane], dfc[j + 3], a3);
             }
             sm.Gn[lane] = sm.G[lane] + ((a0 + a1) + (a2 + a3));
         }
@@ -342,7 +343,7 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
         PROF_MARK(sm, 6);
         // ---- P2: C = [A | B_r]^T M :  6 x Qxx (lower, M = Y, parked in H) ; 6 x Qux_r (M = Y) ; 4 x Quu_r (M = Z) ----
         // (the sparse additive term of Qxx, lxx + reg I, is applied in P3 by the warp that is idle there)
-        const double* yB = sm.Y + t * TS + g;
+        const double* yB = sm.Y + ro(t) + g;
         if (warp < 2) {  // Qxx = Y + At^T Y : warp 0 column block 0 (shared b operand), warp 1 tiles (1,1), (2,1), (2,2)
             int pa = -1, pb = -1;
             double a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
@@ -352,7 +353,7 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                 const double2 y2 = *reinterpret_cast<const double2*>(yC + d.z);
                 double c2[2] = {y2.x, y2.y};
                 if (d.x != pa) { const double* a = rB + d.x; a0 = a[0]; a1 = a[4 * hkd::kRld]; a2 = a[8 * hkd::kRld]; pa = d.x; }
-                if (d.y != pb) { const double* b = yB + d.y; b0 = b[0]; b1 = b[4 * TS]; b2 = b[8 * TS]; pb = d.y; }
+                if (d.y != pb) { const double* b = yB + d.y; b0 = b[0]; b1 = b[RO4]; b2 = b[RO8]; pb = d.y; }
                 dmma884(c2, a0, b0);
                 dmma884(c2, a1, b1);
                 dmma884(c2, a2, b2);
@@ -370,11 +371,11 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                 double c2[2] = {0.0, 0.0};
                 const double* b = yB + d.y;
                 dmma884(c2, a0, b[0]);
-                dmma884(c2, a1, b[4 * TS]);
-                dmma884(c2, a2, b[8 * TS]);
+                dmma884(c2, a1, b[RO4]);
+                dmma884(c2, a2, b[RO8]);
                 if (c < 12) {
                     if (sw != 0.0) {  // swing row: (B_r^T Y)[c][:] = (1-c_l) dt * Y[12+c][:]
-                        const double2 m2 = *reinterpret_cast<const double2*>(sm.Y + (12 + c) * TS + d.y + 2 * t);
+                        const double2 m2 = *reinterpret_cast<const double2*>(sm.Y + ro(12 + c) + d.y + 2 * t);
                         c2[0] = fma(sw, m2.x, c2[0]);
                         c2[1] = fma(sw, m2.y, c2[1]);
                     }
@@ -386,15 +387,15 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
             const int4 d = c_uu[warp];
             double c2[2] = {0.0, 0.0};
             const double* a = rB + d.x;
-            const double* b = sm.Z + t * ZS + g + d.y;
+            const double* b = sm.Z + zo(t) + g + d.y;
             dmma884(c2, a[0], b[0]);
-            dmma884(c2, a[4 * hkd::kRld], b[4 * ZS]);
-            dmma884(c2, a[8 * hkd::kRld], b[8 * ZS]);
+            dmma884(c2, a[4 * hkd::kRld], b[ZO4]);
+            dmma884(c2, a[8 * hkd::kRld], b[ZO8]);
             const int c = 8 * d.w + g;  // reduced control row
             if (c < 12) {
                 const double sw = sm.swc[c];
                 if (sw != 0.0) {  // swing row: (B_r^T Z)[c][:] = (1-c_l) dt * Z[12+c][:]
-                    const double2 m2 = *reinterpret_cast<const double2*>(sm.Z + (12 + c) * ZS + d.y + 2 * t);
+                    const double2 m2 = *reinterpret_cast<const double2*>(sm.Z + zo(12 + c) + d.y + 2 * t);
                     c2[0] = fma(sw, m2.x, c2[0]);
                     c2[1] = fma(sw, m2.y, c2[1]);
                 }
@@ -448,9 +449,8 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                 const bool is_inv = (warp == 1 && lane >= 17 && lane < 29);
                 // idle lanes carry a copy of a Quu_r column along (harmless, never stored)
                 const double* src = is_gain ? sm.Qux + j : is_ff ? sm.Qu : sm.Quu + (lane % 12);
-                const int stride = is_ff ? 1 : TS;
 #pragma unroll
-                for (int r = 0; r < 12; ++r) col[r] = src[r * stride];
+                for (int r = 0; r < 12; ++r) col[r] = src[is_ff ? r : ro(r)];
                 if (is_inv) {
 #pragma unroll
                     for (int r = 0; r < 12; ++r) col[r] = (r == lane - 17) ? 1.0 : 0.0;
@@ -501,8 +501,8 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                 if (warp == 2) {
                     // sparse additive part of Qxx (parked in H): lxx + reg I on the diagonal, the foot-regulariser coupling
                     // (12+c, 3 + c%3) of the lower triangle (P4 mirrors it)
-                    if (lane < 24) sm.H[lane * (TS + 1)] = (sm.H[lane * (TS + 1)] + sm.lxxd[lane]) + reg;
-                    if (lane < 12) sm.H[(12 + lane) * TS + 3 + lane % 3] -= sm.lxxw[lane];
+                    if (lane < 24) sm.H[ro(lane) + lane] = (sm.H[ro(lane) + lane] + sm.lxxd[lane]) + reg;
+                    if (lane < 12) sm.H[ro(12 + lane) + 3 + lane % 3] -= sm.lxxw[lane];
                 } else if (lane < 16) {
                     // decoupled controls: Quu_ii = dt R_i + reg, Qu_i = lu_i, K row = 0
                     double dv = 0.0;
@@ -534,8 +534,8 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                 const double* a = qA + d.x;
                 const double* b = kB + d.y;
                 dmma884(c2, a[0], b[0]);
-                dmma884(c2, a[4 * TS], b[4]);
-                dmma884(c2, a[8 * TS], b[8]);
+                dmma884(c2, a[RO4], b[4]);
+                dmma884(c2, a[RO8], b[8]);
                 // symmetrise the diagonal tile: partner of (g, 2t+q') is (2t+q', g), held by lane 4*(2t+q') + g/2, slot g&1
                 const double p00 = __shfl_sync(0xffffffffu, c2[0], 4 * (2 * t) + (g >> 1));
                 const double p01 = __shfl_sync(0xffffffffu, c2[1], 4 * (2 * t) + (g >> 1));
@@ -552,18 +552,18 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                 const double* a = qA + d.x;
                 const double* b = kB + d.y;
                 dmma884(c2, a[0], b[0]);
-                dmma884(c2, a[4 * TS], b[4]);
-                dmma884(c2, a[8 * TS], b[8]);
+                dmma884(c2, a[RO4], b[4]);
+                dmma884(c2, a[RO8], b[8]);
                 hT[d.w] = c2[0];
-                hT[d.w + TS] = c2[1];
+                hT[d.w + 24] = c2[1];  // row 2t+1 starts 24 after the even row 2t
                 *reinterpret_cast<double2*>(hC + d.z) = make_double2(c2[0], c2[1]);
             }
         } else if (lane < 24) {  // G' = Qx + Qux_r^T dU_r
             double a0 = sm.Qx[lane], a1 = 0.0;
 #pragma unroll
             for (int r = 0; r < 12; r += 2) {
-                a0 = fma(sm.Qux[r * TS + lane], sm.wu[r], a0);
-                a1 = fma(sm.Qux[(r + 1) * TS + lane], sm.wu[r + 1], a1);
+                a0 = fma(sm.Qux[ro(r) + lane], sm.wu[r], a0);
+                a1 = fma(sm.Qux[ro(r + 1) + lane], sm.wu[r + 1], a1);
             }
             sm.G[lane] = a0 + a1;
         }
@@ -582,7 +582,7 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
         double acc = 0.0;
         if (tid < 24) {
 #pragma unroll
-            for (int j = 0; j < 24; ++j) acc = fma(sm.H[j * TS + tid], sm.vtmp[j], acc);  // H symmetric: conflict-free column read
+            for (int j = 0; j < 24; ++j) acc = fma(sm.H[ro(j) + tid], sm.vtmp[j], acc);  // H symmetric: conflict-free column read
         }
         __syncthreads();
         if (tid < 24) sm.G[tid] += acc;
@@ -601,22 +601,22 @@ __device__ inline bool backward_sweep_block(Smem& sm, double reg) {
     zero_stage_buffers(sm);
     for (int ph = sc.n_phases - 1; ph >= 0; --ph) {
         if (ph == sc.n_phases - 1) {
-            for (int e = tid; e < 24 * TS; e += kThreads) sm.H[e] = 0.0;
+            for (int e = tid; e < ro(24); e += kThreads) sm.H[e] = 0.0;
             if (tid < 24) sm.G[tid] = 0.0;
             __syncthreads();
         } else {
             // impact-aware step: G' = Px^T G0, H' = Px^T H0 Px at the phase's terminal state.  Both products are
             // C = A^T B with A, B stored row (= k) major, i.e. the tile shape of P1: W = H^T P (= H P, H is symmetric),
             // then H' = P^T W; 9 tiles x 6 DMMA each, dealt round-robin to the warps.
-            resetmap_partial_block(sm.tq + ph * TQ_STRIDE + TQ_JC, sc.cmask[ph], sc.nmask[ph], sm.Y, TS);
-            const double* P = sm.Y;  // row-major P[r * TS + c]
-            double* W = sm.Qux;      // 24 x TS temporary spanning Qux|Quu (contiguous, free here)
+            resetmap_partial_block(sm.tq + ph * TQ_STRIDE + TQ_JC, sc.cmask[ph], sc.nmask[ph], sm.Y);
+            const double* P = sm.Y;  // P[ro(r) + c]
+            double* W = sm.Qux;      // 24-row temporary spanning Qux|Quu (contiguous, free here)
             const int lane = tid & 31, wrp = tid >> 5, g = lane >> 2, t = lane & 3;
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {
-                const double* A = (pass ? P : sm.H) + t * TS + g;
-                const double* B = (pass ? W : P) + t * TS + g;
-                double* Cm = (pass ? sm.H : W) + g * TS + 2 * t;
+                const double* A = (pass ? P : sm.H) + ro(t) + g;
+                const double* B = (pass ? W : P) + ro(t) + g;
+                double* Cm = (pass ? sm.H : W) + ro(g) + 2 * t;
 #pragma unroll 1
                 for (int q = wrp; q < 9; q += 4) {
                     const int4 d = c_y[q];
@@ -624,13 +624,13 @@ __device__ inline bool backward_sweep_block(Smem& sm, double reg) {
                     const double* a = A + d.x;
                     const double* b = B + d.y;
 #pragma unroll
-                    for (int kk = 0; kk < 24; kk += 4) dmma884(c2, a[kk * TS], b[kk * TS]);
+                    for (int kk = 0; kk < 24; kk += 4) dmma884(c2, a[26 * kk], b[26 * kk]);  // ro(t + kk) = ro(t) + 26 kk for kk = 0 mod 4
                     *reinterpret_cast<double2*>(Cm + d.z) = make_double2(c2[0], c2[1]);
                 }
                 if (!pass && tid < 24) {
                     double acc = 0.0;
 #pragma unroll
-                    for (int m = 0; m < 24; ++m) acc = fma(P[m * TS + tid], sm.G[m], acc);
+                    for (int m = 0; m < 24; ++m) acc = fma(P[ro(m) + tid], sm.G[m], acc);
                     sm.vtmp[tid] = acc;
                 }
                 __syncthreads();
@@ -648,7 +648,7 @@ __device__ inline bool backward_sweep_block(Smem& sm, double reg) {
         dV2 += d2;
     }
     if (success) {
-        for (int e = tid; e < 576; e += kThreads) sm.g0h0[24 + e] = sm.H[(e / 24) * TS + e % 24];  // symmetric: row-major == column-major
+        for (int e = tid; e < 576; e += kThreads) sm.g0h0[24 + e] = sm.H[ro(e / 24) + e % 24];  // symmetric: row-major == column-major
         if (tid < 24) sm.g0h0[tid] = sm.G[tid];
     }
     __syncthreads();
