@@ -273,8 +273,8 @@ __device__ inline void bind_problem(Smem& sm, const BatchPtrs& bp, int pid) {
     for (int i = threadIdx.x; i < nw; i += kThreads) ((int*)&sm.sc)[i] = ((const int*)src)[i];
     __syncthreads();
     if (threadIdx.x == 0) {
-        const size_t ro = (size_t)sm.sc.ref_off;
-        sm.xr = bp.xr + ro * 24; sm.ur = bp.ur + ro * 24; sm.prel = bp.prel + ro * 12; sm.xinit = bp.xinit + ro * 24;
+        const size_t roff = (size_t)sm.sc.ref_off;
+        sm.xr = bp.xr + roff * 24; sm.ur = bp.ur + roff * 24; sm.prel = bp.prel + roff * 12; sm.xinit = bp.xinit + roff * 24;
     }
     __syncthreads();
 }
@@ -558,7 +558,7 @@ __device__ inline void compute_cost_block(Smem& sm) {
 }
 
 // ---------------------------------------------------------------------------
-// LQ_approximation: one thread per stage writes the compact record; one thread per
+// LQ_approximation: two threads per stage write the compact record; one thread per
 // phase the terminal record.
 // ---------------------------------------------------------------------------
 __device__ inline void lq_approximation_block(Smem& sm) {

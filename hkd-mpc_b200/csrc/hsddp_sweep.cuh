@@ -74,6 +74,23 @@ __device__ inline void zero_stage_buffers(Smem& sm) {
     __syncthreads();
 }
 
+// 1 / d for a pivot determinant (normal range, positive for a PD block): the hardware seed (20 bits) and two Newton steps,
+// straight-line code.  The compiler's IEEE division carries a slow-path branch and ~70 cycles of dependent latency in
+// the middle of the serial chain of an elimination step; this form is 13-17 % faster per elimination
+// (tools/microbench/gj_variants.cu) and agrees with the division to the last bit or two.
+#ifdef HSDDP_GJ_IEEE_DIV
+__device__ __forceinline__ double pivot_rcp(double d) { return 1.0 / d; }
+#else
+__device__ __forceinline__ double pivot_rcp(double d) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-d, x, 1.0);
+    return fma(x, e, x);
+}
+#endif
+
 // Block Gauss-Jordan with 2x2 pivot blocks on 12 rows, one tableau column per lane (v[0..11]).
 // Lanes 0..11 of the warp hold the columns of the 12x12 pivot matrix.  `sbuf`: 24 doubles per warp.
 // The loop is deliberately NOT unrolled (the stage body must stay inside the instruction cache):
@@ -111,7 +128,7 @@ __device__ __forceinline__ bool gauss_jordan12(double (&v)[12], double* sbuf, un
         const double2 pk1 = *reinterpret_cast<const double2*>(sbuf + 12);
         const double det = pk.x * pk1.y - pk1.x * pk.y;
         if (pk.x < 0.0 || det < 0.0) ok = false;
-        const double rdet = 1.0 / det;
+        const double rdet = pivot_rcp(det);
         const double t0 = (pk1.y * v[0] - pk1.x * v[1]) * rdet;
         const double t1 = (pk.x * v[1] - pk.y * v[0]) * rdet;
 #ifdef HSDDP_PROFILE_GJ
@@ -435,7 +452,8 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
         // ---- P3: Gauss-Jordan tableau (warps 0,1), sparse Qxx terms (warp 2), inactive controls (warp 3) ----
         // PD verdict of the reference, LDLT(Quu - 1e-9 I).isPositive() (Q7), without a third elimination:
         //   * a non-positive pivot of Quu_r itself          => Quu_r - 1e-9 I is not PD           (verdict false)
-        //   * all pivots positive and ||Quu_r^-1||_F < 5e8   => lambda_min(Quu_r) > 2e-9 > 1e-9    (verdict true)
+        //   * all pivots positive and every column of Quu_r^-1 shorter than 5e8 / sqrt(12)
+        //                                  => ||Quu_r^-1||_F < 5e8 => lambda_min(Quu_r) > 2e-9 > 1e-9    (verdict true)
         //   * otherwise (never seen on the benchmark inputs) the shifted matrix is eliminated exactly in a second pass.
         // Quu_r^-1 comes for free: twelve otherwise idle lanes of warp 1 carry the identity columns through the elimination.
 #pragma unroll 1
@@ -469,33 +487,41 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                 PROF_MARK(sm, 14);
                 if (pass) {
                     if (warp == 1 && lane == 0) sm.ibuf[0] = ok ? 1 : 0;
-                } else if (is_gain) {  // gain column j: K_r[:, j] = -Quu_r^-1 Qux_r[:, j]  -> KT[j][0..11] (smem + HBM)
-                    double2* ks = reinterpret_cast<double2*>(sm.Z + 12 * j);
-                    double2* kg = reinterpret_cast<double2*>(sm.K + (size_t)s * 288 + 12 * j);
+                } else {
+                    if (is_gain) {  // gain column j: K_r[:, j] = -Quu_r^-1 Qux_r[:, j]  -> KT[j][0..11] (smem + HBM)
+                        double2* ks = reinterpret_cast<double2*>(sm.Z + 12 * j);
+                        double2* kg = reinterpret_cast<double2*>(sm.K + (size_t)s * 288 + 12 * j);
 #pragma unroll
-                    for (int r = 0; r < 12; r += 2) {
-                        const double2 val = make_double2(-col[r], -col[r + 1]);
-                        ks[r >> 1] = val;
-                        kg[r >> 1] = val;
+                        for (int r = 0; r < 12; r += 2) {
+                            const double2 val = make_double2(-col[r], -col[r + 1]);
+                            ks[r >> 1] = val;
+                            kg[r >> 1] = val;
+                        }
                     }
-                } else if (is_ff) {
-                    double dvk = 0.0;
+                    if (warp == 1) {
+                        // one uniform dot product: lane 16 gets Qu^T (Quu_r^-1 Qu_r) = -Qu^T dU, lanes 17..28 the squared
+                        // norm of their column of Quu_r^-1.  The norm test is per column (each < 0.25e18 / 12, so the sum is
+                        // below 0.25e18): a single vote instead of a warp reduction; a NaN fails it and takes the exact pass.
+                        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-                    for (int r = 0; r < 12; ++r) {
-                        sm.wu[r] = -col[r];                                   // dU_r
-                        sm.dU[24 * s + act_index(r, cm)] = -col[r];
-                        dvk = fma(sm.Qu[r], col[r], dvk);                     // -Qu^T dU
-                    }
-                    sm.dbuf[0] = dvk;
-                }
-                if (!pass && warp == 1) {
-                    double f2 = 0.0;
-                    if (is_inv) {
+                        for (int r = 0; r < 12; r += 4) {
+                            a0 = fma(is_ff ? sm.Qu[r] : col[r], col[r], a0);
+                            a1 = fma(is_ff ? sm.Qu[r + 1] : col[r + 1], col[r + 1], a1);
+                            a2 = fma(is_ff ? sm.Qu[r + 2] : col[r + 2], col[r + 2], a2);
+                            a3 = fma(is_ff ? sm.Qu[r + 3] : col[r + 3], col[r + 3], a3);
+                        }
+                        const double dot = (a0 + a1) + (a2 + a3);
+                        if (is_ff) {
 #pragma unroll
-                        for (int r = 0; r < 12; ++r) f2 = fma(col[r], col[r], f2);
+                            for (int r = 0; r < 12; ++r) {
+                                sm.wu[r] = -col[r];                                   // dU_r
+                                sm.dU[24 * s + act_index(r, cm)] = -col[r];
+                            }
+                            sm.dbuf[0] = dot;
+                        }
+                        const bool big = __any_sync(0xffffffffu, is_inv && !(dot < 0.25e18 / 12));
+                        if (lane == 0) sm.ibuf[0] = !ok ? 0 : big ? 2 : 1;
                     }
-                    f2 = warp_sum(f2);
-                    if (lane == 0) sm.ibuf[0] = !ok ? 0 : (f2 < 0.25e18) ? 1 : 2;
                 }
             } else if (!pass) {
                 if (warp == 2) {
