@@ -327,7 +327,7 @@ def main():
             "roofline": {"bound": "tensor", "pipe": "FP64 (DFMA / DMMA m8n8k4)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per solve (dram__bytes_read.sum + dram__bytes_write.sum over its launches)",
                          "traffic_source": traffic_src,
-                         "kernel": "one solve of the batch = the k_phase<begin|prep|sweep|forward> launches of the phased driver (k_solve when the persistent kernel is selected); the backward-sweep kernel is 56 % of it (profiles/)",
+                         "kernel": "one solve of the batch = the k_phase<begin|prep|sweep|forward> launches of the phased driver (k_solve when the persistent kernel is selected); the backward-sweep kernel is 58 % of it (profiles/r01j_phased_solve_launches.json)",
                          "kernel_ms": kernel_ms,
                          "flop_per_launch": flop_launch,
                          "peak_source": "measured in this run by hsddp_fp64_peak_tflops: DFMA %.1f, DMMA %.1f TFLOP/s "
