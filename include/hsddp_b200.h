@@ -172,9 +172,9 @@ int hsddp_batch_sync(hsddp_batch* b);
 /* How solve() is scheduled on the GPU (results agree to rounding; each mode is bitwise reproducible):
  *   1 persistent — one kernel, every block runs whole solves pulled from a queue (small batches, latency)
  *   2 phased     — per DDP iteration one kernel per phase (prep / backward sweep / forward sweep) over the
- *                  problems still running, four index ranges driven concurrently on their own streams; the host
- *                  reads one counter per range and iteration, so hsddp_batch_solve_async blocks in this mode
- *   0 auto       — phased when the batch fills the GPU about twelve times over (>= 10,656 problems on a B200). */
+ *                  problems still running, up to eight index ranges driven concurrently on their own streams; the
+ *                  host reads one counter per range and iteration, so hsddp_batch_solve_async blocks in this mode
+ *   0 auto       — phased when the batch fills the GPU about 4.5 times over (>= 3,996 problems on a B200). */
 int hsddp_batch_set_solve_mode(hsddp_batch* b, int mode);
 /* milliseconds of the last solve kernel, CUDA events on the handle's stream */
 int hsddp_batch_last_solve_ms(hsddp_batch* b, float* ms);
