@@ -117,6 +117,7 @@ struct BatchPtrs {
     // problem-major workspace
     double *Xbar, *X, *Xsim_t, *Defect, *dX;  // [P][max_nodes][24]
     double *Ubar, *U, *U_t, *dU;              // [P][max_stages][24]
+    double* KdX;                              // [P][max_stages][12] K_r dX of the last linear rollout (reduced control index)
     double* K;                                // [P][max_stages][24][12] compact gains, transposed: KT[j][c] = K_r[c][j] (c <-> coupled control of leg c/3)
     double* lq;                               // [P][max_stages][CR_STRIDE] compact stage records
     double* tq;                               // [P][MAXPH][TQ_STRIDE]
@@ -160,7 +161,7 @@ struct __align__(16) Smem {
     hsddp_constraint_params cp;
     hsddp_options opt;
     // per-problem base pointers
-    double *Xbar, *X, *Xsim_t, *Defect, *dX, *Ubar, *U, *U_t, *dU, *K, *lqg, *tq, *gcon, *reb, *hcon, *al, *g0h0;
+    double *Xbar, *X, *Xsim_t, *Defect, *dX, *Ubar, *U, *U_t, *dU, *KdX, *K, *lqg, *tq, *gcon, *reb, *hcon, *al, *g0h0;
     const double *xr, *ur, *prel, *xinit, *x0;
     unsigned long long* prof;
     unsigned long long profacc[16];
@@ -255,6 +256,7 @@ __device__ inline void bind_problem(Smem& sm, const BatchPtrs& bp, int pid) {
         sm.Defect = bp.Defect + pid * sn; sm.dX = bp.dX + pid * sn;
         sm.Ubar = bp.Ubar + pid * ss; sm.U = bp.U + pid * ss; sm.U_t = bp.U_t + pid * ss; sm.dU = bp.dU + pid * ss;
         sm.K = bp.K + (size_t)pid * bp.max_stages * 288;
+        sm.KdX = bp.KdX + (size_t)pid * bp.max_stages * 12;
         sm.lqg = bp.lq + (size_t)pid * bp.max_stages * CR_STRIDE;
         sm.tq = bp.tq + (size_t)pid * MAXPH * TQ_STRIDE;
         sm.gcon = bp.gcon + (size_t)pid * bp.max_stages * 20;
@@ -327,6 +329,13 @@ __device__ inline void resetmap_partial_block(const double* Jc_all, unsigned c, 
 // trial controls / simulated states; the commit pass reproduces the reference's
 // partial-update semantics when a stage diverges.
 // ---------------------------------------------------------------------------
+// LINEARISED = true (inside solve(), where the linear rollout of the same iteration precedes every trial): with
+// multiple shooting the trial states are X = Xbar + eps dX, so the feedback term K (X - Xbar) equals eps (K dX), and
+// K_r dX was already formed by the linear rollout (sm.KdX).  The trial then needs no gain at all: one fused
+// multiply-add per control instead of re-reading 2.3 KB of gains per stage and trial.  Differs from the literal form
+// by the rounding of (Xbar + eps dX) - Xbar only.  LINEARISED = false evaluates the literal form (step-level API,
+// where the caller decides what precedes a rollout).
+template <bool LINEARISED>
 __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
     const DevSchedule& sc = sm.sc;
     const int tid = virtual_tid(sm), lane = tid & 31, warp = tid >> 5;
@@ -341,14 +350,25 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
         const double xb = sm.Xbar[e];
         const double x = xb + eps * sm.dX[e];
         xs[e] = x;
-        if (dev_in_smem) xd[e] = x - xb;
+        if (dev_in_smem && !LINEARISED) xd[e] = x - xb;
     }
     __syncthreads();
     // (a) controls: U = (Ubar + eps dU) + K (X - Xbar), one warp per stage.  K is stored compactly as
     //     K_r^T [24][12] (only the coupled control of each leg has a non-zero gain row, see hsddp_sweep.cuh).
     //     Lane (p, q) = (lane & 7, lane >> 3) accumulates the control pair (2p, 2p+1) over the state
     //     components j = q, q+4, ..: every load is a 16-byte piece of a 384-byte contiguous run of K.
-    {
+    if (LINEARISED) {
+        for (int e = tid; e < N * 24; e += kThreads) {
+            const int s = e / 24, i = e % 24, c = i % 12;
+            int ph, k;
+            phase_of_stage(sc, s, ph, k);
+            const bool stance = (sc.cmask[ph] >> (c / 3)) & 1u;
+            double u = sm.Ubar[e] + eps * sm.dU[e];
+            if ((i < 12) == stance) u += eps * sm.KdX[12 * s + c];  // the coupled control of the leg
+            sm.U_t[e] = u;
+            if (dev_in_smem) xd[24 * (sc.node_off[ph] + k) + i] = u;
+        }
+    } else {
         const int p = lane & 7, q = lane >> 3;
         const bool kact = p < 6;
         for (int s = warp; s < N; s += kWarps) {
@@ -760,6 +780,7 @@ __device__ inline void cold_start_block(Smem& sm) {
     }
     for (int e = threadIdx.x; e < sc.n_stages * 24; e += kThreads) { sm.Ubar[e] = 0.0; sm.U[e] = 0.0; sm.dU[e] = 0.0; sm.U_t[e] = 0.0; }
     for (size_t e = threadIdx.x; e < (size_t)sc.n_stages * 288; e += kThreads) sm.K[e] = 0.0;
+    for (int e = threadIdx.x; e < sc.n_stages * 12; e += kThreads) sm.KdX[e] = 0.0;
     for (int e = threadIdx.x; e < sc.n_stages * 20; e += kThreads) {
         sm.gcon[e] = 0.0; sm.reb[2 * e] = sm.cp.grf_eps; sm.reb[2 * e + 1] = sm.cp.grf_delta;
     }

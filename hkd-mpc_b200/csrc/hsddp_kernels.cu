@@ -35,6 +35,7 @@ __device__ inline void prepare_merit_block(Smem& sm) {  // MultiPhaseDDP.cpp:331
 }
 
 // MultiPhaseDDP::line_search.  Returns success; eps_out = accepted step (0 if none).
+template <bool LINEARISED>
 __device__ inline bool line_search_block(Smem& sm, double& eps_out, int& n_trials) {
     double eps = 1;
     const double merit_prev = sm.st.merit;
@@ -45,7 +46,7 @@ __device__ inline bool line_search_block(Smem& sm, double& eps_out, int& n_trial
     n_trials = 0;
     __syncthreads();
     while (eps > 1e-3) {  // 1, .1, .010000000000000002, .0010000000000000002 (Q6)
-        const bool rollout_success = hybrid_rollout_block(sm, eps);
+        const bool rollout_success = hybrid_rollout_block<LINEARISED>(sm, eps);
         compute_cost_block(sm);
         const double merit = sm.st.actual_cost + merit_rho * sm.st.feas;
         ++n_trials;
@@ -114,7 +115,7 @@ __device__ inline void solve_begin_block(Smem& sm) {
         sm.st.actual_cost = 0; sm.st.max_pconstr = 0; sm.st.max_pconstr_prev = 0; sm.st.max_tconstr = 0; sm.st.max_tconstr_prev = 0;
     }
     __syncthreads();
-    hybrid_rollout_block(sm, 0.0);
+    hybrid_rollout_block<true>(sm, 0.0);  // (eps = 0: both forms give U = Ubar)
     update_nominal_block(sm);
     compute_cost_block(sm);
     if (tid == 0) { sm.ctl.cost0 = sm.st.actual_cost; sm.ctl.feas0 = sm.st.feas; }
@@ -178,7 +179,7 @@ __device__ inline void iter_forward_block(Smem& sm, const BatchPtrs& bp) {
     } else {
         double eps_acc = 0;
         int ntr = 0;
-        if (line_search_block(sm, eps_acc, ntr)) {
+        if (line_search_block<true>(sm, eps_acc, ntr)) {
             update_nominal_block(sm);
         } else {  // Q2: only the scalars are restored
             __syncthreads();
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, HSDDP_MIN_BLOCKS) k_step(BatchPtrs b
     int okv = 1;
     switch (op) {
         case OP_RESET: cold_start_block(sm); break;
-        case OP_ROLLOUT: okv = hybrid_rollout_block(sm, arg) ? 1 : 0; break;
+        case OP_ROLLOUT: okv = hybrid_rollout_block<false>(sm, arg) ? 1 : 0; break;
         case OP_COST: compute_cost_block(sm); break;
         case OP_LQ: lq_approximation_block(sm); break;
         case OP_SWEEP: okv = backward_sweep_block(sm, arg) ? 1 : 0; break;
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, HSDDP_MIN_BLOCKS) k_step(BatchPtrs b
         case OP_FORWARD: {
             const double cost_prev = sm.st.actual_cost, merit_prev = sm.st.merit;
             double eps_acc; int ntr;
-            okv = line_search_block(sm, eps_acc, ntr) ? 1 : 0;
+            okv = line_search_block<false>(sm, eps_acc, ntr) ? 1 : 0;
             if (!okv) { __syncthreads(); if (threadIdx.x == 0) { sm.st.actual_cost = cost_prev; sm.st.merit = merit_prev; } }
             if (threadIdx.x == 0 && darg) darg[pid] = eps_acc;
         } break;
@@ -727,6 +728,7 @@ static int alloc_workspace(hsddp_batch* b, int n_problems, int max_stages, int m
     if ((rc = dalloc(b, &bp.U, P * SS))) return rc;
     if ((rc = dalloc(b, &bp.U_t, P * SS))) return rc;
     if ((rc = dalloc(b, &bp.dU, P * SS))) return rc;
+    if ((rc = dalloc(b, &bp.KdX, P * max_stages * 12))) return rc;
     if ((rc = dalloc(b, &bp.K, P * max_stages * 288))) return rc;
     if ((rc = dalloc(b, &bp.lq, P * max_stages * CR_STRIDE))) return rc;
     if ((rc = dalloc(b, &bp.tq, P * MAXPH * TQ_STRIDE))) return rc;

@@ -860,7 +860,9 @@ __device__ inline void linear_rollout_block(Smem& sm, double eps) {
                         a3 = fma(KT[(j + 3) * 12 + lane], sdx[j + 3], a3);
                     }
                     const int i = act_index(lane, cm);
-                    const double du = eps * dUs[i] + ((a0 + a1) + (a2 + a3));
+                    const double kdx = (a0 + a1) + (a2 + a3);
+                    const double du = eps * dUs[i] + kdx;
+                    sm.KdX[12 * s + lane] = kdx;  // kept for the trial rollouts of this iteration (hybrid_rollout_block<true>)
                     sdu[lane] = du;
                     sm.U_t[24 * s + i] = du;
                 } else if (lane < 24) {
