@@ -326,7 +326,7 @@ def main():
                     "what": "set_initial_condition(x0 from pinned host) + reset + solve + copy-out to pinned host of the result record and the MPC command of every problem (hkd_command_lcmt payload: 8 controls, body states, 12x12 feedback blocks, foot placements; HKDMPC.cpp:207-298)"},
             "roofline": {"bound": "tensor", "pipe": "FP64 (DFMA / DMMA m8n8k4)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per solve (dram__bytes_read.sum + dram__bytes_write.sum over its launches)",
-                         "traffic_source": traffic_src,
+                         "traffic_source": traffic_src + "; captured before the trial rollouts stopped re-reading the gains, which removes about 138 KB per trial (~88 GB per solve of this workload) -- not re-measured",
                          "kernel": "one solve of the batch = the k_phase<begin|prep|sweep|forward> launches of the phased driver (k_solve when the persistent kernel is selected); the backward-sweep kernel is 58 % of it (profiles/r01j_phased_solve_launches.json)",
                          "kernel_ms": kernel_ms,
                          "flop_per_launch": flop_launch,
