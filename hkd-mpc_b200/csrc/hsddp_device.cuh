@@ -104,8 +104,9 @@ struct SolverState {
 struct SolveCtl {
     int iter, iter_ou, iter_in, n_sweeps, n_trials, status;
     int active;  // 1 while the solve is running
-    int _pad;
+    int have_trial;  // 1: trial_cost / trial_feas hold the last compute_cost of this outer iteration's line search
     double cost0, feas0;
+    double trial_cost, trial_feas;
 };
 
 struct BatchPtrs {

@@ -48,6 +48,7 @@ __device__ inline bool line_search_block(Smem& sm, double& eps_out, int& n_trial
     while (eps > 1e-3) {  // 1, .1, .010000000000000002, .0010000000000000002 (Q6)
         const bool rollout_success = hybrid_rollout_block<LINEARISED>(sm, eps);
         compute_cost_block(sm);
+        if (threadIdx.x == 0) { sm.ctl.trial_cost = sm.st.actual_cost; sm.ctl.trial_feas = sm.st.feas; sm.ctl.have_trial = 1; }
         const double merit = sm.st.actual_cost + merit_rho * sm.st.feas;
         ++n_trials;
         const double exp_cost_change = eps * dV_1 + 0.5 * eps * eps * dV_2;
@@ -77,6 +78,7 @@ __device__ inline void outer_start_block(Smem& sm) {  // :283-302
     if (threadIdx.x == 0) {
         sm.ctl.iter_ou++;
         sm.ctl.iter_in = 0;
+        sm.ctl.have_trial = 0;  // the AL / ReB parameters have changed: the next iteration evaluates the cost afresh
         sm.st.max_tconstr_prev = sm.st.max_tconstr; sm.st.max_pconstr_prev = sm.st.max_pconstr; sm.st.reg = 0;
     }
     __syncthreads();
@@ -130,7 +132,15 @@ __device__ inline void solve_begin_block(Smem& sm) {
 }
 
 __device__ inline void iter_prep_block(Smem& sm, const BatchPtrs& bp) {
-    compute_cost_block(sm);
+    // compute_cost + measure_dynamics_feasibility at the top of the inner loop (:306-308).  After the first iteration
+    // of an outer iteration the trajectories and parameters are exactly those of the last line-search trial (accepted or
+    // not, Q2), whose cost and feasibility were just evaluated: reuse them instead of a second identical pass.
+    if (sm.ctl.have_trial) {
+        if (threadIdx.x == 0) { sm.st.actual_cost = sm.ctl.trial_cost; sm.st.feas = sm.ctl.trial_feas; }
+        __syncthreads();
+    } else {
+        compute_cost_block(sm);
+    }
     if (threadIdx.x == 0) {
         sm.ctl.iter_in++; sm.ctl.iter++;
         if (sm.ctl.iter <= HSDDP_TRACE_CAP) {
