@@ -130,3 +130,32 @@ def test_survey_probe_numbers(orc):
     for (gait, k0, plan), (iters, cost) in expect.items():
         s, _ = orc.Problem(_table(orc, gait), k0, plan).solve()
         assert s["n_iter"] == iters and abs(s["cost"] - cost) < 1e-4
+
+
+def test_trial_control_identity_of_the_linearised_rollout(orc):
+    """Inside solve() the CUDA trial rollout uses U = (Ubar + eps dU) + eps (K dX) with K dX taken from the linear
+    rollout of the same iteration (hybrid_rollout_block<true>), the reference evaluates
+    (Ubar + eps dU) + K ((Xbar + eps dX) - Xbar) (SinglePhase.cpp:182-233).  On the oracle's own iterates the two
+    differ by rounding only, for every step size of the line search."""
+    for gait, plan in (("trot", 0.6), ("bound", 0.5), ("pronk", 0.4)):
+        P = orc.Problem(_table(orc, gait), 0, plan)
+        assert P.hybrid_rollout(0.0)
+        P.update_nominal()
+        for it in range(3):
+            P.compute_cost()
+            P.lq_approximation()
+            assert P.backward_sweep(0.0 if it == 0 else 1e-3)
+            P.linear_rollout(1.0)
+            K, dX, dU, Xbar, Ubar = P.get("K"), P.get("dX"), P.get("dU"), P.get("Xbar"), P.get("Ubar")
+            # node of stage s = s + (index of its phase): every phase owns horizon + 1 nodes
+            node = np.concatenate([np.arange(ph["horizon"]) + off + i for i, (ph, off) in
+                                   enumerate(zip(P.phases, np.cumsum([0] + [p["horizon"] for p in P.phases[:-1]])))])
+            KdX = np.einsum("sij,sj->si", K, dX[node])
+            for eps in (1.0, 0.1, 0.010000000000000002, 0.0010000000000000002):
+                assert P.hybrid_rollout(eps)
+                U_ref = P.get("U")
+                U_lin = (Ubar + eps * dU) + eps * KdX
+                scale = np.abs(K).sum(axis=2) * np.abs(Xbar[node]).max(axis=1, keepdims=True) + np.abs(U_ref) + 1.0
+                assert (np.abs(U_lin - U_ref) <= 1e-14 * scale).all(), (gait, it, eps, np.abs(U_lin - U_ref).max())
+            assert P.hybrid_rollout(1.0)
+            P.update_nominal()
