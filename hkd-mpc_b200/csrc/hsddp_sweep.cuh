@@ -360,6 +360,65 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
         PROF_MARK(sm, 6);
         // ---- P2: C = [A | B_r]^T M :  6 x Qxx (lower, M = Y, parked in H) ; 6 x Qux_r (M = Y) ; 4 x Quu_r (M = Z) ----
         // (the sparse additive term of Qxx, lxx + reg I, is applied in P3 by the warp that is idle there)
+#ifdef HSDDP_QXX_IN_P3  // experiment: Qxx and Qx are not inputs of the elimination -> computed in P3 by its idle warps
+        const double* yB = sm.Y + ro(t) + g;
+        if (warp < 2) {  // Qux_r = B_r^T Y : warp 0 rows 0..7, warp 1 rows 8..11; the three column blocks share the a operand
+            const int Ci = warp;
+            const double* a = rB + 24 + 8 * Ci;
+            const double a0 = a[0], a1 = a[4 * hkd::kRld], a2 = a[8 * hkd::kRld];
+            const int c = 8 * Ci + g;  // reduced control row
+            const double sw = (c < 12) ? sm.swc[c] : 0.0;
+#pragma unroll 1
+            for (int q = 3 * Ci; q < 3 * Ci + 3; ++q) {
+                const int4 d = c_ux[q];
+                double c2[2] = {0.0, 0.0};
+                const double* b = yB + d.y;
+                dmma884(c2, a0, b[0]);
+                dmma884(c2, a1, b[RO4]);
+                dmma884(c2, a2, b[RO8]);
+                if (c < 12) {
+                    if (sw != 0.0) {  // swing row: (B_r^T Y)[c][:] = (1-c_l) dt * Y[12+c][:]
+                        const double2 m2 = *reinterpret_cast<const double2*>(sm.Y + ro(12 + c) + d.y + 2 * t);
+                        c2[0] = fma(sw, m2.x, c2[0]);
+                        c2[1] = fma(sw, m2.y, c2[1]);
+                    }
+                    *reinterpret_cast<double2*>(quxC + d.z) = make_double2(c2[0], c2[1]);
+                }
+            }
+        } else {  // Quu_r = luu_r + B_r^T Z : warp 2 the two tiles of rows 0..7, warp 3 those of rows 8..11
+#pragma unroll 1
+            for (int q = 2 * (warp - 2); q < 2 * (warp - 2) + 2; ++q) {
+                const int4 d = c_uu[q];
+                double c2[2] = {0.0, 0.0};
+                const double* a = rB + d.x;
+                const double* b = sm.Z + zo(t) + g + d.y;
+                dmma884(c2, a[0], b[0]);
+                dmma884(c2, a[4 * hkd::kRld], b[ZO4]);
+                dmma884(c2, a[8 * hkd::kRld], b[ZO8]);
+                const int c = 8 * d.w + g;  // reduced control row
+                if (c < 12) {
+                    const double sw = sm.swc[c];
+                    if (sw != 0.0) {  // swing row: (B_r^T Z)[c][:] = (1-c_l) dt * Z[12+c][:]
+                        const double2 m2 = *reinterpret_cast<const double2*>(sm.Z + zo(12 + c) + d.y + 2 * t);
+                        c2[0] = fma(sw, m2.x, c2[0]);
+                        c2[1] = fma(sw, m2.y, c2[1]);
+                    }
+                    // + luu_r: dt R + reg on the diagonal, the ReB Hessian block of a stance leg
+                    const bool stance = sw == 0.0;
+                    const int cc = d.y + 2 * t, l3 = 3 * (c / 3);
+                    const double diag = dt * (stance ? .2 : .1) + reg;  // weight_R(act_index(c, cm))
+                    if (c == cc) c2[0] += diag;
+                    if (c == cc + 1) c2[1] += diag;
+                    if (stance) {
+                        const double* lb = luu + 3 * c;  // luu[9 (c/3) + 3 (c%3) + k]
+                        if (cc >= l3 && cc < l3 + 3) c2[0] += lb[cc - l3];
+                        if (cc + 1 >= l3 && cc + 1 < l3 + 3) c2[1] += lb[cc + 1 - l3];
+                    }
+                    *reinterpret_cast<double2*>(quuC + d.z) = make_double2(c2[0], c2[1]);
+                }
+            }
+        }
+#else
         const double* yB = sm.Y + ro(t) + g;
         if (warp < 2) {  // Qxx = Y + At^T Y : warp 0 column block 0 (shared b operand), warp 1 tiles (1,1), (2,1), (2,2)
             int pa = -1, pb = -1;
@@ -436,6 +495,7 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
             for (int r = 0; r < 9; ++r) acc = fma(R[r * hkd::kRld + lane], sm.Gn[r], acc);
             sm.Qx[lane] = lxv[lane] + acc;
         }
+#endif
         if (warp == 2 && lane < 12) {  // Qu_r = lu_r + B_r^T Gn
             const int c = lane;
             double acc = 0.0;
@@ -524,12 +584,46 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                     }
                 }
             } else if (!pass) {
+#ifdef HSDDP_QXX_IN_P3
+                {   // Qxx = Y + At^T Y : warp 2 column block 0 (tiles (0,0), (1,0), (2,0)), warp 3 tiles (1,1), (2,1), (2,2)
+                    int pa = -1, pb = -1;
+                    double a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
+#pragma unroll 1
+                    for (int q = 3 * (warp - 2); q < 3 * (warp - 2) + 3; ++q) {
+                        const int4 d = c_xx[q];
+                        const double2 y2 = *reinterpret_cast<const double2*>(yC + d.z);
+                        double c2[2] = {y2.x, y2.y};
+                        if (d.x != pa) { const double* a = rB + d.x; a0 = a[0]; a1 = a[4 * hkd::kRld]; a2 = a[8 * hkd::kRld]; pa = d.x; }
+                        if (d.y != pb) { const double* b = yB + d.y; b0 = b[0]; b1 = b[RO4]; b2 = b[RO8]; pb = d.y; }
+                        dmma884(c2, a0, b0);
+                        dmma884(c2, a1, b1);
+                        dmma884(c2, a2, b2);
+                        *reinterpret_cast<double2*>(hC + d.z) = make_double2(c2[0], c2[1]);
+                    }
+                }
+                __syncwarp();
+                // sparse additive part of Qxx, applied by the warp that owns the tile of each entry
+                if (warp == 2) {
+                    if (lane < 8) sm.H[ro(lane) + lane] = (sm.H[ro(lane) + lane] + sm.lxxd[lane]) + reg;
+                    if (lane < 12) sm.H[ro(12 + lane) + 3 + lane % 3] -= sm.lxxw[lane];
+                } else {
+                    if (lane >= 8 && lane < 24) sm.H[ro(lane) + lane] = (sm.H[ro(lane) + lane] + sm.lxxd[lane]) + reg;
+                    if (lane < 24) {  // Qx = lx + A^T Gn
+                        double acc = sm.Gn[lane];
+#pragma unroll
+                        for (int r = 0; r < 9; ++r) acc = fma(R[r * hkd::kRld + lane], sm.Gn[r], acc);
+                        sm.Qx[lane] = lxv[lane] + acc;
+                    }
+                }
+                if (warp == 3 && lane < 16) {
+#else
                 if (warp == 2) {
                     // sparse additive part of Qxx (parked in H): lxx + reg I on the diagonal, the foot-regulariser coupling
                     // (12+c, 3 + c%3) of the lower triangle (P4 mirrors it)
                     if (lane < 24) sm.H[ro(lane) + lane] = (sm.H[ro(lane) + lane] + sm.lxxd[lane]) + reg;
                     if (lane < 12) sm.H[ro(12 + lane) + 3 + lane % 3] -= sm.lxxw[lane];
                 } else if (lane < 16) {
+#endif
                     // decoupled controls: Quu_ii = dt R_i + reg, Qu_i = lu_i, K row = 0
                     double dv = 0.0;
                     if (lane < 12) {
