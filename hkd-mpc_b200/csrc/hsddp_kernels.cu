@@ -610,7 +610,7 @@ struct hsddp_batch {
     int* d_count = nullptr;
     int* h_count = nullptr;        // pinned
     int last_rounds = 0;
-    static constexpr int kMaxGroups = 8;
+    static constexpr int kMaxGroups = 16;  // (default phased_groups = 8; HSDDP_PHASED_GROUPS may raise it for experiments)
     int phased_groups = 8;         // index ranges driven concurrently on their own streams (config 3, 16,384 problems: 2: 408 ms, 4: 401, 8: 397)
     cudaStream_t gstream[kMaxGroups] = {};
     cudaEvent_t gevent[kMaxGroups] = {};
