@@ -180,8 +180,8 @@ __device__ __forceinline__ bool gauss_jordan12_b3(double (&v)[12], double* sbuf)
         const double c10 = p12 * p20 - p10 * p22, c11 = p00 * p22 - p02 * p20, c12 = p02 * p10 - p00 * p12;
         const double c20 = p10 * p21 - p11 * p20, c21 = p01 * p20 - p00 * p21, c22 = p00 * p11 - p01 * p10;
         const double det = fma(p00, c00, fma(p01, c10, p02 * c20));
-        if (!(p00 > 0.0) || !(c22 > 0.0) || !(det > 0.0)) ok = false;
-        const double rdet = 1.0 / det;
+        if (p00 < 0.0 || c22 < 0.0 || det < 0.0) ok = false;  // (same comparisons as gauss_jordan12: zero and NaN pass, and are caught by the norm test)
+        const double rdet = pivot_rcp(det);
         const double t0 = fma(c00, v[0], fma(c01_, v[1], c02 * v[2])) * rdet;
         const double t1 = fma(c10, v[0], fma(c11, v[1], c12 * v[2])) * rdet;
         const double t2 = fma(c20, v[0], fma(c21, v[1], c22 * v[2])) * rdet;
