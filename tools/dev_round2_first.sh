@@ -9,6 +9,6 @@ for v in qxxp3 b3 b4; do
   HSDDP_LIB=$P/libhsddp_b200_$v.so timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "not full_size" 2>&1 | tail -3
 done
 echo "#### throughput / latency A/B (- = default build)"
-bash tools/dev_ab_lat.sh - qxxp3 b3 b4 2>&1 | grep -v "^$"
+bash tools/dev_ab_lat.sh - qxxp3 b3 b4 sw6 sw4 2>&1 | grep -v "^$"
 echo "#### 16 groups"
 HSDDP_PHASED_GROUPS=16 python tools/profile_case.py 16384 config3 2 | tail -1
