@@ -168,13 +168,20 @@ __device__ inline void iter_sweep_block(Smem& sm, const BatchPtrs& bp) {
         if (!success) { sm.ctl.status = HSDDP_STATUS_REG_OVERFLOW; sm.ctl.active = 0; }  // bad_solve (:321-324,421-427)
     }
     __syncthreads();
+#ifdef HSDDP_LR_IN_SWEEP
+    // experiment: the linear rollout right behind the sweep of the same block, while the gains it reads are
+    // still in L2 (in the phased driver it otherwise runs one kernel later, after ~1 GB of other problems' gains)
+    if (success && sm.opt.MS) linear_rollout_block(sm, 1.0);
+#endif
 }
 
 __device__ inline void iter_forward_block(Smem& sm, const BatchPtrs& bp) {
     const int tid = threadIdx.x;
     const hsddp_options& opt = sm.opt;
     hsddp_iter_record* rec = (sm.ctl.iter <= HSDDP_TRACE_CAP) ? bp.trace + (size_t)sm.pid * HSDDP_TRACE_CAP + sm.ctl.iter - 1 : nullptr;
+#ifndef HSDDP_LR_IN_SWEEP
     if (opt.MS) linear_rollout_block(sm, 1.0);
+#endif
     prepare_merit_block(sm);
     const double cost_prev = sm.st.actual_cost, merit_prev = sm.st.merit;
     const double dV_abs = fabs(sm.st.dV_1 + 0.5 * sm.st.dV_2);
