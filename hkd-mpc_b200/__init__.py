@@ -29,7 +29,7 @@ TRACE_CAP = 64
 STATUS_NAMES = {0: "converged", 1: "stalled", 2: "max_iter", 3: "reg_overflow"}
 
 ARR = dict(Xbar=0, X=1, Defect=3, dX=4, G0=5, Ubar=10, U=11, dU=12, K=20, A=21, B=22, lxx=24, luu=25, H0=27,
-           lx=30, lu=31, h=50, al=51, g=52)
+           lx=30, lu=31, h=50, al=51, g=52, reb=53)
 
 
 class HsddpError(RuntimeError):
@@ -429,7 +429,7 @@ class MultiPhaseDDPBatch:
         S, N = self.max_nodes, self.max_stages
         shape = {"Xbar": (S, 24), "X": (S, 24), "Defect": (S, 24), "dX": (S, 24), "Ubar": (N, 24), "U": (N, 24), "dU": (N, 24),
                  "K": (N, 24, 24), "A": (N, 24, 24), "B": (N, 24, 24), "lxx": (N, 24, 24), "luu": (N, 24, 24), "lx": (N, 24),
-                 "lu": (N, 24), "G0": (24,), "H0": (24, 24), "g": (N, 20), "h": (MAX_PHASES, 4), "al": (MAX_PHASES, 4, 2)}[name]
+                 "lu": (N, 24), "G0": (24,), "H0": (24, 24), "g": (N, 20), "h": (MAX_PHASES, 4), "al": (MAX_PHASES, 4, 2), "reb": (N, 20, 2)}[name]
         out = np.zeros((self.n,) + shape)
         _check(lib().hsddp_batch_get_array(self.h, which, _dp(out)), "get_array")
         if name in ("K", "A", "B", "lxx", "luu", "H0"):
@@ -437,7 +437,7 @@ class MultiPhaseDDPBatch:
         return out
 
     def get_rows(self, name, row0, nrows, out=None):
-        cols = {"K": 576, "g": 20, "h": 4, "al": 8}.get(name, 24)
+        cols = {"K": 576, "g": 20, "h": 4, "al": 8, "reb": 40}.get(name, 24)
         if out is None:
             out = np.zeros((self.n, nrows, cols))
         _check(lib().hsddp_batch_get_array_rows(self.h, ARR[name], int(row0), int(nrows), _dp(out)), "get_array_rows")

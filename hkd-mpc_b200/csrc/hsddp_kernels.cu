@@ -168,20 +168,13 @@ __device__ inline void iter_sweep_block(Smem& sm, const BatchPtrs& bp) {
         if (!success) { sm.ctl.status = HSDDP_STATUS_REG_OVERFLOW; sm.ctl.active = 0; }  // bad_solve (:321-324,421-427)
     }
     __syncthreads();
-#ifdef HSDDP_LR_IN_SWEEP
-    // experiment: the linear rollout right behind the sweep of the same block, while the gains it reads are
-    // still in L2 (in the phased driver it otherwise runs one kernel later, after ~1 GB of other problems' gains)
-    if (success && sm.opt.MS) linear_rollout_block(sm, 1.0);
-#endif
 }
 
 __device__ inline void iter_forward_block(Smem& sm, const BatchPtrs& bp) {
     const int tid = threadIdx.x;
     const hsddp_options& opt = sm.opt;
     hsddp_iter_record* rec = (sm.ctl.iter <= HSDDP_TRACE_CAP) ? bp.trace + (size_t)sm.pid * HSDDP_TRACE_CAP + sm.ctl.iter - 1 : nullptr;
-#ifndef HSDDP_LR_IN_SWEEP
     if (opt.MS) linear_rollout_block(sm, 1.0);
-#endif
     prepare_merit_block(sm);
     const double cost_prev = sm.st.actual_cost, merit_prev = sm.st.merit;
     const double dV_abs = fabs(sm.st.dV_1 + 0.5 * sm.st.dV_2);
@@ -655,6 +648,19 @@ hsddp_options default_options() {
 int check_opt(const hsddp_options* opt) {
     if (!opt) return HSDDP_OK;
     if (!opt->MS) { g_last_error = "single shooting (MS = false) is not implemented: the reference ships MS = true"; return HSDDP_ERR_UNSUPPORTED; }
+    // The reference's loops `while (eps > 1e-3) eps *= alpha` (MultiPhaseDDP.cpp:113,132) and `reg = max(reg * update_regularization,
+    // 1e-3)` until PD or reg > 1e2 (:159-167) terminate only for 0 < alpha < 1 and update_regularization > 1.  On the host a
+    // bad value spins one thread; on the device it would hang the stream, so such options are refused here.
+    auto fin = [](double v) { return v == v && v - v == 0.0; };
+    const char* bad = nullptr;
+    if (!(opt->alpha > 0.0 && opt->alpha < 1.0)) bad = "alpha must be in (0, 1)";
+    else if (!(opt->update_regularization > 1.0) || !fin(opt->update_regularization)) bad = "update_regularization must be finite and > 1";
+    else if (!fin(opt->gamma) || !fin(opt->update_penalty) || !fin(opt->update_relax) || !fin(opt->update_ReB)) bad = "gamma / update_penalty / update_relax / update_ReB must be finite";
+    else if (!fin(opt->cost_thresh) || !fin(opt->tconstr_thresh) || !fin(opt->pconstr_thresh) || !fin(opt->dynamics_feas_thresh)) bad = "thresholds must be finite";
+    else if (!fin(opt->merit_scale) || opt->merit_scale == 1.0 || !fin(opt->merit_offset)) bad = "merit_scale must be finite and != 1, merit_offset finite";
+    else if (opt->max_DDP_iter < 0 || opt->max_AL_iter < 0) bad = "max_DDP_iter / max_AL_iter must be >= 0";
+    else if ((long long)opt->max_DDP_iter * (long long)opt->max_AL_iter > 1000000LL) bad = "max_DDP_iter x max_AL_iter exceeds 1e6";
+    if (bad) { g_last_error = std::string("invalid hsddp_options: ") + bad; return HSDDP_ERR_ARG; }
     return HSDDP_OK;
 }
 
@@ -1194,6 +1200,7 @@ static int array_spec(hsddp_batch* b, int which, double** dev, size_t* per_probl
         case HSDDP_ARR_GCON: *dev = bp.gcon; *per_problem = (size_t)bp.max_stages * 20; return 0;
         case HSDDP_ARR_HCON: *dev = bp.hcon; *per_problem = (size_t)MAXPH * 4; return 0;
         case HSDDP_ARR_AL: *dev = bp.al; *per_problem = (size_t)MAXPH * 8; return 0;
+        case HSDDP_ARR_REB: *dev = bp.reb; *per_problem = (size_t)bp.max_stages * 40; return 0;
         case HSDDP_ARR_G0: *dev = bp.g0h0; *per_problem = 600; return 1;  // strided special cases
         case HSDDP_ARR_H0: *dev = bp.g0h0; *per_problem = 600; return 2;
         default: return -1;
@@ -1292,6 +1299,7 @@ int hsddp_batch_get_array_rows(hsddp_batch* b, int which, int row0, int nrows, d
         case HSDDP_ARR_GCON: cols = 20; break;
         case HSDDP_ARR_HCON: cols = 4; break;
         case HSDDP_ARR_AL: cols = 8; break;
+        case HSDDP_ARR_REB: cols = 40; break;
         default: cols = 24; break;
     }
     if ((size_t)(row0 + nrows) * cols > per) return HSDDP_ERR_ARG;

@@ -153,47 +153,6 @@ __device__ __forceinline__ bool gauss_jordan12(double (&v)[12], double* sbuf, un
     return ok;
 }
 
-// Same elimination with 3x3 pivot blocks: four sequential steps instead of six (the chain of publish -> barrier ->
-// load -> invert -> eliminate is what a stage waits for, so fewer, fatter steps win).  The pivot block is inverted
-// with its adjugate; its leading minors p00, p00 p11 - p01 p10 and det are the signs of the three scalar pivots
-// (Sylvester), so the verdict is the same "no non-positive pivot".  `sbuf`: 36 doubles per warp.
-// Columns rotate by three per step; four steps rotate by 12 = identity.
-__device__ __forceinline__ bool gauss_jordan12_b3(double (&v)[12], double* sbuf) {
-    const int lane = threadIdx.x & 31;
-    bool ok = true;
-#pragma unroll 1
-    for (int step = 0; step < 4; ++step) {
-        const int pl = lane - 3 * step;
-        if (pl >= 0 && pl < 3) {  // the three pivot columns (lanes 3*step .. 3*step+2 < 12)
-            double2* dst = reinterpret_cast<double2*>(sbuf + 12 * pl);
-#pragma unroll
-            for (int r = 0; r < 12; r += 2) dst[r >> 1] = make_double2(v[r], v[r + 1]);
-        }
-        __syncwarp();
-        // pivot block P[i][j] = column j, row i (rotated frame: rows 0..2)
-        const double2 a01 = *reinterpret_cast<const double2*>(sbuf);        // p00 p10
-        const double2 b01 = *reinterpret_cast<const double2*>(sbuf + 12);   // p01 p11
-        const double2 c01 = *reinterpret_cast<const double2*>(sbuf + 24);   // p02 p12
-        const double p20 = sbuf[2], p21 = sbuf[14], p22 = sbuf[26];
-        const double p00 = a01.x, p10 = a01.y, p01 = b01.x, p11 = b01.y, p02 = c01.x, p12 = c01.y;
-        const double c00 = p11 * p22 - p12 * p21, c01_ = p02 * p21 - p01 * p22, c02 = p01 * p12 - p02 * p11;
-        const double c10 = p12 * p20 - p10 * p22, c11 = p00 * p22 - p02 * p20, c12 = p02 * p10 - p00 * p12;
-        const double c20 = p10 * p21 - p11 * p20, c21 = p01 * p20 - p00 * p21, c22 = p00 * p11 - p01 * p10;
-        const double det = fma(p00, c00, fma(p01, c10, p02 * c20));
-        if (p00 < 0.0 || c22 < 0.0 || det < 0.0) ok = false;  // (same comparisons as gauss_jordan12: zero and NaN pass, and are caught by the norm test)
-        const double rdet = pivot_rcp(det);
-        const double t0 = fma(c00, v[0], fma(c01_, v[1], c02 * v[2])) * rdet;
-        const double t1 = fma(c10, v[0], fma(c11, v[1], c12 * v[2])) * rdet;
-        const double t2 = fma(c20, v[0], fma(c21, v[1], c22 * v[2])) * rdet;
-#pragma unroll
-        for (int r = 3; r < 12; ++r)  // eliminate and rotate in one go
-            v[r - 3] = fma(-sbuf[24 + r], t2, fma(-sbuf[12 + r], t1, fma(-sbuf[r], t0, v[r])));
-        v[9] = t0; v[10] = t1; v[11] = t2;
-        __syncwarp();
-    }
-    return ok;
-}
-
 // 4x4 pivot blocks: three sequential steps.  The block is inverted through its 2x2 blocks (A, Schur complement S),
 // and the multipliers t = P^-1 v[0..3] come from the block solve y = A^-1 v01, t23 = S^-1 (v23 - C y), t01 = y - A^-1 B t23,
 // so the two reciprocals are the only long-latency operations of a step.  Columns rotate by four per step.
@@ -411,7 +370,6 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
         PROF_MARK(sm, 6);
         // ---- P2: C = [A | B_r]^T M :  6 x Qxx (lower, M = Y, parked in H) ; 6 x Qux_r (M = Y) ; 4 x Quu_r (M = Z) ----
         // (the sparse additive term of Qxx, lxx + reg I, is applied in P3 by the warp that is idle there)
-#ifdef HSDDP_QXX_IN_P3  // experiment: Qxx and Qx are not inputs of the elimination -> computed in P3 by its idle warps
         const double* yB = sm.Y + ro(t) + g;
         if (warp < 2) {  // Qux_r = B_r^T Y : warp 0 rows 0..7, warp 1 rows 8..11; the three column blocks share the a operand
             const int Ci = warp;
@@ -469,84 +427,6 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                 }
             }
         }
-#else
-        const double* yB = sm.Y + ro(t) + g;
-        if (warp < 2) {  // Qxx = Y + At^T Y : warp 0 column block 0 (shared b operand), warp 1 tiles (1,1), (2,1), (2,2)
-            int pa = -1, pb = -1;
-            double a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
-#pragma unroll 1
-            for (int q = 3 * warp; q < 3 * warp + 3; ++q) {
-                const int4 d = c_xx[q];
-                const double2 y2 = *reinterpret_cast<const double2*>(yC + d.z);
-                double c2[2] = {y2.x, y2.y};
-                if (d.x != pa) { const double* a = rB + d.x; a0 = a[0]; a1 = a[4 * hkd::kRld]; a2 = a[8 * hkd::kRld]; pa = d.x; }
-                if (d.y != pb) { const double* b = yB + d.y; b0 = b[0]; b1 = b[RO4]; b2 = b[RO8]; pb = d.y; }
-                dmma884(c2, a0, b0);
-                dmma884(c2, a1, b1);
-                dmma884(c2, a2, b2);
-                *reinterpret_cast<double2*>(hC + d.z) = make_double2(c2[0], c2[1]);
-            }
-        } else {  // Qux_r = B_r^T Y : warp 2 rows 0..7, warp 3 rows 8..11; the three column blocks share the a operand
-            const int Ci = warp - 2;
-            const double* a = rB + 24 + 8 * Ci;
-            const double a0 = a[0], a1 = a[4 * hkd::kRld], a2 = a[8 * hkd::kRld];
-            const int c = 8 * Ci + g;  // reduced control row
-            const double sw = (c < 12) ? sm.swc[c] : 0.0;
-#pragma unroll 1
-            for (int q = 3 * Ci; q < 3 * Ci + 3; ++q) {
-                const int4 d = c_ux[q];
-                double c2[2] = {0.0, 0.0};
-                const double* b = yB + d.y;
-                dmma884(c2, a0, b[0]);
-                dmma884(c2, a1, b[RO4]);
-                dmma884(c2, a2, b[RO8]);
-                if (c < 12) {
-                    if (sw != 0.0) {  // swing row: (B_r^T Y)[c][:] = (1-c_l) dt * Y[12+c][:]
-                        const double2 m2 = *reinterpret_cast<const double2*>(sm.Y + ro(12 + c) + d.y + 2 * t);
-                        c2[0] = fma(sw, m2.x, c2[0]);
-                        c2[1] = fma(sw, m2.y, c2[1]);
-                    }
-                    *reinterpret_cast<double2*>(quxC + d.z) = make_double2(c2[0], c2[1]);
-                }
-            }
-        }
-        {   // Quu_r = luu_r + B_r^T Z : one tile per warp
-            const int4 d = c_uu[warp];
-            double c2[2] = {0.0, 0.0};
-            const double* a = rB + d.x;
-            const double* b = sm.Z + zo(t) + g + d.y;
-            dmma884(c2, a[0], b[0]);
-            dmma884(c2, a[4 * hkd::kRld], b[ZO4]);
-            dmma884(c2, a[8 * hkd::kRld], b[ZO8]);
-            const int c = 8 * d.w + g;  // reduced control row
-            if (c < 12) {
-                const double sw = sm.swc[c];
-                if (sw != 0.0) {  // swing row: (B_r^T Z)[c][:] = (1-c_l) dt * Z[12+c][:]
-                    const double2 m2 = *reinterpret_cast<const double2*>(sm.Z + zo(12 + c) + d.y + 2 * t);
-                    c2[0] = fma(sw, m2.x, c2[0]);
-                    c2[1] = fma(sw, m2.y, c2[1]);
-                }
-                // + luu_r: dt R + reg on the diagonal, the ReB Hessian block of a stance leg
-                const bool stance = sw == 0.0;
-                const int cc = d.y + 2 * t, l3 = 3 * (c / 3);
-                const double diag = dt * (stance ? .2 : .1) + reg;  // weight_R(act_index(c, cm))
-                if (c == cc) c2[0] += diag;
-                if (c == cc + 1) c2[1] += diag;
-                if (stance) {
-                    const double* lb = luu + 3 * c;  // luu[9 (c/3) + 3 (c%3) + k]
-                    if (cc >= l3 && cc < l3 + 3) c2[0] += lb[cc - l3];
-                    if (cc + 1 >= l3 && cc + 1 < l3 + 3) c2[1] += lb[cc + 1 - l3];
-                }
-                *reinterpret_cast<double2*>(quuC + d.z) = make_double2(c2[0], c2[1]);
-            }
-        }
-        if (warp == 3 && lane < 24) {  // Qx = lx + A^T Gn
-            double acc = sm.Gn[lane];
-#pragma unroll
-            for (int r = 0; r < 9; ++r) acc = fma(R[r * hkd::kRld + lane], sm.Gn[r], acc);
-            sm.Qx[lane] = lxv[lane] + acc;
-        }
-#endif
         if (warp == 2 && lane < 12) {  // Qu_r = lu_r + B_r^T Gn
             const int c = lane;
             double acc = 0.0;
@@ -589,10 +469,7 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                     for (int r = 0; r < 12; ++r) if (r == lane) col[r] -= 1e-9;
                 }
                 PROF_MARK(sm, 13);
-                #ifdef HSDDP_GJ_BLOCK3  // four 3x3 steps: 16 % less latency alone (tools/microbench/gj3.cu), but more FP64 instructions:
-                        // single-solve latency 6.05 -> 5.9 ms, throughput unchanged to slightly worse -> off by default
-                const bool ok = gauss_jordan12_b3(col, sm.red + 40 * warp);
-#elif defined(HSDDP_GJ_BLOCK4)
+#ifdef HSDDP_GJ_BLOCK4
                 const bool ok = gauss_jordan12_b4(col, sm.red + 64 * warp);
 #else
                 const bool ok = gauss_jordan12(col, sm.red + 40 * warp, sm.profacc + 10);
@@ -637,7 +514,6 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                     }
                 }
             } else if (!pass) {
-#ifdef HSDDP_QXX_IN_P3
                 {   // Qxx = Y + At^T Y : warp 2 column block 0 (tiles (0,0), (1,0), (2,0)), warp 3 tiles (1,1), (2,1), (2,2)
                     int pa = -1, pb = -1;
                     double a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
@@ -669,14 +545,6 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                     }
                 }
                 if (warp == 3 && lane < 16) {
-#else
-                if (warp == 2) {
-                    // sparse additive part of Qxx (parked in H): lxx + reg I on the diagonal, the foot-regulariser coupling
-                    // (12+c, 3 + c%3) of the lower triangle (P4 mirrors it)
-                    if (lane < 24) sm.H[ro(lane) + lane] = (sm.H[ro(lane) + lane] + sm.lxxd[lane]) + reg;
-                    if (lane < 12) sm.H[ro(12 + lane) + 3 + lane % 3] -= sm.lxxw[lane];
-                } else if (lane < 16) {
-#endif
                     // decoupled controls: Quu_ii = dt R_i + reg, Qu_i = lu_i, K row = 0
                     double dv = 0.0;
                     if (lane < 12) {

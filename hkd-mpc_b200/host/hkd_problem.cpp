@@ -64,15 +64,21 @@ extern "C" {
 
 int hkd_gait_create(int n, float dt, const float* body_state, const float* qJ, const float* foot_placements,
                     const float* grf, const int32_t* contact, hkd_gait** out) {
-    if (!out || n <= 0 || !body_state || !qJ || !foot_placements || !grf || !contact) return HSDDP_ERR_ARG;
-    hkd_gait* g = new hkd_gait();
-    g->n = n;
-    g->dt = dt;
-    g->body_state.assign(body_state, body_state + 12 * (size_t)n);
-    g->qJ.assign(qJ, qJ + 12 * (size_t)n);
-    g->foot.assign(foot_placements, foot_placements + 12 * (size_t)n);
-    g->grf.assign(grf, grf + 12 * (size_t)n);
-    g->contact.assign(contact, contact + 4 * (size_t)n);
+    if (!out || n <= 0 || !(dt > 0.f) || !body_state || !qJ || !foot_placements || !grf || !contact) return HSDDP_ERR_ARG;
+    hkd_gait* g = nullptr;
+    try {  // (no C++ exception may cross the C ABI)
+        g = new hkd_gait();
+        g->n = n;
+        g->dt = dt;
+        g->body_state.assign(body_state, body_state + 12 * (size_t)n);
+        g->qJ.assign(qJ, qJ + 12 * (size_t)n);
+        g->foot.assign(foot_placements, foot_placements + 12 * (size_t)n);
+        g->grf.assign(grf, grf + 12 * (size_t)n);
+        g->contact.assign(contact, contact + 4 * (size_t)n);
+    } catch (...) {
+        delete g;
+        return HSDDP_ERR_ARG;
+    }
     *out = g;
     return HSDDP_OK;
 }
@@ -80,9 +86,11 @@ int hkd_gait_create(int n, float dt, const float* body_state, const float* qJ, c
 // Text loader: keys matched by substring in a fixed order; every number through stof.
 int hkd_gait_load(const char* path, hkd_gait** out) {
     if (!path || !out) return HSDDP_ERR_ARG;
+    hkd_gait* g = nullptr;
+    try {  // std::stof / std::stoi throw on malformed text, the vectors on allocation failure: report HSDDP_ERR_IO instead
     std::ifstream f(path);
     if (!f.is_open()) return HSDDP_ERR_IO;
-    hkd_gait* g = new hkd_gait();
+    g = new hkd_gait();
     std::string line;
     double body[12] = {0}, qj[12] = {0}, foot[12] = {0}, grf[12] = {0}, sdur[12] = {0};
     int contact[4] = {0, 0, 0, 0};
@@ -114,6 +122,10 @@ int hkd_gait_load(const char* path, hkd_gait** out) {
         }
     }
     if (g->n == 0 || !(g->dt > 0.f)) { delete g; return HSDDP_ERR_IO; }
+    } catch (...) {
+        delete g;
+        return HSDDP_ERR_IO;
+    }
     *out = g;
     return HSDDP_OK;
 }
@@ -122,7 +134,7 @@ int hkd_gait_size(const hkd_gait* g) { return g ? g->n : 0; }
 void hkd_gait_destroy(hkd_gait* g) { delete g; }
 
 int hkd_schedule_build(const hkd_gait* g, int window_start, float plan_duration, hsddp_schedule* out) {
-    if (!g || !out || window_start < 0) return HSDDP_ERR_ARG;
+    if (!g || !out || window_start < 0 || !(plan_duration > 0.f) || !(g->dt > 0.f)) return HSDDP_ERR_ARG;
     std::memset(out, 0, sizeof *out);
     const float dt_sim = 0.01f;          // HKDMPC.cpp:28
     const float dt_mpc = dt_sim * 1;     // nsteps_between_mpc = 1, HKDProblem.h:104-108

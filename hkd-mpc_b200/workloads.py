@@ -5,15 +5,22 @@ initial state per problem.  Initial-state perturbations follow §8(d) config 2:
 uniform in eul +-0.05 rad, pos +-0.02 m, omega +-0.2 rad/s, vel +-0.1 m/s on the
 body states only, splitmix64 seeded 0xB200 + i, 12 draws per problem; qdummy is
 recomputed by the compute_hkd_state rule (HKDModel.h:65-96) with qJ unchanged.
-The gait tables come from tests/golden/gait_*.npz (tools/make_fixtures.py).
+The gait tables are hkd-mpc_b200/data/gait_*.npz (generated from the reference's
+data files by tools/make_fixtures.py).
+
+The workload DEFINITION (which gait, which window, which initial state) is pure
+NumPy: `entries_*` + `initial_states` need only a compute_hkd_state function, so
+the CPU arm of bench.py builds the identical inputs without loading the CUDA
+library.  `config1..4(pkg, ...)` add the flattened schedules for the GPU path.
 """
 import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-GOLDEN = os.path.join(_HERE, "..", "tests", "golden")
+DATA = os.path.join(_HERE, "data")
 GAITS = ("trot", "bound", "pronk")
 DEFAULT_QJ = np.array([0, -0.8, 1.6] * 4, np.float64)  # HKDMPC.cpp:47
+DEFAULT_BODY = np.array([0, 0, 0, 0, 0, 0.2486, 0, 0, 0, 0, 0, 0], np.float64)  # HKDMPC.cpp:44-46
 _MASK = (1 << 64) - 1
 _AMP = np.array([0.05] * 3 + [0.02] * 3 + [0.2] * 3 + [0.1] * 3)
 
@@ -38,100 +45,142 @@ def perturbation(i):
 
 
 def gait_path(name):
-    return os.path.join(GOLDEN, f"gait_{name}.npz")
+    return os.path.join(DATA, f"gait_{name}.npz")
+
+
+_tables = {}
+
+
+def gait_table(name):
+    if name not in _tables:
+        d = np.load(gait_path(name))
+        _tables[name] = {k: d[k] for k in d.files}
+    return _tables[name]
+
+
+# ---------------------------------------------------------------------------
+# workload definitions: one entry per problem = (gait, window start, x0 mode, perturbation index or None)
+# ---------------------------------------------------------------------------
+def entries_config1():
+    return [("trot", 0, "default", None)]
+
+
+def entries_config2(n):
+    return [("trot", 0, "default", (i if i >= 1 else None)) for i in range(n)]
+
+
+def entries_config3(n, plan=0.6, first=0):
+    sizes = {g: gait_table(g)["body_state"].shape[0] for g in GAITS}
+    out = []
+    for j in range(n):
+        i = first + j
+        g = GAITS[i % 3]
+        k0 = (7 * (i // 3)) % (sizes[g] - (int(round(plan / 0.01)) + 3))  # (n_samples - 63 for the 0.6 s horizon of SURVEY.md §8d)
+        out.append((g, int(k0), "reference", i))
+    return out
+
+
+def entries_config4(n):
+    out = []
+    for i in range(n):
+        k0 = 236 + int(splitmix64_uniform(0xB200 + (1 << 20) + i, 1)[0] * 31)
+        out.append(("bound", min(k0, 266), "reference", i))
+    return out
+
+
+def initial_states(entries, hkd_state):
+    """x0 [n, 24] of the entries.  hkd_state(eul, pos, qJ, contact[4]) -> qdummy[12] (compute_hkd_state, HKDModel.h:65-96);
+    the contact is that of the first phase = the reference sample at the window start."""
+    x0 = np.zeros((len(entries), 24))
+    for j, (gait, k0, mode, pidx) in enumerate(entries):
+        t = gait_table(gait)
+        body = DEFAULT_BODY.copy() if mode == "default" else t["body_state"][k0].astype(np.float64)
+        if pidx is not None:
+            body = body + perturbation(pidx)
+        x0[j, :12] = body
+        x0[j, 12:] = hkd_state(body[0:3], body[3:6], DEFAULT_QJ, np.asarray(t["contact"][k0], np.int32))
+    return x0
+
+
+def schedule_keys(entries):
+    """Deduplicated (gait, window start) pairs and the schedule id of every entry."""
+    index, keys, sid = {}, [], []
+    for gait, k0, _, _ in entries:
+        key = (gait, int(k0))
+        if key not in index:
+            index[key] = len(keys)
+            keys.append(key)
+        sid.append(index[key])
+    return keys, np.asarray(sid, np.int32)
 
 
 class Workload:
-    def __init__(self, name, schedules, schedule_id, x0, keys, plan):
+    def __init__(self, name, schedules, schedule_id, x0, keys, plan, entries=None):
         self.name = name
-        self.schedules = schedules          # list of pkg.Schedule
+        self.schedules = schedules          # list of pkg.Schedule (None for the CPU-only form)
         self.schedule_id = np.asarray(schedule_id, np.int32)
         self.x0 = np.ascontiguousarray(x0, np.float64)
         self.keys = keys                    # per schedule: (gait, window_start)
         self.plan = plan
+        self.entries = entries
         self.n = len(self.schedule_id)
 
 
-def _build(pkg, name, entries, plan, perturb_from):
-    """entries: per problem (gait, k0, x0_mode) ; x0_mode 'default' or 'reference'."""
+NAMES = {"config1": "config1: single trot solve", "config2": "config2: {n} trot problems, perturbed x0",
+         "config3": "config3: {n} mixed-gait problems (trot/bound/pronk)", "config4": "config4: {n} bound+jump problems"}
+
+
+def define(config, n=None, plan=0.6, first=0):
+    """(name, entries) of a configuration — no library needed."""
+    if config == "config1":
+        e = entries_config1()
+    elif config == "config2":
+        e = entries_config2(n)
+    elif config == "config3":
+        e = entries_config3(n, plan, first)
+    elif config == "config4":
+        e = entries_config4(n)
+    else:
+        raise ValueError(config)
+    return NAMES[config].format(n=len(e)), e
+
+
+def build_cpu(config, hkd_state, n=None, plan=0.6, first=0):
+    """The workload without schedules (CPU arm / oracle side): keys, schedule ids, x0."""
+    name, e = define(config, n, plan, first)
+    keys, sid = schedule_keys(e)
+    return Workload(name, None, sid, initial_states(e, hkd_state), keys, plan, e)
+
+
+def _build(pkg, config, n=None, plan=0.6, first=0):
+    name, e = define(config, n, plan, first)
+    keys, sid = schedule_keys(e)
     refs = {}
-    tables = {}
-    sched_index = {}
-    schedules, keys, sid = [], [], []
-    x0 = np.zeros((len(entries), 24))
-    for i, (gait, k0, mode) in enumerate(entries):
+    schedules = []
+    for gait, k0 in keys:
         if gait not in refs:
             refs[gait] = pkg.QuadReference(gait_path(gait))
-            tables[gait] = np.load(gait_path(gait))
-        key = (gait, int(k0))
-        if key not in sched_index:
-            sched_index[key] = len(schedules)
-            schedules.append(pkg.Schedule(refs[gait], int(k0), plan))
-            keys.append(key)
-        s = schedules[sched_index[key]]
-        sid.append(sched_index[key])
-        if mode == "default":
-            body = s.default_x0()[:12].copy()
-        else:
-            body = tables[gait]["body_state"][int(k0)].astype(np.float64)
-        if perturb_from is not None and i >= perturb_from:
-            body = body + perturbation(i)
-        x0[i, :12] = body
-        x0[i, 12:] = pkg.compute_hkd_state(body[0:3], body[3:6], DEFAULT_QJ, s.contact[0])
-    return Workload(name, schedules, sid, x0, keys, plan)
+        schedules.append(pkg.Schedule(refs[gait], int(k0), plan))
+    return Workload(name, schedules, sid, initial_states(e, pkg.compute_hkd_state), keys, plan, e)
 
 
 def config1(pkg, plan=0.6):
     """single HKD-MPC solve, Mini Cheetah trot, window 0, x0 of HKDMPC.cpp:44-54."""
-    return _build(pkg, "config1: single trot solve", [("trot", 0, "default")], plan, None)
+    return _build(pkg, "config1", None, plan)
 
 
 def config2(pkg, n=1024, plan=0.6):
     """n trot problems with perturbed initial body states (problem 0 unperturbed)."""
-    return _build(pkg, f"config2: {n} trot problems, perturbed x0", [("trot", 0, "default")] * n, plan, 1)
+    return _build(pkg, "config2", n, plan)
 
 
 def config3(pkg, n=16384, plan=0.6, first=0):
     """n mixed-gait problems: gait i mod 3, window start (7*(i div 3)) mod (n_samples-63),
     x0 = reference body state at the window start + perturbation.  `first` offsets the
     problem index (used to shard by index across ranks)."""
-    sizes = {g: np.load(gait_path(g))["body_state"].shape[0] for g in GAITS}
-    entries = []
-    for j in range(n):
-        i = first + j
-        g = GAITS[i % 3]
-        k0 = (7 * (i // 3)) % (sizes[g] - (int(round(plan / 0.01)) + 3))  # (n_samples - 63 for the 0.6 s horizon of SURVEY.md §8d)
-        entries.append((g, k0, "reference"))
-    w = _build_indexed(pkg, f"config3: {n} mixed-gait problems (trot/bound/pronk)", entries, plan, first)
-    return w
+    return _build(pkg, "config3", n, plan, first)
 
 
 def config4(pkg, n=4096, plan=0.6):
     """n bound-then-jump problems, window starts uniform in [236, 266] (long flight phase in the horizon)."""
-    entries = []
-    for i in range(n):
-        k0 = 236 + int(splitmix64_uniform(0xB200 + (1 << 20) + i, 1)[0] * 31)
-        entries.append(("bound", min(k0, 266), "reference"))
-    return _build(pkg, f"config4: {n} bound+jump problems", entries, plan, 0)
-
-
-def _build_indexed(pkg, name, entries, plan, first):
-    """like _build with perturbation index = global problem index."""
-    refs, tables, sched_index = {}, {}, {}
-    schedules, keys, sid = [], [], []
-    x0 = np.zeros((len(entries), 24))
-    for j, (gait, k0, mode) in enumerate(entries):
-        if gait not in refs:
-            refs[gait] = pkg.QuadReference(gait_path(gait))
-            tables[gait] = np.load(gait_path(gait))
-        key = (gait, int(k0))
-        if key not in sched_index:
-            sched_index[key] = len(schedules)
-            schedules.append(pkg.Schedule(refs[gait], int(k0), plan))
-            keys.append(key)
-        s = schedules[sched_index[key]]
-        sid.append(sched_index[key])
-        body = tables[gait]["body_state"][int(k0)].astype(np.float64) + perturbation(first + j)
-        x0[j, :12] = body
-        x0[j, 12:] = pkg.compute_hkd_state(body[0:3], body[3:6], DEFAULT_QJ, s.contact[0])
-    return Workload(name, schedules, sid, x0, keys, plan)
+    return _build(pkg, "config4", n, plan)

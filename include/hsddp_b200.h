@@ -224,6 +224,7 @@ int hsddp_batch_get_scalars(hsddp_batch* b, double* out /*[n_problems][8]*/);
 #define HSDDP_ARR_GCON 52  /* [stages][20] GRF constraint values, 5 per leg (swing legs zero) */
 #define HSDDP_ARR_HCON 50  /* [HSDDP_MAX_PHASES][4] touchdown constraint values per phase/leg */
 #define HSDDP_ARR_AL 51    /* [HSDDP_MAX_PHASES][4][2] (sigma, lambda) */
+#define HSDDP_ARR_REB 53   /* [stages][20][2] ReB parameters (eps, delta) of the GRF rows, 5 per leg (REB_Param_Struct, ConstraintsBase.h:58-70) */
 int hsddp_batch_get_array(hsddp_batch* b, int which, double* out);
 /* overwrite Xbar/X/Ubar/U (warm start); same layout as the getter */
 int hsddp_batch_set_array(hsddp_batch* b, int which, const double* in);

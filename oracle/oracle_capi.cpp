@@ -131,6 +131,17 @@ void orc_problem_get(void* pv, int which, double* out) {
             case 50: for (int i = 0; i < 4; ++i) out[o++] = (i < ph.n_td) ? ph.h[i] : 0.0; break;
             case 51: for (int i = 0; i < 4; ++i) { out[o++] = ph.al[i].sigma; out[o++] = ph.al[i].lambda; } break;
             case 52: for (int k = 0; k < N; ++k) for (int i = 0; i < 20; ++i) out[o++] = (i < ph.n_path) ? ph.g[(size_t)k * ph.n_path + i] : 0.0; break;
+            case 53:  // ReB parameters (eps, delta) per stage, 5 rows per LEG like the GPU layout; swing legs keep the initial values
+                for (int k = 0; k < N; ++k) {
+                    for (int i = 0; i < 20; ++i) { out[o + 2 * i] = p->cparams.grf_eps; out[o + 2 * i + 1] = p->cparams.grf_delta; }
+                    for (int sl = 0; sl < ph.n_stance; ++sl)
+                        for (int r = 0; r < 5; ++r) {
+                            const RebParam& q = ph.reb[(size_t)k * ph.n_path + 5 * sl + r];
+                            out[o + 2 * (5 * ph.stance_legs[sl] + r)] = q.eps; out[o + 2 * (5 * ph.stance_legs[sl] + r) + 1] = q.delta;
+                        }
+                    o += 40;
+                }
+                break;
             default: break;
         }
     }
@@ -188,8 +199,13 @@ int orc_solve(void* pv, const double* o, double* summary, double* trace, int tra
 // ---- CPU baseline: one problem per std::thread ----
 // tables: n_prob pointers (one gait table per problem), k0: window starts, x0: n_prob x 24.
 // Returns wall seconds; per-problem summary rows (10 doubles) written to `summaries` when non-null.
-double orc_batch_solve(void** tables, const int* k0, const double* x0, int n_prob, float plan, int model_kind,
-                       const double* o, const double* cparams, int n_threads, double* summaries) {
+// Optional trajectory outputs for parity checks at scale (bench.py, tests): xbar_out [n_prob][max_nodes][24],
+// ubar_out [n_prob][max_stages][24] (rows beyond a problem's own count are left untouched), k_out [n_prob][k_rows][576]
+// = the column-major gains of the first k_rows stages (what HKDMPC.cpp:245-275 ships), trials_out [n_prob] = total
+// line-search trials.
+double orc_batch_solve_traj(void** tables, const int* k0, const double* x0, int n_prob, float plan, int model_kind,
+                            const double* o, const double* cparams, int n_threads, double* summaries,
+                            double* xbar_out, double* ubar_out, int max_nodes, int max_stages, double* k_out, int k_rows, int* trials_out) {
     Options opt; options_from_array(o, opt);
     ConstraintParams cp;
     if (cparams) cparams_from_array(cparams, cp);
@@ -213,12 +229,29 @@ double orc_batch_solve(void** tables, const int* k0, const double* x0, int n_pro
                     s[0] = r.status; s[1] = r.n_iter; s[2] = r.n_outer; s[3] = r.n_sweeps; s[4] = r.cost; s[5] = r.feas;
                     s[6] = r.max_tconstr; s[7] = r.max_pconstr; s[8] = r.cost0; s[9] = r.feas0;
                 }
+                if (trials_out) { int nt = 0; for (auto& rec : r.trace) nt += rec.n_trials; trials_out[i] = nt; }
+                if (xbar_out || ubar_out || k_out) {
+                    size_t node = 0, stage = 0;
+                    for (auto& ph : p.phases) {
+                        for (int k = 0; k <= ph.horizon; ++k, ++node)
+                            if (xbar_out && (int)node < max_nodes) std::memcpy(xbar_out + ((size_t)i * max_nodes + node) * 24, ph.Xbar[k].v, 192);
+                        for (int k = 0; k < ph.horizon; ++k, ++stage) {
+                            if (ubar_out && (int)stage < max_stages) std::memcpy(ubar_out + ((size_t)i * max_stages + stage) * 24, ph.Ubar[k].v, 192);
+                            if (k_out && (int)stage < k_rows) std::memcpy(k_out + ((size_t)i * k_rows + stage) * 576, ph.K[k].m, 4608);
+                        }
+                    }
+                }
             }
         });
     }
     for (auto& th : pool) th.join();
     auto t1 = std::chrono::steady_clock::now();
     return std::chrono::duration<double>(t1 - t0).count();
+}
+
+double orc_batch_solve(void** tables, const int* k0, const double* x0, int n_prob, float plan, int model_kind,
+                       const double* o, const double* cparams, int n_threads, double* summaries) {
+    return orc_batch_solve_traj(tables, k0, x0, n_prob, plan, model_kind, o, cparams, n_threads, summaries, nullptr, nullptr, 0, 0, nullptr, 0, nullptr);
 }
 
 int orc_hardware_concurrency() { return (int)std::thread::hardware_concurrency(); }

@@ -90,6 +90,11 @@ def lib():
         L.orc_batch_solve.restype = C.c_double
         L.orc_batch_solve.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_int, C.c_float,
                                       C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]
+        L.orc_batch_solve_traj.restype = C.c_double
+        L.orc_batch_solve_traj.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_int, C.c_float,
+                                           C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double),
+                                           C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int,
+                                           C.POINTER(C.c_int)]
         L.orc_load_ref.argtypes = [C.c_char_p]
         L.orc_load_ref.restype = C.c_int
         L.orc_model_dynamics.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_double)]
@@ -105,6 +110,41 @@ def lib():
             L.orc_load_ref(_REF_PATH.encode())
         _lib = L
     return _lib
+
+
+_variants = {}
+
+
+def _variant_path(name):
+    return os.path.join(_HERE, f"liboracle_hsddp_{name}.so")
+
+
+def variant_available(name):
+    """Other builds of the same restatement (oracle/Makefile): "fma" = FMA-contracted arithmetic."""
+    try:
+        return _variant_lib(name) is not None
+    except Exception:
+        return False
+
+
+def _variant_lib(name):
+    if name in (None, "", "base"):
+        return lib()
+    if name not in _variants:
+        lib()
+        path = _variant_path(name)
+        srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".hpp"))]
+        if not os.path.exists(path) or any(os.path.getmtime(f) > os.path.getmtime(path) for f in srcs):
+            subprocess.check_call(["make", "-C", _HERE, os.path.basename(path)], stdout=subprocess.DEVNULL)
+        L = C.CDLL(path)
+        L.orc_batch_solve_traj.restype = C.c_double
+        L.orc_batch_solve_traj.argtypes = lib().orc_batch_solve_traj.argtypes
+        L.orc_load_ref.argtypes = [C.c_char_p]
+        L.orc_load_ref.restype = C.c_int
+        if os.path.exists(_REF_PATH):
+            L.orc_load_ref(_REF_PATH.encode())
+        _variants[name] = L
+    return _variants[name]
 
 
 def ref_available():
@@ -222,16 +262,16 @@ class Problem:
         return xr, ur, br, fr, idx.value
 
     _SHAPES = {0: "s", 1: "s", 2: "s", 3: "s", 4: "s", 5: "s", 10: "u", 11: "u", 12: "u", 20: "m", 21: "m", 22: "m",
-               24: "m", 25: "m", 26: "m", 27: "ms", 30: "u", 31: "u", 32: "l", 40: "pv", 41: "pm", 42: "p", 50: "p4", 51: "p8", 52: "g"}
+               24: "m", 25: "m", 26: "m", 27: "ms", 30: "u", 31: "u", 32: "l", 40: "pv", 41: "pm", 42: "p", 50: "p4", 51: "p8", 52: "g", 53: "r"}
     NAMES = dict(Xbar=0, X=1, Xsim=2, Defect=3, dX=4, G=5, Ubar=10, U=11, dU=12, K=20, A=21, B=22, lxx=24, luu=25, lux=26,
-                 H=27, lx=30, lu=31, l=32, Phix=40, Phixx=41, Phi=42, h=50, al=51, g=52)
+                 H=27, lx=30, lu=31, l=32, Phix=40, Phixx=41, Phi=42, h=50, al=51, g=52, reb=53)
 
     def get(self, name):
         which = self.NAMES[name]
         kind = self._SHAPES[which]
         N, S, P = self.n_stages, self.n_states, self.n_phases
         shape = {"s": (S, 24), "u": (N, 24), "m": (N, 24, 24), "ms": (S, 24, 24), "l": (N,), "pv": (P, 24), "pm": (P, 24, 24),
-                 "p": (P,), "p4": (P, 4), "p8": (P, 4, 2), "g": (N, 20)}[kind]
+                 "p": (P,), "p4": (P, 4), "p8": (P, 4, 2), "g": (N, 20), "r": (N, 20, 2)}[kind]
         out = np.zeros(shape)
         lib().orc_problem_get(self.h, which, _dp(out))
         if kind in ("m", "ms", "pm"):
@@ -284,6 +324,25 @@ def batch_solve(tables, k0, x0, plan=0.6, model=None, opts=None, cparams=None, n
     wall = lib().orc_batch_solve(tp, _ip(k0), _dp(x0), n, C.c_float(plan), model, _dp(o), _dp(cp), int(n_threads),
                                  _dp(summ) if want_summaries else None)
     return wall, summ
+
+
+def batch_solve_traj(tables, k0, x0, max_nodes, max_stages, k_rows=8, plan=0.6, model=None, opts=None, cparams=None, n_threads=0, variant=None):
+    """batch_solve that also returns the solutions: dict(wall, summary [n,10], Xbar [n,max_nodes,24], Ubar [n,max_stages,24],
+    K [n,k_rows,24,24] (row, col), n_trials [n]).  Rows beyond a problem's own node / stage count are zero."""
+    n = len(tables)
+    tp = (C.c_void_p * n)(*[t.handle for t in tables])
+    k0 = np.ascontiguousarray(k0, np.int32)
+    x0 = np.ascontiguousarray(x0, np.float64)
+    o = options_array(**(opts or {})); cp = cparams_array(**(cparams or {}))
+    summ = np.zeros((n, 10)); Xb = np.zeros((n, max_nodes, 24)); Ub = np.zeros((n, max_stages, 24))
+    K = np.zeros((n, k_rows, 24, 24)) if k_rows > 0 else None
+    ntr = np.zeros(n, np.int32)
+    model = default_model() if model is None else model
+    wall = _variant_lib(variant).orc_batch_solve_traj(tp, _ip(k0), _dp(x0), n, C.c_float(plan), model, _dp(o), _dp(cp), int(n_threads), _dp(summ),
+                                      _dp(Xb), _dp(Ub), int(max_nodes), int(max_stages), _dp(K) if K is not None else None, int(k_rows), _ip(ntr))
+    if K is not None:
+        K = np.ascontiguousarray(np.swapaxes(K, -1, -2))
+    return dict(wall=wall, summary=summ, Xbar=Xb, Ubar=Ub, K=K, n_trials=ntr)
 
 
 def hardware_concurrency():

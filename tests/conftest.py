@@ -19,6 +19,12 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
         sys.path.insert(0, p)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+GAIT_DATA = os.path.join(ROOT, "hkd-mpc_b200", "data")
+
+
+def GAIT_PATH(gait):
+    """Gait tables (inputs of the product's workloads; generated from the reference data by tools/make_fixtures.py)."""
+    return os.path.join(GAIT_DATA, f"gait_{gait}.npz")
 
 
 def pytest_configure(config):

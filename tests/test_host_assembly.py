@@ -4,7 +4,7 @@ import os
 import re
 import numpy as np
 import pytest
-from conftest import GOLDEN, ROOT
+from conftest import GOLDEN, GAIT_PATH, ROOT
 
 
 def test_library_exports_every_declared_symbol(pkg):
@@ -37,8 +37,8 @@ def test_no_gpu_means_loud_failure(pkg):
 
 @pytest.mark.parametrize("gait,starts", [("trot", [0, 7, 100, 333, 680]), ("bound", [0, 250, 266, 500]), ("pronk", [0, 50, 300, 687])])
 def test_schedule_builder_equals_oracle_assembly(pkg, orc, gait, starts):
-    T = orc.GaitTable(os.path.join(GOLDEN, f"gait_{gait}.npz"))
-    R = pkg.QuadReference(os.path.join(GOLDEN, f"gait_{gait}.npz"))
+    T = orc.GaitTable(GAIT_PATH(gait))
+    R = pkg.QuadReference(GAIT_PATH(gait))
     for k0 in starts:
         for plan in (0.25, 0.5, 0.6, 1.0):
             if k0 + round(plan / 0.01) + 2 > T.n:
@@ -60,7 +60,7 @@ def test_schedule_builder_equals_oracle_assembly(pkg, orc, gait, starts):
 
 
 def test_window_past_the_table_is_rejected(pkg):
-    R = pkg.QuadReference(os.path.join(GOLDEN, "gait_trot.npz"))
+    R = pkg.QuadReference(GAIT_PATH("trot"))
     with pytest.raises(pkg.HsddpError):
         pkg.Schedule(R, R.n - 10, 0.6)
 
@@ -70,7 +70,7 @@ def test_text_loader_reproduces_the_fixture(pkg):
     if not os.path.exists(path):
         pytest.skip("reference tree not present")
     S1 = pkg.Schedule(pkg.QuadReference(path), 0, 0.6)
-    S2 = pkg.Schedule(pkg.QuadReference(os.path.join(GOLDEN, "gait_trot.npz")), 0, 0.6)
+    S2 = pkg.Schedule(pkg.QuadReference(GAIT_PATH("trot")), 0, 0.6)
     for name in ("xr", "ur", "prel_r", "xinit"):
         assert np.array_equal(S1.array(name), S2.array(name))
 

@@ -9,7 +9,7 @@ vectors generated from that code (tools/make_model_vectors.py) pin
 import os
 import numpy as np
 import pytest
-from conftest import GOLDEN, rel_err
+from conftest import GOLDEN, GAIT_PATH, rel_err
 
 TOL = 1e-13  # FP64; differences are association order of a few dozen operations
 

@@ -11,11 +11,11 @@ import ctypes as C
 import os
 import numpy as np
 import pytest
-from conftest import GOLDEN, rel_err
+from conftest import GOLDEN, GAIT_PATH, rel_err
 
 
 def _table(orc, gait):
-    return orc.GaitTable(os.path.join(GOLDEN, f"gait_{gait}.npz"))
+    return orc.GaitTable(GAIT_PATH(gait))
 
 
 def test_ldlt_sign_test_matches_eigenvalues(orc):

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Generate the committed input fixtures under tests/golden/ from the reference tree.
+"""Generate the committed gait tables under hkd-mpc_b200/data/ from the reference tree.
 
 Runs ONLY in the build container (needs /root/reference).  Nothing at test or
 bench time reads /root/reference: the GPU box gets these fixtures instead.
@@ -22,7 +22,7 @@ import sys
 import numpy as np
 
 REF = os.environ.get("HKD_REFERENCE", "/root/reference")
-OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "hkd-mpc_b200", "data")
 
 
 def load_quad_reference(path):

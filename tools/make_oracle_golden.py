@@ -29,7 +29,7 @@ def main():
     assert op.ref_available()
     out = {}
     for name, gait, k0, plan, mode in CASES:
-        T = op.GaitTable(os.path.join(ROOT, "tests", "golden", f"gait_{gait}.npz"))
+        T = op.GaitTable(os.path.join(ROOT, "hkd-mpc_b200", "data", f"gait_{gait}.npz"))
         P = op.Problem(T, k0, plan, model=op.MODEL_REF)
         if mode == "reference":
             body = T.body_state[k0].astype(np.float64)
