@@ -42,7 +42,7 @@ BYTES_STAGE = 6400.0             # minimum HBM bytes per stage per iteration (fu
 # FLOP the sweep kernel actually EXECUTES per stage (structure exploited: A = I + 12 dense rows, 12 coupled controls;
 # DESIGN.md §4.3): 37 output tiles x 3 DMMA m8n8k4 (512 FLOP each) + the 12x12 block Gauss-Jordan on 49 tableau columns
 # (6 steps x (20 eliminate + 8 pivot) DFMA per column) + ~1.5k FLOP of vector work
-F_STAGE_EXECUTED = 37 * 3 * 512.0 + 49 * 6 * 28 * 2.0 + 1500.0
+F_STAGE_EXECUTED = 120.5 * 512.0 + 49 * 6 * 28 * 2.0 + 1500.0  # (120.5 DMMA per stage executed: profiles/r02_sweep_sass_dmma.txt)
 
 
 def parse():

@@ -13,6 +13,7 @@
 #include <vector>
 #include "hsddp_device.cuh"
 #include "hsddp_sweep.cuh"
+#include "hsddp_sweep_w1.cuh"
 
 // resident blocks per SM the kernels are compiled for (register budget = 65536 / (128 * HSDDP_MIN_BLOCKS))
 #ifndef HSDDP_MIN_BLOCKS
@@ -610,6 +611,11 @@ struct hsddp_batch {
     int* d_count = nullptr;
     int* h_count = nullptr;        // pinned
     int last_rounds = 0;
+    // phased driver's backward-sweep kernel: 0 four warps per problem (k_phase<PH_SWEEP>), 1 one warp per problem (k_sweep_w1),
+    // 2 auto: one warp per problem for launches of at least `w1_min_blocks` problems (full waves: fewer instructions and
+    // shared-memory wavefronts per stage), four warps below (shorter dependent chain per problem when the GPU is not full)
+    int sweep_kind = 2;
+    int w1_min_blocks = 1554;
     static constexpr int kMaxGroups = 16;  // (default phased_groups = 8; HSDDP_PHASED_GROUPS may raise it for experiments)
     int phased_groups = 8;         // index ranges driven concurrently on their own streams (config 3, 16,384 problems: 2: 408 ms, 4: 401, 8: 397)
     cudaStream_t gstream[kMaxGroups] = {};
@@ -710,6 +716,9 @@ int hsddp_batch_create(int device, hsddp_batch** out) {
         const int v = atoi(e);
         if (v >= 1 && v <= hsddp_batch::kMaxGroups) b->phased_groups = v;
     }
+    if (const char* e = getenv("HSDDP_SWEEP_KIND")) b->sweep_kind = atoi(e);  // tuning / experiments only
+    CK(cudaFuncSetAttribute(k_sweep_w1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (const char* e = getenv("HSDDP_W1_MIN_BLOCKS")) b->w1_min_blocks = atoi(e);  // tuning / experiments only
     if (const char* e = getenv("HSDDP_SOLVE_MODE")) {  // tuning / experiments only
         const int v = atoi(e);
         if (v >= 0 && v <= 2) b->solve_mode = v;
@@ -1021,7 +1030,8 @@ static int solve_phased(hsddp_batch* b, const hsddp_options& o) {
             bp[g].active = b->d_active[cur[g]] + off[g]; bp[g].next_active = b->d_active[cur[g] ^ 1] + off[g];
             CK(cudaMemsetAsync(b->d_count + g, 0, sizeof(int), b->gstream[g]));
             k_phase<PH_PREP><<<n_active[g], kThreads, 0, b->gstream[g]>>>(bp[g], o);
-            k_phase<PH_SWEEP><<<n_active[g], kThreads, 0, b->gstream[g]>>>(bp[g], o);
+            if (b->sweep_kind == 1 || (b->sweep_kind == 2 && n_active[g] >= b->w1_min_blocks)) k_sweep_w1<<<n_active[g], 32, 0, b->gstream[g]>>>(bp[g], o);
+            else k_phase<PH_SWEEP><<<n_active[g], kThreads, 0, b->gstream[g]>>>(bp[g], o);
             k_phase<PH_FORWARD><<<n_active[g], kThreads, 0, b->gstream[g]>>>(bp[g], o);
             CK(cudaGetLastError());
             b->n_solve_launches += 3;

@@ -21,7 +21,7 @@ for r in rows[1:]:
 ids = sorted(launches)
 iota = [i for i in ids if "k_iota" in launches[i]["kernel"]]
 assert len(iota) >= 2, "need two phased solves in the capture"
-names = {"k_phase<0>": "begin", "k_phase<1>": "prep (cost + LQ)", "k_phase<2>": "backward sweep",
+names = {"k_phase<0>": "begin", "k_phase<1>": "prep (cost + LQ)", "k_phase<2>": "backward sweep", "k_sweep_w1": "backward sweep", "k_sweep_w2": "backward sweep",
          "k_phase<3>": "forward (linear rollout + line search)"}
 agg = collections.OrderedDict()
 for i in ids:
