@@ -129,9 +129,17 @@ struct BatchPtrs {
     double* g0h0;                             // [P][600] value gradient / Hessian at the first node
     SolverState* state;                       // [P]
     SolveCtl* ctl;                            // [P]
-    const int* active;                        // phased driver: problem indices of this round (nullptr: blockIdx.x)
-    int* next_active;                         // phased driver: problems still running after this round
+    // phased driver: the problems of this round are active[0 .. *n_active), survivors are appended to next_active /
+    // next_count.  All four live in HBM, so a whole solve is queued without a host round trip: every round is launched
+    // with the group's full grid and blocks beyond *n_active leave at once.  active == nullptr: problem = blockIdx.x.
+    const int* active;
+    const int* n_active;
+    int* next_active;
     int* next_count;
+    int* zero_count;                          // counter the first kernel of a round clears for the round after next (nullptr: none)
+    int sweep_w1_min;                         // phased driver: rounds with at least this many problems run k_sweep_w1 instead of k_phase<PH_SWEEP> (0: never)
+    int _pad2;
+    const int* order;                         // persistent kernel: the work queue visits problems in this order (nullptr: by index)
     hsddp_info* info;                         // [P]
     hsddp_iter_record* trace;                 // [P][HSDDP_TRACE_CAP]
     unsigned long long* counters;             // [0] = sum over problems of (backward sweeps x stages)

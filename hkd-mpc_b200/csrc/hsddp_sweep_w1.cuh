@@ -606,6 +606,7 @@ __device__ inline bool w1_backward_sweep(SweepW1& sm, const SweepW1Ptrs& p, doub
 __global__ void __launch_bounds__(32, HSDDP_W1_MINB) k_sweep_w1(BatchPtrs bp, hsddp_options opt) {
     __shared__ SweepW1 sm;
     const int lane = threadIdx.x;
+    if (bp.n_active && ((int)blockIdx.x >= *bp.n_active || *bp.n_active < bp.sweep_w1_min)) return;  // (see BatchPtrs::active, sweep_w1_min)
     const int pid = bp.active ? bp.active[blockIdx.x] : (int)blockIdx.x;
     const DevSchedule* sc = bp.sched + bp.sched_id[pid];
     if (lane == 0) { sm.n_phases = sc->n_phases; sm.n_stages = sc->n_stages; }

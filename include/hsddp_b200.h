@@ -170,11 +170,14 @@ int hsddp_batch_solve(hsddp_batch* b, const hsddp_options* opt);
 int hsddp_batch_solve_async(hsddp_batch* b, const hsddp_options* opt);
 int hsddp_batch_sync(hsddp_batch* b);
 /* How solve() is scheduled on the GPU (results agree to rounding; each mode is bitwise reproducible):
- *   1 persistent — one kernel, every block runs whole solves pulled from a queue (small batches, latency)
- *   2 phased     — per DDP iteration one kernel per phase (prep / backward sweep / forward sweep) over the
- *                  problems still running, up to eight index ranges driven concurrently on their own streams; the
- *                  host reads one counter per range and iteration, so hsddp_batch_solve_async blocks in this mode
- *   0 auto       — phased when the batch fills the GPU about 4.5 times over (>= 3,996 problems on a B200). */
+ *   1 persistent — one kernel, every block runs whole solves pulled from a queue (small batches, latency).  From the
+ *                  second solve of a problem set on, the queue visits the problems in the order of their previous
+ *                  iteration counts, longest first (a scheduling hint only: results do not depend on it)
+ *   2 phased     — per DDP iteration one kernel per phase (prep / backward sweep / forward sweep) over the problems
+ *                  still running, up to eight index ranges driven concurrently on their own streams.  The list of
+ *                  running problems and its length stay in HBM, so the whole solve is queued without a host round trip
+ *                  and hsddp_batch_solve_async returns as soon as the launches are queued
+ *   0 auto       — phased when the batch fills the GPU about nine times over (>= 7,992 problems on a B200). */
 int hsddp_batch_set_solve_mode(hsddp_batch* b, int mode);
 /* milliseconds of the last solve kernel, CUDA events on the handle's stream */
 int hsddp_batch_last_solve_ms(hsddp_batch* b, float* ms);

@@ -26,6 +26,19 @@ void QuadReference::initialize(const GaitTable* table, int window_start, float p
     k0 = window_start;
     dt = table->dt;
     sz = (int)std::round(plan_horizon / dt) + 1;
+    t_cur = 0.f;
+    dur = plan_horizon;
+    start_time = t_cur;
+    end_time = t_cur + dur;
+}
+
+void QuadReference::step(float dt_sim) {
+    for (int i = 1; approx_leq_scalar((float)i * dt, dt_sim); i++) {
+        k0++;
+        t_cur += dt;
+        start_time = t_cur;
+        end_time = t_cur + dur;
+    }
 }
 
 int QuadReference::index_at_t(float t) const {
@@ -64,6 +77,8 @@ void Problem::build(const GaitTable* table, int window_start, float plan_dur, Mo
             Phase ph;
             ph.horizon = (int)std::round((phase_end_time - phase_start_time) / dt_sim);
             ph.start_time = phase_start_time;
+            ph.end_time = phase_end_time;
+            ph.reach_end = false;  // (contact_prev != contact_prev).any(): always false, HKDProblem.cpp:59
             std::copy(contact_prev, contact_prev + 4, ph.contact);
             phases.push_back(ph);
             std::copy(contact_cur, contact_cur + 4, contact_prev);
@@ -75,17 +90,8 @@ void Problem::build(const GaitTable* table, int window_start, float plan_dur, Mo
     const int n_phases = (int)phases.size();
     for (int i = 0; i < n_phases; ++i) {
         Phase& ph = phases[i];
+        create_phase(ph, ph.horizon);
         const int N = ph.horizon;
-        ph.dt = (double)dt_sim;  // Trajectory(dt_sim, horizon): float widened to T
-        ph.t_offset = ph.start_time - phases[0].start_time;
-        ph.Xbar.assign(N + 1, Vec24{}); ph.X.assign(N + 1, Vec24{}); ph.Xsim.assign(N + 1, Vec24{});
-        ph.Defect.assign(N + 1, Vec24{}); ph.Defect_bar.assign(N + 1, Vec24{}); ph.dX.assign(N + 1, Vec24{});
-        ph.G.assign(N + 1, Vec24{});
-        ph.Ubar.assign(N, Vec24{}); ph.U.assign(N, Vec24{}); ph.dU.assign(N, Vec24{});
-        ph.A.assign(N + 1, Mat24{}); ph.B.assign(N, Mat24{}); ph.H.assign(N + 1, Mat24{}); ph.K.assign(N + 1, Mat24{});
-        ph.rcost.assign(N, RCost{});
-        for (auto& r : ph.rcost) r.zero();
-        ph.tcost.zero();
         // initial guess: state reference, zero control (HKDProblem.cpp:84-90)
         for (int k = 0; k <= N; ++k) {
             float tk = ph.start_time + (float)k * dt_sim;
@@ -93,30 +99,147 @@ void Problem::build(const GaitTable* table, int window_start, float plan_dur, Mo
             reference_at_t(tk, xr, ur, nullptr);
             for (int j = 0; j < 24; ++j) { ph.X[k][j] = xr[j]; ph.Xbar[k][j] = xr[j]; }
         }
-        // GRF constraint on phases with a stance leg (HKDProblem.cpp:255-263)
-        ph.n_stance = 0;
-        for (int l = 0; l < 4; ++l) if (ph.contact[l] == 1) ph.stance_legs[ph.n_stance++] = l;
-        ph.n_path = 5 * ph.n_stance;
-        ph.g.assign((size_t)N * ph.n_path, 0.0);
-        ph.reb.assign((size_t)N * ph.n_path, RebParam{cp.grf_delta, cp.grf_delta_min, cp.grf_eps});
-        ph.path_max_violation = 0.0;
-        // reset map / touchdown constraint (HKDProblem.cpp:268-310), Q17
-        if (i < n_phases - 1) std::copy(phases[i + 1].contact, phases[i + 1].contact + 4, ph.next_contact);
-        else {
-            const int* cn = ref.contact_at_t(plan_duration + dt_mpc);
-            std::copy(cn, cn + 4, ph.next_contact);
-        }
-        ph.n_td = 0;
-        for (int l = 0; l < 4; ++l)
-            if (ph.contact[l] == 0 && ph.next_contact[l] == 1) ph.td_legs[ph.n_td++] = l;
-        for (int c = 0; c < 4; ++c) {
-            ph.h[c] = 0; ph.hx[c].zero();
-            ph.al[c] = AlParam{cp.td_lambda, cp.td_sigma, cp.td_sigma_max};
-        }
-        ph.td_max_violation = 0.0;
-        ph.x_init.zero(); ph.dx_init.zero();
+    }
+    for (int i = 0; i < n_phases; ++i) {
+        add_tconstr(i);  // every phase, the last one with the contact at plan_duration + dt_mpc (Q17)
+        phases[i].t_offset = phases[i].start_time - phases[0].start_time;
+        phases[i].ss_size = phases[i].horizon + 1;  // update_SS_config(horizon + 1), HKDProblem.cpp:104
     }
     default_x0(x0);
+}
+
+// Trajectory<T,24,24,0>::create_data (TrajectoryManagement.cpp:5-35) + create_problem_one_phase (HKDProblem.cpp:225-265)
+// + SinglePhase::initialization (SinglePhase.cpp:22-35: the shooting set starts EMPTY)
+void Problem::create_phase(Phase& ph, int horizon) {
+    const int N = horizon;
+    ph.horizon = N;
+    ph.dt = (double)dt_sim;  // Trajectory(dt_sim, horizon): float widened to T
+    ph.Xbar.assign(N + 1, Vec24{}); ph.X.assign(N + 1, Vec24{}); ph.Xsim.assign(N + 1, Vec24{});
+    ph.Defect.assign(N + 1, Vec24{}); ph.Defect_bar.assign(N + 1, Vec24{}); ph.dX.assign(N + 1, Vec24{});
+    ph.G.assign(N + 1, Vec24{});
+    ph.Ubar.assign(N, Vec24{}); ph.U.assign(N, Vec24{}); ph.dU.assign(N, Vec24{});
+    ph.A.assign(N + 1, Mat24{}); ph.B.assign(N, Mat24{}); ph.H.assign(N + 1, Mat24{}); ph.K.assign(N + 1, Mat24{});
+    ph.rcost.assign(N, RCost{});
+    for (auto& r : ph.rcost) r.zero();
+    ph.tcost.zero();
+    // GRF constraint on phases with a stance leg (HKDProblem.cpp:255-263)
+    ph.n_stance = 0;
+    for (int l = 0; l < 4; ++l) if (ph.contact[l] == 1) ph.stance_legs[ph.n_stance++] = l;
+    ph.n_path = 5 * ph.n_stance;
+    ph.g.assign((size_t)N * ph.n_path, 0.0);
+    ph.reb.assign((size_t)N * ph.n_path, RebParam{cparams.grf_delta, cparams.grf_delta_min, cparams.grf_eps});
+    ph.path_max_violation = 0.0;
+    ph.tds.clear();
+    ph.has_tconstr = false;
+    ph.ss_size = 0;
+    ph.x_init.zero(); ph.dx_init.zero();
+}
+
+// add_tconstr_one_phase (HKDProblem.cpp:268-310): binds the reset map to (contact, next contact) and ADDS a touchdown
+// constraint object if a leg goes 0 -> 1.  Called for every phase at initialisation and again by update() when the last
+// phase reaches its end (Q17).
+void Problem::add_tconstr(int idx) {
+    Phase& ph = phases[idx];
+    const int n_phases = (int)phases.size();
+    if (idx < n_phases - 1) std::copy(phases[idx + 1].contact, phases[idx + 1].contact + 4, ph.next_contact);
+    else {
+        const int* cn = ref.contact_at_t(plan_duration + dt_mpc);
+        std::copy(cn, cn + 4, ph.next_contact);
+    }
+    ph.has_tconstr = true;
+    Phase::TdSet td;
+    for (int l = 0; l < 4; ++l)
+        if (ph.contact[l] == 0 && ph.next_contact[l] == 1) td.td_legs[td.n_td++] = l;
+    if (td.n_td > 0) {
+        for (int c = 0; c < 4; ++c) {
+            td.h[c] = 0; td.hx[c].zero();
+            td.al[c] = AlParam{cparams.td_lambda, cparams.td_sigma, cparams.td_sigma_max};
+        }
+        td.max_violation = 0.0;
+        ph.tds.push_back(td);
+    }
+}
+
+// SinglePhase::pop_front: Trajectory::pop_front (TrajectoryManagement.cpp:118-146) + PathConstraintBase::pop_front
+// (ConstraintsBase.h:271-275)
+void Problem::phase_pop_front(Phase& ph) {
+    ph.Xbar.erase(ph.Xbar.begin()); ph.X.erase(ph.X.begin()); ph.Xsim.erase(ph.Xsim.begin());
+    ph.Defect.erase(ph.Defect.begin()); ph.Defect_bar.erase(ph.Defect_bar.begin()); ph.dX.erase(ph.dX.begin());
+    ph.G.erase(ph.G.begin());
+    ph.Ubar.erase(ph.Ubar.begin()); ph.U.erase(ph.U.begin()); ph.dU.erase(ph.dU.begin());
+    ph.A.erase(ph.A.begin()); ph.B.erase(ph.B.begin()); ph.H.erase(ph.H.begin()); ph.K.erase(ph.K.begin());
+    ph.rcost.erase(ph.rcost.begin());
+    ph.horizon--;
+    if (ph.n_path > 0) {
+        ph.g.erase(ph.g.begin(), ph.g.begin() + ph.n_path);
+        ph.reb.erase(ph.reb.begin(), ph.reb.begin() + ph.n_path);
+    }
+}
+
+// SinglePhase::push_back_default: Trajectory::push_back_state(X.back()) (TrajectoryManagement.cpp:178-207) +
+// PathConstraintBase::push_back (ConstraintsBase.h:276-280: the new stage copies the LAST stage's ReB parameters)
+void Problem::phase_push_back_default(Phase& ph) {
+    const Vec24 xb = ph.X.back();
+    ph.Xbar.push_back(xb); ph.X.push_back(xb);
+    ph.Ubar.push_back(Vec24{}); ph.U.push_back(Vec24{});
+    ph.Xsim.push_back(Vec24{}); ph.Defect.push_back(Vec24{}); ph.Defect_bar.push_back(Vec24{});
+    ph.A.push_back(Mat24{}); ph.B.push_back(Mat24{});
+    ph.dU.push_back(Vec24{}); ph.G.push_back(Vec24{}); ph.H.push_back(Mat24{}); ph.K.push_back(Mat24{}); ph.dX.push_back(Vec24{});
+    RCost rc; rc.zero();
+    ph.rcost.push_back(rc);
+    ph.horizon++;
+    if (ph.n_path > 0) {
+        for (int i = 0; i < ph.n_path; ++i) ph.g.push_back(0.0);
+        const size_t last = ph.reb.size() - ph.n_path;
+        for (int i = 0; i < ph.n_path; ++i) ph.reb.push_back(ph.reb[last + i]);
+    }
+}
+
+// HKDProblem::update (HKDProblem.cpp:117-222), nsteps_between_mpc = 1
+void Problem::update() {
+    // update the reference by one simulation time step
+    ref.step(dt_sim);
+    const float new_start_time = ref.start_time;
+    const float new_end_time = ref.end_time;
+    // ---- front end ----
+    phases.front().start_time += dt_sim;
+    if (approx_leq_scalar(phases.front().end_time, new_start_time)) {
+        phases.erase(phases.begin());  // pop_front_phase: the first phase has shrunk to a point
+    } else {
+        phase_pop_front(phases.front());
+        phases.front().start_time = new_start_time;
+    }
+    // ---- back end ----
+    const int* cnew = ref.contact_at_t(new_end_time - new_start_time);
+    int new_contact[4];
+    std::copy(cnew, cnew + 4, new_contact);
+    bool contact_change = false;
+    for (int l = 0; l < 4; ++l) contact_change = contact_change || (new_contact[l] != phases.back().contact[l]);
+    if (contact_change && phases.back().reach_end) {
+        // grow the multi-phase problem by a new phase (zero-initialised trajectory, empty shooting set, no reset map yet)
+        Phase ph;
+        ph.start_time = phases.back().end_time;
+        ph.end_time = new_end_time;
+        const int hz = (int)std::round((ph.end_time - ph.start_time) / dt_sim);
+        ph.reach_end = false;
+        std::copy(new_contact, new_contact + 4, ph.contact);
+        phases.push_back(ph);
+        create_phase(phases.back(), hz);
+    } else {
+        // grow the last phase by one time step
+        phases.back().end_time = new_end_time;
+        if (contact_change) phases.back().reach_end = true;
+        phase_push_back_default(phases.back());
+    }
+    if (phases.back().reach_end) add_tconstr((int)phases.size() - 1);
+    // ---- shooting configuration ----
+    const int n = (int)phases.size();
+    for (int i = 0; i < n; ++i) {
+        phases[i].t_offset = phases[i].start_time - phases[0].start_time;
+        // reset_params(): a no-op in the reference (ConstraintsBase.h:165-167,341-348): ReB / AL parameters persist
+        if ((i == n - 1 && phases[i].horizon > 2) || i < n - 1) phases[i].ss_size = phases[i].horizon + 1;
+        phases.front().Ubar[0].zero();
+    }
 }
 
 // HKDMPC.cpp:44-54
@@ -213,30 +336,32 @@ void Problem::grf_violation(Phase& ph, int k) {
 }
 
 void Problem::td_violation(Phase& ph) {
-    if (ph.n_td == 0) return;
     const Vec24& x = ph.X[ph.horizon];
-    for (int i = 0; i < ph.n_td; ++i) {
-        const int l = ph.td_legs[i];
-        double qleg[3] = {x[12 + 3 * l], x[13 + 3 * l], x[14 + 3 * l]};
-        double pf[3];
-        model.foot_position(&x.v[3], &x.v[0], qleg, l, pf);
-        ph.h[i] = pf[2] - 0.0;
+    for (auto& td : ph.tds) {  // ConstraintContainer::compute_terminal_constraints: every constraint object
+        for (int i = 0; i < td.n_td; ++i) {
+            const int l = td.td_legs[i];
+            double qleg[3] = {x[12 + 3 * l], x[13 + 3 * l], x[14 + 3 * l]};
+            double pf[3];
+            model.foot_position(&x.v[3], &x.v[0], qleg, l, pf);
+            td.h[i] = pf[2] - 0.0;
+        }
+        td.max_violation = 0.0;
+        for (int i = 0; i < td.n_td; ++i) td.max_violation = std::max(td.max_violation, std::fabs(td.h[i]));
     }
-    ph.td_max_violation = 0.0;
-    for (int i = 0; i < ph.n_td; ++i) ph.td_max_violation = std::max(ph.td_max_violation, std::fabs(ph.h[i]));
 }
 
 void Problem::td_partial(Phase& ph) {
     const Vec24& x = ph.X[ph.horizon];
-    for (int i = 0; i < ph.n_td; ++i) {
-        const int l = ph.td_legs[i];
-        double qleg[3] = {x[12 + 3 * l], x[13 + 3 * l], x[14 + 3 * l]};
-        double J[54];
-        model.foot_jacobian(&x.v[3], &x.v[0], qleg, l, J);
-        // Jz = bottom row; hx = [Jz(eul) Jz(pos) 0(6) Jz(qJ)]; entries 6..11 stay zero
-        for (int c = 0; c < 3; ++c) { ph.hx[i][c] = J[2 + 3 * (3 + c)]; ph.hx[i][3 + c] = J[2 + 3 * c]; }
-        for (int c = 0; c < 12; ++c) ph.hx[i][12 + c] = J[2 + 3 * (6 + c)];
-    }
+    for (auto& td : ph.tds)
+        for (int i = 0; i < td.n_td; ++i) {
+            const int l = td.td_legs[i];
+            double qleg[3] = {x[12 + 3 * l], x[13 + 3 * l], x[14 + 3 * l]};
+            double J[54];
+            model.foot_jacobian(&x.v[3], &x.v[0], qleg, l, J);
+            // Jz = bottom row; hx = [Jz(eul) Jz(pos) 0(6) Jz(qJ)]; entries 6..11 stay zero
+            for (int c = 0; c < 3; ++c) { td.hx[i][c] = J[2 + 3 * (3 + c)]; td.hx[i][3 + c] = J[2 + 3 * c]; }
+            for (int c = 0; c < 12; ++c) td.hx[i][12 + c] = J[2 + 3 * (6 + c)];
+        }
 }
 
 // ---------------------------------------------------------------------------
@@ -381,8 +506,11 @@ void Problem::terminal_cost_par(const Phase& ph, TCost& tc) const {
 bool Problem::phase_hybrid_rollout(Phase& ph, double eps, const Options& opt) {
     const int N = ph.horizon;
     ph.Xsim[0] = ph.x_init;
-    // SS_set = {0..horizon}: the first state is always a shooting state (Q9)
-    for (int j = 0; j < 24; ++j) ph.X[0][j] = ph.Xbar[0][j] + eps * ph.dX[0][j];
+    // the first state is a shooting state iff SS_set is non-empty and starts at 0, whatever option.MS says (SinglePhase.cpp:187-193,
+    // Q9); SS_set = {0 .. ss_size-1}: all nodes after initialisation, EMPTY for a phase created by HKDProblem::update until its
+    // horizon exceeds 2, one short for a last phase that grew while its horizon was <= 2 (HKDProblem.cpp:212-218)
+    if (ph.ss_size > 0) { for (int j = 0; j < 24; ++j) ph.X[0][j] = ph.Xbar[0][j] + eps * ph.dX[0][j]; }
+    else ph.X[0] = ph.x_init;
     int k = 0;
     for (k = 0; k < N; ++k) {
         // U = Ubar + eps dU + K (X - Xbar)
@@ -394,7 +522,7 @@ bool Problem::phase_hybrid_rollout(Phase& ph, double eps, const Options& opt) {
         double nrm2 = 0;
         for (int j = 0; j < 24; ++j) nrm2 += ph.Xsim[k + 1][j] * ph.Xsim[k + 1][j];
         if (std::sqrt(nrm2) > 1e6) return false;  // Q16 (NaN passes)
-        if (opt.MS) {
+        if (opt.MS && k + 1 < ph.ss_size) {  // k+1 is a shooting state (SinglePhase.cpp:211-220)
             for (int j = 0; j < 24; ++j) ph.X[k + 1][j] = ph.Xbar[k + 1][j] + eps * ph.dX[k + 1][j];
         } else {
             ph.X[k + 1] = ph.Xsim[k + 1];
@@ -461,13 +589,15 @@ void Problem::phase_compute_cost(Phase& ph, const Options& opt) {
         ph.actual_cost += ph.rcost[k].l;
     }
     terminal_cost(ph, ph.tcost);
-    if (opt.AL_active && ph.n_td > 0) {
-        double al_cost = 0;  // compute_AL_cost, ConstraintsBase.h:374-385
-        for (int i = 0; i < ph.n_td; ++i) {
-            al_cost += 0.5 * ph.al[i].sigma * ph.h[i] * ph.h[i];
-            al_cost += ph.al[i].lambda * ph.h[i];
+    if (opt.AL_active) {
+        for (auto& td : ph.tds) {  // update_terminal_cost_with_tconstr, SinglePhase.cpp:402-411: one AL_cost per constraint object
+            double al_cost = 0;    // compute_AL_cost, ConstraintsBase.h:374-385
+            for (int i = 0; i < td.n_td; ++i) {
+                al_cost += 0.5 * td.al[i].sigma * td.h[i] * td.h[i];
+                al_cost += td.al[i].lambda * td.h[i];
+            }
+            ph.tcost.Phi += al_cost;
         }
-        ph.tcost.Phi += al_cost;
     }
     ph.actual_cost += ph.tcost.Phi;
 }
@@ -503,15 +633,22 @@ void Problem::phase_LQ_approximation(Phase& ph, const Options& opt) {
         }
     }
     terminal_cost_par(ph, ph.tcost);
-    if (opt.AL_active && ph.n_td > 0) {
+    if (opt.AL_active && !ph.tds.empty()) {
         td_partial(ph);
-        // compute_AL_partials, ConstraintsBase.h:386-399 (Q3: Hessian weight sigma(1+h)+lambda)
-        for (int i = 0; i < ph.n_td; ++i) {
-            const double wg = ph.al[i].sigma * ph.h[i] + ph.al[i].lambda;
-            const double wh = ph.al[i].sigma * (1 + ph.h[i]) + ph.al[i].lambda;
-            for (int a = 0; a < 24; ++a) ph.tcost.Phix[a] += wg * ph.hx[i][a];
-            for (int b = 0; b < 24; ++b)
-                for (int a = 0; a < 24; ++a) ph.tcost.Phixx(a, b) += wh * (ph.hx[i][a] * ph.hx[i][b]);
+        // compute_AL_partials, ConstraintsBase.h:386-399 (Q3: Hessian weight sigma(1+h)+lambda), one gradient / Hessian per
+        // constraint object, added to the terminal cost in turn (SinglePhase.cpp:414-426)
+        for (auto& td : ph.tds) {
+            Vec24 grad; grad.zero();
+            Mat24 hess; hess.zero();
+            for (int i = 0; i < td.n_td; ++i) {
+                const double wg = td.al[i].sigma * td.h[i] + td.al[i].lambda;
+                const double wh = td.al[i].sigma * (1 + td.h[i]) + td.al[i].lambda;
+                for (int a = 0; a < 24; ++a) grad[a] += wg * td.hx[i][a];
+                for (int b = 0; b < 24; ++b)
+                    for (int a = 0; a < 24; ++a) hess(a, b) += wh * (td.hx[i][a] * td.hx[i][b]);
+            }
+            for (int a = 0; a < 24; ++a) ph.tcost.Phix[a] += grad[a];
+            for (int j = 0; j < 576; ++j) ph.tcost.Phixx.m[j] += hess.m[j];
         }
     }
 }
@@ -600,7 +737,8 @@ bool Problem::hybrid_rollout(double eps, const Options& opt) {
         if (!phase_hybrid_rollout(phases[i], eps, opt)) { success = false; break; }
         // ConstraintContainer::get_max_{p,t}constrs: 0 when the phase has no such constraint
         double mp = phases[i].n_path > 0 ? std::min(0.0, phases[i].path_max_violation) : 0.0;
-        double mt = phases[i].n_td > 0 ? std::max(0.0, phases[i].td_max_violation) : 0.0;
+        double mt = 0.0;
+        for (auto& td : phases[i].tds) mt = std::max(mt, td.max_violation);
         max_pconstr = std::min(max_pconstr, mp);
         max_tconstr = std::max(max_tconstr, mt);
     }
@@ -691,15 +829,16 @@ void Problem::update_nominal_trajectory() {
 
 void Problem::update_AL_params(const Options& opt) {
     for (auto& ph : phases)
-        for (int i = 0; i < ph.n_td; ++i) {  // TerminalConstraintBase::update_params, ConstraintsBase.h:349-365
-            if (std::fabs(ph.h[i]) < opt.tconstr_thresh) continue;
-            if (std::fabs(ph.h[i]) > 0.005) {
-                ph.al[i].sigma *= opt.update_penalty;
-                ph.al[i].sigma = std::min(ph.al[i].sigma, ph.al[i].sigma_max);
-            } else {
-                ph.al[i].lambda += ph.h[i] * ph.al[i].sigma;
+        for (auto& td : ph.tds)
+            for (int i = 0; i < td.n_td; ++i) {  // TerminalConstraintBase::update_params, ConstraintsBase.h:349-365
+                if (std::fabs(td.h[i]) < opt.tconstr_thresh) continue;
+                if (std::fabs(td.h[i]) > 0.005) {
+                    td.al[i].sigma *= opt.update_penalty;
+                    td.al[i].sigma = std::min(td.al[i].sigma, td.al[i].sigma_max);
+                } else {
+                    td.al[i].lambda += td.h[i] * td.al[i].sigma;
+                }
             }
-        }
 }
 
 void Problem::update_REB_params(const Options& opt) {

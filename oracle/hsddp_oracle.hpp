@@ -73,10 +73,12 @@ struct GaitTable {
 // QuadReference restricted to what the solve touches.
 struct QuadReference {
     const GaitTable* tp = nullptr;
-    int k0 = 0;   // window start inside the top-level table
+    int k0 = 0;   // window start inside the top-level table (k_cur of the reference, offset by the initial window start)
     int sz = 0;   // round(plan/dt)+1 ; the window holds sz+1 samples
     float dt = 0.f;
+    float t_cur = 0.f, dur = 0.f, start_time = 0.f, end_time = 0.f;  // QuadReference.cpp:6-26,33-47
     void initialize(const GaitTable* table, int window_start, float plan_horizon);
+    void step(float dt_sim);                       // QuadReference.cpp:33-47: shift the window by dt_sim
     int index_at_t(float t) const;                 // QuadReference.cpp:65-80 (nearest sample, float arithmetic)
     const int* contact_at_t(float t) const;        // :86-100
     const double* body_state(int k) const { return &tp->body_state[12 * (size_t)(k0 + k)]; }
@@ -119,13 +121,23 @@ struct Phase {
     std::vector<double> g;                // horizon x n_path
     std::vector<RebParam> reb;            // horizon x n_path
     double path_max_violation = 0.0;
-    // touchdown terminal constraint (legs going 0 -> 1)
-    int n_td = 0;
-    int td_legs[4];
-    double h[4];
-    Vec24 hx[4];
-    AlParam al[4];
-    double td_max_violation = 0.0;
+    // touchdown terminal constraints (legs going 0 -> 1).  One TouchDownConstraint OBJECT per add_tconstr_one_phase call
+    // that found a touchdown leg: HKDProblem::update calls it again when a phase reaches its end, so a phase can carry
+    // two objects on the same legs, each with its own AL parameters (HKDProblem.cpp:205-208,268-310)
+    struct TdSet {
+        int n_td = 0;
+        int td_legs[4] = {0, 0, 0, 0};
+        double h[4] = {0, 0, 0, 0};
+        Vec24 hx[4];
+        AlParam al[4];
+        double max_violation = 0.0;
+    };
+    std::vector<TdSet> tds;
+    bool has_tconstr = false;   // add_tconstr_one_phase has run: next_contact / reset map are bound
+    bool reach_end = false;     // pdata->is_phase_reach_end
+    float end_time = 0.f;       // pdata->phase_end_times[i]
+    int ss_size = 0;            // SS_set = {0 .. ss_size-1} (update_SS_config); 0 = empty (SinglePhase::initialization)
+    int n_td_total() const { int n = 0; for (auto& t : tds) n += t.n_td; return n; }
 
     // Trajectory
     std::vector<Vec24> Xbar, X, Xsim, Defect, Defect_bar, dX, G;  // horizon+1
@@ -175,6 +187,12 @@ struct Problem {
 
     // ---- HKDProblem::initialization (HKDProblem.cpp:15-111) ----
     void build(const GaitTable* table, int window_start, float plan_dur, ModelKind kind, const ConstraintParams& cp);
+    // ---- HKDProblem::update (HKDProblem.cpp:117-222): receding-horizon shift by one MPC step ----
+    void update();
+    void create_phase(Phase& ph, int horizon);      // Trajectory(dt, horizon) + create_problem_one_phase (:225-265) + SinglePhase::initialization
+    void add_tconstr(int idx);                      // add_tconstr_one_phase (:268-310)
+    void phase_pop_front(Phase& ph);                // SinglePhase::pop_front (SinglePhase.cpp:496-501)
+    void phase_push_back_default(Phase& ph);        // SinglePhase::push_back_default (:486-491)
     // default initial condition of HKDMPC.cpp:44-54
     void default_x0(Vec24& x) const;
 

@@ -79,7 +79,7 @@ int orc_problem_n_phases(void* p) { return (int)((Problem*)p)->phases.size(); }
 int orc_problem_n_stages(void* p) { int n = 0; for (auto& ph : ((Problem*)p)->phases) n += ph.horizon; return n; }
 void orc_problem_phase_info(void* p, int i, int* horizon, int* contact, int* next_contact, float* start_time, int* n_td, int* n_path) {
     const Phase& ph = ((Problem*)p)->phases[i];
-    *horizon = ph.horizon; *start_time = ph.start_time; *n_td = ph.n_td; *n_path = ph.n_path;
+    *horizon = ph.horizon; *start_time = ph.start_time; *n_td = ph.n_td_total(); *n_path = ph.n_path;
     for (int l = 0; l < 4; ++l) { contact[l] = ph.contact[l]; next_contact[l] = ph.next_contact[l]; }
 }
 void orc_problem_set_x0(void* p, const double* x0) { std::memcpy(((Problem*)p)->x0.v, x0, 24 * sizeof(double)); }
@@ -128,8 +128,24 @@ void orc_problem_get(void* pv, int which, double* out) {
             case 40: std::memcpy(out + o, ph.tcost.Phix.v, 192); o += 24; break;
             case 41: std::memcpy(out + o, ph.tcost.Phixx.m, 4608); o += 576; break;
             case 42: out[o++] = ph.tcost.Phi; break;
-            case 50: for (int i = 0; i < 4; ++i) out[o++] = (i < ph.n_td) ? ph.h[i] : 0.0; break;
-            case 51: for (int i = 0; i < 4; ++i) { out[o++] = ph.al[i].sigma; out[o++] = ph.al[i].lambda; } break;
+            case 50: {  // touchdown values of the FIRST constraint object, packed by constraint
+                for (int i = 0; i < 4; ++i) out[o++] = (!ph.tds.empty() && i < ph.tds[0].n_td) ? ph.tds[0].h[i] : 0.0;
+            } break;
+            case 51: {  // (sigma, lambda) of the first constraint object (initial values when the phase has none)
+                for (int i = 0; i < 4; ++i) {
+                    out[o++] = ph.tds.empty() ? p->cparams.td_sigma : ph.tds[0].al[i].sigma;
+                    out[o++] = ph.tds.empty() ? p->cparams.td_lambda : ph.tds[0].al[i].lambda;
+                }
+            } break;
+            case 54: {  // per LEG: [sum over constraint objects of sigma, sum of lambda, h, number of objects on the leg]
+                for (int l = 0; l < 4; ++l) {
+                    double ss = 0, sl = 0, hh = 0; int cnt = 0;
+                    for (auto& td : ph.tds)
+                        for (int i = 0; i < td.n_td; ++i)
+                            if (td.td_legs[i] == l) { ss += td.al[i].sigma; sl += td.al[i].lambda; hh = td.h[i]; ++cnt; }
+                    out[o++] = ss; out[o++] = sl; out[o++] = hh; out[o++] = cnt;
+                }
+            } break;
             case 52: for (int k = 0; k < N; ++k) for (int i = 0; i < 20; ++i) out[o++] = (i < ph.n_path) ? ph.g[(size_t)k * ph.n_path + i] : 0.0; break;
             case 53:  // ReB parameters (eps, delta) per stage, 5 rows per LEG like the GPU layout; swing legs keep the initial values
                 for (int k = 0; k < N; ++k) {
@@ -173,6 +189,14 @@ void orc_lq_approximation(void* p, const double* o) { Options opt; options_from_
 int orc_backward_sweep(void* p, double reg) { return ((Problem*)p)->backward_sweep(reg) ? 1 : 0; }
 void orc_linear_rollout(void* p, double eps, const double* o) { Options opt; options_from_array(o, opt); ((Problem*)p)->linear_rollout(eps, opt); }
 void orc_update_nominal(void* p) { ((Problem*)p)->update_nominal_trajectory(); }
+// HKDProblem::update: receding-horizon shift by one MPC step
+void orc_mpc_update(void* p) { ((Problem*)p)->update(); }
+int orc_problem_phase_flags(void* p, int i, int* ss_size, int* has_tconstr, int* reach_end, int* n_td_objects) {
+    const Phase& ph = ((Problem*)p)->phases[i];
+    *ss_size = ph.ss_size; *has_tconstr = ph.has_tconstr ? 1 : 0; *reach_end = ph.reach_end ? 1 : 0; *n_td_objects = (int)ph.tds.size();
+    return 0;
+}
+int orc_problem_window_start(void* p) { return ((Problem*)p)->ref.k0; }
 
 // ---- full solve ----
 // summary: [status, n_iter, n_outer, n_sweeps, cost, feas, max_tconstr, max_pconstr, cost0, feas0]

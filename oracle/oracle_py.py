@@ -65,7 +65,10 @@ def lib():
         L.orc_table_destroy.argtypes = [C.c_void_p]
         L.orc_problem_create.restype = C.c_void_p
         L.orc_problem_create.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, C.POINTER(C.c_double)]
-        for f in ("orc_problem_destroy", "orc_update_nominal"):
+        L.orc_problem_phase_flags.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 4
+        L.orc_problem_window_start.argtypes = [C.c_void_p]
+        L.orc_problem_window_start.restype = C.c_int
+        for f in ("orc_problem_destroy", "orc_update_nominal", "orc_mpc_update"):
             getattr(L, f).argtypes = [C.c_void_p]
         for f in ("orc_problem_n_phases", "orc_problem_n_stages"):
             getattr(L, f).argtypes = [C.c_void_p]
@@ -232,15 +235,27 @@ class Problem:
         self.model = default_model() if model is None else model
         self._cp = cparams_array(**(cparams or {}))
         self.h = lib().orc_problem_create(table.handle, int(k0), C.c_float(plan), self.model, _dp(self._cp))
+        self._refresh()
+
+    def _refresh(self):
         self.n_phases = lib().orc_problem_n_phases(self.h)
         self.n_stages = lib().orc_problem_n_stages(self.h)
         self.phases = []
         for i in range(self.n_phases):
             hz = C.c_int(); c = (C.c_int * 4)(); cn = (C.c_int * 4)(); st = C.c_float(); ntd = C.c_int(); npth = C.c_int()
             lib().orc_problem_phase_info(self.h, i, C.byref(hz), c, cn, C.byref(st), C.byref(ntd), C.byref(npth))
+            ss = C.c_int(); ht = C.c_int(); re = C.c_int(); no = C.c_int()
+            lib().orc_problem_phase_flags(self.h, i, C.byref(ss), C.byref(ht), C.byref(re), C.byref(no))
             self.phases.append(dict(horizon=hz.value, contact=list(c), next_contact=list(cn), start_time=st.value,
-                                    n_td=ntd.value, n_path=npth.value))
+                                    n_td=ntd.value, n_path=npth.value, ss_size=ss.value, has_tconstr=bool(ht.value),
+                                    reach_end=bool(re.value), n_td_objects=no.value))
         self.n_states = self.n_stages + self.n_phases
+        self.window_start = lib().orc_problem_window_start(self.h)
+
+    def mpc_update(self):
+        """HKDProblem::update (HKDProblem.cpp:117-222): shift the horizon by one MPC step."""
+        lib().orc_mpc_update(self.h)
+        self._refresh()
 
     def __del__(self):
         try:
@@ -262,16 +277,16 @@ class Problem:
         return xr, ur, br, fr, idx.value
 
     _SHAPES = {0: "s", 1: "s", 2: "s", 3: "s", 4: "s", 5: "s", 10: "u", 11: "u", 12: "u", 20: "m", 21: "m", 22: "m",
-               24: "m", 25: "m", 26: "m", 27: "ms", 30: "u", 31: "u", 32: "l", 40: "pv", 41: "pm", 42: "p", 50: "p4", 51: "p8", 52: "g", 53: "r"}
+               24: "m", 25: "m", 26: "m", 27: "ms", 30: "u", 31: "u", 32: "l", 40: "pv", 41: "pm", 42: "p", 50: "p4", 51: "p8", 52: "g", 53: "r", 54: "p16"}
     NAMES = dict(Xbar=0, X=1, Xsim=2, Defect=3, dX=4, G=5, Ubar=10, U=11, dU=12, K=20, A=21, B=22, lxx=24, luu=25, lux=26,
-                 H=27, lx=30, lu=31, l=32, Phix=40, Phixx=41, Phi=42, h=50, al=51, g=52, reb=53)
+                 H=27, lx=30, lu=31, l=32, Phix=40, Phixx=41, Phi=42, h=50, al=51, g=52, reb=53, td_by_leg=54)
 
     def get(self, name):
         which = self.NAMES[name]
         kind = self._SHAPES[which]
         N, S, P = self.n_stages, self.n_states, self.n_phases
         shape = {"s": (S, 24), "u": (N, 24), "m": (N, 24, 24), "ms": (S, 24, 24), "l": (N,), "pv": (P, 24), "pm": (P, 24, 24),
-                 "p": (P,), "p4": (P, 4), "p8": (P, 4, 2), "g": (N, 20), "r": (N, 20, 2)}[kind]
+                 "p": (P,), "p4": (P, 4), "p8": (P, 4, 2), "g": (N, 20), "r": (N, 20, 2), "p16": (P, 4, 4)}[kind]
         out = np.zeros(shape)
         lib().orc_problem_get(self.h, which, _dp(out))
         if kind in ("m", "ms", "pm"):
