@@ -134,6 +134,8 @@ def lib():
         L.hsddp_batch_set_problems.argtypes = [vp, C.c_int, C.POINTER(ScheduleStruct), C.c_int, ip, C.POINTER(ConstraintParams)]
         L.hsddp_batch_set_initial_condition.argtypes = [vp, dp]
         L.hsddp_batch_reset.argtypes = [vp]
+        L.hsddp_batch_mpc_update.argtypes = [vp]
+        L.hsddp_batch_last_update_ms.argtypes = [vp, C.POINTER(C.c_float)]
         for f in ("hsddp_batch_solve", "hsddp_batch_solve_async", "hsddp_batch_compute_cost", "hsddp_batch_lq_approximation",
                   "hsddp_batch_prepare_merit", "hsddp_batch_update_al_params", "hsddp_batch_update_reb_params"):
             getattr(L, f).argtypes = [vp, C.POINTER(Options)]
@@ -345,6 +347,15 @@ class MultiPhaseDDPBatch:
     def reset(self):
         _check(lib().hsddp_batch_reset(self.h), "hsddp_batch_reset")
 
+    def mpc_update(self):
+        """HKDProblem::update for every problem (receding-horizon shift by one MPC step, on the device)."""
+        _check(lib().hsddp_batch_mpc_update(self.h), "hsddp_batch_mpc_update")
+
+    def last_update_ms(self):
+        ms = C.c_float()
+        _check(lib().hsddp_batch_last_update_ms(self.h, C.byref(ms)), "hsddp_batch_last_update_ms")
+        return ms.value
+
     def solve(self, opt=None):
         opt = opt or Options()
         _check(lib().hsddp_batch_solve(self.h, C.byref(opt)), "hsddp_batch_solve")
@@ -429,7 +440,7 @@ class MultiPhaseDDPBatch:
         S, N = self.max_nodes, self.max_stages
         shape = {"Xbar": (S, 24), "X": (S, 24), "Defect": (S, 24), "dX": (S, 24), "Ubar": (N, 24), "U": (N, 24), "dU": (N, 24),
                  "K": (N, 24, 24), "A": (N, 24, 24), "B": (N, 24, 24), "lxx": (N, 24, 24), "luu": (N, 24, 24), "lx": (N, 24),
-                 "lu": (N, 24), "G0": (24,), "H0": (24, 24), "g": (N, 20), "h": (MAX_PHASES, 4), "al": (MAX_PHASES, 4, 2), "reb": (N, 20, 2)}[name]
+                 "lu": (N, 24), "G0": (24,), "H0": (24, 24), "g": (N, 20), "h": (MAX_PHASES, 4), "al": (MAX_PHASES, 2, 4, 2), "reb": (N, 20, 2)}[name]
         out = np.zeros((self.n,) + shape)
         _check(lib().hsddp_batch_get_array(self.h, which, _dp(out)), "get_array")
         if name in ("K", "A", "B", "lxx", "luu", "H0"):
@@ -437,7 +448,7 @@ class MultiPhaseDDPBatch:
         return out
 
     def get_rows(self, name, row0, nrows, out=None):
-        cols = {"K": 576, "g": 20, "h": 4, "al": 8, "reb": 40}.get(name, 24)
+        cols = {"K": 576, "g": 20, "h": 4, "al": 16, "reb": 40}.get(name, 24)
         if out is None:
             out = np.zeros((self.n, nrows, cols))
         _check(lib().hsddp_batch_get_array_rows(self.h, ARR[name], int(row0), int(nrows), _dp(out)), "get_array_rows")

@@ -89,7 +89,15 @@ struct DevSchedule {
     double dt;
     unsigned char ph_of_stage[HSDDP_MAX_STAGES];           // filled on the host (hsddp_batch_set_problems)
     unsigned char ph_of_node[HSDDP_MAX_STAGES + MAXPH];
+    // shooting set of the phase: nodes 0 .. ss_size-1 (SinglePhase::update_SS_config).  horizon + 1 = every node (what
+    // HKDProblem::initialization sets); after a receding-horizon update the LAST phase can have fewer: 0 for a phase created
+    // by HKDProblem::update until its horizon exceeds 2 (HKDProblem.cpp:212-218)
+    unsigned char ss_size[MAXPH];
+    // leg masks of the touchdown-constraint OBJECTS of the phase (add_tconstr_one_phase runs again when a phase reaches
+    // its end during an update, so a phase can carry two objects, each with its own AL parameters)
+    unsigned char tdmask[2][MAXPH];
 };
+static_assert(sizeof(DevSchedule) % 4 == 0, "bind_problem copies the schedule word by word");
 
 // solver scalars of one problem (MultiPhaseDDP.h:92-104) + bookkeeping
 struct SolverState {
@@ -125,7 +133,7 @@ struct BatchPtrs {
     double* gcon;                             // [P][max_stages][20]
     double* reb;                              // [P][max_stages][20][2]  (eps, delta)
     double* hcon;                             // [P][MAXPH][4]
-    double* al;                               // [P][MAXPH][4][2]        (sigma, lambda)
+    double* al;                               // [P][MAXPH][2][4][2]     (sigma, lambda) per touchdown-constraint object and leg
     double* g0h0;                             // [P][600] value gradient / Hessian at the first node
     SolverState* state;                       // [P]
     SolveCtl* ctl;                            // [P]
@@ -271,7 +279,7 @@ __device__ inline void bind_problem(Smem& sm, const BatchPtrs& bp, int pid) {
         sm.gcon = bp.gcon + (size_t)pid * bp.max_stages * 20;
         sm.reb = bp.reb + (size_t)pid * bp.max_stages * 40;
         sm.hcon = bp.hcon + (size_t)pid * MAXPH * 4;
-        sm.al = bp.al + (size_t)pid * MAXPH * 8;
+        sm.al = bp.al + (size_t)pid * MAXPH * 16;
         sm.g0h0 = bp.g0h0 + (size_t)pid * 600;
         sm.x0 = bp.x0 + (size_t)pid * 24;
         sm.prof = bp.counters + 8;
@@ -432,7 +440,7 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
         double nrm2 = 0.0;
 #pragma unroll
         for (int j = 0; j < 24; ++j) nrm2 = fma(slot[j], slot[j], nrm2);
-        if (sqrt(nrm2) > 1e6) first_bad = min(first_bad, s);
+        if (sqrt(nrm2) > 1e6 && k < sc.ss_size[ph]) first_bad = min(first_bad, s);  // (stages of non-shooting nodes are redone in (b2))
     }
     if (tid >= 64 && tid < 64 + sc.n_phases) {
         const int ph = tid - 64;
@@ -442,6 +450,41 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
         } else {
             const int ne = sc.node_off[ph - 1] + sc.horizon[ph - 1];
             resetmap_thread(xs + 24 * ne, sc.cmask[ph - 1], sc.nmask[ph - 1], xi);
+        }
+    }
+    // (b2) nodes OUTSIDE the shooting set.  HKDProblem::initialization makes every node a shooting node; after a receding-horizon
+    //      update the LAST phase can have fewer (DevSchedule::ss_size): those nodes are propagated, X[k] = Xsim[k] (X[0] = x_init
+    //      when the set is empty), and their controls see the true feedback K (X - Xbar) (SinglePhase.cpp:185-220).  At most
+    //      three stages, walked by one thread after the parallel pass.
+    {
+        const int L = sc.n_phases - 1;
+        const int hz = sc.horizon[L], ss = sc.ss_size[L];
+        if (ss < hz + 1) {
+            __syncthreads();
+            if (tid == 0) {
+                const unsigned cm = sc.cmask[L];
+                for (int k = ss; k <= hz; ++k) {
+                    const int n = sc.node_off[L] + k, s = sc.stage_off[L] + k;
+                    double* x = xs + 24 * n;
+                    const double* xsim = (k == 0) ? sm.Xsim_t + 24 * n : (dev_in_smem ? xd + 24 * (n - 1) : sm.Xsim_t + 24 * n);
+                    for (int j = 0; j < 24; ++j) x[j] = xsim[j];
+                    if (k == hz) break;
+                    double dxl[24], ul[24];
+                    for (int j = 0; j < 24; ++j) { dxl[j] = x[j] - sm.Xbar[24 * n + j]; ul[j] = sm.Ubar[24 * s + j] + eps * sm.dU[24 * s + j]; }
+                    const double* KT = sm.K + 288 * (size_t)s;
+                    for (int c = 0; c < 12; ++c) {
+                        double acc = 0.0;
+                        for (int j = 0; j < 24; ++j) acc = fma(KT[12 * j + c], dxl[j], acc);
+                        ul[((cm >> (c / 3)) & 1u) ? c : 12 + c] += acc;  // the coupled control of the leg
+                    }
+                    double* slot = dev_in_smem ? xd + 24 * n : sm.Xsim_t + 24 * (n + 1);
+                    for (int j = 0; j < 24; ++j) sm.U_t[24 * s + j] = ul[j];
+                    hkd::dynamics(x, ul, sc.dt, cm, slot);
+                    double nrm2 = 0.0;
+                    for (int j = 0; j < 24; ++j) nrm2 = fma(slot[j], slot[j], nrm2);
+                    if (sqrt(nrm2) > 1e6) { first_bad = min(first_bad, s); break; }
+                }
+            }
         }
     }
     // first diverged stage in the reference's sequential order
@@ -485,7 +528,7 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
     double hmax = 0.0;
     if (tid < sc.n_phases * 4) {  // TouchDownConstraint::compute_violation
         const int ph = tid >> 2, l = tid & 3;
-        const bool td = !((sc.cmask[ph] >> l) & 1u) && ((sc.nmask[ph] >> l) & 1u);
+        const bool td = ((sc.tdmask[0][ph] | sc.tdmask[1][ph]) >> l) & 1u;
         if (td && ph < bad_ph) {
             const int ne = sc.node_off[ph] + sc.horizon[ph];
             const double* xe = xs + 24 * ne;
@@ -572,10 +615,13 @@ __device__ inline void compute_cost_block(Smem& sm) {
     // (5) augmented-Lagrangian terms of the touchdown constraints, (phase, leg)  (compute_AL_cost, ConstraintsBase.h:374-385)
     if (sm.opt.AL_active && tid < sc.n_phases * 4) {
         const int ph = tid >> 2, l = tid & 3;
-        if (!((sc.cmask[ph] >> l) & 1u) && ((sc.nmask[ph] >> l) & 1u)) {
-            const double h = sm.hcon[4 * ph + l], sigma = sm.al[8 * ph + 2 * l], lambda = sm.al[8 * ph + 2 * l + 1];
-            csum += 0.5 * sigma * h * h + lambda * h;
-        }
+        const double h = sm.hcon[4 * ph + l];
+#pragma unroll
+        for (int ob = 0; ob < 2; ++ob)
+            if ((sc.tdmask[ob][ph] >> l) & 1u) {
+                const double sigma = sm.al[16 * ph + 8 * ob + 2 * l], lambda = sm.al[16 * ph + 8 * ob + 2 * l + 1];
+                csum += 0.5 * sigma * h * h + lambda * h;
+            }
     }
     double dsum = 0.0;
     for (int e = tid; e < sc.n_nodes * 24; e += kThreads) { const double d = sm.Defect[e]; dsum += d * d; }
@@ -716,20 +762,27 @@ __device__ inline void lq_approximation_block(Smem& sm) {
             double* hx = rec + TQ_HX + 24 * l;
             for (int j = 0; j < 24; ++j) hx[j] = 0.0;
             rec[TQ_WH + l] = 0.0;
-            const bool td = !((cm >> l) & 1u) && ((sc.nmask[ph] >> l) & 1u);
-            if (td) {  // reset-map Jacobian of a touchdown leg, cached for the sweep and the linear rollout
+            const bool rm = !((cm >> l) & 1u) && ((sc.nmask[ph] >> l) & 1u);  // reset map moves this leg's foot (touchdown)
+            const unsigned tdo = ((sc.tdmask[0][ph] >> l) & 1u) | (((sc.tdmask[1][ph] >> l) & 1u) << 1);  // constraint objects on this leg
+            if (rm || tdo) {  // foot Jacobian, cached for the sweep and the linear rollout (reset-map Jacobian) and used by the AL terms
                 double Jc[18];
                 foot_jacobian_nl(x, l, Jc);
                 for (int c = 0; c < 18; ++c) rec[TQ_JC + 18 * l + c] = Jc[c];
             }
-            if (td && sm.opt.AL_active) {
+            if (tdo && sm.opt.AL_active) {
                 const double* Jc = rec + TQ_JC + 18 * l;
                 for (int c = 0; c < 3; ++c) { hx[c] = Jc[2 * 6 + c]; hx[12 + 3 * l + c] = Jc[2 * 6 + 3 + c]; }
                 hx[5] = 1.0;
-                const double h = sm.hcon[4 * ph + l], sigma = sm.al[8 * ph + 2 * l], lambda = sm.al[8 * ph + 2 * l + 1];
-                const double wg = sigma * h + lambda;
+                const double h = sm.hcon[4 * ph + l];
+                double wg = 0.0, wh = 0.0;
+                for (int ob = 0; ob < 2; ++ob)
+                    if ((tdo >> ob) & 1u) {
+                        const double sigma = sm.al[16 * ph + 8 * ob + 2 * l], lambda = sm.al[16 * ph + 8 * ob + 2 * l + 1];
+                        wg += sigma * h + lambda;
+                        wh += sigma * (1 + h) + lambda;  // Q3
+                    }
                 for (int j = 0; j < 24; ++j) phix[j] += wg * hx[j];
-                rec[TQ_WH + l] = sigma * (1 + h) + lambda;  // Q3
+                rec[TQ_WH + l] = wh;
             }
         }
         for (int j = 0; j < 24; ++j) rec[TQ_PHIX + j] = phix[j];
@@ -752,11 +805,11 @@ __device__ inline void update_al_block(Smem& sm) {
     const DevSchedule& sc = sm.sc;
     if (threadIdx.x < sc.n_phases * 4) {
         const int ph = threadIdx.x >> 2, l = threadIdx.x & 3;
-        const bool td = !((sc.cmask[ph] >> l) & 1u) && ((sc.nmask[ph] >> l) & 1u);
-        if (td) {
-            const double h = sm.hcon[4 * ph + l];
-            double& sigma = sm.al[8 * ph + 2 * l];
-            double& lambda = sm.al[8 * ph + 2 * l + 1];
+        const double h = sm.hcon[4 * ph + l];
+        for (int ob = 0; ob < 2; ++ob) {
+            if (!((sc.tdmask[ob][ph] >> l) & 1u)) continue;
+            double& sigma = sm.al[16 * ph + 8 * ob + 2 * l];
+            double& lambda = sm.al[16 * ph + 8 * ob + 2 * l + 1];
             if (!(fabs(h) < sm.opt.tconstr_thresh)) {
                 if (fabs(h) > 0.005) { sigma *= sm.opt.update_penalty; sigma = fmin(sigma, sm.cp.td_sigma_max); }
                 else lambda += h * sigma;
@@ -793,7 +846,8 @@ __device__ inline void cold_start_block(Smem& sm) {
     for (int e = threadIdx.x; e < sc.n_stages * 20; e += kThreads) {
         sm.gcon[e] = 0.0; sm.reb[2 * e] = sm.cp.grf_eps; sm.reb[2 * e + 1] = sm.cp.grf_delta;
     }
-    for (int e = threadIdx.x; e < MAXPH * 4; e += kThreads) { sm.hcon[e] = 0.0; sm.al[2 * e] = sm.cp.td_sigma; sm.al[2 * e + 1] = sm.cp.td_lambda; }
+    for (int e = threadIdx.x; e < MAXPH * 4; e += kThreads) sm.hcon[e] = 0.0;
+    for (int e = threadIdx.x; e < MAXPH * 8; e += kThreads) { sm.al[2 * e] = sm.cp.td_sigma; sm.al[2 * e + 1] = sm.cp.td_lambda; }
     if (threadIdx.x == 0) {
         SolverState z = {};
         z.rollout_ok = 1; z.sweep_ok = 1;

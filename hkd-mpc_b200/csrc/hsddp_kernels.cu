@@ -437,6 +437,23 @@ struct GaitLib {
     const float* dt;                             // sample period of gait g
 };
 
+// Per-schedule state of the receding-horizon update (HKDProblemData of HKDProblem.h:28-66 + QuadReference::k_cur / t_cur):
+// everything HKDProblem::update needs beyond the phase table itself.
+struct MpcSched {
+    float start[MAXPH], end[MAXPH];        // pdata->phase_start_times / phase_end_times (absolute, float)
+    unsigned char reach_end[MAXPH];        // pdata->is_phase_reach_end
+    unsigned char has_tconstr[MAXPH];      // add_tconstr_one_phase has bound a reset map to the phase
+    int k_cur;                             // samples the reference window has moved since initialisation
+    float t_cur;                           // QuadReference::t_cur (accumulated in float)
+    // what the last update did, for the per-problem shift kernel
+    int front_nodes;                       // nodes dropped at the front: 1 (pop_front) or horizon+1 of a popped phase
+    int front_phase_popped;                // 1: the first phase was removed
+    int back_new_phase;                    // 1: a new last phase was created (horizon 1), 0: the last phase grew by one stage
+    int old_n_nodes;                       // node count before the update
+    int new_td_phase, new_td_object;       // touchdown-constraint object added by this update (-1: none)
+    int status;                            // 0 ok, 1 reference exhausted, 2 table limits exceeded
+};
+
 __device__ __forceinline__ bool approx_eq_f(float a, float b) { return fabsf(__fsub_rn(a, b)) <= 1e-6f; }
 __device__ __forceinline__ bool approx_leq_f(float a, float b) { return a < b || approx_eq_f(a, b); }
 __device__ __forceinline__ bool approx_geq_f(float a, float b) { return a > b || approx_eq_f(a, b); }
@@ -451,7 +468,7 @@ __device__ __forceinline__ int ref_index_at(float t, float dt, int sz) {
 
 // pass 1: phase tables, one thread per schedule.  status[i] != 0 marks an unusable window.
 __global__ void k_build_phase_tables(GaitLib lib, int n_sched, const int* sched_gait, const int* sched_window, float plan, int node_stride,
-                                     DevSchedule* out, int* status) {
+                                     DevSchedule* out, int* status, MpcSched* mpc) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_sched) return;
     const int gi = sched_gait[i], k0 = sched_window[i];
@@ -459,6 +476,9 @@ __global__ void k_build_phase_tables(GaitLib lib, int n_sched, const int* sched_
     const int sz = (int)roundf(__fdiv_rn(plan, dtg)) + 1;
     DevSchedule d;
     memset(&d, 0, sizeof d);
+    MpcSched m;
+    memset(&m, 0, sizeof m);
+    m.new_td_phase = -1; m.new_td_object = -1;
     int st = 0;
     if (k0 < 0 || k0 + sz >= lib.n_rows[gi]) st = 1;
     const int* contact = lib.contact + 4 * (size_t)(lib.row_off[gi] + k0);
@@ -482,6 +502,8 @@ __global__ void k_build_phase_tables(GaitLib lib, int n_sched, const int* sched_
                 d.cmask[n_phases] = cm;
                 // phase start time, kept as float bits in nmask until the table is complete
                 d.nmask[n_phases] = __float_as_uint(phase_start);
+                d.ss_size[n_phases] = (unsigned char)(hz + 1);  // update_SS_config(horizon + 1), HKDProblem.cpp:104
+                m.start[n_phases] = phase_start; m.end[n_phases] = t; m.reach_end[n_phases] = 0; m.has_tconstr[n_phases] = 1;
                 for (int k = 0; k < hz; ++k) d.ph_of_stage[so + k] = (unsigned char)n_phases;
                 for (int k = 0; k <= hz; ++k) d.ph_of_node[no + k] = (unsigned char)n_phases;
                 no += hz + 1; so += hz;
@@ -497,6 +519,8 @@ __global__ void k_build_phase_tables(GaitLib lib, int n_sched, const int* sched_
     d.ref_off = (long long)i * node_stride;
     out[i] = d;
     status[i] = st;
+    m.status = st;
+    if (mpc) mpc[i] = m;
     (void)dt_mpc;
 }
 
@@ -552,7 +576,206 @@ __global__ void k_build_reference_rows(GaitLib lib, int n_sched, const int* sche
             for (int l = 0; l < 4; ++l) nm |= (c[l] ? 1u : 0u) << l;
         }
         d.nmask[p] = nm;
+        d.tdmask[0][p] = (unsigned char)(~d.cmask[p] & nm & 15u);  // legs going swing -> stance: one touchdown-constraint object
+        d.tdmask[1][p] = 0;
     }
+}
+
+// ---------------------------------------------------------------------------
+// N1: receding-horizon update on the device (HKDProblem::update, HKDMPC/HKD-TrajOpt/HKDProblem.cpp:117-222, as
+// HKDMPCSolver::update drives it every MPC step, HKDMPC.cpp:97-166).  All problems of a batch tick together, so a
+// schedule (gait, initial window) stays shared by the problems that use it:
+//   k_mpc_update_schedules  one thread per schedule: QuadReference::step (QuadReference.cpp:33-47), front end (drop the first
+//                           node or the whole first phase), back end (grow the last phase or open a new one; add_tconstr_one_phase
+//                           when the last phase has reached its end), shooting sets -- with the reference's float time arithmetic
+//   k_mpc_reference_rows    the per-node reference rows of the shifted window (HKDReference.cpp:8-57)
+//   k_mpc_shift             one block per problem: Trajectory::pop_front / push_back_state (TrajectoryManagement.cpp:118-207),
+//                           PathConstraintBase::pop_front / push_back (ConstraintsBase.h:271-280) on the problem-major arrays
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned contact_mask_at(const GaitLib& lib, size_t row) {
+    const int* c = lib.contact + 4 * row;
+    return (c[0] ? 1u : 0u) | (c[1] ? 2u : 0u) | (c[2] ? 4u : 0u) | (c[3] ? 8u : 0u);
+}
+
+__global__ void k_mpc_update_schedules(GaitLib lib, int n_sched, const int* sched_gait, const int* sched_window, float plan, int node_stride,
+                                       DevSchedule* scheds, MpcSched* mpc, int* err) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sched) return;
+    DevSchedule d = scheds[i];
+    MpcSched m = mpc[i];
+    const int gi = sched_gait[i];
+    const float dtg = lib.dt[gi];
+    const float dt_sim = 0.01f, dt_mpc = 0.01f;
+    const int sz = (int)roundf(__fdiv_rn(plan, dtg)) + 1;
+    m.old_n_nodes = d.n_nodes;
+    m.new_td_phase = -1; m.new_td_object = -1;
+    // QuadReference::step(dt_sim)
+    for (int q = 1; approx_leq_f(__fmul_rn((float)q, dtg), dt_sim); ++q) { m.k_cur++; m.t_cur = __fadd_rn(m.t_cur, dtg); }
+    const float new_start = m.t_cur, new_end = __fadd_rn(m.t_cur, plan);
+    const size_t row0 = (size_t)(lib.row_off[gi] + sched_window[i] + m.k_cur);
+    if (sched_window[i] + m.k_cur + sz >= lib.n_rows[gi]) { m.status = 1; mpc[i] = m; atomicMax(err, 1); return; }
+    int n = d.n_phases;
+    // ---- front end ----
+    m.start[0] = __fadd_rn(m.start[0], dt_sim);
+    if (approx_leq_f(m.end[0], new_start)) {  // the first phase has shrunk to a point: pop_front_phase
+        m.front_nodes = d.horizon[0] + 1; m.front_phase_popped = 1;
+        for (int p = 0; p + 1 < n; ++p) {
+            d.horizon[p] = d.horizon[p + 1]; d.cmask[p] = d.cmask[p + 1]; d.nmask[p] = d.nmask[p + 1]; d.ss_size[p] = d.ss_size[p + 1];
+            d.tdmask[0][p] = d.tdmask[0][p + 1]; d.tdmask[1][p] = d.tdmask[1][p + 1];
+            m.start[p] = m.start[p + 1]; m.end[p] = m.end[p + 1]; m.reach_end[p] = m.reach_end[p + 1]; m.has_tconstr[p] = m.has_tconstr[p + 1];
+        }
+        --n;
+    } else {
+        m.front_nodes = 1; m.front_phase_popped = 0;
+        d.horizon[0]--;
+        m.start[0] = new_start;
+    }
+    // ---- back end ----
+    const unsigned newc = contact_mask_at(lib, row0 + ref_index_at(__fsub_rn(new_end, new_start), dtg, sz));
+    const bool change = newc != d.cmask[n - 1];
+    if (change && m.reach_end[n - 1]) {
+        if (n >= MAXPH) { m.status = 2; mpc[i] = m; atomicMax(err, 2); return; }
+        m.start[n] = m.end[n - 1]; m.end[n] = new_end; m.reach_end[n] = 0; m.has_tconstr[n] = 0;
+        d.horizon[n] = (int)roundf(__fdiv_rn(__fsub_rn(m.end[n], m.start[n]), dt_sim));
+        d.cmask[n] = newc; d.nmask[n] = 0; d.tdmask[0][n] = 0; d.tdmask[1][n] = 0; d.ss_size[n] = 0;  // (SinglePhase::initialization clears SS_set)
+        m.back_new_phase = 1;
+        ++n;
+    } else {
+        m.end[n - 1] = new_end;
+        if (change) m.reach_end[n - 1] = 1;
+        d.horizon[n - 1]++;
+        m.back_new_phase = 0;
+    }
+    if (m.reach_end[n - 1]) {  // add_tconstr_one_phase(last phase): the contact after it is the reference's at plan_duration + dt_mpc
+        const unsigned nm = contact_mask_at(lib, row0 + ref_index_at(__fadd_rn(plan, dt_mpc), dtg, sz));
+        d.nmask[n - 1] = nm; m.has_tconstr[n - 1] = 1;
+        const unsigned td = ~d.cmask[n - 1] & nm & 15u;
+        if (td) {
+            const int ob = d.tdmask[0][n - 1] ? (d.tdmask[1][n - 1] ? 2 : 1) : 0;
+            if (ob >= 2) { m.status = 2; mpc[i] = m; atomicMax(err, 2); return; }  // (needs a one-sample contact blip in the reference)
+            d.tdmask[ob][n - 1] = (unsigned char)td;
+            m.new_td_phase = n - 1; m.new_td_object = ob;
+        }
+    }
+    // ---- shooting configuration (HKDProblem.cpp:205-221) and the derived tables ----
+    int so = 0, no = 0;
+    for (int p = 0; p < n; ++p) {
+        if ((p == n - 1 && d.horizon[p] > 2) || p < n - 1) d.ss_size[p] = (unsigned char)(d.horizon[p] + 1);
+        d.node_off[p] = no; d.stage_off[p] = so;
+        if (d.horizon[p] < 1 || so + d.horizon[p] > HSDDP_MAX_STAGES || no + d.horizon[p] + 1 > node_stride) { m.status = 2; mpc[i] = m; atomicMax(err, 2); return; }
+        for (int k = 0; k < d.horizon[p]; ++k) d.ph_of_stage[so + k] = (unsigned char)p;
+        for (int k = 0; k <= d.horizon[p]; ++k) d.ph_of_node[no + k] = (unsigned char)p;
+        no += d.horizon[p] + 1; so += d.horizon[p];
+    }
+    d.n_phases = n; d.n_stages = so; d.n_nodes = no;
+    scheds[i] = d;
+    mpc[i] = m;
+}
+
+__global__ void k_mpc_reference_rows(GaitLib lib, int n_sched, const int* sched_gait, const int* sched_window, float plan,
+                                     const DevSchedule* scheds, const MpcSched* mpc, double* xr, double* ur, double* prel) {
+    const int i = blockIdx.x;
+    if (i >= n_sched || mpc[i].status) return;
+    const DevSchedule& d = scheds[i];
+    const MpcSched& m = mpc[i];
+    const int gi = sched_gait[i];
+    const float dtg = lib.dt[gi];
+    const int sz = (int)roundf(__fdiv_rn(plan, dtg)) + 1;
+    const size_t row0 = (size_t)(lib.row_off[gi] + sched_window[i] + m.k_cur);
+    for (int n = threadIdx.x; n < d.n_nodes; n += blockDim.x) {
+        const int ph = d.ph_of_node[n], k = n - d.node_off[ph];
+        const size_t node = (size_t)d.ref_off + n;
+        // time seen by the cost callbacks: float(t_offset + k*dt), t_offset = start - start[0] in float (set_time_offset)
+        const float t_offset = __fsub_rn(m.start[ph], m.start[0]);
+        const float tc = (float)__dadd_rn((double)t_offset, __dmul_rn((double)k, d.dt));
+        const size_t r = row0 + ref_index_at(tc, dtg, sz);
+        double* x = xr + 24 * node;
+        for (int j = 0; j < 12; ++j) x[j] = lib.body_state[12 * r + j];
+        for (int l = 0; l < 4; ++l)
+            for (int j = 0; j < 3; ++j)
+                x[12 + 3 * l + j] = (lib.contact[4 * r + l] > 0) ? lib.foot[12 * r + 3 * l + j] : lib.qJ[12 * r + 3 * l + j];
+        for (int j = 0; j < 12; ++j) { ur[24 * node + j] = lib.grf[12 * r + j]; ur[24 * node + 12 + j] = 0.0; }
+        for (int l = 0; l < 4; ++l)
+            for (int j = 0; j < 3; ++j) prel[12 * node + 3 * l + j] = lib.foot[12 * r + 3 * l + j] - lib.body_state[12 * r + 3 + j];
+    }
+}
+
+// rows [shift, total) of a row-major array move down to [0, total - shift); the last `shift` rows are then filled by the caller.
+// In place: a chunk is read by every thread before any thread writes it (the destination of a chunk overlaps only chunks
+// that have been read already).
+__device__ inline void shift_rows_down(double* a, int total_rows, int row_len, int shift_rows) {
+    const int n = (total_rows - shift_rows) * row_len, off = shift_rows * row_len;
+    for (int c = 0; c < n; c += 4 * kThreads) {
+        double v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const int e = c + q * kThreads + threadIdx.x; v[q] = (e < n) ? a[e + off] : 0.0; }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const int e = c + q * kThreads + threadIdx.x; if (e < n) a[e] = v[q]; }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_mpc_shift(BatchPtrs bp, const MpcSched* mpc) {
+    const int pid = blockIdx.x, tid = threadIdx.x;
+    const int sid = bp.sched_id[pid];
+    const MpcSched& m = mpc[sid];
+    if (m.status) return;
+    const DevSchedule& sc = bp.sched[sid];  // the schedule AFTER the update
+    __shared__ double xback[24];
+    const size_t sn = (size_t)bp.max_nodes * 24, ss = (size_t)bp.max_stages * 24;
+    double *Xbar = bp.Xbar + pid * sn, *X = bp.X + pid * sn, *Ubar = bp.Ubar + pid * ss, *U = bp.U + pid * ss;
+    double* K = bp.K + (size_t)pid * bp.max_stages * 288;
+    double* reb = bp.reb + (size_t)pid * bp.max_stages * 40;
+    double* al = bp.al + (size_t)pid * MAXPH * 16;
+    double* hcon = bp.hcon + (size_t)pid * MAXPH * 4;
+    const int N = sc.n_stages;              // unchanged by an update: one stage leaves at the front, one arrives at the back
+    const int old_nodes = m.old_n_nodes, new_nodes = sc.n_nodes, kept = old_nodes - m.front_nodes;
+    if (tid < 24) xback[tid] = X[24 * (old_nodes - 1) + tid];  // X.back() of the last phase, before anything moves
+    __syncthreads();
+    shift_rows_down(Xbar, old_nodes, 24, m.front_nodes);
+    shift_rows_down(X, old_nodes, 24, m.front_nodes);
+    shift_rows_down(Ubar, N, 24, 1);
+    shift_rows_down(U, N, 24, 1);
+    shift_rows_down(K, N, 288, 1);
+    shift_rows_down(reb, N, 40, 1);
+    // back end
+    for (int e = tid; e < (new_nodes - kept) * 24; e += kThreads) {
+        const double v = m.back_new_phase ? 0.0 : xback[e % 24];  // push_back_state(X.back()) / a zero-initialised Trajectory
+        Xbar[24 * kept + e] = v; X[24 * kept + e] = v;
+    }
+    for (int e = tid; e < 24; e += kThreads) { Ubar[24 * (N - 1) + e] = 0.0; U[24 * (N - 1) + e] = 0.0; }
+    for (int e = tid; e < 288; e += kThreads) K[288 * (size_t)(N - 1) + e] = 0.0;
+    for (int e = tid; e < 20; e += kThreads) {
+        // the new stage's ReB parameters: a copy of the phase's last stage (params.push_back(params.back())), the initial
+        // values for a new phase
+        const bool copy = !m.back_new_phase && N >= 2;
+        reb[40 * (N - 1) + 2 * e] = copy ? reb[40 * (N - 2) + 2 * e] : bp.cp.grf_eps;
+        reb[40 * (N - 1) + 2 * e + 1] = copy ? reb[40 * (N - 2) + 2 * e + 1] : bp.cp.grf_delta;
+    }
+    __syncthreads();
+    // per-phase touchdown data: phases move down by one when the first phase was removed
+    if (m.front_phase_popped) {
+        double v[2];
+        for (int q = 0; q < 2; ++q) { const int e = tid + q * kThreads; v[q] = (e < (MAXPH - 1) * 16) ? al[e + 16] : 0.0; }
+        const double hv = (tid < (MAXPH - 1) * 4) ? hcon[tid + 4] : 0.0;
+        __syncthreads();
+        for (int q = 0; q < 2; ++q) { const int e = tid + q * kThreads; if (e < (MAXPH - 1) * 16) al[e] = v[q]; }
+        if (tid < (MAXPH - 1) * 4) hcon[tid] = hv;
+        __syncthreads();
+    }
+    if (tid < 8) {
+        const int L = sc.n_phases - 1;
+        if (m.back_new_phase) {  // a new phase starts with fresh constraint objects
+            al[16 * L + 2 * tid] = bp.cp.td_sigma; al[16 * L + 2 * tid + 1] = bp.cp.td_lambda;
+            if (tid < 4) hcon[4 * L + tid] = 0.0;
+        }
+        if (m.new_td_phase >= 0 && tid < 4) {  // a touchdown-constraint object added by this update: initial AL parameters
+            al[16 * m.new_td_phase + 8 * m.new_td_object + 2 * tid] = bp.cp.td_sigma;
+            al[16 * m.new_td_phase + 8 * m.new_td_object + 2 * tid + 1] = bp.cp.td_lambda;
+        }
+    }
+    if (tid < 24) Ubar[tid] = 0.0;  // trajectory_ptrs.front()->Ubar[0].setZero(), HKDProblem.cpp:220
 }
 
 // FP64 throughput probes (roofline denominators measured on the box)
@@ -630,6 +853,15 @@ struct hsddp_batch {
     cudaEvent_t gevent[kMaxGroups] = {};
     cudaEvent_t ev_fork = nullptr;
     hsddp_mpc_command* d_cmd = nullptr;  // lives in `allocs` (freed with the problem set)
+    // receding-horizon update (problems set through hsddp_batch_set_problems_from_gaits: the gait library is resident in HBM)
+    bool mpc_ready = false;
+    GaitLib lib{};
+    int *d_sched_gait = nullptr, *d_sched_window = nullptr, *d_mpc_err = nullptr;
+    MpcSched* d_mpc = nullptr;
+    float plan = 0.f;
+    int node_stride = 0, n_sched = 0;
+    bool h_sched_stale = false;
+    cudaEvent_t ev_u0 = nullptr, ev_u1 = nullptr;
 };
 
 namespace {
@@ -648,6 +880,8 @@ void free_problem_allocs(hsddp_batch* b) {
     b->allocs.clear();
     b->d_cmd = nullptr;
     b->has_problems = false;
+    b->mpc_ready = false;
+    b->h_sched_stale = false;
 }
 
 hsddp_options default_options() {
@@ -708,6 +942,8 @@ int hsddp_batch_create(int device, hsddp_batch** out) {
     CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&b->ev0));
     CK(cudaEventCreate(&b->ev1));
+    CK(cudaEventCreate(&b->ev_u0));
+    CK(cudaEventCreate(&b->ev_u1));
     for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&b->slots[i]));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
@@ -741,6 +977,8 @@ int hsddp_batch_destroy(hsddp_batch* b) {
     free_problem_allocs(b);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->ev_u0) cudaEventDestroy(b->ev_u0);
+    if (b->ev_u1) cudaEventDestroy(b->ev_u1);
     for (int i = 0; i < 8; ++i) if (b->slots[i]) cudaEventDestroy(b->slots[i]);
     if (b->stream) cudaStreamDestroy(b->stream);
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
@@ -774,7 +1012,7 @@ static int alloc_workspace(hsddp_batch* b, int n_problems, int max_stages, int m
     if ((rc = dalloc(b, &bp.gcon, P * max_stages * 20))) return rc;
     if ((rc = dalloc(b, &bp.reb, P * max_stages * 40))) return rc;
     if ((rc = dalloc(b, &bp.hcon, P * MAXPH * 4))) return rc;
-    if ((rc = dalloc(b, &bp.al, P * MAXPH * 8))) return rc;
+    if ((rc = dalloc(b, &bp.al, P * MAXPH * 16))) return rc;
     if ((rc = dalloc(b, &bp.g0h0, P * 600))) return rc;
     if ((rc = dalloc(b, &bp.state, P))) return rc;
     if ((rc = dalloc(b, &bp.ctl, P))) return rc;
@@ -827,6 +1065,8 @@ int hsddp_batch_set_problems(hsddp_batch* b, int n_schedules, const hsddp_schedu
             unsigned cm = 0, nm = 0;
             for (int l = 0; l < 4; ++l) { cm |= (s.contact[p][l] ? 1u : 0u) << l; nm |= (s.next_contact[p][l] ? 1u : 0u) << l; }
             d.cmask[p] = cm; d.nmask[p] = nm;
+            d.ss_size[p] = (unsigned char)(s.horizon[p] + 1);
+            d.tdmask[0][p] = (unsigned char)(~cm & nm & 15u); d.tdmask[1][p] = 0;
             for (int k = 0; k < s.horizon[p] && so + k < HSDDP_MAX_STAGES; ++k) d.ph_of_stage[so + k] = (unsigned char)p;
             for (int k = 0; k <= s.horizon[p] && no + k < HSDDP_MAX_STAGES + MAXPH; ++k) d.ph_of_node[no + k] = (unsigned char)p;
             no += s.horizon[p] + 1; so += s.horizon[p];
@@ -923,7 +1163,10 @@ int hsddp_batch_set_problems_from_gaits(hsddp_batch* b, int n_gaits, const int32
         (rc = dalloc(b, &d_ur, total_nodes * 24)) || (rc = dalloc(b, &d_prel, total_nodes * 12)) || (rc = dalloc(b, &d_xinit, total_nodes * 24)))
         return rc;
     CK(cudaMemcpy(d_sid, schedule_id, sizeof(int) * n_problems, cudaMemcpyHostToDevice));
-    k_build_phase_tables<<<(n_schedules + 127) / 128, 128, 0, b->stream>>>(lib, n_schedules, d_sg, d_sw, plan_duration, node_stride, d_sched, d_status);
+    MpcSched* d_mpc; int* d_err;
+    if ((rc = dalloc(b, &d_mpc, (size_t)n_schedules)) || (rc = dalloc(b, &d_err, (size_t)4))) return rc;
+    CK(cudaMemsetAsync(d_err, 0, 4 * sizeof(int), b->stream));
+    k_build_phase_tables<<<(n_schedules + 127) / 128, 128, 0, b->stream>>>(lib, n_schedules, d_sg, d_sw, plan_duration, node_stride, d_sched, d_status, d_mpc);
     k_build_reference_rows<<<n_schedules, 128, 0, b->stream>>>(lib, n_schedules, d_sg, d_sw, plan_duration, node_stride, d_sched, d_status, d_xr, d_ur, d_prel, d_xinit);
     CK(cudaGetLastError());
     b->n_step_launches += 2;
@@ -940,11 +1183,60 @@ int hsddp_batch_set_problems_from_gaits(hsddp_batch* b, int n_gaits, const int32
         max_nodes = std::max(max_nodes, b->h_sched[i].n_nodes);
     }
     b->h_sched_id.assign(schedule_id, schedule_id + n_problems);
+    // (node rows with headroom: a receding-horizon update can add phases, i.e. nodes, while the stage count stays the same)
+    max_nodes = std::min(node_stride, max_stages + MAXPH);
     bp.n_problems = n_problems; bp.max_stages = max_stages; bp.max_nodes = max_nodes;
     bp.sched = d_sched; bp.sched_id = d_sid; bp.xr = d_xr; bp.ur = d_ur; bp.prel = d_prel; bp.xinit = d_xinit;
     if ((rc = alloc_workspace(b, n_problems, max_stages, max_nodes))) return rc;
     b->has_problems = true;
+    b->lib = lib; b->d_sched_gait = d_sg; b->d_sched_window = d_sw; b->d_mpc = d_mpc; b->d_mpc_err = d_err;
+    b->plan = plan_duration; b->node_stride = node_stride; b->n_sched = n_schedules; b->mpc_ready = true;
     return hsddp_batch_reset(b);
+}
+
+/* HKDProblem::update for every problem of the batch (see the kernels above).  The solver state that the reference keeps
+ * across MPC steps stays in the handle: nominal trajectories, gains, ReB / AL parameters. */
+int hsddp_batch_mpc_update(hsddp_batch* b) {
+    if (!b || !b->has_problems) { g_last_error = "no problems set"; return HSDDP_ERR_STATE; }
+    if (!b->mpc_ready) { g_last_error = "hsddp_batch_mpc_update needs the gait library on the device: set the problems with hsddp_batch_set_problems_from_gaits"; return HSDDP_ERR_STATE; }
+    CK(cudaSetDevice(b->device));
+    CK(cudaEventRecord(b->ev_u0, b->stream));
+    DevSchedule* d_sched = const_cast<DevSchedule*>(b->bp.sched);
+    k_mpc_update_schedules<<<(b->n_sched + 127) / 128, 128, 0, b->stream>>>(b->lib, b->n_sched, b->d_sched_gait, b->d_sched_window, b->plan, b->node_stride,
+                                                                              d_sched, b->d_mpc, b->d_mpc_err);
+    k_mpc_reference_rows<<<b->n_sched, 128, 0, b->stream>>>(b->lib, b->n_sched, b->d_sched_gait, b->d_sched_window, b->plan, d_sched, b->d_mpc,
+                                                            const_cast<double*>(b->bp.xr), const_cast<double*>(b->bp.ur), const_cast<double*>(b->bp.prel));
+    k_mpc_shift<<<b->bp.n_problems, kThreads, 0, b->stream>>>(b->bp, b->d_mpc);
+    CK(cudaGetLastError());
+    b->n_step_launches += 3;
+    CK(cudaEventRecord(b->ev_u1, b->stream));
+    int err = 0;
+    CK(cudaMemcpyAsync(&err, b->d_mpc_err, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    b->h_sched_stale = true;
+    b->cold = false;
+    b->have_order = false;  // (the queue order of the previous problem layout is still a good hint, but the solve after a tick is 2 iterations long)
+    if (err) {
+        g_last_error = err == 1 ? "receding-horizon update: the reference table is exhausted" : "receding-horizon update: schedule exceeds HSDDP_MAX_PHASES / node capacity";
+        return err == 1 ? HSDDP_ERR_ARG : HSDDP_ERR_UNSUPPORTED;
+    }
+    return HSDDP_OK;
+}
+
+int hsddp_batch_last_update_ms(hsddp_batch* b, float* ms) {
+    if (!b || !ms) return HSDDP_ERR_ARG;
+    CK(cudaSetDevice(b->device));
+    CK(cudaEventSynchronize(b->ev_u1));
+    CK(cudaEventElapsedTime(ms, b->ev_u0, b->ev_u1));
+    return HSDDP_OK;
+}
+
+// the host copy of the phase tables (dense gain / Jacobian getters) after a receding-horizon update
+static int refresh_host_schedules(hsddp_batch* b) {
+    if (!b->h_sched_stale) return HSDDP_OK;
+    CK(cudaMemcpy(b->h_sched.data(), b->bp.sched, sizeof(DevSchedule) * b->h_sched.size(), cudaMemcpyDeviceToHost));
+    b->h_sched_stale = false;
+    return HSDDP_OK;
 }
 
 /* device-built schedule i back on the host (tests): phase table + reference rows, row counts as in hsddp_schedule */
@@ -1202,7 +1494,9 @@ int hsddp_batch_get_scalars(hsddp_batch* b, double* out) {
 }
 
 // Dense column-major 24x24 feedback gains for stages [row0, row0+nrows) from the compact K_r store.
+static int refresh_host_schedules(hsddp_batch* b);
 static int get_gains(hsddp_batch* b, int row0, int nrows, double* out) {
+    if (int rc = refresh_host_schedules(b)) return rc;
     const BatchPtrs& bp = b->bp;
     const size_t P = (size_t)bp.n_problems;
     if (row0 < 0 || nrows <= 0 || row0 + nrows > bp.max_stages) return HSDDP_ERR_ARG;
@@ -1242,7 +1536,7 @@ static int array_spec(hsddp_batch* b, int which, double** dev, size_t* per_probl
         case HSDDP_ARR_K: *dev = bp.K; *per_problem = (size_t)bp.max_stages * 288; return 3;
         case HSDDP_ARR_GCON: *dev = bp.gcon; *per_problem = (size_t)bp.max_stages * 20; return 0;
         case HSDDP_ARR_HCON: *dev = bp.hcon; *per_problem = (size_t)MAXPH * 4; return 0;
-        case HSDDP_ARR_AL: *dev = bp.al; *per_problem = (size_t)MAXPH * 8; return 0;
+        case HSDDP_ARR_AL: *dev = bp.al; *per_problem = (size_t)MAXPH * 16; return 0;
         case HSDDP_ARR_REB: *dev = bp.reb; *per_problem = (size_t)bp.max_stages * 40; return 0;
         case HSDDP_ARR_G0: *dev = bp.g0h0; *per_problem = 600; return 1;  // strided special cases
         case HSDDP_ARR_H0: *dev = bp.g0h0; *per_problem = 600; return 2;
@@ -1258,6 +1552,7 @@ int hsddp_batch_get_array(hsddp_batch* b, int which, double* out) {
     if (which == HSDDP_ARR_A || which == HSDDP_ARR_B || which == HSDDP_ARR_LX || which == HSDDP_ARR_LU ||
         which == HSDDP_ARR_LUU || which == HSDDP_ARR_LXX) {
         // dense views reconstructed on the host from the compact LQ records
+        if (int rc = refresh_host_schedules(b)) return rc;
         std::vector<double> lq(P * bp.max_stages * CR_STRIDE);
         CK(cudaMemcpy(lq.data(), bp.lq, lq.size() * sizeof(double), cudaMemcpyDeviceToHost));
         const bool vec = (which == HSDDP_ARR_LX || which == HSDDP_ARR_LU);
@@ -1341,7 +1636,7 @@ int hsddp_batch_get_array_rows(hsddp_batch* b, int which, int row0, int nrows, d
         case HSDDP_ARR_K: cols = 576; break;
         case HSDDP_ARR_GCON: cols = 20; break;
         case HSDDP_ARR_HCON: cols = 4; break;
-        case HSDDP_ARR_AL: cols = 8; break;
+        case HSDDP_ARR_AL: cols = 16; break;
         case HSDDP_ARR_REB: cols = 40; break;
         default: cols = 24; break;
     }

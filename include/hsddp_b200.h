@@ -163,6 +163,24 @@ int hsddp_batch_set_initial_condition(hsddp_batch* b, const double* x0);
 /* re-arm the cold-start guess and the ReB/AL parameters without re-uploading schedules */
 int hsddp_batch_reset(hsddp_batch* b);
 
+/* HKDProblem::update (HKDMPC/HKD-TrajOpt/HKDProblem.cpp:117-222) for every problem of the batch: the receding-horizon shift
+ * by one MPC step that HKDMPCSolver::update runs before each re-solve (HKDMPC/HKDMPC.cpp:97-166), on the device.
+ *   - the reference window moves by one sample (QuadReference::step, Reference/QuadReference.cpp:33-47);
+ *   - front end: the first node of the first phase is dropped (Trajectory::pop_front, TrajectoryManagement.cpp:118-146;
+ *     PathConstraintBase::pop_front, ConstraintsBase.h:271-275), or the whole phase once it has shrunk to a point;
+ *   - back end: the last phase grows by one stage whose state is a copy of the last trial state
+ *     (Trajectory::push_back_state, TrajectoryManagement.cpp:178-207) or, one step after a contact change of the reference,
+ *     a new phase of horizon 1 is opened with a zero-initialised trajectory, an EMPTY shooting set and no reset map;
+ *     a phase that reaches its end gets its reset map and touchdown constraint then (add_tconstr_one_phase, a second
+ *     constraint object if it already had one);
+ *   - shooting sets, time offsets and the first control (zeroed) as HKDProblem.cpp:205-221; ReB / AL parameters persist
+ *     (reset_params is a no-op in the reference).
+ * Needs the gait library on the device (hsddp_batch_set_problems_from_gaits).  Follow with
+ * hsddp_batch_set_initial_condition (the measured state) and hsddp_batch_solve with max_AL_iter = 2, max_DDP_iter = 1. */
+int hsddp_batch_mpc_update(hsddp_batch* b);
+/* milliseconds of the last update's kernels (CUDA events) */
+int hsddp_batch_last_update_ms(hsddp_batch* b, float* ms);
+
 /* MultiPhaseDDP::solve(HSDDP_OPTION) (MultiPhaseDDP.cpp:232-428) for every problem:
  * one persistent kernel, one thread block per problem, iteration control on the device. */
 int hsddp_batch_solve(hsddp_batch* b, const hsddp_options* opt);
@@ -226,7 +244,7 @@ int hsddp_batch_get_scalars(hsddp_batch* b, double* out /*[n_problems][8]*/);
 #define HSDDP_ARR_H0 27    /* [1][576]  value Hessian at the first node after the last sweep  */
 #define HSDDP_ARR_GCON 52  /* [stages][20] GRF constraint values, 5 per leg (swing legs zero) */
 #define HSDDP_ARR_HCON 50  /* [HSDDP_MAX_PHASES][4] touchdown constraint values per phase/leg */
-#define HSDDP_ARR_AL 51    /* [HSDDP_MAX_PHASES][4][2] (sigma, lambda) */
+#define HSDDP_ARR_AL 51    /* [HSDDP_MAX_PHASES][2][4][2] (sigma, lambda) per touchdown-constraint object (0, 1) and leg */
 #define HSDDP_ARR_REB 53   /* [stages][20][2] ReB parameters (eps, delta) of the GRF rows, 5 per leg (REB_Param_Struct, ConstraintsBase.h:58-70) */
 int hsddp_batch_get_array(hsddp_batch* b, int which, double* out);
 /* overwrite Xbar/X/Ubar/U (warm start); same layout as the getter */

@@ -351,6 +351,73 @@ def test_parity_at_scale_config4_all_schedules(pkg, orc, workloads):
     assert np.all(well[conv]) and conv.sum() >= 30
 
 
+def test_receding_horizon_ticks_match_oracle(pkg, orc, workloads):
+    """N1: HKDProblem::update on the device + warm re-solve with the reference's MPC budget (2 AL x 1 DDP, HKDMPC.cpp:97-166),
+    30 consecutive ticks of nine problems (three gaits, several windows, two problems sharing a schedule), against the oracle's
+    restated update.  The windows are chosen so that the ticks exercise: a first phase shrinking to a point and being removed, a
+    last phase growing, a phase reaching its end (second touchdown-constraint object: trot window 0 at tick 0), a new last
+    phase with an empty shooting set (horizon 1 and 2), and the shooting set being restored at horizon 3."""
+    order = list(workloads.GAITS)
+    refs = {g: pkg.QuadReference(workloads.gait_path(g)) for g in order}
+    cases = [("trot", 0), ("trot", 0), ("trot", 23), ("bound", 0), ("bound", 5), ("bound", 240), ("pronk", 0), ("pronk", 100), ("pronk", 40)]
+    keys, sid = [], []
+    for c in cases:
+        if c not in keys:
+            keys.append(c)
+        sid.append(keys.index(c))
+    B = pkg.MultiPhaseDDPBatch(0)
+    B.set_problems_from_gaits([refs[g] for g in order], [order.index(g) for g, _ in keys], [k for _, k in keys], 0.6, sid)
+    tables = {g: _table(orc, g) for g in order}
+    models = [orc.default_model()] + ([orc.MODEL_PORT] if orc.ref_available() else [])
+    P = [[orc.Problem(tables[g], k0, 0.6, model=m) for m in models] for g, k0 in cases]
+    x0 = np.zeros((len(cases), 24))
+    for i, (g, k0) in enumerate(cases):
+        body = np.load(workloads.gait_path(g))["body_state"][k0].astype(np.float64)
+        if i == 1:
+            body = body + workloads.perturbation(1)
+        x0[i, :12] = body
+        x0[i, 12:] = pkg.compute_hkd_state(body[0:3], body[3:6], workloads.DEFAULT_QJ, P[i][0].phases[0]["contact"])
+    tick_opt = dict(max_AL_iter=2, max_DDP_iter=1)
+    alive = np.ones(len(cases), bool)  # problems still well-posed (the oracle's two model back ends take the same decisions)
+    seen = dict(pop_phase=False, new_phase=False, two_objects=False, empty_ss=False)
+    for tick in range(-1, 30):
+        if tick >= 0:
+            x0 = np.stack([P[i][0].get("Xbar")[1] for i in range(len(cases))])  # "measured" state: the plan's next node
+            B.mpc_update()
+        B.set_initial_condition(x0)
+        B.solve(pkg.Options(**tick_opt) if tick >= 0 else None)
+        info, Xb, Ub, K = B.info(), B.get("Xbar"), B.get("Ubar"), B.get("K")
+        for i in range(len(cases)):
+            res = []
+            for Q in P[i]:
+                if tick >= 0:
+                    seen["pop_phase"] |= Q.phases[0]["horizon"] == 1  # (a first phase of one stage shrinks to a point: removed)
+                    Q.mpc_update()
+                Q.x0 = x0[i]
+                res.append(Q.solve(tick_opt if tick >= 0 else None)[0])
+            Q = P[i][0]
+            seen["new_phase"] |= tick >= 0 and Q.phases[-1]["horizon"] == 1
+            seen["two_objects"] |= any(p["n_td_objects"] > 1 for p in Q.phases)
+            seen["empty_ss"] |= Q.phases[-1]["ss_size"] == 0
+            if len(res) > 1 and not (res[0]["n_iter"] == res[1]["n_iter"] and res[0]["status"] == res[1]["status"]
+                                     and abs(res[0]["cost"] - res[1]["cost"]) <= 1e-10 * abs(res[0]["cost"])):
+                alive[i] = False
+            if not alive[i]:
+                continue
+            s = res[0]
+            d = B.device_schedule(sid[i])
+            assert d["n_phases"] == Q.n_phases and d["horizon"] == [p["horizon"] for p in Q.phases], (tick, i, d["horizon"], Q.phases)
+            assert d["contact"] == [p["contact"] for p in Q.phases], (tick, i)
+            assert info["n_iter"][i] == int(s["n_iter"]) and info["status"][i] == int(s["status"]), (tick, i, s, info[i])
+            assert abs(info["cost"][i] - s["cost"]) <= RTOL * abs(s["cost"]), (tick, i, info["cost"][i], s["cost"])
+            S, N = Q.n_states, Q.n_stages
+            assert N == 60
+            assert rel_err_rows(Xb[i, :S], Q.get("Xbar")) < RTOL and rel_err_rows(Ub[i, :N], Q.get("Ubar")) < RTOL, (tick, i)
+            assert rel_err_rows(K[i, :N], Q.get("K")) < RTOL, (tick, i)
+    assert alive.sum() >= 7, alive
+    assert all(seen.values()), seen
+
+
 def test_reb_update_rule_off_the_noop(pkg, orc, workloads):
     """update_REB_params with update_relax, update_ReB != 1 (the shipped settings make it a no-op, ConstraintsBase.h:168-183):
     a weak barrier (small eps) lets the GRF constraints be violated, so the rule fires: eps *= update_ReB and
