@@ -365,17 +365,51 @@ def main():
                    "reps": len(dev_ms), "iterations": int(i1["n_iter"][0]),
                    "what": "one cold Mini Cheetah trot solve (config 1), batch 1: p50_ms = solve kernel on the device (CUDA events), "
                            "p50_wall_ms = host wall clock of reset + solve + info read-back"}
-        # the reference's MPC tick (HKDMPC.cpp:97-166): shift the horizon by one step (HKDProblem::update), warm re-solve with
-        # 2 AL x 1 DDP iterations from the shifted previous solution
-        if hasattr(B1, "mpc_update"):
-            tick_ms = []
-            for rep in range(40):
-                B1.mpc_update()
-                B1.solve(pkg.Options(max_AL_iter=2, max_DDP_iter=1))
-                if rep >= 3:
-                    tick_ms.append(B1.last_solve_ms() + B1.last_update_ms())
-            latency["mpc_tick_p50_ms"] = float(np.median(tick_ms))
-            latency["mpc_tick_what"] = "HKDProblem::update (receding-horizon shift on the device) + warm re-solve, 2 AL x 1 DDP iteration, device time"
+        # the reference's MPC tick (HKDMPC.cpp:97-166): shift the horizon by one step (HKDProblem::update), take the "measured"
+        # state (here: the plan's next node), warm re-solve with 2 AL x 1 DDP iterations, ship the command
+        tick_opt = pkg.Options(max_AL_iter=2, max_DDP_iter=1)
+        Bt = wl.gait_batch(pkg, w1, local_rank)
+        Bt.solve(opt)
+        tick_ms, tick_wall = [], []
+        for rep in range(43):
+            x_next = Bt.get_rows("Xbar", 1, 1)[:, 0, :].copy()
+            t1 = time.perf_counter()
+            Bt.mpc_update()
+            Bt.set_initial_condition(x_next)
+            Bt.solve(tick_opt)
+            Bt.mpc_command(n_cmd)
+            t2 = time.perf_counter()
+            if rep >= 3:
+                tick_ms.append(Bt.last_solve_ms() + Bt.last_update_ms()); tick_wall.append((t2 - t1) * 1e3)
+        latency["mpc_tick_p50_ms"] = float(np.median(tick_ms))
+        latency["mpc_tick_p50_wall_ms"] = float(np.median(tick_wall))
+        latency["mpc_tick_what"] = ("one robot, one MPC step: HKDProblem::update on the device (receding-horizon shift) + warm re-solve, 2 AL x 1 DDP "
+                                    "iteration; p50_ms = device time of the update and solve kernels, p50_wall_ms = host wall clock incl. the "
+                                    "initial-state upload and the command read-back")
+        del Bt
+        # the same tick for a batch of robots: 4,096 config-3 problems (or the batch, if smaller)
+        nb = min(4096, w.n)
+        _, eb = wl.define(args.config, 2 * nb, args.plan)
+        wb = wl.from_entries(pkg, "mpc tick batch", wl.with_room_for_ticks(eb, 16, args.plan)[:nb], args.plan)
+        Bb = wl.gait_batch(pkg, wb, local_rank)
+        Bb.solve(opt)
+        cmd_b = np.zeros(wb.n, dtype=pkg.CMD_DTYPE)
+        walls = []
+        for rep in range(13):
+            x_next = Bb.get_rows("Xbar", 1, 1)[:, 0, :].copy()
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            Bb.mpc_update()
+            Bb.set_initial_condition(x_next)
+            Bb.solve(tick_opt)
+            Bb.mpc_command(n_cmd, out=cmd_b)
+            t2 = time.perf_counter()
+            if rep >= 3:
+                walls.append(t2 - t1)
+        latency["mpc_batch"] = {"robots": wb.n, "tick_ms": float(np.median(walls) * 1e3), "ticks_per_s": float(wb.n / np.median(walls)),
+                                "update_ms": Bb.last_update_ms(), "solve_ms": Bb.last_solve_ms(),
+                                "what": "wall clock of one MPC step of every robot: update + initial states from the host + re-solve + commands to the host"}
+        del Bb
         del B1
 
     if rank == 0:

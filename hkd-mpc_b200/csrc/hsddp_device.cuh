@@ -352,6 +352,40 @@ __device__ inline void resetmap_partial_block(const double* Jc_all, unsigned c, 
 // multiply-add per control instead of re-reading 2.3 KB of gains per stage and trial.  Differs from the literal form
 // by the rounding of (Xbar + eps dX) - Xbar only.  LINEARISED = false evaluates the literal form (step-level API,
 // where the caller decides what precedes a rollout).
+// Nodes OUTSIDE the shooting set.  HKDProblem::initialization makes every node a shooting node; after a receding-horizon
+// update the LAST phase can have fewer (DevSchedule::ss_size): those nodes are propagated, X[k] = Xsim[k] (X[0] = x_init when
+// the set is empty), and their controls see the true feedback K (X - Xbar) (SinglePhase.cpp:185-220).  At most three stages,
+// walked by ONE thread after the parallel pass of hybrid_rollout_block; out of line so that its local arrays cost the
+// common path nothing.  Returns the first diverged stage (0x7fffffff: none).
+__device__ __noinline__ int rollout_unshot_tail(Smem& sm, double eps, double* xs, double* xd, bool dev_in_smem) {
+    const DevSchedule& sc = sm.sc;
+    const int L = sc.n_phases - 1;
+    const int hz = sc.horizon[L], ss = sc.ss_size[L];
+    const unsigned cm = sc.cmask[L];
+    for (int k = ss; k <= hz; ++k) {
+        const int n = sc.node_off[L] + k, s = sc.stage_off[L] + k;
+        double* x = xs + 24 * n;
+        const double* xsim = (k == 0) ? sm.Xsim_t + 24 * n : (dev_in_smem ? xd + 24 * (n - 1) : sm.Xsim_t + 24 * n);
+        for (int j = 0; j < 24; ++j) x[j] = xsim[j];
+        if (k == hz) break;
+        double dxl[24], ul[24];
+        for (int j = 0; j < 24; ++j) { dxl[j] = x[j] - sm.Xbar[24 * n + j]; ul[j] = sm.Ubar[24 * s + j] + eps * sm.dU[24 * s + j]; }
+        const double* KT = sm.K + 288 * (size_t)s;
+        for (int c = 0; c < 12; ++c) {
+            double acc = 0.0;
+            for (int j = 0; j < 24; ++j) acc = fma(KT[12 * j + c], dxl[j], acc);
+            ul[((cm >> (c / 3)) & 1u) ? c : 12 + c] += acc;  // the coupled control of the leg
+        }
+        double* slot = dev_in_smem ? xd + 24 * n : sm.Xsim_t + 24 * (n + 1);
+        for (int j = 0; j < 24; ++j) sm.U_t[24 * s + j] = ul[j];
+        hkd::dynamics(x, ul, sc.dt, cm, slot);
+        double nrm2 = 0.0;
+        for (int j = 0; j < 24; ++j) nrm2 = fma(slot[j], slot[j], nrm2);
+        if (sqrt(nrm2) > 1e6) return s;
+    }
+    return 0x7fffffff;
+}
+
 template <bool LINEARISED>
 __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
     const DevSchedule& sc = sm.sc;
@@ -452,40 +486,10 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
             resetmap_thread(xs + 24 * ne, sc.cmask[ph - 1], sc.nmask[ph - 1], xi);
         }
     }
-    // (b2) nodes OUTSIDE the shooting set.  HKDProblem::initialization makes every node a shooting node; after a receding-horizon
-    //      update the LAST phase can have fewer (DevSchedule::ss_size): those nodes are propagated, X[k] = Xsim[k] (X[0] = x_init
-    //      when the set is empty), and their controls see the true feedback K (X - Xbar) (SinglePhase.cpp:185-220).  At most
-    //      three stages, walked by one thread after the parallel pass.
-    {
-        const int L = sc.n_phases - 1;
-        const int hz = sc.horizon[L], ss = sc.ss_size[L];
-        if (ss < hz + 1) {
-            __syncthreads();
-            if (tid == 0) {
-                const unsigned cm = sc.cmask[L];
-                for (int k = ss; k <= hz; ++k) {
-                    const int n = sc.node_off[L] + k, s = sc.stage_off[L] + k;
-                    double* x = xs + 24 * n;
-                    const double* xsim = (k == 0) ? sm.Xsim_t + 24 * n : (dev_in_smem ? xd + 24 * (n - 1) : sm.Xsim_t + 24 * n);
-                    for (int j = 0; j < 24; ++j) x[j] = xsim[j];
-                    if (k == hz) break;
-                    double dxl[24], ul[24];
-                    for (int j = 0; j < 24; ++j) { dxl[j] = x[j] - sm.Xbar[24 * n + j]; ul[j] = sm.Ubar[24 * s + j] + eps * sm.dU[24 * s + j]; }
-                    const double* KT = sm.K + 288 * (size_t)s;
-                    for (int c = 0; c < 12; ++c) {
-                        double acc = 0.0;
-                        for (int j = 0; j < 24; ++j) acc = fma(KT[12 * j + c], dxl[j], acc);
-                        ul[((cm >> (c / 3)) & 1u) ? c : 12 + c] += acc;  // the coupled control of the leg
-                    }
-                    double* slot = dev_in_smem ? xd + 24 * n : sm.Xsim_t + 24 * (n + 1);
-                    for (int j = 0; j < 24; ++j) sm.U_t[24 * s + j] = ul[j];
-                    hkd::dynamics(x, ul, sc.dt, cm, slot);
-                    double nrm2 = 0.0;
-                    for (int j = 0; j < 24; ++j) nrm2 = fma(slot[j], slot[j], nrm2);
-                    if (sqrt(nrm2) > 1e6) { first_bad = min(first_bad, s); break; }
-                }
-            }
-        }
+    // (b2) nodes OUTSIDE the shooting set (rollout_unshot_tail)
+    if (sc.ss_size[sc.n_phases - 1] < sc.horizon[sc.n_phases - 1] + 1) {
+        __syncthreads();
+        if (tid == 0) first_bad = min(first_bad, rollout_unshot_tail(sm, eps, xs, xd, dev_in_smem));
     }
     // first diverged stage in the reference's sequential order
     const int bad = (int)block_reduce<1>(sm, (double)first_bad);

@@ -1381,12 +1381,12 @@ int hsddp_batch_solve_async(hsddp_batch* b, const hsddp_options* opt) {
     CK(cudaSetDevice(b->device));
     const hsddp_options o = opt ? *opt : default_options();
     b->cold = false;
-    // auto: the persistent kernel up to ~9 waves of blocks (its work queue visits the problems longest-first from the second
+    // auto: the persistent kernel up to ~7 waves of blocks (its work queue visits the problems longest-first from the second
     // solve on, which keeps the tail short); beyond that the phased driver, whose phase-homogeneous kernels keep the
     // instruction cache hot and whose launch tails are hidden by driving four index ranges on their own streams
-    // (measured on config 3, persistent vs phased, ms: 2,048 problems 57 vs 73, 4,096: 97 vs 108, 8,192: 191 vs 188,
+    // (measured on config 3, persistent vs phased, ms: 2,048 problems 57 vs 73, 4,096: 101 vs 108, 8,192: 199 vs 188,
     // 16,384: 455 vs 336 -- DESIGN.md §4)
-    const bool phased = b->solve_mode == 2 || (b->solve_mode == 0 && b->bp.n_problems >= 9 * b->n_sm * b->blocks_per_sm);
+    const bool phased = b->solve_mode == 2 || (b->solve_mode == 0 && b->bp.n_problems >= 7 * b->n_sm * b->blocks_per_sm);
     if (phased) return solve_phased(b, o);
     CK(cudaMemsetAsync(b->bp.work_counter, 0, sizeof(int), b->stream));
     CK(cudaEventRecord(b->ev0, b->stream));

@@ -726,7 +726,7 @@ __device__ inline bool backward_sweep_regularized_block(Smem& sm, int& n_sweeps)
 // cost change (dV_1, dV_2) does not feed back into the recursion, so it is accumulated
 // afterwards by all threads in parallel.
 // ---------------------------------------------------------------------------
-constexpr int LR_SLOT = 436;   // doubles per stage slot: KT 288 | compact record entries 0..99 (rows 0..2, 6..8 of [A - I | B_r]) 100 | defect 24 | dU 24
+constexpr int LR_SLOT = 436;   // doubles per stage slot: KT 288 | compact record entries 0..99 (rows 0..2, 6..8 of [A - I | B_r]; entry 99 is padding) 100 | defect 24 | dU 24
 #ifndef HSDDP_LR_CHUNK
 #define HSDDP_LR_CHUNK 4
 #endif
@@ -800,15 +800,19 @@ __device__ inline void linear_rollout_block(Smem& sm, double eps) {
     const double dt = sc.dt;
     const int N = sc.n_stages;
     double* scratch = sm.H;  // H, Y, Z, Qux, Quu, KrS, rec are contiguous and free outside the sweep
-    double* sdx = sm.vtmp;   // current dx, shared for broadcast
-    double* sdu = sm.vtmp2;  // coupled controls du_r[0..11]
+    double* sdx = sm.vtmp;   // V = [current dx (24) | coupled controls du_r (12) | 0], shared for broadcast (vtmp and vtmp2 are contiguous)
     PROF_DECL
     __syncthreads();
     if (tid >= 32) lr_prefetch(sm, scratch, 0, min(LR_CHUNK, N), tid - 32);
     cp_async_wait_all();
     __syncthreads();
-    int ph = 0;
+    int ph = -1;
+    unsigned cm = 0;
+    unsigned long long cpack = 0, vpack = 0;
     double dx = 0.0;
+    if (tid < 9) sdx[36 + tid] = 0.0;  // V[36..44] = 0 (read after the __syncwarp of the first phase start)
+    double* lrc = sdx + 45;            // constants {0, dt, dt / m} of the sparse rows
+    if (tid == 0) { lrc[0] = 0.0; lrc[1] = dt; lrc[2] = (1.0 / hkd::kMass) * dt; }
     double dV1 = 0.0, dV2 = 0.0;   // expected cost change: the three warps that do not run the recursion accumulate the
     int last_c0 = 0;               // terms of the chunk that has just been finished while warp 0 works on the next one
     for (int c0 = 0; c0 < N; c0 += LR_CHUNK) {
@@ -823,12 +827,13 @@ __device__ inline void linear_rollout_block(Smem& sm, double eps) {
         }
         if (tid < 32) {
             for (int s = c0; s < c1; ++s) {
-                while (ph + 1 < sc.n_phases && s >= sc.stage_off[ph + 1]) ++ph;
-                const unsigned cm = sc.cmask[ph];
-                const int k = s - sc.stage_off[ph];
-                const int n = sc.node_off[ph] + k;
-                if (k == 0) {
-                    // phase start: dx_init = Px dX_end(prev) (zero for the first phase); dX[0] = dx_init + eps Defect[0]
+                if (ph < 0 || (ph + 1 < sc.n_phases && s >= sc.stage_off[ph + 1])) {
+                    // ---- phase start ----
+                    ++ph;
+                    while (ph + 1 < sc.n_phases && s >= sc.stage_off[ph + 1]) ++ph;
+                    cm = sc.cmask[ph];
+                    const int n = sc.node_off[ph];
+                    // dx_init = Px dX_end(prev) (zero for the first phase); dX[0] = dx_init + eps Defect[0]
                     double dxi = 0.0;
                     if (ph > 0 && lane < 24) {
                         const unsigned pc_ = sc.cmask[ph - 1], pn_ = sc.nmask[ph - 1];
@@ -857,69 +862,86 @@ __device__ inline void linear_rollout_block(Smem& sm, double eps) {
                         sm.dX[24 * n + lane] = dx;
                         sdx[lane] = dx;
                     }
+                    // per-lane description of the sparse rows of [A - I | B_r] that are NOT the angular-acceleration rows:
+                    // dx+_i = dx_i + sum_q coef_q V[vidx_q], V = [dx (24) | du_r (12) | 0].  coef_q is entry cidx_q of the stage's
+                    // compact record for cidx_q < 100, else one of the constants C[cidx_q - 100] = {0, dt, dt / m}; five
+                    // (cidx, vidx) byte pairs packed into two registers each
+                    {
+                        unsigned char ci[5] = {100, 100, 100, 100, 100}, vi[5] = {36, 36, 36, 36, 36};
+                        if (lane == 0) { ci[0] = 0; ci[1] = 1; ci[2] = 2; ci[3] = 3; vi[0] = 1; vi[1] = 2; vi[2] = 7; vi[3] = 8; }               // yaw rate
+                        else if (lane == 1) { ci[0] = 4; ci[1] = 5; ci[2] = 6; vi[0] = 2; vi[1] = 7; vi[2] = 8; }                               // pitch rate
+                        else if (lane == 2) { ci[0] = 7; ci[1] = 8; ci[2] = 9; ci[3] = 10; ci[4] = 11; vi[0] = 1; vi[1] = 2; vi[2] = 6; vi[3] = 7; vi[4] = 8; }  // roll rate
+                        else if (lane < 6) { ci[0] = 101; vi[0] = (unsigned char)(lane + 6); }
+                        else if (lane >= 9 && lane < 12) {
+                            for (int l = 0; l < 4; ++l) { ci[l] = ((cm >> l) & 1u) ? 102 : 100; vi[l] = (unsigned char)(24 + 3 * l + lane - 9); }
+                        } else if (lane >= 12 && lane < 24) {
+                            if (!((cm >> ((lane - 12) / 3)) & 1u)) { ci[0] = 101; vi[0] = (unsigned char)(24 + lane - 12); }
+                        }
+                        cpack = 0; vpack = 0;
+                        for (int q = 0; q < 5; ++q) { cpack |= (unsigned long long)ci[q] << (8 * q); vpack |= (unsigned long long)vi[q] << (8 * q); }
+                    }
                     __syncwarp();
                 }
+                const int k = s - sc.stage_off[ph];
+                const int n = sc.node_off[ph] + k;
                 const double* slot = buf + (s - c0) * LR_SLOT;
                 const double* KT = slot;
                 const double* Rc = slot + 288;   // compact entries of rows 0..2 and 6..8 of [A - I | B_r] (hkd_model.cuh)
                 const double* dfn = slot + 388;
                 const double* dUs = slot + 412;
-                // du = eps dU + K dx : lanes 0..11 the coupled controls, lanes 12..23 the decoupled ones
-                if (lane < 12) {
-                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                // ---- phase A: feedback K_r dx (lanes 0..23: control c = lane % 12, state half lane / 12) and the state part of the
+                //      angular-acceleration rows (lanes 24..29: row 6 + a, columns 0..8 | the eight foot columns) ----
+                double pa = 0.0, pb = 0.0;
+                if (lane < 24) {
+                    const int c = (lane < 12) ? lane : lane - 12, j0 = (lane < 12) ? 0 : 12;
+                    const double* kt = KT + j0 * 12 + c;
+                    const double* v = sdx + j0;
 #pragma unroll
-                    for (int j = 0; j < 24; j += 4) {
-                        a0 = fma(KT[j * 12 + lane], sdx[j], a0);
-                        a1 = fma(KT[(j + 1) * 12 + lane], sdx[j + 1], a1);
-                        a2 = fma(KT[(j + 2) * 12 + lane], sdx[j + 2], a2);
-                        a3 = fma(KT[(j + 3) * 12 + lane], sdx[j + 3], a3);
+                    for (int j = 0; j < 12; j += 2) { pa = fma(kt[j * 12], v[j], pa); pb = fma(kt[(j + 1) * 12], v[j + 1], pb); }
+                } else if (lane < 30) {
+                    const int a = (lane - 24) >> 1;
+                    const double* W = Rc + 12 + 29 * a;
+                    if ((lane & 1) == 0) {
+#pragma unroll
+                        for (int q = 0; q < 8; q += 2) { pa = fma(W[q], sdx[q], pa); pb = fma(W[q + 1], sdx[q + 1], pb); }
+                        pa = fma(W[8], sdx[8], pa);
+                    } else {
+#pragma unroll
+                        for (int l = 0; l < 4; ++l) { pa = fma(W[9 + 2 * l], sdx[12 + 3 * l], pa); pb = fma(W[10 + 2 * l], sdx[13 + 3 * l], pb); }
                     }
+                }
+                const double part = pa + pb;
+                const double hi = __shfl_down_sync(0xffffffffu, part, 12);
+                const int l6 = 24 + 2 * min(max(lane - 6, 0), 2);
+                const double w0 = __shfl_sync(0xffffffffu, part, l6), w1 = __shfl_sync(0xffffffffu, part, l6 + 1);
+                if (lane < 12) {
                     const int i = act_index(lane, cm);
-                    const double kdx = (a0 + a1) + (a2 + a3);
+                    const double kdx = part + hi;
                     const double du = eps * dUs[i] + kdx;
                     sm.KdX[12 * s + lane] = kdx;  // kept for the trial rollouts of this iteration (hybrid_rollout_block<true>)
-                    sdu[lane] = du;
+                    sdx[24 + lane] = du;
                     sm.U_t[24 * s + i] = du;
                 } else if (lane < 24) {
                     const int i = inact_index(lane - 12, cm);
                     sm.U_t[24 * s + i] = eps * dUs[i];
                 }
                 __syncwarp();
+                // ---- phase B: dx+ = dx + (A - I) dx + B_r du_r + eps d ----
                 if (lane < 24) {
                     double acc = dx;
-                    if (lane == 0) {         // yaw rate: columns {1,2,7,8}
-                        acc += (fma(Rc[0], sdx[1], Rc[1] * sdx[2])) + (fma(Rc[2], sdx[7], Rc[3] * sdx[8]));
-                    } else if (lane == 1) {  // pitch rate: columns {2,7,8}
-                        acc += fma(Rc[4], sdx[2], fma(Rc[5], sdx[7], Rc[6] * sdx[8]));
-                    } else if (lane == 2) {  // roll rate: columns {1,2,6,7,8}
-                        acc += (fma(Rc[7], sdx[1], Rc[8] * sdx[2])) + fma(Rc[9], sdx[6], fma(Rc[10], sdx[7], Rc[11] * sdx[8]));
-                    } else if (lane >= 6 && lane < 9) {  // angular acceleration rows: 9 body columns, 8 foot columns, 12 B_r columns
-                        const double* W = Rc + 12 + 29 * (lane - 6);
-                        double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0;
+                    if (lane >= 6 && lane < 9) {  // angular acceleration: the state part from phase A, then the 12 coupled controls
+                        const double* W = Rc + 12 + 29 * (lane - 6) + 17;
+                        double b0 = 0.0, b1 = 0.0;
 #pragma unroll
-                        for (int q = 0; q < 9; q += 3) {
-                            a0 = fma(W[q], sdx[q], a0);
-                            a1 = fma(W[q + 1], sdx[q + 1], a1);
-                            a2 = fma(W[q + 2], sdx[q + 2], a2);
-                        }
-#pragma unroll
-                        for (int l = 0; l < 4; ++l) {
-                            a0 = fma(W[9 + 2 * l], sdx[12 + 3 * l], a0);
-                            a1 = fma(W[10 + 2 * l], sdx[13 + 3 * l], a1);
-                        }
-#pragma unroll
-                        for (int c = 0; c < 12; c += 2) { b0 = fma(W[17 + c], sdu[c], b0); b1 = fma(W[18 + c], sdu[c + 1], b1); }
-                        acc += ((a0 + a1) + a2) + (b0 + b1);
-                    } else if (lane < 6) {
-                        acc = fma(dt, sdx[lane + 6], acc);
-                    } else if (lane < 12) {
-                        double b = 0.0;
-#pragma unroll
-                        for (int l = 0; l < 4; ++l) b = fma(((cm >> l) & 1u) ? (1.0 / hkd::kMass) * dt : 0.0, sdu[3 * l + lane - 9], b);
-                        acc += b;
+                        for (int c = 0; c < 12; c += 2) { b0 = fma(W[c], sdx[24 + c], b0); b1 = fma(W[c + 1], sdx[25 + c], b1); }
+                        acc += (w0 + w1) + (b0 + b1);
                     } else {
-                        const int l = (lane - 12) / 3;
-                        if (!((cm >> l) & 1u)) acc = fma(dt, sdu[lane - 12], acc);
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) {
+                            const unsigned ci = (unsigned)(cpack >> (8 * q)) & 255u, vi = (unsigned)(vpack >> (8 * q)) & 255u;
+                            const double coef = (ci < 100u) ? Rc[ci] : lrc[ci - 100u];
+                            acc = fma(coef, sdx[vi], acc);
+                        }
                     }
                     dx = acc + eps * dfn[lane];
                 }

@@ -154,6 +154,11 @@ def build_cpu(config, hkd_state, n=None, plan=0.6, first=0):
 
 def _build(pkg, config, n=None, plan=0.6, first=0):
     name, e = define(config, n, plan, first)
+    return from_entries(pkg, name, e, plan)
+
+
+def from_entries(pkg, name, e, plan=0.6):
+    """A workload from explicit entries (gait, window start, x0 mode, perturbation index)."""
     keys, sid = schedule_keys(e)
     refs = {}
     schedules = []
@@ -184,3 +189,20 @@ def config3(pkg, n=16384, plan=0.6, first=0):
 def config4(pkg, n=4096, plan=0.6):
     """n bound-then-jump problems, window starts uniform in [236, 266] (long flight phase in the horizon)."""
     return _build(pkg, "config4", n, plan)
+
+
+def with_room_for_ticks(entries, ticks, plan=0.6):
+    """The entries whose reference table is long enough for `ticks` receding-horizon updates."""
+    need = int(round(plan / 0.01)) + 3 + ticks
+    return [e for e in entries if e[1] + need < gait_table(e[0])["body_state"].shape[0]]
+
+
+def gait_batch(pkg, w, device=0, cparams=None):
+    """The workload `w` as a batch whose schedules are built ON THE DEVICE from the gait library
+    (hsddp_batch_set_problems_from_gaits): the form that supports the receding-horizon update (mpc_update)."""
+    order = list(GAITS)
+    refs = [pkg.QuadReference(gait_path(g)) for g in order]
+    B = pkg.MultiPhaseDDPBatch(device)
+    B.set_problems_from_gaits(refs, [order.index(g) for g, _ in w.keys], [k for _, k in w.keys], w.plan, w.schedule_id, cparams)
+    B.set_initial_condition(w.x0)
+    return B

@@ -195,7 +195,7 @@ int hsddp_batch_sync(hsddp_batch* b);
  *                  still running, up to eight index ranges driven concurrently on their own streams.  The list of
  *                  running problems and its length stay in HBM, so the whole solve is queued without a host round trip
  *                  and hsddp_batch_solve_async returns as soon as the launches are queued
- *   0 auto       — phased when the batch fills the GPU about nine times over (>= 7,992 problems on a B200). */
+ *   0 auto       — phased when the batch fills the GPU about seven times over (>= 6,216 problems on a B200). */
 int hsddp_batch_set_solve_mode(hsddp_batch* b, int mode);
 /* milliseconds of the last solve kernel, CUDA events on the handle's stream */
 int hsddp_batch_last_solve_ms(hsddp_batch* b, float* ms);
