@@ -26,6 +26,21 @@ int main(int argc, char** argv) {
         solver.solve(ddp_options);
         for (const hsddp_info& info : solver.get_info())
             std::printf("status %d  iterations %d  total cost = %.8f  dynamics infeasibility = %.3e\n", info.status, info.n_iter, info.cost, info.feas);
+        // the phase interface of the reference's problem assembly compiles against the shim (its plug-ins are accepted and ignored)
+        hsddp_b200::SinglePhase<double, 24, 24, 0> phase;
+        phase.set_dynamics([](double*, double*, double*, double*, double) {});
+        phase.set_time_offset(0.f);
+        phase.update_SS_config(12);
+        const std::vector<double> feas = solver.measure_dynamics_feasibility();
+        if (feas.size() != (size_t)n) return 3;
+        // the same batch sharded over "two GPUs" (device 0 twice: the logic is what is checked here)
+        hsddp_b200::MultiGpuDDP multi({0, 0});
+        multi.set_multiPhaseProblem({&schedule}, std::vector<int32_t>(n, 0));
+        multi.set_initial_condition(x0);
+        multi.solve(ddp_options);
+        const std::vector<hsddp_info> a = solver.get_info(), b2 = multi.get_info();
+        for (int i = 0; i < n; ++i)
+            if (a[i].n_iter != b2[i].n_iter || a[i].status != b2[i].status || a[i].cost != b2[i].cost) { std::fprintf(stderr, "multi-GPU shard %d differs\n", i); return 4; }
         // what the reference publishes on "mpc_command" (HKDMPC.cpp:243-298)
         const std::vector<hsddp_mpc_command> cmd = solver.get_mpc_command(8);
         std::printf("command of problem 0: %d steps, first GRF z of leg 0 = %.4f N, feedback[0][2][5] = %.4f\n", cmd[0].N_mpcsteps,

@@ -352,21 +352,25 @@ __device__ inline void resetmap_partial_block(const double* Jc_all, unsigned c, 
 // multiply-add per control instead of re-reading 2.3 KB of gains per stage and trial.  Differs from the literal form
 // by the rounding of (Xbar + eps dX) - Xbar only.  LINEARISED = false evaluates the literal form (step-level API,
 // where the caller decides what precedes a rollout).
-// Nodes OUTSIDE the shooting set.  HKDProblem::initialization makes every node a shooting node; after a receding-horizon
-// update the LAST phase can have fewer (DevSchedule::ss_size): those nodes are propagated, X[k] = Xsim[k] (X[0] = x_init when
-// the set is empty), and their controls see the true feedback K (X - Xbar) (SinglePhase.cpp:185-220).  At most three stages,
-// walked by ONE thread after the parallel pass of hybrid_rollout_block; out of line so that its local arrays cost the
-// common path nothing.  Returns the first diverged stage (0x7fffffff: none).
-__device__ __noinline__ int rollout_unshot_tail(Smem& sm, double eps, double* xs, double* xd, bool dev_in_smem) {
+// Nodes OUTSIDE the shooting set are propagated: X[k] = Xsim[k] (X[0] = x_init when the set is empty), and their controls see
+// the true feedback K (X - Xbar) (SinglePhase.cpp:185-220).  HKDProblem::initialization makes every node a shooting node, so
+// with multiple shooting this path is empty; it is taken
+//   * after a receding-horizon update, by the LAST phase while its shooting set is short (DevSchedule::ss_size): <= 3 stages;
+//   * with single shooting (option.MS = false): every phase is propagated from its first node (which stays a shooting node:
+//     SS_set is non-empty and starts at 0, SinglePhase.cpp:187-193).
+// One thread walks phase `ph` from node `kf` on, after the parallel pass of hybrid_rollout_block; out of line so that its
+// local arrays cost the common path nothing.  Returns the first diverged stage (0x7fffffff: none).
+__device__ __noinline__ int rollout_sequential_phase(Smem& sm, double eps, double* xs, double* xd, bool dev_in_smem, int ph, int kf, int ss_eff) {
     const DevSchedule& sc = sm.sc;
-    const int L = sc.n_phases - 1;
-    const int hz = sc.horizon[L], ss = sc.ss_size[L];
-    const unsigned cm = sc.cmask[L];
-    for (int k = ss; k <= hz; ++k) {
-        const int n = sc.node_off[L] + k, s = sc.stage_off[L] + k;
+    const int hz = sc.horizon[ph];
+    const unsigned cm = sc.cmask[ph];
+    for (int k = kf; k <= hz; ++k) {
+        const int n = sc.node_off[ph] + k, s = sc.stage_off[ph] + k;
         double* x = xs + 24 * n;
-        const double* xsim = (k == 0) ? sm.Xsim_t + 24 * n : (dev_in_smem ? xd + 24 * (n - 1) : sm.Xsim_t + 24 * n);
-        for (int j = 0; j < 24; ++j) x[j] = xsim[j];
+        if (k >= ss_eff) {
+            const double* xsim = (k == 0) ? sm.Xsim_t + 24 * n : (dev_in_smem ? xd + 24 * (n - 1) : sm.Xsim_t + 24 * n);
+            for (int j = 0; j < 24; ++j) x[j] = xsim[j];
+        }
         if (k == hz) break;
         double dxl[24], ul[24];
         for (int j = 0; j < 24; ++j) { dxl[j] = x[j] - sm.Xbar[24 * n + j]; ul[j] = sm.Ubar[24 * s + j] + eps * sm.dU[24 * s + j]; }
@@ -391,6 +395,7 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
     const DevSchedule& sc = sm.sc;
     const int tid = virtual_tid(sm), lane = tid & 31, warp = tid >> 5;
     const int N = sc.n_stages;
+    const bool ms = sm.opt.MS != 0;
     PROF_DECL
     double* xs = sm.H;  // trial states of all nodes [n_nodes][24] (the sweep's tile storage is free here)
     // (a0) trial states X = Xbar + eps dX for every node, and the deviations X - Xbar the feedback acts on
@@ -474,7 +479,7 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
         double nrm2 = 0.0;
 #pragma unroll
         for (int j = 0; j < 24; ++j) nrm2 = fma(slot[j], slot[j], nrm2);
-        if (sqrt(nrm2) > 1e6 && k < sc.ss_size[ph]) first_bad = min(first_bad, s);  // (stages of non-shooting nodes are redone in (b2))
+        if (sqrt(nrm2) > 1e6 && k < (ms ? (int)sc.ss_size[ph] : 0)) first_bad = min(first_bad, s);  // (the other stages are redone in (b2))
     }
     if (tid >= 64 && tid < 64 + sc.n_phases) {
         const int ph = tid - 64;
@@ -486,10 +491,23 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
             resetmap_thread(xs + 24 * ne, sc.cmask[ph - 1], sc.nmask[ph - 1], xi);
         }
     }
-    // (b2) nodes OUTSIDE the shooting set (rollout_unshot_tail)
-    if (sc.ss_size[sc.n_phases - 1] < sc.horizon[sc.n_phases - 1] + 1) {
+    // (b2) nodes outside the shooting set (rollout_sequential_phase): the last phase after a receding-horizon update, every
+    //      phase with single shooting
+    if (!ms || sc.ss_size[sc.n_phases - 1] < sc.horizon[sc.n_phases - 1] + 1) {
         __syncthreads();
-        if (tid == 0) first_bad = min(first_bad, rollout_unshot_tail(sm, eps, xs, xd, dev_in_smem));
+        if (tid < sc.n_phases && sc.ss_size[tid] >= 1) {  // phases whose first node is a shooting node are independent of each other
+            const int ss_eff = ms ? (int)sc.ss_size[tid] : 1;
+            if (ss_eff <= sc.horizon[tid]) first_bad = min(first_bad, rollout_sequential_phase(sm, eps, xs, xd, dev_in_smem, tid, ms ? ss_eff : 0, ss_eff));
+        }
+        __syncthreads();
+        if (tid >= 64 && tid < 64 + sc.n_phases && tid > 64) {  // phase-initial simulated states again: the previous phase's end state may have moved
+            const int ph = tid - 64;
+            const int ne = sc.node_off[ph - 1] + sc.horizon[ph - 1];
+            resetmap_thread(xs + 24 * ne, sc.cmask[ph - 1], sc.nmask[ph - 1], sm.Xsim_t + 24 * sc.node_off[ph]);
+        }
+        __syncthreads();
+        if (tid == 0 && sc.ss_size[sc.n_phases - 1] == 0)  // a last phase with an EMPTY shooting set starts from x_init
+            first_bad = min(first_bad, rollout_sequential_phase(sm, eps, xs, xd, dev_in_smem, sc.n_phases - 1, 0, 0));
     }
     // first diverged stage in the reference's sequential order
     const int bad = (int)block_reduce<1>(sm, (double)first_bad);

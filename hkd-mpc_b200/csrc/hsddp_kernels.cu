@@ -895,7 +895,6 @@ hsddp_options default_options() {
 
 int check_opt(const hsddp_options* opt) {
     if (!opt) return HSDDP_OK;
-    if (!opt->MS) { g_last_error = "single shooting (MS = false) is not implemented: the reference ships MS = true"; return HSDDP_ERR_UNSUPPORTED; }
     // The reference's loops `while (eps > 1e-3) eps *= alpha` (MultiPhaseDDP.cpp:113,132) and `reg = max(reg * update_regularization,
     // 1e-3)` until PD or reg > 1e2 (:159-167) terminate only for 0 < alpha < 1 and update_regularization > 1.  On the host a
     // bad value spins one thread; on the device it would hang the stream, so such options are refused here.

@@ -69,6 +69,29 @@ private:
     hsddp_schedule s_{};
 };
 
+// SinglePhase<T,24,24,0> (HSDDPSolver/header/SinglePhase.h:28-170) as the reference's problem-assembly code sees it.
+// Host callables cannot run on the device: the HKD model, costs, reset map and constraints are the device-compiled ones,
+// selected by the schedule, so every plug-in setter ACCEPTS its argument and ignores it.  Code written against the
+// reference's phase interface (HKDProblem::create_problem_one_phase / add_tconstr_one_phase, HKDProblem.cpp:225-310)
+// therefore compiles unchanged; what it configures comes from the schedule instead.
+template <typename T, size_t xs, size_t us, size_t ys>
+class SinglePhase {
+    static_assert(xs == 24 && us == 24 && ys == 0, "only the <double,24,24,0> HKD instantiation is built for the device");
+public:
+    template <class F> void set_dynamics(F&&) {}                    // SinglePhase.h:41-44
+    template <class F> void set_dynamics_partial(F&&) {}            // :45-50
+    template <class F> void set_resetmap(F&&) {}                    // :66-72
+    template <class F> void set_resetmap_partial(F&&) {}            // :73-80
+    template <class P> void add_cost(P&&) {}                        // :84-86
+    template <class P> void add_pathConstraint(P&&) {}              // :88-90
+    template <class P> void add_terminalConstraint(P&&) {}          // :92-94
+    template <class P> void set_trajectory(P&&) {}                  // SinglePhase.cpp:130-135
+    void set_time_offset(float) {}                                  // :82
+    void initialization() {}                                        // SinglePhase.cpp:22-35
+    void update_SS_config(int) {}                                   // :161-164
+    void reset_params() {}                                          // :155 (a no-op in the reference as well)
+};
+
 template <typename T>
 class MultiPhaseDDP;
 
@@ -89,12 +112,36 @@ public:
         n_ = (int)schedule_id.size();
         check(hsddp_batch_dims(b_, nullptr, &max_stages_, &max_nodes_), "hsddp_batch_dims");
     }
+    // the same from the gait library resident on the device (schedules built by a kernel): the form that supports update()
+    void set_multiPhaseProblem_from_gaits(const std::vector<int32_t>& gait_rows, const std::vector<float>& gait_dt, const std::vector<double>& body_state,
+                                          const std::vector<double>& qJ, const std::vector<double>& foot_placements, const std::vector<double>& grf,
+                                          const std::vector<int32_t>& contact, const std::vector<int32_t>& sched_gait, const std::vector<int32_t>& sched_window,
+                                          float plan_duration, const std::vector<int32_t>& schedule_id, const hsddp_constraint_params* cparams = nullptr) {
+        check(hsddp_batch_set_problems_from_gaits(b_, (int)gait_rows.size(), gait_rows.data(), gait_dt.data(), body_state.data(), qJ.data(), foot_placements.data(),
+                                                  grf.data(), contact.data(), (int)sched_gait.size(), sched_gait.data(), sched_window.data(), plan_duration,
+                                                  (int)schedule_id.size(), schedule_id.data(), cparams), "hsddp_batch_set_problems_from_gaits");
+        n_ = (int)schedule_id.size();
+        check(hsddp_batch_dims(b_, nullptr, &max_stages_, &max_nodes_), "hsddp_batch_dims");
+    }
+    // HKDProblem::update (HKDProblem.cpp:117-222) for every problem: the receding-horizon shift before an MPC re-solve
+    void update() { check(hsddp_batch_mpc_update(b_), "hsddp_batch_mpc_update"); }
     void set_initial_condition(const std::vector<double>& x0) {
         if ((int)x0.size() != 24 * n_) throw std::invalid_argument("x0 must hold 24 doubles per problem");
         check(hsddp_batch_set_initial_condition(b_, x0.data()), "hsddp_batch_set_initial_condition");
     }
     void reset() { check(hsddp_batch_reset(b_), "hsddp_batch_reset"); }
     void solve(HSDDP_OPTION option) { check(hsddp_batch_solve(b_, &option), "hsddp_batch_solve"); }
+    void solve_async(HSDDP_OPTION option) { check(hsddp_batch_solve_async(b_, &option), "hsddp_batch_solve_async"); }
+    void sync() { check(hsddp_batch_sync(b_), "hsddp_batch_sync"); }
+    // measure_dynamics_feasibility(norm_id) (MultiPhaseDDP.cpp:514-529; the reference's solve() uses the default norm_id = 2):
+    // sqrt(sum ||Defect||^2) of every problem, as evaluated by the last compute_cost / solve
+    std::vector<double> measure_dynamics_feasibility(int norm_id = 2) {
+        if (norm_id != 2) throw std::invalid_argument("only the 2-norm (the one solve() uses) is evaluated on the device");
+        std::vector<double> sc((size_t)n_ * 8), f(n_);
+        check(hsddp_batch_get_scalars(b_, sc.data()), "hsddp_batch_get_scalars");
+        for (int i = 0; i < n_; ++i) f[i] = sc[(size_t)8 * i + 2];
+        return f;
+    }
 
     // step-level API (same names as the reference's public methods)
     void linear_rollout(double eps, HSDDP_OPTION& o) { check(hsddp_batch_linear_rollout(b_, eps, &o), "linear_rollout"); }
@@ -150,6 +197,65 @@ private:
     hsddp_batch* b_ = nullptr;
     int n_ = 0;
     int32_t max_stages_ = 0, max_nodes_ = 0;
+};
+
+// One solver object over SEVERAL GPUs of a box: problems are independent, so problem i goes to device i * n_dev / n (contiguous
+// index ranges, no data-path traffic between the GPUs).  solve() queues the work on every device before it waits for any
+// (hsddp_batch_solve_async returns as soon as the launches are queued), so one host thread keeps all GPUs busy.
+class MultiGpuDDP {
+public:
+    explicit MultiGpuDDP(const std::vector<int>& devices) {
+        for (int d : devices) parts_.emplace_back(new MultiPhaseDDP<double>(d));
+    }
+    int n_devices() const { return (int)parts_.size(); }
+    // contiguous shard [lo, hi) of device g (sizes differ by at most one)
+    static void shard_range(int n_total, int g, int n_dev, int& lo, int& hi) {
+        const int base = n_total / n_dev, rem = n_total % n_dev;
+        lo = g * base + (g < rem ? g : rem);
+        hi = lo + base + (g < rem ? 1 : 0);
+    }
+    void set_multiPhaseProblem(const std::vector<const Schedule*>& schedules, const std::vector<int32_t>& schedule_id, const hsddp_constraint_params* cparams = nullptr) {
+        n_ = (int)schedule_id.size();
+        for (int g = 0; g < n_devices(); ++g) {
+            int lo, hi;
+            shard_range(n_, g, n_devices(), lo, hi);
+            // every device gets only the schedules its problems use
+            std::vector<int32_t> remap(schedules.size(), -1), sid;
+            std::vector<const Schedule*> used;
+            for (int i = lo; i < hi; ++i) {
+                int32_t& r = remap[schedule_id[i]];
+                if (r < 0) { r = (int32_t)used.size(); used.push_back(schedules[schedule_id[i]]); }
+                sid.push_back(r);
+            }
+            parts_[g]->set_multiPhaseProblem(used, sid, cparams);
+        }
+    }
+    void set_initial_condition(const std::vector<double>& x0) {
+        for (int g = 0; g < n_devices(); ++g) {
+            int lo, hi;
+            shard_range(n_, g, n_devices(), lo, hi);
+            parts_[g]->set_initial_condition(std::vector<double>(x0.begin() + (size_t)24 * lo, x0.begin() + (size_t)24 * hi));
+        }
+    }
+    void reset() { for (auto& p : parts_) p->reset(); }
+    void solve(HSDDP_OPTION option) {
+        for (auto& p : parts_) p->solve_async(option);
+        for (auto& p : parts_) p->sync();
+    }
+    std::vector<hsddp_info> get_info() {
+        std::vector<hsddp_info> all;
+        for (auto& p : parts_) { auto v = p->get_info(); all.insert(all.end(), v.begin(), v.end()); }
+        return all;
+    }
+    std::vector<hsddp_mpc_command> get_mpc_command(int n_steps = 8) {
+        std::vector<hsddp_mpc_command> all;
+        for (auto& p : parts_) { auto v = p->get_mpc_command(n_steps); all.insert(all.end(), v.begin(), v.end()); }
+        return all;
+    }
+    MultiPhaseDDP<double>& part(int g) { return *parts_[g]; }
+private:
+    std::vector<std::unique_ptr<MultiPhaseDDP<double>>> parts_;
+    int n_ = 0;
 };
 
 }  // namespace hsddp_b200

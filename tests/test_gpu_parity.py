@@ -524,11 +524,48 @@ def test_rollout_divergence_partial_update(pkg, orc, workloads):
     assert abs(so["actual_cost"] - sg[0]) <= RTOL * abs(so["actual_cost"])
 
 
-def test_single_shooting_is_refused_loudly(pkg, workloads):
+def test_single_shooting_matches_oracle(pkg, orc, workloads):
+    """option.MS = false (SinglePhase.cpp:211-220): every phase is propagated from its first node (which stays a shooting node,
+    :187-193), no linear rollout, the expected cost change comes from the backward sweep (MultiPhaseDDP.cpp:326-329)."""
+    w = workloads.config3(pkg, 9)
+    B = _batch_for(pkg, w)
+    o = dict(MS=0)
+    B.solve(pkg.Options(**o))
+    info, tr = B.info(), B.trace()
+    Xb, Ub, K = B.get("Xbar"), B.get("Ubar"), B.get("K")
+    tables, checked = {}, 0
+    for i in range(w.n):
+        P = _oracle_problem(orc, w, i, tables)
+        s, otr = P.solve(o)
+        Q = _oracle_problem(orc, w, i, tables)  # sensitivity: the same solve on the other model back end
+        if orc.ref_available():
+            gait, k0 = w.keys[w.schedule_id[i]]
+            Q = orc.Problem(tables[gait], k0, w.plan, model=orc.MODEL_PORT)
+            Q.x0 = w.x0[i]
+        s2, otr2 = Q.solve(o)
+        if not (s["n_iter"] == s2["n_iter"] and s["status"] == s2["status"] and np.array_equal(otr[:, 9], otr2[:, 9])
+                and abs(s["cost"] - s2["cost"]) <= 1e-11 * abs(s["cost"])):
+            continue  # ill-posed for parity
+        n = int(s["n_iter"])
+        assert info["n_iter"][i] == n and info["status"][i] == int(s["status"]) and info["n_sweeps"][i] == int(s["n_sweeps"]), (i, s, info[i])
+        assert np.array_equal(tr[i, :n, 9], otr[:, 9]) and np.array_equal(tr[i, :n, 10], otr[:, 10]), i
+        for col in (2, 3, 11, 12, 6, 7):
+            assert rel_err(tr[i, :n, col], otr[:, col]) < RTOL, (i, col)
+        assert rel_err_rows(Xb[i, :P.n_states], P.get("Xbar")) < RTOL and rel_err_rows(Ub[i, :P.n_stages], P.get("Ubar")) < RTOL, i
+        assert rel_err_rows(K[i, :P.n_stages], P.get("K")) < RTOL, i
+        checked += 1
+    assert checked >= 6, checked
+
+
+def test_invalid_options_are_refused(pkg, workloads):
+    """Options for which the reference's own loops do not terminate would hang the stream: refused with an error."""
     w = workloads.config1(pkg)
     B = _batch_for(pkg, w)
-    with pytest.raises(pkg.HsddpError):
-        B.solve(pkg.Options(MS=0))
+    for bad in (dict(alpha=1.0), dict(alpha=0.0), dict(update_regularization=1.0), dict(cost_thresh=float("nan")), dict(max_DDP_iter=-1)):
+        with pytest.raises(pkg.HsddpError):
+            B.solve(pkg.Options(**bad))
+    B.solve()
+    assert B.info()["n_iter"][0] == 13
 
 
 def test_full_size_config2_properties(pkg, orc, workloads):

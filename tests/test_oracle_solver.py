@@ -159,3 +159,55 @@ def test_trial_control_identity_of_the_linearised_rollout(orc):
                 assert (np.abs(U_lin - U_ref) <= 1e-14 * scale).all(), (gait, it, eps, np.abs(U_lin - U_ref).max())
             assert P.hybrid_rollout(1.0)
             P.update_nominal()
+
+
+def _solve_ld(M, R):
+    """M^-1 R in extended precision (np.longdouble), Gauss-Jordan with partial pivoting: an inverse algorithm that shares
+    nothing with oracle/linalg.hpp (LU + LDLT in double)."""
+    M = np.array(M, np.longdouble); R = np.array(R, np.longdouble)
+    n = M.shape[0]
+    T = np.concatenate([M, R.reshape(n, -1)], axis=1)
+    for c in range(n):
+        p = c + int(np.argmax(np.abs(T[c:, c])))
+        T[[c, p]] = T[[p, c]]
+        T[c] = T[c] / T[c, c]
+        for r in range(n):
+            if r != c:
+                T[r] = T[r] - T[r, c] * T[c]
+    return T[:, n:].reshape(R.shape)
+
+
+def test_riccati_stage_against_independent_extended_precision_restatement(orc):
+    """a second, independent restatement of the Riccati stage (SinglePhase.cpp:307-363) in NumPy
+    extended precision, textbook form (dense products, a different inverse algorithm), checked against the oracle's
+    K, dU, G, H at every stage of every phase, for a trot and a bound problem after two DDP iterations."""
+    for gait, k0 in (("trot", 0), ("bound", 5)):
+        P = orc.Problem(_table(orc, gait), k0, 0.6)
+        P.solve(dict(max_AL_iter=1, max_DDP_iter=2))
+        P.compute_cost(); P.lq_approximation()
+        assert P.backward_sweep(0.0)
+        ld = np.longdouble
+        A, B = P.get("A").astype(ld), P.get("B").astype(ld)
+        lx, lu, lxx, luu, lux = (P.get(n).astype(ld) for n in ("lx", "lu", "lxx", "luu", "lux"))
+        D, G, H, K, dU = P.get("Defect").astype(ld), P.get("G"), P.get("H"), P.get("K"), P.get("dU")
+        s0 = n0 = 0
+        worst = 0.0
+        for ph in P.phases:
+            N = ph["horizon"]
+            for k in range(N - 1, -1, -1):
+                s, n = s0 + k, n0 + k
+                Hn, Gn = H[n + 1].astype(ld), G[n + 1].astype(ld) + H[n + 1].astype(ld) @ D[n + 1]
+                Qx, Qu = lx[s] + A[s].T @ Gn, lu[s] + B[s].T @ Gn
+                Qxx, Quu, Qux = lxx[s] + A[s].T @ Hn @ A[s], luu[s] + B[s].T @ Hn @ B[s], lux[s] + B[s].T @ Hn @ A[s]
+                assert np.all(np.linalg.eigvalsh(np.array(0.5 * (Quu + Quu.T), np.float64)) > 1e-9)
+                Kk, dUk = -_solve_ld(Quu, Qux), -_solve_ld(Quu, Qu)
+                Gk = Qx + Qux.T @ dUk
+                Hk = 0.5 * (Qxx + Qxx.T) + Qux.T @ Kk
+                if k == 0:
+                    Gk = Gk + Hk @ D[n]  # G[0] += H[0] Defect[0] at the end of the phase (SinglePhase.cpp:365)
+                for mine, theirs in ((Kk, K[s]), (dUk, dU[s]), (Gk, G[n]), (Hk, H[n])):
+                    e = float(np.abs(np.array(mine, np.float64) - theirs).max() / max(1e-300, np.abs(theirs).max()))
+                    worst = max(worst, e)
+                    assert e < 1e-10, (gait, s, e)
+            s0 += N; n0 += N + 1
+        assert worst > 0.0  # (the two paths are different computations: they do not agree bit for bit)
