@@ -147,6 +147,11 @@ struct BatchPtrs {
     int* zero_count;                          // counter the first kernel of a round clears for the round after next (nullptr: none)
     int sweep_w1_min;                         // phased driver: rounds with at least this many problems run k_sweep_w1 instead of k_phase<PH_SWEEP> (0: never)
     int _pad2;
+    // concurrent line search of the latency kernel (k_solve_lat4): per problem and step size, the arrays a trial writes
+    // (X, Defect, Xsim: [P][4][max_nodes][24]; U, U scratch: [P][4][max_stages][24]; gcon [P][4][max_stages][20];
+    // hcon [P][4][MAXPH][4]); results [P][4][8] = cost, feas, max_pconstr, max_tconstr, rollout ok; mail [P] = 1 trial, 2 exit
+    double *ls_X, *ls_Defect, *ls_Xsim, *ls_U, *ls_Ut, *ls_gcon, *ls_hcon, *ls_res;
+    int* ls_mail;
     const int* order;                         // persistent kernel: the work queue visits problems in this order (nullptr: by index)
     hsddp_info* info;                         // [P]
     hsddp_iter_record* trace;                 // [P][HSDDP_TRACE_CAP]

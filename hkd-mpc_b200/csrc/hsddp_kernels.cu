@@ -6,6 +6,7 @@
 // One thread block per problem; k_solve is persistent (blocks pull problem indices
 // from a device-side queue so problems with few iterations retire early).
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -62,6 +63,131 @@ __device__ inline bool line_search_block(Smem& sm, double& eps_out, int& n_trial
     }
     eps_out = success ? eps : 0.0;
     return success;
+}
+
+// ---------------------------------------------------------------------------
+// Concurrent line search (north_star (3): "all line-search step sizes concurrently").  The latency kernel k_solve_lat4 gives
+// every problem a CLUSTER of four blocks: block 0 runs the solve; at a line search the four blocks evaluate the reference's
+// first four step sizes (1, alpha, alpha^2, alpha^3) at the same time, each into its own trial arrays, and block 0 then
+// accepts the first one that passes IN THE REFERENCE'S ORDER and commits its arrays -- exactly the state the sequential
+// search leaves (MultiPhaseDDP.cpp:98-138; Q2: if none passes, the state of the last trial).  A diverged rollout leaves a
+// partially updated state that depends on the trial before it (Q16), so in that (rare) case the concurrent results are
+// discarded and the sequential search runs instead.  For throughput the sequential search with early exit is the better
+// schedule (1.63 trials per iteration on the benchmark workload); this one is for the latency of a single solve.
+// ---------------------------------------------------------------------------
+struct TrialPtrs { double *X, *U, *U_t, *Xsim_t, *Defect, *gcon, *hcon; };
+
+__device__ inline TrialPtrs swap_trial_arrays(Smem& sm, const TrialPtrs& t) {
+    TrialPtrs old = {sm.X, sm.U, sm.U_t, sm.Xsim_t, sm.Defect, sm.gcon, sm.hcon};
+    __syncthreads();
+    if (threadIdx.x == 0) { sm.X = t.X; sm.U = t.U; sm.U_t = t.U_t; sm.Xsim_t = t.Xsim_t; sm.Defect = t.Defect; sm.gcon = t.gcon; sm.hcon = t.hcon; }
+    __syncthreads();
+    return old;
+}
+__device__ inline TrialPtrs trial_arrays(const BatchPtrs& bp, int pid, int r) {
+    const size_t q = (size_t)pid * 4 + r, sn = (size_t)bp.max_nodes * 24, ss = (size_t)bp.max_stages * 24;
+    return TrialPtrs{bp.ls_X + q * sn, bp.ls_U + q * ss, bp.ls_Ut + q * ss, bp.ls_Xsim + q * sn, bp.ls_Defect + q * sn,
+                     bp.ls_gcon + q * bp.max_stages * 20, bp.ls_hcon + q * MAXPH * 4};
+}
+// one trial into the trial arrays of step r; the block's own arrays are untouched
+__device__ inline void run_trial(Smem& sm, const BatchPtrs& bp, int r, double eps) {
+    const TrialPtrs keep = swap_trial_arrays(sm, trial_arrays(bp, sm.pid, r));
+    // (touchdown values of legs without a constraint are never written by a rollout: start from the current ones)
+    for (int e = threadIdx.x; e < MAXPH * 4; e += kThreads) sm.hcon[e] = keep.hcon[e];
+    for (int e = threadIdx.x; e < sm.sc.n_stages * 20; e += kThreads) sm.gcon[e] = keep.gcon[e];  // (likewise the rows of swing legs)
+    __syncthreads();
+    const bool ok = hybrid_rollout_block<true>(sm, eps);
+    compute_cost_block(sm);
+    if (threadIdx.x == 0) {
+        double* res = bp.ls_res + ((size_t)sm.pid * 4 + r) * 8;
+        res[0] = sm.st.actual_cost; res[1] = sm.st.feas; res[2] = sm.st.max_pconstr; res[3] = sm.st.max_tconstr; res[4] = ok ? 1.0 : 0.0;
+    }
+    swap_trial_arrays(sm, keep);
+}
+__device__ inline void commit_trial(Smem& sm, const BatchPtrs& bp, int r) {
+    const TrialPtrs t = trial_arrays(bp, sm.pid, r);
+    const DevSchedule& sc = sm.sc;
+    for (int e = threadIdx.x; e < sc.n_nodes * 24; e += kThreads) { sm.X[e] = t.X[e]; sm.Defect[e] = t.Defect[e]; }
+    for (int e = threadIdx.x; e < sc.n_stages * 24; e += kThreads) sm.U[e] = t.U[e];
+    for (int e = threadIdx.x; e < sc.n_stages * 20; e += kThreads) sm.gcon[e] = t.gcon[e];
+    for (int e = threadIdx.x; e < MAXPH * 4; e += kThreads) sm.hcon[e] = t.hcon[e];
+    if (threadIdx.x == 0) {
+        const double* res = bp.ls_res + ((size_t)sm.pid * 4 + r) * 8;
+        sm.st.actual_cost = res[0]; sm.st.feas = res[1]; sm.st.max_pconstr = res[2]; sm.st.max_tconstr = res[3]; sm.st.rollout_ok = 1;
+        sm.ctl.trial_cost = res[0]; sm.ctl.trial_feas = res[1]; sm.ctl.have_trial = 1;
+    }
+    __syncthreads();
+}
+
+// block 0 of the cluster: the line search of one DDP iteration
+__device__ inline bool line_search_cluster(Smem& sm, const BatchPtrs& bp, double& eps_out, int& n_trials) {
+    namespace cg = cooperative_groups;
+    const double merit_prev = sm.st.merit, feas_prev = sm.st.feas, merit_rho = sm.st.merit_rho;
+    const double dV_1 = sm.st.dV_1, dV_2 = sm.st.dV_2;
+    double epsv[4];
+    int nv = 0;
+    for (double e = 1; e > 1e-3 && nv < 4; e *= sm.opt.alpha) epsv[nv++] = e;  // 1, .1, .010000000000000002, .0010000000000000002 (Q6)
+    __syncthreads();
+    if (threadIdx.x == 0) { bp.ls_mail[sm.pid] = 1; __threadfence(); }
+    cg::this_cluster().sync();  // [A] the helpers start their trials
+    if (nv > 0) run_trial(sm, bp, 0, epsv[0]);
+    __threadfence();
+    cg::this_cluster().sync();  // [B] every trial is in its arrays
+    bool diverged = false;
+    int accepted = -1;
+    for (int r = 0; r < nv; ++r) {
+        const double* res = bp.ls_res + ((size_t)sm.pid * 4 + r) * 8;
+        const double cost = __ldcg(res), feas = __ldcg(res + 1);
+        const bool ok = __ldcg(res + 4) != 0.0;
+        if (!ok) { diverged = true; break; }
+        const double merit = cost + merit_rho * feas;
+        const double exp_merit_change = (epsv[r] * dV_1 + 0.5 * epsv[r] * epsv[r] * dV_2) - epsv[r] * merit_rho * feas_prev;
+        if (merit <= merit_prev + sm.opt.gamma * exp_merit_change) { accepted = r; break; }
+    }
+    if (diverged) return line_search_block<true>(sm, eps_out, n_trials);  // (nothing has been committed: the sequential search starts afresh)
+    const int last = accepted >= 0 ? accepted : nv - 1;
+    if (last >= 0) {
+        commit_trial(sm, bp, last);
+        if (threadIdx.x == 0) sm.st.merit = sm.st.actual_cost + merit_rho * sm.st.feas;
+        __syncthreads();
+    }
+    n_trials = last + 1;
+    if (accepted >= 0) { eps_out = epsv[accepted]; return true; }
+    // more than four step sizes (alpha > 0.1...): the search goes on sequentially from the state of the fourth trial
+    double eps = (nv > 0 ? epsv[nv - 1] : 1.0) * sm.opt.alpha;
+    bool success = false;
+    while (nv == 4 && eps > 1e-3) {
+        const bool rollout_success = hybrid_rollout_block<true>(sm, eps);
+        compute_cost_block(sm);
+        if (threadIdx.x == 0) { sm.ctl.trial_cost = sm.st.actual_cost; sm.ctl.trial_feas = sm.st.feas; sm.ctl.have_trial = 1; }
+        const double merit = sm.st.actual_cost + merit_rho * sm.st.feas;
+        ++n_trials;
+        const double exp_merit_change = (eps * dV_1 + 0.5 * eps * eps * dV_2) - eps * merit_rho * feas_prev;
+        __syncthreads();
+        if (threadIdx.x == 0) sm.st.merit = merit;
+        __syncthreads();
+        if ((merit <= merit_prev + sm.opt.gamma * exp_merit_change) && rollout_success) { success = true; break; }
+        eps *= sm.opt.alpha;
+    }
+    eps_out = success ? eps : 0.0;
+    return success;
+}
+
+// blocks 1..3 of the cluster
+__device__ inline void line_search_helper_loop(Smem& sm, const BatchPtrs& bp, int r) {
+    namespace cg = cooperative_groups;
+    for (;;) {
+        cg::this_cluster().sync();  // [A]
+        const int op = *((volatile int*)(bp.ls_mail + sm.pid));
+        if (op != 1) break;
+        double eps = 1;
+        for (int q = 0; q < r; ++q) eps *= sm.opt.alpha;
+        // the solver scalars and the state the trial starts from live in HBM and in block 0: Xbar, Ubar, dX, dU, K dX and the
+        // ReB / AL parameters are read from HBM (written by block 0 before [A])
+        if (eps > 1e-3) run_trial(sm, bp, r, eps);
+        __threadfence();
+        cg::this_cluster().sync();  // [B]
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -171,6 +297,7 @@ __device__ inline void iter_sweep_block(Smem& sm, const BatchPtrs& bp) {
     __syncthreads();
 }
 
+template <bool CLUSTER_LS = false>
 __device__ inline void iter_forward_block(Smem& sm, const BatchPtrs& bp) {
     const int tid = threadIdx.x;
     const hsddp_options& opt = sm.opt;
@@ -190,7 +317,7 @@ __device__ inline void iter_forward_block(Smem& sm, const BatchPtrs& bp) {
     } else {
         double eps_acc = 0;
         int ntr = 0;
-        if (line_search_block<true>(sm, eps_acc, ntr)) {
+        if (CLUSTER_LS ? line_search_cluster(sm, bp, eps_acc, ntr) : line_search_block<true>(sm, eps_acc, ntr)) {
             update_nominal_block(sm);
         } else {  // Q2: only the scalars are restored
             __syncthreads();
@@ -223,13 +350,14 @@ __device__ inline void solve_finish_block(Smem& sm, const BatchPtrs& bp) {
     __syncthreads();
 }
 
+template <bool CLUSTER_LS = false>
 __device__ inline void solve_block(Smem& sm, const BatchPtrs& bp) {
     solve_begin_block(sm);
     while (sm.ctl.active) {
         iter_prep_block(sm, bp);
         iter_sweep_block(sm, bp);
         if (!sm.ctl.active) break;
-        iter_forward_block(sm, bp);
+        iter_forward_block<CLUSTER_LS>(sm, bp);
     }
     solve_finish_block(sm, bp);
 }
@@ -247,6 +375,25 @@ __global__ void __launch_bounds__(kThreads, HSDDP_MIN_BLOCKS) k_solve(BatchPtrs 
 __global__ void __launch_bounds__(kThreads, 2) k_solve_lat(BatchPtrs bp, hsddp_options opt, int cold_start) {
     __shared__ Smem sm;
     solve_persistent<1>(sm, bp, opt, cold_start);
+}
+
+// latency build with the concurrent line search: one cluster of four blocks per problem (block rank 0 solves, ranks 1..3 evaluate
+// the other step sizes of every line search)
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kThreads, 2) k_solve_lat4(BatchPtrs bp, hsddp_options opt) {
+    namespace cg = cooperative_groups;
+    __shared__ Smem sm;
+    const int pid = blockIdx.x >> 2, r = (int)cg::this_cluster().block_rank();
+    if (threadIdx.x == 0) assign_rotation(bp.sm_slots, sm.rot);
+    bind_problem(sm, bp, pid);
+    if (threadIdx.x == 0) sm.opt = opt;
+    __syncthreads();
+    if (r == 0) {
+        solve_block<true>(sm, bp);
+        if (threadIdx.x == 0) { bp.state[pid] = sm.st; bp.ctl[pid] = sm.ctl; bp.ls_mail[pid] = 2; __threadfence(); }
+        cg::this_cluster().sync();  // [A] of the helpers' last round: exit
+    } else {
+        line_search_helper_loop(sm, bp, r);
+    }
 }
 
 template <int MINB>
@@ -847,6 +994,8 @@ struct hsddp_batch {
     int w1_min_blocks = 1554;
     int* d_order = nullptr;        // persistent kernel: queue order by the previous solve's iteration counts (k_order_by_iterations)
     bool have_order = false, use_order = true;
+    bool cluster_ls = true;        // latency kernel with the concurrent line search (k_solve_lat4) for batches of at most kClusterLsMax problems
+    static constexpr int kClusterLsMax = 32;  // 4 blocks per problem: every block of every cluster still gets an SM of its own (148 SMs); beyond that the helpers compete with the solving blocks (64 problems: 13.0 ms without, 13.8 ms with)
     static constexpr int kMaxGroups = 16;  // (default phased_groups = 8; HSDDP_PHASED_GROUPS may raise it for experiments)
     int phased_groups = 4;         // index ranges driven concurrently on their own streams (config 3, 16,384 problems, round 2: 1: 381 ms, 2: 354, 4: 336, 8: 341, 16: 354)
     cudaStream_t gstream[kMaxGroups] = {};
@@ -962,6 +1111,7 @@ int hsddp_batch_create(int device, hsddp_batch** out) {
     CK(cudaFuncSetAttribute(k_sweep_w1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     if (const char* e = getenv("HSDDP_W1_MIN_BLOCKS")) b->w1_min_blocks = atoi(e);  // tuning / experiments only
     if (const char* e = getenv("HSDDP_QUEUE_ORDER")) b->use_order = atoi(e) != 0;   // tuning / experiments only
+    if (const char* e = getenv("HSDDP_CLUSTER_LS")) b->cluster_ls = atoi(e) != 0;   // tuning / experiments only
     if (const char* e = getenv("HSDDP_SOLVE_MODE")) {  // tuning / experiments only
         const int v = atoi(e);
         if (v >= 0 && v <= 2) b->solve_mode = v;
@@ -1018,6 +1168,20 @@ static int alloc_workspace(hsddp_batch* b, int n_problems, int max_stages, int m
     if ((rc = dalloc(b, &b->d_active[0], P))) return rc;
     if ((rc = dalloc(b, &b->d_active[1], P))) return rc;
     if ((rc = dalloc(b, &b->d_order, P))) return rc;
+    if (n_problems <= hsddp_batch::kClusterLsMax) {  // trial arrays of the concurrent line search (small batches only)
+        const size_t Q = P * 4;
+        if ((rc = dalloc(b, &bp.ls_X, Q * SN)) || (rc = dalloc(b, &bp.ls_Defect, Q * SN)) || (rc = dalloc(b, &bp.ls_Xsim, Q * SN)) ||
+            (rc = dalloc(b, &bp.ls_U, Q * SS)) || (rc = dalloc(b, &bp.ls_Ut, Q * SS)) || (rc = dalloc(b, &bp.ls_gcon, Q * max_stages * 20)) ||
+            (rc = dalloc(b, &bp.ls_hcon, Q * MAXPH * 4)) || (rc = dalloc(b, &bp.ls_res, Q * 8)) || (rc = dalloc(b, &bp.ls_mail, P)))
+            return rc;
+        CK(cudaMemset(bp.ls_X, 0, Q * SN * sizeof(double)));
+        CK(cudaMemset(bp.ls_Defect, 0, Q * SN * sizeof(double)));
+        CK(cudaMemset(bp.ls_Xsim, 0, Q * SN * sizeof(double)));
+        CK(cudaMemset(bp.ls_U, 0, Q * SS * sizeof(double)));
+        CK(cudaMemset(bp.ls_Ut, 0, Q * SS * sizeof(double)));
+        CK(cudaMemset(bp.ls_res, 0, Q * 8 * sizeof(double)));
+        CK(cudaMemset(bp.ls_mail, 0, P * sizeof(int)));
+    }
     b->have_order = false;
     if ((rc = dalloc(b, &b->d_count, (size_t)2 * hsddp_batch::kMaxGroups))) return rc;
     CK(cudaMemset(bp.ctl, 0, P * sizeof(SolveCtl)));
@@ -1389,7 +1553,9 @@ int hsddp_batch_solve_async(hsddp_batch* b, const hsddp_options* opt) {
     if (phased) return solve_phased(b, o);
     CK(cudaMemsetAsync(b->bp.work_counter, 0, sizeof(int), b->stream));
     CK(cudaEventRecord(b->ev0, b->stream));
-    if (b->bp.n_problems <= 2 * b->n_sm) {
+    if (b->cluster_ls && b->bp.ls_mail && b->bp.n_problems <= hsddp_batch::kClusterLsMax && o.MS) {
+        k_solve_lat4<<<4 * b->bp.n_problems, kThreads, 0, b->stream>>>(b->bp, o);
+    } else if (b->bp.n_problems <= 2 * b->n_sm) {
         k_solve_lat<<<b->bp.n_problems, kThreads, 0, b->stream>>>(b->bp, o, 0);
     } else {
         const int grid = std::min(b->bp.n_problems, b->n_sm * b->blocks_per_sm);
