@@ -244,11 +244,12 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL's init lines (rank / nranks, transports) go to stderr so that the launcher's record shows N ranks;
-        # stdout stays ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL's init lines (rank / nranks, transports) must reach the launcher's record, and stdout must stay ONE JSON line:
+        # NCCL writes them to a per-process file, which every rank copies to its stderr at the end of the run
+        os.environ["NCCL_DEBUG"] = os.environ.get("HSDDP_NCCL_DEBUG", "INFO")
+        os.environ["NCCL_DEBUG_SUBSYS"] = os.environ.get("HSDDP_NCCL_DEBUG_SUBSYS", "INIT")
+        nccl_log = "/tmp/hsddp_nccl_%d_%d.log" % (os.getpid(), rank)
+        os.environ["NCCL_DEBUG_FILE"] = nccl_log
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -508,6 +509,12 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+        try:
+            with open(nccl_log) as f:
+                sys.stderr.write(f.read())
+            os.remove(nccl_log)
+        except OSError:
+            pass
     return 0
 
 
