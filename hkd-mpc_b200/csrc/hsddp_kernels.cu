@@ -1015,6 +1015,23 @@ struct hsddp_batch {
 
 namespace {
 
+// No C++ exception may cross the C ABI (std::vector staging buffers can throw bad_alloc: 4.5 GB of dense gains at 16k problems)
+template <class F>
+int guarded(F&& body) {
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        g_last_error = "out of host memory";
+        return HSDDP_ERR_ARG;
+    } catch (const std::exception& e) {
+        g_last_error = std::string("unexpected exception: ") + e.what();
+        return HSDDP_ERR_STATE;
+    } catch (...) {
+        g_last_error = "unexpected exception";
+        return HSDDP_ERR_STATE;
+    }
+}
+
 template <class T>
 int dalloc(hsddp_batch* b, T** p, size_t n) {
     void* q = nullptr;
@@ -1079,13 +1096,8 @@ int launch_step(hsddp_batch* b, const hsddp_options* opt, int op, double arg, do
 
 extern "C" {
 
-int hsddp_batch_create(int device, hsddp_batch** out) {
-    if (!out) return HSDDP_ERR_ARG;
-    int n = 0;
-    CK(cudaGetDeviceCount(&n));
-    if (device < 0 || device >= n) { g_last_error = "no such CUDA device (this library has no CPU fallback)"; return HSDDP_ERR_CUDA; }
+static int batch_init(hsddp_batch* b, int device) {
     CK(cudaSetDevice(device));
-    hsddp_batch* b = new hsddp_batch();
     b->device = device;
     CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&b->ev0));
@@ -1116,8 +1128,22 @@ int hsddp_batch_create(int device, hsddp_batch** out) {
         const int v = atoi(e);
         if (v >= 0 && v <= 2) b->solve_mode = v;
     }
-    *out = b;
     return HSDDP_OK;
+}
+
+int hsddp_batch_create(int device, hsddp_batch** out) {
+    if (!out) return HSDDP_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    CK(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) { g_last_error = "no such CUDA device (this library has no CPU fallback)"; return HSDDP_ERR_CUDA; }
+    return guarded([&]() -> int {
+        hsddp_batch* b = new hsddp_batch();
+        const int rc = batch_init(b, device);
+        if (rc != HSDDP_OK) { hsddp_batch_destroy(b); return rc; }  // (streams / events created so far are released)
+        *out = b;
+        return HSDDP_OK;
+    });
 }
 
 int hsddp_batch_destroy(hsddp_batch* b) {
@@ -1206,6 +1232,7 @@ static int alloc_workspace(hsddp_batch* b, int n_problems, int max_stages, int m
 
 int hsddp_batch_set_problems(hsddp_batch* b, int n_schedules, const hsddp_schedule* schedules, int n_problems,
                              const int32_t* schedule_id, const hsddp_constraint_params* cparams) {
+    return guarded([&]() -> int {
     if (!b || n_schedules <= 0 || !schedules || n_problems <= 0 || !schedule_id) return HSDDP_ERR_ARG;
     CK(cudaSetDevice(b->device));
     free_problem_allocs(b);
@@ -1277,6 +1304,7 @@ int hsddp_batch_set_problems(hsddp_batch* b, int n_schedules, const hsddp_schedu
     if ((rc = alloc_workspace(b, n_problems, max_stages, max_nodes))) return rc;
     b->has_problems = true;
     return hsddp_batch_reset(b);
+    });
 }
 
 
@@ -1284,6 +1312,7 @@ int hsddp_batch_set_problems_from_gaits(hsddp_batch* b, int n_gaits, const int32
                                         const double* body_state, const double* qJ, const double* foot_placements, const double* grf,
                                         const int32_t* contact, int n_schedules, const int32_t* sched_gait, const int32_t* sched_window,
                                         float plan_duration, int n_problems, const int32_t* schedule_id, const hsddp_constraint_params* cparams) {
+    return guarded([&]() -> int {
     if (!b || n_gaits <= 0 || !gait_rows || !gait_dt || !body_state || !qJ || !foot_placements || !grf || !contact || n_schedules <= 0 ||
         !sched_gait || !sched_window || n_problems <= 0 || !schedule_id || !(plan_duration > 0.f))
         return HSDDP_ERR_ARG;
@@ -1355,6 +1384,7 @@ int hsddp_batch_set_problems_from_gaits(hsddp_batch* b, int n_gaits, const int32
     b->lib = lib; b->d_sched_gait = d_sg; b->d_sched_window = d_sw; b->d_mpc = d_mpc; b->d_mpc_err = d_err;
     b->plan = plan_duration; b->node_stride = node_stride; b->n_sched = n_schedules; b->mpc_ready = true;
     return hsddp_batch_reset(b);
+    });
 }
 
 /* HKDProblem::update for every problem of the batch (see the kernels above).  The solver state that the reference keeps
@@ -1405,6 +1435,7 @@ static int refresh_host_schedules(hsddp_batch* b) {
 /* device-built schedule i back on the host (tests): phase table + reference rows, row counts as in hsddp_schedule */
 int hsddp_batch_get_schedule(hsddp_batch* b, int i, int32_t* n_phases, int32_t* horizon, int32_t* contact, int32_t* next_contact,
                              double* xr, double* ur, double* prel_r, double* xinit) {
+    return guarded([&]() -> int {
     if (!b || !b->has_problems || i < 0 || i >= (int)b->h_sched.size()) return HSDDP_ERR_ARG;
     CK(cudaSetDevice(b->device));
     DevSchedule d;
@@ -1423,6 +1454,7 @@ int hsddp_batch_get_schedule(hsddp_batch* b, int i, int32_t* n_phases, int32_t* 
     if (prel_r) CK(cudaMemcpy(prel_r, b->bp.prel + o * 12, nn * 12 * sizeof(double), cudaMemcpyDeviceToHost));
     if (xinit) CK(cudaMemcpy(xinit, b->bp.xinit + o * 24, nn * 24 * sizeof(double), cudaMemcpyDeviceToHost));
     return HSDDP_OK;
+    });
 }
 
 int hsddp_batch_set_initial_condition(hsddp_batch* b, const double* x0) {
@@ -1646,6 +1678,7 @@ int hsddp_batch_get_trace(hsddp_batch* b, hsddp_iter_record* out) {
 }
 
 int hsddp_batch_get_scalars(hsddp_batch* b, double* out) {
+    return guarded([&]() -> int {
     if (!b || !b->has_problems || !out) return HSDDP_ERR_ARG;
     CK(cudaSetDevice(b->device));
     std::vector<SolverState> st(b->bp.n_problems);
@@ -1656,6 +1689,7 @@ int hsddp_batch_get_scalars(hsddp_batch* b, double* out) {
         o[5] = st[i].max_tconstr; o[6] = st[i].max_pconstr; o[7] = st[i].merit_rho;
     }
     return HSDDP_OK;
+    });
 }
 
 // Dense column-major 24x24 feedback gains for stages [row0, row0+nrows) from the compact K_r store.
@@ -1710,6 +1744,7 @@ static int array_spec(hsddp_batch* b, int which, double** dev, size_t* per_probl
 }
 
 int hsddp_batch_get_array(hsddp_batch* b, int which, double* out) {
+    return guarded([&]() -> int {
     if (!b || !b->has_problems || !out) return HSDDP_ERR_ARG;
     CK(cudaSetDevice(b->device));
     const BatchPtrs& bp = b->bp;
@@ -1775,6 +1810,7 @@ int hsddp_batch_get_array(hsddp_batch* b, int which, double* out) {
         CK(cudaStreamSynchronize(b->stream));
     }
     return HSDDP_OK;
+    });
 }
 
 int hsddp_batch_set_array(hsddp_batch* b, int which, const double* in) {
@@ -1791,6 +1827,7 @@ int hsddp_batch_set_array(hsddp_batch* b, int which, const double* in) {
 }
 
 int hsddp_batch_get_array_rows(hsddp_batch* b, int which, int row0, int nrows, double* out) {
+    return guarded([&]() -> int {
     if (!b || !b->has_problems || !out || row0 < 0 || nrows <= 0) return HSDDP_ERR_ARG;
     CK(cudaSetDevice(b->device));
     if (which == HSDDP_ARR_K) return get_gains(b, row0, nrows, out);
@@ -1810,6 +1847,7 @@ int hsddp_batch_get_array_rows(hsddp_batch* b, int which, int row0, int nrows, d
                          (size_t)nrows * cols * sizeof(double), (size_t)b->bp.n_problems, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
     return HSDDP_OK;
+    });
 }
 
 int hsddp_batch_get_gains_compact(hsddp_batch* b, int row0, int nrows, double* out) {
