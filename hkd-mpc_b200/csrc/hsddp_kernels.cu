@@ -23,6 +23,8 @@
 
 namespace hsddp {
 
+constexpr int hsddp_batch_max_groups = 16;
+
 // ---------------------------------------------------------------------------
 // iteration control
 // ---------------------------------------------------------------------------
@@ -421,6 +423,47 @@ __device__ __forceinline__ void solve_persistent(Smem& sm, const BatchPtrs& bp, 
 #ifdef HSDDP_PROFILE
         if (threadIdx.x == 0) for (int i = 0; i < 16; ++i) atomicAdd(&sm.prof[i], sm.profacc[i]);
 #endif
+    }
+}
+
+// Tail of a phased solve (hybrid driver): the problems still running after the phased rounds -- listed per group in HBM, the
+// lengths known only on the device -- are finished by a persistent kernel that resumes solve() at the top of a DDP iteration.
+// Late rounds of a phased solve are latency-bound (every round costs at least one problem's iteration, however few problems
+// are left); here every survivor gets a block of its own and runs at single-problem speed.
+struct ResumeLists {
+    const int* list[hsddp_batch_max_groups];
+    const int* count[hsddp_batch_max_groups];
+    int n;
+};
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_solve_resume(BatchPtrs bp, hsddp_options opt, ResumeLists rl) {
+    __shared__ Smem sm;
+    if (threadIdx.x == 0) assign_rotation(bp.sm_slots, sm.rot);
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int q = atomicAdd(bp.work_counter, 1), pid = -1;
+            for (int g = 0; g < rl.n; ++g) {
+                const int c = *rl.count[g];
+                if (q < c) { pid = rl.list[g][q]; break; }
+                q -= c;
+            }
+            sm.ibuf[3] = pid;
+        }
+        __syncthreads();
+        const int pid = sm.ibuf[3];
+        if (pid < 0) break;
+        bind_problem(sm, bp, pid);
+        if (threadIdx.x == 0) sm.opt = opt;
+        __syncthreads();
+        while (sm.ctl.active) {  // (a listed problem is running: its state was saved at the end of a forward phase)
+            iter_prep_block(sm, bp);
+            iter_sweep_block(sm, bp);
+            if (!sm.ctl.active) break;
+            iter_forward_block(sm, bp);
+        }
+        solve_finish_block(sm, bp);
+        if (threadIdx.x == 0) { bp.state[pid] = sm.st; bp.ctl[pid] = sm.ctl; }
     }
 }
 
@@ -997,6 +1040,9 @@ struct hsddp_batch {
     bool cluster_ls = true;        // latency kernel with the concurrent line search (k_solve_lat4) for batches of at most kClusterLsMax problems
     static constexpr int kClusterLsMax = 32;  // 4 blocks per problem: every block of every cluster still gets an SM of its own (148 SMs); beyond that the helpers compete with the solving blocks (64 problems: 13.0 ms without, 13.8 ms with)
     static constexpr int kMaxGroups = 16;  // (default phased_groups = 8; HSDDP_PHASED_GROUPS may raise it for experiments)
+    int phased_min_group = 1024;   // smallest index range the phased driver drives on its own stream
+    // hybrid driver (mid-size batches): phased rounds while the GPU is full, then a persistent kernel finishes the survivors
+    int hybrid_rounds = 20, hybrid_groups = 4, hybrid_min_group = 256;
     int phased_groups = 4;         // index ranges driven concurrently on their own streams (config 3, 16,384 problems, round 2: 1: 381 ms, 2: 354, 4: 336, 8: 341, 16: 354)
     cudaStream_t gstream[kMaxGroups] = {};
     cudaEvent_t gevent[kMaxGroups] = {};
@@ -1119,6 +1165,9 @@ static int batch_init(hsddp_batch* b, int device) {
         const int v = atoi(e);
         if (v >= 1 && v <= hsddp_batch::kMaxGroups) b->phased_groups = v;
     }
+    if (const char* e = getenv("HSDDP_PHASED_MIN_GROUP")) { const int v = atoi(e); if (v >= 1) b->phased_min_group = v; }  // tuning / experiments only
+    if (const char* e = getenv("HSDDP_HYBRID_ROUNDS")) b->hybrid_rounds = atoi(e);  // tuning / experiments only
+    if (const char* e = getenv("HSDDP_HYBRID_GROUPS")) { const int v = atoi(e); if (v >= 1 && v <= hsddp_batch::kMaxGroups) b->hybrid_groups = v; }
     if (const char* e = getenv("HSDDP_SWEEP_KIND")) b->sweep_kind = atoi(e);  // tuning / experiments only
     CK(cudaFuncSetAttribute(k_sweep_w1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     if (const char* e = getenv("HSDDP_W1_MIN_BLOCKS")) b->w1_min_blocks = atoi(e);  // tuning / experiments only
@@ -1126,7 +1175,7 @@ static int batch_init(hsddp_batch* b, int device) {
     if (const char* e = getenv("HSDDP_CLUSTER_LS")) b->cluster_ls = atoi(e) != 0;   // tuning / experiments only
     if (const char* e = getenv("HSDDP_SOLVE_MODE")) {  // tuning / experiments only
         const int v = atoi(e);
-        if (v >= 0 && v <= 2) b->solve_mode = v;
+        if (v >= 0 && v <= 3) b->solve_mode = v;
     }
     return HSDDP_OK;
 }
@@ -1511,10 +1560,10 @@ __global__ void k_order_by_iterations(const hsddp_info* info, int n, int* order)
     }
 }
 
-static int solve_phased(hsddp_batch* b, const hsddp_options& o) {
+static int solve_phased(hsddp_batch* b, const hsddp_options& o, bool hybrid) {
     const int P = b->bp.n_problems;
-    int G = b->phased_groups;
-    G = std::min(G, std::max(1, P / 1024));  // keep at least ~1.5 waves of blocks per group
+    int G = hybrid ? b->hybrid_groups : b->phased_groups;
+    G = std::min(G, std::max(1, P / (hybrid ? b->hybrid_min_group : b->phased_min_group)));  // problems per group at least ..._min_group
     G = std::max(1, std::min(G, hsddp_batch::kMaxGroups));
     for (int g = 0; g < G; ++g) {
         if (!b->gstream[g]) {
@@ -1526,7 +1575,10 @@ static int solve_phased(hsddp_batch* b, const hsddp_options& o) {
     CK(cudaMemsetAsync(b->d_count, 0, 2 * hsddp_batch::kMaxGroups * sizeof(int), b->stream));
     k_iota<<<(P + 255) / 256, 256, 0, b->stream>>>(b->d_active[0], P);
     CK(cudaEventRecord(b->ev_fork, b->stream));
-    const int rounds = (int)std::min<long long>((long long)std::max(0, o.max_AL_iter) * (long long)std::max(0, o.max_DDP_iter), 1000000LL);
+    const int all_rounds = (int)std::min<long long>((long long)std::max(0, o.max_AL_iter) * (long long)std::max(0, o.max_DDP_iter), 1000000LL);
+    const int rounds = hybrid ? std::min(all_rounds, std::max(0, b->hybrid_rounds)) : all_rounds;
+    ResumeLists rl{};
+    rl.n = 0;
     const bool use_block = b->sweep_kind != 1, use_w1 = b->sweep_kind != 0;
     int rc = HSDDP_OK;
     for (int g = 0; g < G && rc == HSDDP_OK; ++g) {
@@ -1552,6 +1604,9 @@ static int solve_phased(hsddp_batch* b, const hsddp_options& o) {
             b->n_solve_launches += 3 + (use_block && use_w1 ? 1 : 0);
         }
         if (cudaGetLastError() != cudaSuccess) { rc = HSDDP_ERR_CUDA; g_last_error = "kernel launch failed in the phased driver"; }
+        // the survivors of the last round: list / counter the next round would have read
+        const int nxt = (rounds + 1) & 1;
+        rl.list[rl.n] = list[nxt]; rl.count[rl.n] = cnt[nxt]; rl.n++;
     }
     b->last_rounds = rounds;
     // join (also on an error exit: the handle's stream continues after every group, so later calls never see half-finished state)
@@ -1559,12 +1614,18 @@ static int solve_phased(hsddp_batch* b, const hsddp_options& o) {
         if (!b->gstream[g]) continue;
         if (cudaEventRecord(b->gevent[g], b->gstream[g]) == cudaSuccess) cudaStreamWaitEvent(b->stream, b->gevent[g], 0);
     }
+    if (hybrid && rounds < all_rounds && rc == HSDDP_OK) {  // the tail: one persistent kernel over the survivors of every group
+        CK(cudaMemsetAsync(b->bp.work_counter, 0, sizeof(int), b->stream));
+        k_solve_resume<4><<<b->n_sm * 4, kThreads, 0, b->stream>>>(b->bp, o, rl);
+        CK(cudaGetLastError());
+        b->n_solve_launches++;
+    }
     CK(cudaEventRecord(b->ev1, b->stream));
     return rc;
 }
 
 int hsddp_batch_set_solve_mode(hsddp_batch* b, int mode) {
-    if (!b || mode < 0 || mode > 2) return HSDDP_ERR_ARG;
+    if (!b || mode < 0 || mode > 3) return HSDDP_ERR_ARG;
     b->solve_mode = mode;
     return HSDDP_OK;
 }
@@ -1582,7 +1643,8 @@ int hsddp_batch_solve_async(hsddp_batch* b, const hsddp_options* opt) {
     // (measured on config 3, persistent vs phased, ms: 2,048 problems 57 vs 73, 4,096: 101 vs 108, 8,192: 199 vs 188,
     // 16,384: 455 vs 336 -- DESIGN.md §4)
     const bool phased = b->solve_mode == 2 || (b->solve_mode == 0 && b->bp.n_problems >= 7 * b->n_sm * b->blocks_per_sm);
-    if (phased) return solve_phased(b, o);
+    if (phased) return solve_phased(b, o, false);
+    if (b->solve_mode == 3) return solve_phased(b, o, true);
     CK(cudaMemsetAsync(b->bp.work_counter, 0, sizeof(int), b->stream));
     CK(cudaEventRecord(b->ev0, b->stream));
     if (b->cluster_ls && b->bp.ls_mail && b->bp.n_problems <= hsddp_batch::kClusterLsMax && o.MS) {

@@ -230,6 +230,17 @@ def test_solve_modes_agree(pkg, orc, workloads):
     B3 = _batch_for(pkg, w3)
     B3.solve()
     _compare_solution(pkg, orc, w3, B3, range(3), {}, max_ill_posed=1)
+    # hybrid driver (mode 3): phased rounds, then a persistent kernel resumes the problems still running
+    Bh = _batch_for(pkg, w)
+    Bh.set_solve_mode(3)
+    Bh.solve()
+    ih = Bh.info()
+    assert (ih["n_iter"] > 20).sum() > 10, "no problem reached the persistent tail"
+    _compare_solution(pkg, orc, w, Bh, range(0, 12), {}, max_ill_posed=2)
+    same = (ih["n_iter"] == i2["n_iter"]) & (ih["status"] == i2["status"])
+    assert same.mean() > 0.95, same.mean()
+    for i in np.nonzero(same)[0]:
+        assert rel_err(Bh.get("Xbar")[i], out[2][1][i]) < RTOL, i
 
 
 def test_mpc_command_extraction(pkg, orc, workloads):
