@@ -15,8 +15,8 @@
 //     shared-memory pipe, its hard floor);
 //   * the 12x12 block Gauss-Jordan carries TWO tableau columns per lane (49 columns: 12 Quu_r, 24 Qux_r, Qu_r, 12
 //     identity), so the pivot columns are published and read once instead of once per eliminating warp.
-// Up to seven problems (warps) are resident per SM; while one warp sits in the latency-bound elimination the other
-// warp of its sub-partition owns the tensor pipe.
+// Eight problems (warps) are resident per SM (27.7 KB of shared memory and 254 registers each): while one warp sits in the
+// latency-bound elimination the other warp of its sub-partition owns the tensor pipe.
 #pragma once
 #include "hsddp_sweep.cuh"
 
@@ -25,11 +25,12 @@ namespace hsddp {
 struct __align__(16) SweepW1 {
     double H[ro(24)], Y[ro(24)];
     double Z[zo(24)];               // H B_r [24][16]; after P2: K_r^T [24][12]
-    double Qux[ro(16) + kQuuPad];   // Qux_r [16][24]; with Quu it is also the 24-row temporary of the impact-aware step
-    double Quu[ro(12)];
+    double Qux[ro(12) + kQuuPad];   // Qux_r [12][24] (rows 12..15 of its second row block are never stored); with Quu it is also
+    double Quu[ro(12)];             // the 24-row temporary of the impact-aware step
     double R[hkd::kRSize];          // dense [A - I | B_r] rows 0..11, [12][44]
-    double cr[2][CR_STRIDE];        // compact stage records (HBM layout), cp.async double buffer
-    double dfc2[2][24];
+    double cr[CR_STRIDE];           // the compact record of the stage (HBM layout): entries for R, then lx, lu, luu; refilled by
+    double dfc[24];                 // cp.async for the NEXT stage once P2 has consumed lx, lu, luu (defect: once P1 has)
+    double zvec[24];                // 0 x 11, 1, 0 x 12: the identity / zero tableau columns are slices of it
     double G[24], Gn[24], Qx[24], vtmp[24];
     double Qu[12], wu[12];
     double lxxd[24], lxxTd[24], lxxw[12], lxxTw[12];
@@ -40,8 +41,9 @@ struct __align__(16) SweepW1 {
     int horizon[MAXPH], node_off[MAXPH], stage_off[MAXPH];
     unsigned cmask[MAXPH], nmask[MAXPH];
 };
-static_assert(offsetof(SweepW1, Quu) - offsetof(SweepW1, Qux) == sizeof(double) * (ro(16) + kQuuPad), "Qux and Quu must be contiguous");
-static_assert(ro(16) + kQuuPad + ro(12) >= ro(24), "Qux|Quu must hold a 24-row temporary");
+static_assert(offsetof(SweepW1, Quu) - offsetof(SweepW1, Qux) == sizeof(double) * (ro(12) + kQuuPad), "Qux and Quu must be contiguous");
+static_assert(ro(12) + kQuuPad + ro(12) >= ro(24), "Qux|Quu must hold a 24-row temporary");
+static_assert(sizeof(SweepW1) + 1024 <= 233472 / 8, "eight problems per SM");
 
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
@@ -90,14 +92,14 @@ struct SweepW1Ptrs {  // per-problem HBM pointers (registers, warp-uniform)
     double *K, *dU, *g0h0;
 };
 
-// fetch the compact record of stage s and the defect of node n1 into buffer `buf`
-__device__ __forceinline__ void w1_prefetch(SweepW1& sm, const SweepW1Ptrs& p, int buf, int s, int n1) {
+// fetch the compact record of stage s and the defect of node n1
+__device__ __forceinline__ void w1_prefetch(SweepW1& sm, const SweepW1Ptrs& p, int s, int n1) {
     const int lane = threadIdx.x & 31;
     const char* src = reinterpret_cast<const char*>(p.lqg + (size_t)s * CR_STRIDE);
-    char* dst = reinterpret_cast<char*>(sm.cr[buf]);
+    char* dst = reinterpret_cast<char*>(sm.cr);
 #pragma unroll
     for (int u = lane; u < 98; u += 32) cp_async16(dst + 16 * u, src + 16 * u);  // 196 doubles: entries, lx, lu, luu
-    if (lane < 12) cp_async16(reinterpret_cast<char*>(sm.dfc2[buf]) + 16 * lane, reinterpret_cast<const char*>(p.Defect + 24 * n1) + 16 * lane);
+    if (lane < 12) cp_async16(reinterpret_cast<char*>(sm.dfc) + 16 * lane, reinterpret_cast<const char*>(p.Defect + 24 * n1) + 16 * lane);
 }
 
 __device__ inline void w1_phase_tables(SweepW1& sm, unsigned cm, double dt) {
@@ -133,7 +135,7 @@ __device__ inline bool w1_phase_sweep(SweepW1& sm, const SweepW1Ptrs& p, int ph,
     const int Nph = sm.horizon[ph];
     const double* trec = p.tq + ph * TQ_STRIDE;
     w1_phase_tables(sm, cm, dt);
-    w1_prefetch(sm, p, 0, sm.stage_off[ph] + Nph - 1, sm.node_off[ph] + Nph);
+    w1_prefetch(sm, p, sm.stage_off[ph] + Nph - 1, sm.node_off[ph] + Nph);
     // fragment base pointers: accumulator element (g, 2t..2t+1), operand element (t, g)
     const double* hA = sm.H + ro(t) + g;
     double* hC = sm.H + ro(g) + 2 * t;
@@ -174,22 +176,19 @@ __device__ inline bool w1_phase_sweep(SweepW1& sm, const SweepW1Ptrs& p, int ph,
 #pragma unroll 1
     for (int k = Nph - 1; k >= 0; --k) {
         const int s = sm.stage_off[ph] + k;
-        const int buf = (Nph - 1 - k) & 1;
         cp_async_wait_all();
         __syncwarp();
         {   // compact record -> dense tile (the other entries of the tile are constant)
-            const double* crb = sm.cr[buf];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int i = lane + 32 * q;
-                if (i < hkd::kCrNnz) sm.R[rpos[q]] = crb[CR_R + i];
+                if (i < hkd::kCrNnz) sm.R[rpos[q]] = sm.cr[CR_R + i];
             }
         }
-        if (k > 0) w1_prefetch(sm, p, buf ^ 1, s - 1, sm.node_off[ph] + k);
-        const double* lxv = sm.cr[buf] + CR_LX;
-        const double* luv = sm.cr[buf] + CR_LU;
-        const double* luu = sm.cr[buf] + CR_LUU;
-        const double* dfc = sm.dfc2[buf];
+        const double* lxv = sm.cr + CR_LX;
+        const double* luv = sm.cr + CR_LU;
+        const double* luu = sm.cr + CR_LUU;
+        const double* dfc = sm.dfc;
         __syncwarp();
         // ---- P1: [Y | Z] = H [A | B_r], Gn = G + H d ----
         {
@@ -373,6 +372,7 @@ __device__ inline bool w1_phase_sweep(SweepW1& sm, const SweepW1Ptrs& p, int ph,
             }
         }
         __syncwarp();
+        if (k > 0) w1_prefetch(sm, p, s - 1, sm.node_off[ph] + k);  // (lx, lu, luu and the defect of this stage have been consumed)
         // ---- P3: block Gauss-Jordan on the tableau [Quu_r | Qux_r | Qu_r | I], two columns per lane ----
         // slot a: lanes 0..11 Quu_r columns, lanes 12..31 Qux_r columns 0..19
         // slot b: lanes 0..3 Qux_r columns 20..23, lane 4 Qu_r, lanes 5..16 identity columns, lanes 17..31 zero
@@ -394,16 +394,10 @@ __device__ inline bool w1_phase_sweep(SweepW1& sm, const SweepW1Ptrs& p, int ph,
                 }
             }
             const bool b_gain = lane < 4, b_ff = lane == 4, b_inv = lane >= 5 && lane < 17;
-            {
-                const double* src = b_gain ? sm.Qux + 20 + lane : sm.Qu;
+            {   // slot b: a strided Qux_r column, or a unit-stride slice: Qu_r, column lane - 5 of the identity (zvec + 11 - (lane - 5)), zeros
+                const double* src = b_gain ? sm.Qux + 20 + lane : b_ff ? sm.Qu : b_inv ? sm.zvec + 16 - lane : sm.zvec + 12;
 #pragma unroll
-                for (int r = 0; r < 12; ++r) {
-                    double v = 0.0;
-                    if (b_gain) v = src[ro(r)];
-                    else if (b_ff) v = src[r];
-                    else if (b_inv) v = (r == lane - 5) ? 1.0 : 0.0;
-                    vb[r] = v;
-                }
+                for (int r = 0; r < 12; ++r) vb[r] = src[b_gain ? ro(r) : r];
             }
             const bool ok = gauss_jordan12x2(va, vb, sm.sbuf);
             if (pass) { verdict = ok ? 1 : 0; break; }
@@ -601,7 +595,7 @@ __device__ inline bool w1_backward_sweep(SweepW1& sm, const SweepW1Ptrs& p, doub
 // The sweep phase of one DDP iteration for every running problem (phased driver): backward_sweep_regularized with
 // the bookkeeping of iter_sweep_block (hsddp_kernels.cu).  One warp = one block = one problem.
 #ifndef HSDDP_W1_MINB
-#define HSDDP_W1_MINB 7
+#define HSDDP_W1_MINB 8
 #endif
 __global__ void __launch_bounds__(32, HSDDP_W1_MINB) k_sweep_w1(BatchPtrs bp, hsddp_options opt) {
     __shared__ SweepW1 sm;
@@ -610,6 +604,7 @@ __global__ void __launch_bounds__(32, HSDDP_W1_MINB) k_sweep_w1(BatchPtrs bp, hs
     const int pid = bp.active ? bp.active[blockIdx.x] : (int)blockIdx.x;
     const DevSchedule* sc = bp.sched + bp.sched_id[pid];
     if (lane == 0) { sm.n_phases = sc->n_phases; sm.n_stages = sc->n_stages; }
+    if (lane < 24) sm.zvec[lane] = (lane == 11) ? 1.0 : 0.0;
     if (lane < MAXPH) {
         sm.horizon[lane] = sc->horizon[lane]; sm.node_off[lane] = sc->node_off[lane]; sm.stage_off[lane] = sc->stage_off[lane];
         sm.cmask[lane] = sc->cmask[lane]; sm.nmask[lane] = sc->nmask[lane];
