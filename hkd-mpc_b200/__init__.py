@@ -166,6 +166,14 @@ def lib():
         L.hsddp_batch_get_counters.argtypes = [vp, C.POINTER(C.c_ulonglong)]
         L.hsddp_batch_reset_counters.argtypes = [vp]
         L.hsddp_batch_get_profile.argtypes = [vp, C.POINTER(C.c_ulonglong)]
+        L.hsddp_phase_batch_create.argtypes = [C.c_int] * 6 + [C.POINTER(vp)]
+        L.hsddp_phase_batch_destroy.argtypes = [vp]
+        L.hsddp_phase_batch_set.argtypes = [vp, C.c_int, dp]
+        L.hsddp_phase_batch_backward_sweep.argtypes = [vp, C.c_double, dp, dp, ip]
+        L.hsddp_phase_batch_linear_rollout.argtypes = [vp, C.c_double, dp]
+        L.hsddp_phase_batch_set_gains.argtypes = [vp, dp, dp]
+        L.hsddp_phase_batch_get.argtypes = [vp, C.c_int, dp]
+        L.hsddp_phase_batch_last_ms.argtypes = [vp, C.POINTER(C.c_float)]
         _lib = L
     return _lib
 
@@ -493,6 +501,76 @@ class MultiPhaseDDPBatch:
         if name == "K":
             arr = np.ascontiguousarray(np.swapaxes(arr, -1, -2))
         _check(lib().hsddp_batch_set_array(self.h, ARR[name], _dp(arr)), "set_array")
+
+
+
+class SinglePhaseBatch:
+    """The model-independent sweeps of SinglePhase<double, xs, us, ys> (HSDDPSolver/source/SinglePhase.cpp:145-178,
+    299-367) for the reference's other instantiations <12,12,0> and <36,12,12> (and <24,24,0>, dense), on a batch of
+    independent phases of equal horizon.  Inputs are what LQ_approximation leaves in the phase's storage; matrices are
+    given and returned as [..., row, col] arrays (the C ABI is column-major)."""
+    INPUTS = ["A", "B", "C", "D", "lx", "lu", "ly", "lxx", "luu", "lux", "lyy", "Phix", "Phixx", "Defect"]
+    OUTPUTS = ["dU", "K", "G", "H", "dX", "dV"]
+    _MATS = {"A", "B", "C", "D", "lxx", "luu", "lux", "lyy", "Phixx", "K", "H"}
+
+    def __init__(self, xs, us, ys, horizon, n_problems, device=0):
+        self.xs, self.us, self.ys, self.N, self.n = int(xs), int(us), int(ys), int(horizon), int(n_problems)
+        self.h = C.c_void_p()
+        _check(lib().hsddp_phase_batch_create(int(device), self.xs, self.us, self.ys, self.N, self.n, C.byref(self.h)), "hsddp_phase_batch_create")
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().hsddp_phase_batch_destroy(self.h)
+        except Exception:
+            pass
+
+    def shape(self, name):
+        xs, us, ys, N, n = self.xs, self.us, self.ys, self.N, self.n
+        return dict(A=(n, N, xs, xs), B=(n, N, xs, us), C=(n, N, ys, xs), D=(n, N, ys, us), lx=(n, N, xs), lu=(n, N, us), ly=(n, N, ys),
+                    lxx=(n, N, xs, xs), luu=(n, N, us, us), lux=(n, N, us, xs), lyy=(n, N, ys, ys), Phix=(n, xs), Phixx=(n, xs, xs),
+                    Defect=(n, N + 1, xs), dU=(n, N, us), K=(n, N, us, xs), G=(n, N + 1, xs), H=(n, N + 1, xs, xs), dX=(n, N + 1, xs),
+                    dV=(n, 2), Gprime=(n, xs), Hprime=(n, xs, xs), dx_init=(n, xs))[name]
+
+    def _to_c(self, name, arr):
+        a = np.asarray(arr, np.float64)
+        if a.shape != self.shape(name):
+            raise ValueError(f"{name}: shape {a.shape}, expected {self.shape(name)}")
+        if name in self._MATS | {"Hprime"}:
+            a = np.swapaxes(a, -1, -2)
+        return np.ascontiguousarray(a)
+
+    def set(self, name, arr):
+        a = self._to_c(name, arr)
+        if a.size:
+            _check(lib().hsddp_phase_batch_set(self.h, self.INPUTS.index(name), _dp(a)), "hsddp_phase_batch_set")
+
+    def backward_sweep(self, reg, Gprime=None, Hprime=None):
+        ok = np.zeros(self.n, np.int32)
+        g = None if Gprime is None else self._to_c("Gprime", Gprime)
+        h = None if Hprime is None else self._to_c("Hprime", Hprime)
+        _check(lib().hsddp_phase_batch_backward_sweep(self.h, float(reg), None if g is None else _dp(g), None if h is None else _dp(h), _ip(ok)),
+               "hsddp_phase_batch_backward_sweep")
+        return ok.astype(bool)
+
+    def linear_rollout(self, eps, dx_init=None):
+        d = None if dx_init is None else self._to_c("dx_init", dx_init)
+        _check(lib().hsddp_phase_batch_linear_rollout(self.h, float(eps), None if d is None else _dp(d)), "hsddp_phase_batch_linear_rollout")
+
+    def set_gains(self, dU, K):
+        _check(lib().hsddp_phase_batch_set_gains(self.h, _dp(self._to_c("dU", dU)), _dp(self._to_c("K", K))), "hsddp_phase_batch_set_gains")
+
+    def get(self, name):
+        shp = self.shape(name)
+        cshape = shp[:-2] + (shp[-1], shp[-2]) if name in self._MATS else shp
+        out = np.zeros(cshape)
+        _check(lib().hsddp_phase_batch_get(self.h, self.OUTPUTS.index(name), _dp(out)), "hsddp_phase_batch_get")
+        return np.ascontiguousarray(np.swapaxes(out, -1, -2)) if name in self._MATS else out
+
+    def last_ms(self):
+        ms = C.c_float()
+        _check(lib().hsddp_phase_batch_last_ms(self.h, C.byref(ms)), "hsddp_phase_batch_last_ms")
+        return ms.value
 
 
 def fp64_peak_tflops(device=0, kind=0):

@@ -999,6 +999,7 @@ using namespace hsddp;
 
 static thread_local std::string g_last_error;
 const char* hsddp_last_error(void) { return g_last_error.c_str(); }
+namespace hsddp { void set_last_error(const std::string& s) { g_last_error = s; } }  // for the other translation units
 
 #define CK(call)                                                                                   \
     do {                                                                                           \

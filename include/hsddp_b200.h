@@ -299,6 +299,59 @@ int hsddp_batch_reset_counters(hsddp_batch* b);
 /* per-phase cycle counters (all zero unless the library was built with -DHSDDP_PROFILE) */
 int hsddp_batch_get_profile(hsddp_batch* b, unsigned long long out[16]);
 
+/* ------------------------------------------------------------------------
+ * The reference's OTHER instantiations: SinglePhase<double,12,12,0> and <36,12,12>
+ * (HSDDPSolver/source/SinglePhase.cpp:538-540; <24,24,0> is accepted too, in its dense form).
+ * The reference ships no model, cost or problem for them and host plug-ins cannot run on the device, so the boundary
+ * is the phase's storage after LQ_approximation (SinglePhase.cpp:265-296): the plug-in outputs go in, the
+ * model-independent sweeps run on the device for a batch of independent phases of equal horizon.
+ * All matrices column-major (Eigen default); arrays are problem-major, then stage-major:
+ *   A [n][N][xs*xs]  B [n][N][xs*us]  C [n][N][ys*xs]  D [n][N][ys*us]                (dynamics_partial, SinglePhase.h:45-50)
+ *   lx [n][N][xs] lu [n][N][us] ly [n][N][ys] lxx [n][N][xs*xs] luu [n][N][us*us] lux [n][N][us*xs] lyy [n][N][ys*ys]
+ *                                                                                      (RCostData, HSDDP_CompoundTypes.h:90-127)
+ *   Phix [n][xs]  Phixx [n][xs*xs]                                                     (TCostData, :129-150)
+ *   Defect [n][N+1][xs]                                                                (Trajectory::Defect)
+ * Inputs never set are zero.
+ * ---------------------------------------------------------------------- */
+typedef struct hsddp_phase_batch hsddp_phase_batch;
+#define HSDDP_PH_A 0
+#define HSDDP_PH_B 1
+#define HSDDP_PH_C 2
+#define HSDDP_PH_D 3
+#define HSDDP_PH_LX 4
+#define HSDDP_PH_LU 5
+#define HSDDP_PH_LY 6
+#define HSDDP_PH_LXX 7
+#define HSDDP_PH_LUU 8
+#define HSDDP_PH_LUX 9
+#define HSDDP_PH_LYY 10
+#define HSDDP_PH_PHIX 11
+#define HSDDP_PH_PHIXX 12
+#define HSDDP_PH_DEFECT 13
+#define HSDDP_PH_N_INPUTS 14
+#define HSDDP_PH_OUT_DU 0 /* [n][N][us]      feed-forward                         */
+#define HSDDP_PH_OUT_K 1  /* [n][N][us*xs]   feedback gains                       */
+#define HSDDP_PH_OUT_G 2  /* [n][N+1][xs]    value gradient                       */
+#define HSDDP_PH_OUT_H 3  /* [n][N+1][xs*xs] value Hessian                        */
+#define HSDDP_PH_OUT_DX 4 /* [n][N+1][xs]    linear-rollout direction             */
+#define HSDDP_PH_OUT_DV 5 /* [n][2]          dV_1, dV_2 of the LAST sweep / rollout */
+#define HSDDP_PH_N_OUTPUTS 6
+/* HSDDP_ERR_UNSUPPORTED for any (xs, us, ys) the reference does not instantiate */
+int hsddp_phase_batch_create(int device, int xs, int us, int ys, int horizon, int n_problems, hsddp_phase_batch** out);
+int hsddp_phase_batch_destroy(hsddp_phase_batch* b);
+int hsddp_phase_batch_set(hsddp_phase_batch* b, int which, const double* host);
+/* SinglePhase::backward_sweep(regularization, Gprime, Hprime) (SinglePhase.cpp:299-367): Gprime [n][xs], Hprime [n][xs*xs]
+ * (null = zero: a last phase); ok [n] (optional) receives the bool the reference returns.  After a failed stage the
+ * stages below it keep what the storage held, and G[0] += H[0] Defect[0] still runs (:365), as in the reference. */
+int hsddp_phase_batch_backward_sweep(hsddp_phase_batch* b, double regularization, const double* Gprime, const double* Hprime, int32_t* ok);
+/* SinglePhase::linear_rollout(eps) (SinglePhase.cpp:145-178) with the gains of the last sweep (or set_gains);
+ * dx_init [n][xs] (null = zero: a first phase) */
+int hsddp_phase_batch_linear_rollout(hsddp_phase_batch* b, double eps, const double* dx_init);
+int hsddp_phase_batch_set_gains(hsddp_phase_batch* b, const double* dU, const double* K);
+int hsddp_phase_batch_get(hsddp_phase_batch* b, int which, double* host);
+/* milliseconds of the last sweep / rollout kernel (CUDA events on the handle's stream) */
+int hsddp_phase_batch_last_ms(hsddp_phase_batch* b, float* ms);
+
 /* device-side FP64 FMA throughput probe (TFLOP/s) used as the measured roofline
  * denominator by bench.py; kind 0 = DFMA on CUDA cores, 1 = DMMA m8n8k4 tensor tiles */
 int hsddp_fp64_peak_tflops(int device, int kind, double* tflops);

@@ -10,6 +10,7 @@
 #include <thread>
 #include <vector>
 #include "hsddp_oracle.hpp"
+#include "single_phase_generic.hpp"
 
 using namespace oracle;
 
@@ -276,6 +277,24 @@ double orc_batch_solve_traj(void** tables, const int* k0, const double* x0, int 
 double orc_batch_solve(void** tables, const int* k0, const double* x0, int n_prob, float plan, int model_kind,
                        const double* o, const double* cparams, int n_threads, double* summaries) {
     return orc_batch_solve_traj(tables, k0, x0, n_prob, plan, model_kind, o, cparams, n_threads, summaries, nullptr, nullptr, 0, 0, nullptr, 0, nullptr);
+}
+
+// ---- generic SinglePhase<T, xs, us, ys> sweeps on plug-in outputs (single_phase_generic.hpp) ----
+// in[14] = {A, B, C, D, lx, lu, ly, lxx, luu, lux, lyy, Phix, Phixx, Defect}; C, D, ly, lyy may be null when ys == 0
+static generic::PhaseData generic_phase(int xs, int us, int ys, int N, const double* const* in) {
+    generic::PhaseData p;
+    p.xs = xs; p.us = us; p.ys = ys; p.N = N;
+    p.A = in[0]; p.B = in[1]; p.C = in[2]; p.D = in[3]; p.lx = in[4]; p.lu = in[5]; p.ly = in[6]; p.lxx = in[7]; p.luu = in[8];
+    p.lux = in[9]; p.lyy = in[10]; p.Phix = in[11]; p.Phixx = in[12]; p.Defect = in[13];
+    return p;
+}
+int orc_generic_backward_sweep(int xs, int us, int ys, int N, const double* const* in, double reg, const double* Gprime,
+                               const double* Hprime, double* dU, double* K, double* G, double* H, double* dV) {
+    return generic::backward_sweep(generic_phase(xs, us, ys, N, in), reg, Gprime, Hprime, dU, K, G, H, dV) ? 1 : 0;
+}
+void orc_generic_linear_rollout(int xs, int us, int ys, int N, const double* const* in, double eps, const double* dx_init,
+                                const double* dU, const double* K, double* dX, double* dV) {
+    generic::linear_rollout(generic_phase(xs, us, ys, N, in), eps, dx_init, dU, K, dX, dV);
 }
 
 int orc_hardware_concurrency() { return (int)std::thread::hardware_concurrency(); }

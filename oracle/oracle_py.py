@@ -360,6 +360,59 @@ def batch_solve_traj(tables, k0, x0, max_nodes, max_stages, k_rows=8, plan=0.6, 
     return dict(wall=wall, summary=summ, Xbar=Xb, Ubar=Ub, K=K, n_trials=ntr)
 
 
+
+# ---- generic SinglePhase<T, xs, us, ys> sweeps on plug-in outputs (oracle/single_phase_generic.hpp) ----
+GENERIC_INPUTS = ["A", "B", "C", "D", "lx", "lu", "ly", "lxx", "luu", "lux", "lyy", "Phix", "Phixx", "Defect"]
+
+
+def generic_shapes(xs, us, ys, N):
+    """[row, col] shapes of one phase's plug-in outputs (matrices are handed to C column-major)."""
+    return dict(A=(N, xs, xs), B=(N, xs, us), C=(N, ys, xs), D=(N, ys, us), lx=(N, xs), lu=(N, us), ly=(N, ys), lxx=(N, xs, xs),
+                luu=(N, us, us), lux=(N, us, xs), lyy=(N, ys, ys), Phix=(xs,), Phixx=(xs, xs), Defect=(N + 1, xs))
+
+
+def _colmajor(a):
+    a = np.asarray(a, np.float64)
+    return np.ascontiguousarray(np.swapaxes(a, -1, -2)) if a.ndim >= 2 and a.shape[-1] != 0 else np.ascontiguousarray(a)
+
+
+def _generic_pack(xs, us, ys, N, data):
+    keep, ptrs = [], (C.POINTER(C.c_double) * len(GENERIC_INPUTS))()
+    shp = generic_shapes(xs, us, ys, N)
+    for i, nm in enumerate(GENERIC_INPUTS):
+        a = np.asarray(data[nm], np.float64) if nm in data else np.zeros(shp[nm])
+        assert a.shape == shp[nm], (nm, a.shape, shp[nm])
+        a = _colmajor(a) if nm in ("A", "B", "C", "D", "lxx", "luu", "lux", "lyy", "Phixx") else np.ascontiguousarray(a)
+        keep.append(a)
+        ptrs[i] = _dp(a)
+    return keep, ptrs
+
+
+def generic_backward_sweep(xs, us, ys, N, data, reg, Gprime=None, Hprime=None):
+    """SinglePhase<double, xs, us, ys>::backward_sweep -> dict(success, dU, K [N, us, xs], G, H [N+1, xs, xs], dV_1, dV_2)."""
+    L = lib()
+    L.orc_generic_backward_sweep.argtypes = [C.c_int] * 4 + [C.POINTER(C.POINTER(C.c_double)), C.c_double] + [C.POINTER(C.c_double)] * 7
+    keep, ptrs = _generic_pack(xs, us, ys, N, data)
+    Gp = np.zeros(xs) if Gprime is None else np.ascontiguousarray(Gprime, np.float64)
+    Hp = np.zeros((xs, xs)) if Hprime is None else _colmajor(Hprime)
+    dU, K, G, H, dV = np.zeros((N, us)), np.zeros((N, xs, us)), np.zeros((N + 1, xs)), np.zeros((N + 1, xs, xs)), np.zeros(2)
+    ok = L.orc_generic_backward_sweep(xs, us, ys, N, ptrs, float(reg), _dp(Gp), _dp(Hp), _dp(dU), _dp(K), _dp(G), _dp(H), _dp(dV))
+    return dict(success=bool(ok), dU=dU, K=np.ascontiguousarray(np.swapaxes(K, 1, 2)), G=G,
+                H=np.ascontiguousarray(np.swapaxes(H, 1, 2)), dV_1=dV[0], dV_2=dV[1])
+
+
+def generic_linear_rollout(xs, us, ys, N, data, eps, dU, K, dx_init=None):
+    """SinglePhase<double, xs, us, ys>::linear_rollout -> dict(dX, dV_1, dV_2)."""
+    L = lib()
+    L.orc_generic_linear_rollout.argtypes = [C.c_int] * 4 + [C.POINTER(C.POINTER(C.c_double)), C.c_double] + [C.POINTER(C.c_double)] * 5
+    keep, ptrs = _generic_pack(xs, us, ys, N, data)
+    dx0 = np.zeros(xs) if dx_init is None else np.ascontiguousarray(dx_init, np.float64)
+    dUc, Kc = np.ascontiguousarray(dU, np.float64), _colmajor(K)
+    dX, dV = np.zeros((N + 1, xs)), np.zeros(2)
+    L.orc_generic_linear_rollout(xs, us, ys, N, ptrs, float(eps), _dp(dx0), _dp(dUc), _dp(Kc), _dp(dX), _dp(dV))
+    return dict(dX=dX, dV_1=dV[0], dV_2=dV[1])
+
+
 def hardware_concurrency():
     return lib().orc_hardware_concurrency()
 
