@@ -16,6 +16,8 @@
 // positive and ||Quu^-1||_F < 5e8 => lambda_min(Quu) > 2e-9 => true; otherwise the shifted matrix is eliminated exactly.
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include "../../include/hsddp_b200.h"
@@ -39,22 +41,25 @@ struct Lay {
     // offsets in doubles; [A | B] and [Y | Z] are contiguous so that H [A | B] is one product
     static constexpr int oH = 0, oAB = oH + XX, oYZ = oAB + XX + XU, oQux = oYZ + XX + XU, oAug = oQux + XU, oQuu = oAug + 2 * UU,
                          oK = oQuu + UU, oC = oK + XU, oD = oC + YX, oLyy = oD + YU, oCtL = oLyy + YY, oDtL = oCtL + YX,
-                         oVec = oDtL + YU, nVec = 5 * XS + 4 * US + YS + 40, total = oVec + nVec;
+                         oVec = oDtL + YU, nVec = 5 * XS + 8 * US + YS + 40, total = oVec + nVec;
 };
 
-// C(i, j) = sum_l Aop(i, l) B(l, j), i < M, j < N, l < K; Aop(i, l) = TA ? A[l + lda i] : A[i + lda l]; B[l + ldb j].
-// epi(i, j, acc) consumes each element.  3 x 4 register tiles, tile index strided over the block.
-template <int T, int M, int N, int K, bool TA, class F>
-__device__ __forceinline__ void gemm_tiles(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb, int tid, F&& epi) {
+// Cout(i, j) = Cin(i, j) + sign * sum_l Aop(i, l) B(l, j), i < M, j < N, l < K (Cin null = 0);
+// Aop(i, l) = TA ? A[l + lda i] : A[i + lda l]; B[l + ldb j].  3 x 4 register tiles, tile index strided over the block.
+// The tile of Cin is read before the product and the tile of Cout written after it, so no memory access of the inner
+// loop has to wait for a store that might alias it.
+template <int T, int M, int N, int K, bool TA, bool NEG = false>
+__device__ __forceinline__ void gemm_tiles(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
+                                           const double* Cin, int ldi, double* Cout, int ldo, int tid) {
     constexpr int TM = 3, TN = 4, MT = M / TM, NT = N / TN;
     static_assert(M % TM == 0 && N % TN == 0, "sizes must be multiples of 12");
     for (int t = tid; t < MT * NT; t += T) {
         const int i0 = (t % MT) * TM, j0 = (t / MT) * TN;
-        double acc[TM][TN];
+        double acc[TM][TN], cin[TM][TN];
 #pragma unroll
         for (int r = 0; r < TM; ++r)
 #pragma unroll
-            for (int c = 0; c < TN; ++c) acc[r][c] = 0.0;
+            for (int c = 0; c < TN; ++c) { acc[r][c] = 0.0; cin[r][c] = Cin ? Cin[i0 + r + ldi * (j0 + c)] : 0.0; }
 #pragma unroll 4
         for (int l = 0; l < K; ++l) {
             double a[TM], b[TN];
@@ -70,7 +75,7 @@ __device__ __forceinline__ void gemm_tiles(const double* __restrict__ A, int lda
 #pragma unroll
         for (int r = 0; r < TM; ++r)
 #pragma unroll
-            for (int c = 0; c < TN; ++c) epi(i0 + r, j0 + c, acc[r][c]);
+            for (int c = 0; c < TN; ++c) Cout[i0 + r + ldo * (j0 + c)] = NEG ? cin[r][c] - acc[r][c] : cin[r][c] + acc[r][c];
     }
 }
 
@@ -105,9 +110,9 @@ __global__ void __launch_bounds__(Lay<XS, US, YS>::T) k_generic_backward_sweep(P
     double* Gnew = Qx + XS;
     double* Qu = Gnew + XS;
     double* dUk = Qu + US;
-    double* colp = dUk + US;
-    double* piv = colp + US;
-    double* ly = piv + US;
+    double* colp = dUk + US;      // two buffers of US
+    double* rowq = colp + 2 * US; // two buffers of 2 US
+    double* ly = rowq + 4 * US;
     double* scal = ly + YS;  // [0] frob^2 partial / flags
     __shared__ int s_flag;
 
@@ -139,24 +144,22 @@ __global__ void __launch_bounds__(Lay<XS, US, YS>::T) k_generic_backward_sweep(P
         }
         __syncthreads();
         // ---- [Y | Z] = H [A | B];  Gnext = G + H Defect[k+1];  C^T lyy, D^T lyy ----
-        gemm_tiles<T, XS, XS + US, XS, false>(H, XS, AB, XS, tid, [&](int i, int j, double v) { YZ[i + XS * j] = v; });
+        gemm_tiles<T, XS, XS + US, XS, false>(H, XS, AB, XS, nullptr, 0, YZ, XS, tid);
         for (int i = tid; i < XS; i += T) {
             double s = 0.0;
             for (int l = 0; l < XS; ++l) s = fma(H[i + XS * l], dfc[l], s);
             Gn[i] = G[i] + s;
         }
         if (YS > 0) {
-            gemm_tiles<T, XS, YS, YS, true>(Cm, YS, Lyy, YS, tid, [&](int i, int j, double v) { CtL[i + XS * j] = v; });
-            gemm_tiles<T, US, YS, YS, true>(Dm, YS, Lyy, YS, tid, [&](int i, int j, double v) { DtL[i + US * j] = v; });
+            gemm_tiles<T, XS, YS, YS, true>(Cm, YS, Lyy, YS, nullptr, 0, CtL, XS, tid);
+            gemm_tiles<T, US, YS, YS, true>(Dm, YS, Lyy, YS, nullptr, 0, DtL, US, tid);
         }
         __syncthreads();
-        // ---- Q function (H's storage takes Qxx) ----
-        const double* lxx = p.lxx + (pN + k) * L::XX;
-        const double* luu = p.luu + (pN + k) * L::UU;
-        const double* lux = p.lux + (pN + k) * L::XU;
-        gemm_tiles<T, XS, XS, XS, true>(AB, XS, YZ, XS, tid, [&](int i, int j, double v) { H[i + XS * j] = lxx[i + XS * j] + v; });
-        gemm_tiles<T, US, XS, XS, true>(AB + L::XX, XS, YZ, XS, tid, [&](int i, int j, double v) { Qux[i + US * j] = lux[i + US * j] + v; });
-        gemm_tiles<T, US, US, XS, true>(AB + L::XX, XS, YZ + L::XX, XS, tid, [&](int i, int j, double v) { Aug[i + US * j] = luu[i + US * j] + v; });
+        // ---- Q function: the running-cost Hessians are copied in first (coalesced, all loads in flight at once; H is
+        //      dead now and its storage takes Qxx), the products accumulate on top ----
+        copy_in<T>(H, p.lxx + (pN + k) * L::XX, L::XX, tid);
+        copy_in<T>(Qux, p.lux + (pN + k) * L::XU, L::XU, tid);
+        copy_in<T>(Aug, p.luu + (pN + k) * L::UU, L::UU, tid);
         for (int i = tid; i < XS + US; i += T) {
             double s = 0.0;
             if (i < XS) {
@@ -173,14 +176,25 @@ __global__ void __launch_bounds__(Lay<XS, US, YS>::T) k_generic_backward_sweep(P
             }
         }
         __syncthreads();
+        gemm_tiles<T, XS, XS, XS, true>(AB, XS, YZ, XS, H, XS, H, XS, tid);
+        gemm_tiles<T, US, XS, XS, true>(AB + L::XX, XS, YZ, XS, Qux, US, Qux, US, tid);
+        gemm_tiles<T, US, US, XS, true>(AB + L::XX, XS, YZ + L::XX, XS, Aug, US, Aug, US, tid);
         if (YS > 0) {
-            gemm_tiles<T, XS, XS, YS, false>(CtL, XS, Cm, YS, tid, [&](int i, int j, double v) { H[i + XS * j] += v; });
-            gemm_tiles<T, US, XS, YS, false>(DtL, US, Cm, YS, tid, [&](int i, int j, double v) { Qux[i + US * j] += v; });
-            gemm_tiles<T, US, US, YS, false>(DtL, US, Dm, YS, tid, [&](int i, int j, double v) { Aug[i + US * j] += v; });
             __syncthreads();
+            gemm_tiles<T, XS, XS, YS, false>(CtL, XS, Cm, YS, H, XS, H, XS, tid);
+            gemm_tiles<T, US, XS, YS, false>(DtL, US, Cm, YS, Qux, US, Qux, US, tid);
+            gemm_tiles<T, US, US, YS, false>(DtL, US, Dm, YS, Aug, US, Aug, US, tid);
         }
-        // regularisation; identity block; copy of Quu
-        for (int e = tid; e < XS; e += T) H[e + XS * e] += 1.0 * reg;
+        __syncthreads();
+        // regularisation; copy of Quu for the exact PD test; Qxx symmetrised in place (each thread owns the pairs (i, j), (j, i))
+        for (int e = tid; e < L::XX; e += T) {
+            const int i = e % XS, j = e / XS;
+            if (i > j) continue;
+            if (i == j) { H[e] += 1.0 * reg; continue; }
+            const double v = (H[i + XS * j] + H[j + XS * i]) / 2;
+            H[i + XS * j] = v;
+            H[j + XS * i] = v;
+        }
         for (int e = tid; e < L::UU; e += T) {
             const int i = e % US, j = e / US;
             double q = Aug[e];
@@ -191,27 +205,45 @@ __global__ void __launch_bounds__(Lay<XS, US, YS>::T) k_generic_backward_sweep(P
         }
         if (tid == 0) s_flag = 0;
         __syncthreads();
-        // ---- Gauss-Jordan on [Quu | I]: thread (column j, row part h) ----
+        // ---- Gauss-Jordan on [Quu | I]: thread (column j, row part h) keeps its RP entries of column j in registers;
+        //      per step the owners publish column q and row q (two buffers alternate, so one barrier per step) ----
         {
-            constexpr int PARTS = (T >= 4 * US) ? 2 : 1;  // row halves when there are threads to spare
+            constexpr int PARTS = (T / (2 * US) >= 4) ? 4 : (T / (2 * US) >= 2) ? 2 : 1;
             constexpr int RP = US / PARTS;
             const int j = tid % (2 * US), h = tid / (2 * US);
             const bool active = tid < 2 * US * PARTS;
+            double a[RP];
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < RP; ++i) a[i] = Aug[h * RP + i + US * j];
+            }
             for (int q = 0; q < US; ++q) {
-                if (tid < US) colp[tid] = Aug[tid + US * q];
-                const double rq = active ? Aug[q + US * j] : 0.0;  // pivot-row entry, read before any thread rewrites it
-                __syncthreads();
-                const double pv = colp[q];
-                if (tid == 0) { piv[q] = pv; if (!(pv > 0.0)) s_flag = 1; }
-                if (active && pv != 0.0) {
-                    const double r = rq / pv;
-                    for (int i = h * RP; i < (h + 1) * RP; ++i) {
-                        if (i == q) Aug[i + US * j] = r;
-                        else Aug[i + US * j] = fma(-colp[i], r, Aug[i + US * j]);
+                double* cq = colp + (q & 1) * US;
+                double* rq = rowq + (q & 1) * 2 * US;
+                if (active) {
+                    double mine = 0.0;
+#pragma unroll
+                    for (int i = 0; i < RP; ++i) {
+                        if (j == q) cq[h * RP + i] = a[i];
+                        if (h * RP + i == q) mine = a[i];
                     }
+                    if (q / RP == h) rq[j] = mine;
                 }
                 __syncthreads();
+                const double pv = cq[q];
+                if (tid == 0 && !(pv > 0.0)) s_flag = 1;
+                if (active) {
+                    const double r = rq[j] / pv;
+#pragma unroll
+                    for (int i = 0; i < RP; ++i) a[i] = (h * RP + i == q) ? r : fma(-cq[h * RP + i], r, a[i]);
+                }
             }
+            __syncthreads();
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < RP; ++i) Aug[h * RP + i + US * j] = a[i];
+            }
+            __syncthreads();
         }
         // PD verdict of Quu - 1e-9 I
         if (s_flag == 0) {
@@ -257,10 +289,10 @@ __global__ void __launch_bounds__(Lay<XS, US, YS>::T) k_generic_backward_sweep(P
             for (int l = 0; l < US; ++l) s = fma(Aug[i + US * l], Qu[l], s);
             dUk[i] = -s;
         }
-        gemm_tiles<T, US, XS, US, false>(Aug, US, Qux, US, tid, [&](int i, int j, double v) { Kk[i + US * j] = -v; });
+        gemm_tiles<T, US, XS, US, false, true>(Aug, US, Qux, US, nullptr, 0, Kk, US, tid);
         __syncthreads();
         // ---- G = Qx + Qux^T dU; H = sym(Qxx) + Qux^T K (into Y's storage, then copied back) ----
-        gemm_tiles<T, XS, XS, US, true>(Qux, US, Kk, US, tid, [&](int i, int j, double v) { YZ[i + XS * j] = (H[i + XS * j] + H[j + XS * i]) / 2 + v; });
+        gemm_tiles<T, XS, XS, US, true>(Qux, US, Kk, US, H, XS, YZ, XS, tid);
         for (int i = tid; i < XS; i += T) {
             double s = 0.0;
             for (int l = 0; l < US; ++l) s = fma(Qux[l + US * i], dUk[l], s);
@@ -429,6 +461,12 @@ static int launch_sweep(hsddp_phase_batch* b, const PhasePtrs& p, double reg) {
     using L = Lay<XS, US, YS>;
     const size_t bytes = (size_t)L::total * sizeof(double);
     CKG(cudaFuncSetAttribute(k_generic_backward_sweep<XS, US, YS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    CKG(cudaFuncSetAttribute(k_generic_backward_sweep<XS, US, YS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (getenv("HSDDP_VERBOSE")) {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_generic_backward_sweep<XS, US, YS>, L::T, bytes);
+        fprintf(stderr, "k_generic_backward_sweep<%d,%d,%d>: %d threads, %zu bytes of shared memory, %d blocks per SM\n", XS, US, YS, L::T, bytes, nb);
+    }
     k_generic_backward_sweep<XS, US, YS><<<b->n, L::T, bytes, b->stream>>>(p, reg);
     return HSDDP_OK;
 }

@@ -258,4 +258,35 @@ private:
     int n_ = 0;
 };
 
+// The reference's other instantiations, SinglePhase<T,12,12,0> and SinglePhase<T,36,12,12> (SinglePhase.cpp:538-540; SURVEY.md 8f
+// N4), and <24,24,0> in its dense form: the model-independent sweeps on a batch of independent phases of equal horizon.
+// The reference ships no model, cost or problem for them and host plug-ins cannot run on the device, so the phase's storage
+// after LQ_approximation goes in (column-major matrices, layouts in include/hsddp_b200.h) and dU, K, G, H, dX, dV come out.
+template <typename T, size_t xs, size_t us, size_t ys>
+class SinglePhaseSweeps {
+    static_assert((xs == 24 && us == 24 && ys == 0) || (xs == 12 && us == 12 && ys == 0) || (xs == 36 && us == 12 && ys == 12),
+                  "the reference instantiates <24,24,0>, <12,12,0> and <36,12,12> only");
+public:
+    SinglePhaseSweeps(int horizon, int n_problems, int device = 0) : n_(n_problems) {
+        check(hsddp_phase_batch_create(device, (int)xs, (int)us, (int)ys, horizon, n_problems, &b_), "hsddp_phase_batch_create");
+    }
+    ~SinglePhaseSweeps() { hsddp_phase_batch_destroy(b_); }
+    SinglePhaseSweeps(const SinglePhaseSweeps&) = delete;
+    SinglePhaseSweeps& operator=(const SinglePhaseSweeps&) = delete;
+    void set(int which, const std::vector<T>& v) { check(hsddp_phase_batch_set(b_, which, v.data()), "hsddp_phase_batch_set"); }
+    // SinglePhase::backward_sweep(regularization, Gprime, Hprime), SinglePhase.cpp:299-367; one bool per problem
+    std::vector<int32_t> backward_sweep(T regularization, const T* Gprime = nullptr, const T* Hprime = nullptr) {
+        std::vector<int32_t> ok(n_problems());
+        check(hsddp_phase_batch_backward_sweep(b_, regularization, Gprime, Hprime, ok.data()), "hsddp_phase_batch_backward_sweep");
+        return ok;
+    }
+    // SinglePhase::linear_rollout(eps, option), SinglePhase.cpp:145-178
+    void linear_rollout(T eps, const T* dx_init = nullptr) { check(hsddp_phase_batch_linear_rollout(b_, eps, dx_init), "hsddp_phase_batch_linear_rollout"); }
+    void get(int which, std::vector<T>& out) { check(hsddp_phase_batch_get(b_, which, out.data()), "hsddp_phase_batch_get"); }
+    int n_problems() const { return n_; }
+private:
+    hsddp_phase_batch* b_ = nullptr;
+    int n_ = 0;
+};
+
 }  // namespace hsddp_b200

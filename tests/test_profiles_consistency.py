@@ -21,6 +21,17 @@ def test_launch_shares_reproduce_from_the_raw_launch_list():
     k = got["kernels"]
     assert k["backward sweep"]["launches"] == k["prep (cost + LQ)"]["launches"] == k["forward (linear rollout + line search)"]["launches"]
     assert abs(sum(v["share"] for v in k.values()) - 1.0) < 1e-12
-    # the traffic figure bench.py reports comes from the same launches
+
+
+def test_traffic_figure_reproduces_from_the_launch_list_it_names():
+    """profiles/k_solve_traffic.json (bench.py's roofline.traffic and kernel_shares) follows from the committed raw ncu
+    launch list named in its `source` field (tools/make_traffic_json.py)."""
     tr = json.load(open(os.path.join(ROOT, "profiles", "k_solve_traffic.json")))
-    assert abs((tr["dram_bytes_read"] + tr["dram_bytes_write"]) - got["total_dram_bytes"]) < 1.0
+    raw = os.path.join(ROOT, tr["source"].split(" ")[0])
+    assert os.path.exists(raw), raw
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_traffic_json.py"), raw, tr["source"].split(" ")[0]],
+                         capture_output=True, text=True, check=True).stdout
+    got = json.loads(out)
+    assert abs(got["dram_bytes_read"] - tr["dram_bytes_read"]) < 1.0 and abs(got["dram_bytes_write"] - tr["dram_bytes_write"]) < 1.0
+    assert got["kernel_shares"] == tr["kernel_shares"]
+    assert abs(sum(v["share"] for v in got["kernel_shares"].values()) - 1.0) < 1e-3
