@@ -228,6 +228,31 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 // block-wide reductions; result valid in every thread.  Contains barriers.
+// Flat pass over n elements, element e = tid, tid + kThreads, ...: the loads of B consecutive elements of a thread are
+// issued together and consumed afterwards.  The plain loop keeps ONE global load in flight per thread — its stores go
+// through pointers the compiler cannot tell from the loads' (shared memory and HBM through generic pointers), so it may
+// not hoist the next element's loads above them — and these passes are then bound by memory latency, not bandwidth.
+// Per-thread order of the elements (and of any sum over them) is unchanged.
+#ifndef HSDDP_FLAT_B
+#define HSDDP_FLAT_B 1
+#endif
+template <int B, class LoadF, class UseF>
+__device__ __forceinline__ void flat_pass(int n, int tid, LoadF&& load, UseF&& use) {
+    for (int e0 = tid; e0 < n; e0 += B * kThreads) {
+        decltype(load(0)) v[B];
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+            const int e = e0 + u * kThreads;
+            if (e < n) v[u] = load(e);
+        }
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+            const int e = e0 + u * kThreads;
+            if (e < n) use(e, v[u]);
+        }
+    }
+}
+
 template <int OP>  // 0 sum, 1 min, 2 max
 __device__ __noinline__ double block_reduce(Smem& sm, double v) {
     v = (OP == 0) ? warp_sum(v) : (OP == 1) ? warp_min(v) : warp_max(v);
@@ -407,28 +432,37 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
     //      (kept in shared memory next to the states when both fit, else re-read from HBM)
     const bool dev_in_smem = sc.n_nodes * 48 <= kSweepDoubles;
     double* xd = xs + sc.n_nodes * 24;
-    for (int e = tid; e < sc.n_nodes * 24; e += kThreads) {
-        const double xb = sm.Xbar[e];
-        const double x = xb + eps * sm.dX[e];
-        xs[e] = x;
-        if (dev_in_smem && !LINEARISED) xd[e] = x - xb;
-    }
+    flat_pass<HSDDP_FLAT_B>(sc.n_nodes * 24, tid, [&](int e) { return make_double2(sm.Xbar[e], sm.dX[e]); },
+                 [&](int e, const double2& v) {
+                     const double x = v.x + eps * v.y;
+                     xs[e] = x;
+                     if (dev_in_smem && !LINEARISED) xd[e] = x - v.x;
+                 });
     __syncthreads();
     // (a) controls: U = (Ubar + eps dU) + K (X - Xbar), one warp per stage.  K is stored compactly as
     //     K_r^T [24][12] (only the coupled control of each leg has a non-zero gain row, see hsddp_sweep.cuh).
     //     Lane (p, q) = (lane & 7, lane >> 3) accumulates the control pair (2p, 2p+1) over the state
     //     components j = q, q+4, ..: every load is a 16-byte piece of a 384-byte contiguous run of K.
     if (LINEARISED) {
-        for (int e = tid; e < N * 24; e += kThreads) {
-            const int s = e / 24, i = e % 24, c = i % 12;
-            int ph, k;
-            phase_of_stage(sc, s, ph, k);
-            const bool stance = (sc.cmask[ph] >> (c / 3)) & 1u;
-            double u = sm.Ubar[e] + eps * sm.dU[e];
-            if ((i < 12) == stance) u += eps * sm.KdX[12 * s + c];  // the coupled control of the leg
-            sm.U_t[e] = u;
-            if (dev_in_smem) xd[24 * (sc.node_off[ph] + k) + i] = u;
-        }
+        flat_pass<HSDDP_FLAT_B>(N * 24, tid,
+                     [&](int e) {
+                         const int s = e / 24, i = e % 24, c = i % 12;
+                         const bool stance = (sc.cmask[sc.ph_of_stage[s]] >> (c / 3)) & 1u;
+                         double3 v;
+                         v.x = sm.Ubar[e]; v.y = sm.dU[e];
+                         v.z = ((i < 12) == stance) ? sm.KdX[12 * s + c] : 0.0;  // the coupled control of the leg
+                         return v;
+                     },
+                     [&](int e, const double3& v) {
+                         const int s = e / 24, i = e % 24, c = i % 12;
+                         int ph, k;
+                         phase_of_stage(sc, s, ph, k);
+                         const bool stance = (sc.cmask[ph] >> (c / 3)) & 1u;
+                         double u = v.x + eps * v.y;
+                         if ((i < 12) == stance) u += eps * v.z;
+                         sm.U_t[e] = u;
+                         if (dev_in_smem) xd[24 * (sc.node_off[ph] + k) + i] = u;
+                     });
     } else {
         const int p = lane & 7, q = lane >> 3;
         const bool kact = p < 6;
@@ -535,12 +569,12 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
     }
     double gmin = 0.0;
     const double mu = sm.cp.mu;
-    for (int e = tid; e < N * 24; e += kThreads) {
-        const int s = e / 24;
-        int ph, k;
-        phase_of_stage(sc, s, ph, k);
-        if (ph < bad_ph || (ph == bad_ph && k <= bad_k)) sm.U[e] = sm.U_t[e];
-    }
+    flat_pass<HSDDP_FLAT_B>(N * 24, tid, [&](int e) { return sm.U_t[e]; },
+                 [&](int e, double u) {
+                     int ph, k;
+                     phase_of_stage(sc, e / 24, ph, k);
+                     if (ph < bad_ph || (ph == bad_ph && k <= bad_k)) sm.U[e] = u;
+                 });
     for (int e = tid; e < N * 4; e += kThreads) {  // GRFConstraint::compute_violation, one (stage, leg) per thread
         const int s = e >> 2, l = e & 3;
         int ph, k;
@@ -598,46 +632,66 @@ __device__ inline void compute_cost_block(Smem& sm) {
     // Every term of the running / terminal costs is a sum over (node or stage, component): the passes below walk
     // those index spaces flat, so all 128 threads work and every global access is coalesced.
     // (1) state tracking, (node, j): running 1/2 dt Q dx^2, terminal 1/2 Qf dx^2
-    for (int e = tid; e < sc.n_nodes * 24; e += kThreads) {
-        const int n = e / 24, j = e % 24;
-        const int ph = sc.ph_of_node[n];
-        const unsigned cm = sc.cmask[ph];
-        const bool terminal = (n - sc.node_off[ph]) == sc.horizon[ph];
-        const double dx = sm.X[e] - sm.xr[e];
-        csum += terminal ? 0.5 * ((dx * weight_Qf(j, cm)) * dx) : ((0.5 * dx * weight_Q(j, cm)) * dx) * dt;
-    }
+    flat_pass<HSDDP_FLAT_B>(sc.n_nodes * 24, tid, [&](int e) { return make_double2(sm.X[e], sm.xr[e]); },
+                 [&](int e, const double2& v) {
+                     const int n = e / 24, j = e % 24;
+                     const int ph = sc.ph_of_node[n];
+                     const unsigned cm = sc.cmask[ph];
+                     const bool terminal = (n - sc.node_off[ph]) == sc.horizon[ph];
+                     const double dx = v.x - v.y;
+                     csum += terminal ? 0.5 * ((dx * weight_Qf(j, cm)) * dx) : ((0.5 * dx * weight_Q(j, cm)) * dx) * dt;
+                 });
     // (2) control effort, (stage, j)
-    for (int e = tid; e < N * 24; e += kThreads) {
-        const int s = e / 24, j = e % 24;
-        int ph, k;
-        phase_of_stage(sc, s, ph, k);
-        const double du = sm.U[e] - sm.ur[24 * (sc.node_off[ph] + k) + j];
-        csum += ((0.5 * du * weight_R(j)) * du) * dt;
-    }
+    flat_pass<HSDDP_FLAT_B>(N * 24, tid,
+                 [&](int e) {
+                     const int s = e / 24, j = e % 24;
+                     int ph, k;
+                     phase_of_stage(sc, s, ph, k);
+                     return make_double2(sm.U[e], sm.ur[24 * (sc.node_off[ph] + k) + j]);
+                 },
+                 [&](int e, const double2& v) {
+                     const double du = v.x - v.y;
+                     csum += ((0.5 * du * weight_R(e % 24)) * du) * dt;
+                 });
     // (3) foot-placement regulariser, (node, leg component)
-    for (int e = tid; e < sc.n_nodes * 12; e += kThreads) {
-        const int n = e / 12, q = e % 12;
-        const int ph = sc.ph_of_node[n];
-        const unsigned cm = sc.cmask[ph];
-        const bool terminal = (n - sc.node_off[ph]) == sc.horizon[ph];
-        const double* x = sm.X + 24 * n;
-        const double d = (x[12 + q] - x[3 + q % 3]) - sm.prel[e];
-        const double w = weight_foot(q / 3, q % 3, cm);
-        csum += terminal ? (10 * d * w) * d : ((.5 * d * w) * d) * dt;
-    }
+    flat_pass<HSDDP_FLAT_B>(sc.n_nodes * 12, tid,
+                 [&](int e) {
+                     const int n = e / 12, q = e % 12;
+                     const double* x = sm.X + 24 * n;
+                     double3 v;
+                     v.x = x[12 + q]; v.y = x[3 + q % 3]; v.z = sm.prel[e];
+                     return v;
+                 },
+                 [&](int e, const double3& v) {
+                     const int n = e / 12, q = e % 12;
+                     const int ph = sc.ph_of_node[n];
+                     const unsigned cm = sc.cmask[ph];
+                     const bool terminal = (n - sc.node_off[ph]) == sc.horizon[ph];
+                     const double d = (v.x - v.y) - v.z;
+                     const double w = weight_foot(q / 3, q % 3, cm);
+                     csum += terminal ? (10 * d * w) * d : ((.5 * d * w) * d) * dt;
+                 });
     // (4) relaxed-barrier terms of the GRF constraints, (stage, row)  (compute_ReB_cost, ConstraintsBase.h:204-222)
     if (sm.opt.ReB_active) {
         const double2* reb2 = reinterpret_cast<const double2*>(sm.reb);
-        for (int i = tid; i < N * 20; i += kThreads) {
-            const int s = i / 20, e = i % 20;
-            if (!((sc.cmask[sc.ph_of_stage[s]] >> (e / 5)) & 1u)) continue;
-            const double g = sm.gcon[i];
-            const double2 p = reb2[i];  // (eps, delta)
-            double barr;
-            if (g > p.y) barr = -hkd::log_nl(g);
-            else { const double z = (g - 2 * p.y) / p.y; barr = .5 * (z * z - 1); barr -= hkd::log_nl(p.y); }
-            csum += dt * (p.x * barr);
-        }
+        flat_pass<HSDDP_FLAT_B>(N * 20, tid,
+                     [&](int i) {
+                         double3 v;
+                         v.x = 0.0; v.y = 0.0; v.z = 0.0;
+                         if ((sc.cmask[sc.ph_of_stage[i / 20]] >> ((i % 20) / 5)) & 1u) {
+                             const double2 p = reb2[i];  // (eps, delta)
+                             v.x = sm.gcon[i]; v.y = p.x; v.z = p.y;
+                         }
+                         return v;
+                     },
+                     [&](int i, const double3& v) {
+                         if (!((sc.cmask[sc.ph_of_stage[i / 20]] >> ((i % 20) / 5)) & 1u)) return;
+                         const double g = v.x;
+                         double barr;
+                         if (g > v.z) barr = -hkd::log_nl(g);
+                         else { const double z = (g - 2 * v.z) / v.z; barr = .5 * (z * z - 1); barr -= hkd::log_nl(v.z); }
+                         csum += dt * (v.y * barr);
+                     });
     }
     // (5) augmented-Lagrangian terms of the touchdown constraints, (phase, leg)  (compute_AL_cost, ConstraintsBase.h:374-385)
     if (sm.opt.AL_active && tid < sc.n_phases * 4) {
@@ -651,7 +705,7 @@ __device__ inline void compute_cost_block(Smem& sm) {
             }
     }
     double dsum = 0.0;
-    for (int e = tid; e < sc.n_nodes * 24; e += kThreads) { const double d = sm.Defect[e]; dsum += d * d; }
+    flat_pass<HSDDP_FLAT_B>(sc.n_nodes * 24, tid, [&](int e) { return sm.Defect[e]; }, [&](int, double d) { dsum += d * d; });
     const double cost = block_reduce<0>(sm, csum);
     const double f2 = block_reduce<0>(sm, dsum);
     if (tid == 0) { sm.st.actual_cost = cost; sm.st.feas = sqrt(f2); }
@@ -669,6 +723,67 @@ __device__ inline void lq_approximation_block(Smem& sm) {
     PROF_DECL
     const int N = sc.n_stages;
     const double dt = sc.dt;
+    // (0) terminal records, one thread per phase ON THE FOURTH WARP, before anything else: the thread's work is a long
+    //     dependent chain (foot Jacobians, AL weights), so it runs while warps 0 and 1 compute the dynamics Jacobians of
+    //     (1) instead of after them with the whole block waiting at the last barrier (that wait was 23 % of the prep
+    //     kernel's stall samples, profiles/r02x_*).  Jacobians and the touchdown gradients stay in registers; only the
+    //     non-zero entries of hx (columns 0..2, 5 and the leg's three foot columns) feed Phix.
+    if (tid >= 96 && tid - 96 < sc.n_phases) {
+        const int ph = tid - 96;
+        const unsigned cm = sc.cmask[ph];
+        const int n = sc.node_off[ph] + sc.horizon[ph];
+        const double* x = sm.X + 24 * n;
+        const double* xr = sm.xr + 24 * n;
+        double* rec = sm.tq + ph * TQ_STRIDE;
+        double phix[24];
+        for (int j = 0; j < 24; ++j) phix[j] = weight_Qf(j, cm) * (x[j] - xr[j]);
+        double d[12];
+        foot_rel_error(x, sm.prel + 12 * n, d);
+        for (int l = 0; l < 4; ++l) {
+            const double c = (double)((cm >> l) & 1u);
+            for (int j = 0; j < 3; ++j) {
+                const double w = 20 * c * weight_foot(l, j, cm);
+                phix[3 + j] += -(w * d[3 * l + j]);
+                phix[12 + 3 * l + j] += w * d[3 * l + j];
+            }
+        }
+        for (int l = 0; l < 4; ++l) {
+            double* hx = rec + TQ_HX + 24 * l;
+            const bool rm = !((cm >> l) & 1u) && ((sc.nmask[ph] >> l) & 1u);  // reset map moves this leg's foot (touchdown)
+            const unsigned tdo = ((sc.tdmask[0][ph] >> l) & 1u) | (((sc.tdmask[1][ph] >> l) & 1u) << 1);  // constraint objects on this leg
+            const bool al = tdo && sm.opt.AL_active;
+            double h = 0.0, sg[2] = {0.0, 0.0}, lm[2] = {0.0, 0.0};
+            if (al) {  // (loads issued before the Jacobian's long chain)
+                h = sm.hcon[4 * ph + l];
+                for (int ob = 0; ob < 2; ++ob)
+                    if ((tdo >> ob) & 1u) { sg[ob] = sm.al[16 * ph + 8 * ob + 2 * l]; lm[ob] = sm.al[16 * ph + 8 * ob + 2 * l + 1]; }
+            }
+            double Jc[18];
+            if (rm || tdo) {  // foot Jacobian, cached for the sweep and the linear rollout (reset-map Jacobian) and used by the AL terms
+                foot_jacobian_nl(x, l, Jc);
+                for (int c = 0; c < 18; ++c) rec[TQ_JC + 18 * l + c] = Jc[c];
+            }
+            double wh = 0.0;
+            for (int j = 0; j < 24; ++j) hx[j] = 0.0;
+            if (al) {
+                double wg = 0.0;
+                for (int ob = 0; ob < 2; ++ob)
+                    if ((tdo >> ob) & 1u) {
+                        wg += sg[ob] * h + lm[ob];
+                        wh += sg[ob] * (1 + h) + lm[ob];  // Q3
+                    }
+                for (int c = 0; c < 3; ++c) {
+                    hx[c] = Jc[2 * 6 + c]; hx[12 + 3 * l + c] = Jc[2 * 6 + 3 + c];
+                    phix[c] += wg * Jc[2 * 6 + c];
+                    phix[12 + 3 * l + c] += wg * Jc[2 * 6 + 3 + c];
+                }
+                hx[5] = 1.0;
+                phix[5] += wg * 1.0;
+            }
+            rec[TQ_WH + l] = wh;
+        }
+        for (int j = 0; j < 24; ++j) rec[TQ_PHIX + j] = phix[j];
+    }
     // (1) dynamics Jacobians.  Two threads share a stage (disjoint halves of the record, hkd_model.cuh) and write its
     //     compact record into shared memory (row stride 113 doubles: the per-thread rows do not collide on banks);
     //     after each pass of 32 stages all threads copy the rows out with coalesced stores.
@@ -693,39 +808,73 @@ __device__ inline void lq_approximation_block(Smem& sm) {
             __syncthreads();
         }
     }
-    // (2) cost gradients, flat over (stage, component): lx (24) and the lu of the joint-velocity commands (12);
-    //     coalesced reads, 192-byte runs of writes.  Foot-placement regulariser: the position rows accumulate over
-    //     the legs in order, the foot rows get one term each.
-    for (int e = tid; e < N * 36; e += kThreads) {
-        const int s = e / 36, j = e % 36;
-        int ph, k;
-        phase_of_stage(sc, s, ph, k);
-        const int n = sc.node_off[ph] + k;
-        const unsigned cm = sc.cmask[ph];
-        double* rec = sm.lqg + (size_t)s * CR_STRIDE;
-        if (j >= 24) {
-            const int i = j - 12;
-            rec[CR_LU + i] = (dt * weight_R(i)) * (sm.U[24 * s + i] - sm.ur[24 * n + i]);
-            continue;
-        }
-        const double* x = sm.X + 24 * n;
-        double v = (dt * weight_Q(j, cm)) * (x[j] - sm.xr[24 * n + j]);
-        if (j >= 3 && j < 6) {
+    // (2) cost gradients, flat over (stage, component), loads batched (flat_pass): the lu of the joint-velocity commands
+    //     (12 per stage); lx of every component but the position (21); lx of the position rows (3), which accumulate the
+    //     foot-placement regulariser over the legs in order.
+    flat_pass<HSDDP_FLAT_B>(N * 12, tid,
+                 [&](int e) {
+                     const int s = e / 12, i = 12 + e % 12;
+                     int ph, k;
+                     phase_of_stage(sc, s, ph, k);
+                     return make_double2(sm.U[24 * s + i], sm.ur[24 * (sc.node_off[ph] + k) + i]);
+                 },
+                 [&](int e, const double2& v) {
+                     const int s = e / 12, i = 12 + e % 12;
+                     sm.lqg[(size_t)s * CR_STRIDE + CR_LU + i] = (dt * weight_R(i)) * (v.x - v.y);
+                 });
+    flat_pass<HSDDP_FLAT_B>(N * 21, tid,
+                 [&](int e) {
+                     const int s = e / 21, jr = e % 21, j = jr < 3 ? jr : jr + 3;
+                     int ph, k;
+                     phase_of_stage(sc, s, ph, k);
+                     const int n = sc.node_off[ph] + k;
+                     const double* x = sm.X + 24 * n;
+                     double4 v;
+                     v.x = x[j]; v.y = sm.xr[24 * n + j]; v.z = 0.0; v.w = 0.0;
+                     if (j >= 12) { v.z = x[3 + (j - 12) % 3]; v.w = sm.prel[12 * n + j - 12]; }
+                     return v;
+                 },
+                 [&](int e, const double4& q) {
+                     const int s = e / 21, jr = e % 21, j = jr < 3 ? jr : jr + 3;
+                     const unsigned cm = sc.cmask[sc.ph_of_stage[s]];
+                     double v = (dt * weight_Q(j, cm)) * (q.x - q.y);
+                     if (j >= 12) {
+                         const int l = (j - 12) / 3, jj = (j - 12) % 3;
+                         const double c = (double)((cm >> l) & 1u);
+                         const double d = (q.x - q.z) - q.w;
+                         const double w = dt * c * weight_foot(l, jj, cm);
+                         v += w * d;
+                     }
+                     sm.lqg[(size_t)s * CR_STRIDE + CR_LX + j] = v;
+                 });
+    {
+        struct PosRow { double xj, xrj, xf[4], pr[4]; };
+        flat_pass<(HSDDP_FLAT_B > 2 ? 2 : HSDDP_FLAT_B)>(N * 3, tid,
+                     [&](int e) {
+                         const int s = e / 3, j = 3 + e % 3;
+                         int ph, k;
+                         phase_of_stage(sc, s, ph, k);
+                         const int n = sc.node_off[ph] + k;
+                         const double* x = sm.X + 24 * n;
+                         PosRow r;
+                         r.xj = x[j]; r.xrj = sm.xr[24 * n + j];
 #pragma unroll
-            for (int l = 0; l < 4; ++l) {
-                const double c = (double)((cm >> l) & 1u);
-                const double d = (x[12 + 3 * l + j - 3] - x[j]) - sm.prel[12 * n + 3 * l + j - 3];
-                const double w = dt * c * weight_foot(l, j - 3, cm);
-                v += -(w * d);
-            }
-        } else if (j >= 12) {
-            const int l = (j - 12) / 3, jj = (j - 12) % 3;
-            const double c = (double)((cm >> l) & 1u);
-            const double d = (x[j] - x[3 + jj]) - sm.prel[12 * n + j - 12];
-            const double w = dt * c * weight_foot(l, jj, cm);
-            v += w * d;
-        }
-        rec[CR_LX + j] = v;
+                         for (int l = 0; l < 4; ++l) { r.xf[l] = x[12 + 3 * l + j - 3]; r.pr[l] = sm.prel[12 * n + 3 * l + j - 3]; }
+                         return r;
+                     },
+                     [&](int e, const PosRow& r) {
+                         const int s = e / 3, j = 3 + e % 3;
+                         const unsigned cm = sc.cmask[sc.ph_of_stage[s]];
+                         double v = (dt * weight_Q(j, cm)) * (r.xj - r.xrj);
+#pragma unroll
+                         for (int l = 0; l < 4; ++l) {
+                             const double c = (double)((cm >> l) & 1u);
+                             const double d = (r.xf[l] - r.xj) - r.pr[l];
+                             const double w = dt * c * weight_foot(l, j - 3, cm);
+                             v += -(w * d);
+                         }
+                         sm.lqg[(size_t)s * CR_STRIDE + CR_LX + j] = v;
+                     });
     }
     // (3) GRF controls and the ReB folding, flat over (stage, leg)  (compute_ReB_partials, ConstraintsBase.h:224-263;
     //     only gu is non-zero)
@@ -766,54 +915,6 @@ __device__ inline void lq_approximation_block(Smem& sm) {
             for (int a = 0; a < 9; ++a) rec[CR_LUU + 9 * l + a] = dt * hess[a];
         }
     }
-    if (tid < sc.n_phases) {
-        const int ph = tid;
-        const unsigned cm = sc.cmask[ph];
-        const int n = sc.node_off[ph] + sc.horizon[ph];
-        const double* x = sm.X + 24 * n;
-        const double* xr = sm.xr + 24 * n;
-        double* rec = sm.tq + ph * TQ_STRIDE;
-        double phix[24];
-        for (int j = 0; j < 24; ++j) phix[j] = weight_Qf(j, cm) * (x[j] - xr[j]);
-        double d[12];
-        foot_rel_error(x, sm.prel + 12 * n, d);
-        for (int l = 0; l < 4; ++l) {
-            const double c = (double)((cm >> l) & 1u);
-            for (int j = 0; j < 3; ++j) {
-                const double w = 20 * c * weight_foot(l, j, cm);
-                phix[3 + j] += -(w * d[3 * l + j]);
-                phix[12 + 3 * l + j] += w * d[3 * l + j];
-            }
-        }
-        for (int l = 0; l < 4; ++l) {
-            double* hx = rec + TQ_HX + 24 * l;
-            for (int j = 0; j < 24; ++j) hx[j] = 0.0;
-            rec[TQ_WH + l] = 0.0;
-            const bool rm = !((cm >> l) & 1u) && ((sc.nmask[ph] >> l) & 1u);  // reset map moves this leg's foot (touchdown)
-            const unsigned tdo = ((sc.tdmask[0][ph] >> l) & 1u) | (((sc.tdmask[1][ph] >> l) & 1u) << 1);  // constraint objects on this leg
-            if (rm || tdo) {  // foot Jacobian, cached for the sweep and the linear rollout (reset-map Jacobian) and used by the AL terms
-                double Jc[18];
-                foot_jacobian_nl(x, l, Jc);
-                for (int c = 0; c < 18; ++c) rec[TQ_JC + 18 * l + c] = Jc[c];
-            }
-            if (tdo && sm.opt.AL_active) {
-                const double* Jc = rec + TQ_JC + 18 * l;
-                for (int c = 0; c < 3; ++c) { hx[c] = Jc[2 * 6 + c]; hx[12 + 3 * l + c] = Jc[2 * 6 + 3 + c]; }
-                hx[5] = 1.0;
-                const double h = sm.hcon[4 * ph + l];
-                double wg = 0.0, wh = 0.0;
-                for (int ob = 0; ob < 2; ++ob)
-                    if ((tdo >> ob) & 1u) {
-                        const double sigma = sm.al[16 * ph + 8 * ob + 2 * l], lambda = sm.al[16 * ph + 8 * ob + 2 * l + 1];
-                        wg += sigma * h + lambda;
-                        wh += sigma * (1 + h) + lambda;  // Q3
-                    }
-                for (int j = 0; j < 24; ++j) phix[j] += wg * hx[j];
-                rec[TQ_WH + l] = wh;
-            }
-        }
-        for (int j = 0; j < 24; ++j) rec[TQ_PHIX + j] = phix[j];
-    }
     __syncthreads();
     PROF_MARK(sm, 4);
 }
@@ -822,8 +923,8 @@ __device__ inline void lq_approximation_block(Smem& sm) {
 // update_nominal_trajectory (TrajectoryManagement.cpp:110-115)
 // ---------------------------------------------------------------------------
 __device__ inline void update_nominal_block(Smem& sm) {
-    for (int e = threadIdx.x; e < sm.sc.n_nodes * 24; e += kThreads) sm.Xbar[e] = sm.X[e];
-    for (int e = threadIdx.x; e < sm.sc.n_stages * 24; e += kThreads) sm.Ubar[e] = sm.U[e];
+    flat_pass<HSDDP_FLAT_B>(sm.sc.n_nodes * 24, (int)threadIdx.x, [&](int e) { return sm.X[e]; }, [&](int e, double v) { sm.Xbar[e] = v; });
+    flat_pass<HSDDP_FLAT_B>(sm.sc.n_stages * 24, (int)threadIdx.x, [&](int e) { return sm.U[e]; }, [&](int e, double v) { sm.Ubar[e] = v; });
     __syncthreads();
 }
 

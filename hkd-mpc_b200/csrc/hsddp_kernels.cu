@@ -1541,11 +1541,19 @@ __global__ void k_iota(int* a, int n) {
 // benchmark workload) and change little between consecutive solves of the same problems (MPC ticks, repeated cold solves),
 // so starting the long ones first keeps the tail of the launch short (longest-processing-time-first list scheduling).
 // It only permutes the order in which blocks pick problems up: results do not depend on it.
+// The key is the previous solve's WORK, not its iteration count alone: an iteration costs one prep + one linear rollout
+// (~ 1/3 of a nominal iteration), every backward sweep ~ 1/2 (regularisation retries repeat it) and every line-search trial
+// ~ 1/8; problems that regularise or reject steps run several times longer per iteration than the others, and with the
+// count alone they were started late (the eight 2,048-problem shards of config 3 ranged from 50 to 69 ms).
+__device__ __forceinline__ int order_bin(const hsddp_info& q) {
+    const int work = 33 * q.n_iter + 48 * q.n_sweeps + 12 * q.n_trials;  // in 1/93 of a nominal iteration
+    return 255 - min(max(work >> 6, 0), 255);
+}
 __global__ void k_order_by_iterations(const hsddp_info* info, int n, int* order) {
     __shared__ int bins[256], start[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) bins[i] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&bins[255 - min(max(info[i].n_iter, 0), 255)], 1);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&bins[order_bin(info[i])], 1);
     __syncthreads();
     if (threadIdx.x == 0) {
         int acc = 0;
@@ -1557,7 +1565,7 @@ __global__ void k_order_by_iterations(const hsddp_info* info, int n, int* order)
         if (!bins[bi]) continue;
         int pos = start[bi];
         for (int i = 0; i < n; ++i)
-            if (255 - min(max(info[i].n_iter, 0), 255) == bi) order[pos++] = i;
+            if (order_bin(info[i]) == bi) order[pos++] = i;
     }
 }
 
