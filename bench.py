@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of ONE pass of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--no-generic", action="store_true", help="skip the generic SinglePhase<12,12,0> / <36,12,12> sweep timing")
     ap.add_argument("--no-latency", action="store_true")
     return ap.parse_args()
 
@@ -413,6 +414,26 @@ def main():
         del Bb
         del B1
 
+    # ---- the reference's other instantiations: generic sweeps on synthetic plug-in outputs, 4,096 phases x 60 stages ----
+    other = None
+    if rank == 0 and not args.no_generic:
+        other = []
+        for xs, us, ys in ((12, 12, 0), (36, 12, 12)):
+            ng, Ng = 4096, 60
+            one = wl.random_phase(xs, us, ys, Ng, 1, n=8)
+            Bg = pkg.SinglePhaseBatch(xs, us, ys, Ng, ng, local_rank)
+            for nm in Bg.INPUTS:
+                Bg.set(nm, np.ascontiguousarray(np.broadcast_to(one[nm][None], (ng // 8,) + one[nm].shape).reshape((ng,) + one[nm].shape[1:])))
+            ts = []
+            for _ in range(5):
+                ok = Bg.backward_sweep(1e-3)
+                ts.append(Bg.last_ms())
+            ms = float(np.median(ts[2:]))
+            Fg = wl.generic_flop_per_stage(xs, us, ys)
+            other.append({"instantiation": "SinglePhase<double,%d,%d,%d>" % (xs, us, ys), "phases": ng, "horizon": Ng, "sweeps_ok": int(ok.sum()),
+                          "backward_sweep_ms": ms, "stages_per_s": ng * Ng / (ms * 1e-3), "flop_per_stage": Fg, "tflops": ng * Ng * Fg / (ms * 1e-3) / 1e12})
+            del Bg
+
     if rank == 0:
         mean_stages = float(np.mean([w.schedules[s].n_stages for s in w.schedule_id]))
         info = t["info"]
@@ -466,6 +487,7 @@ def main():
                          "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                                  "bytes_per_launch": bytes_launch, "peak_source": hbm_src}},
             "latency": latency,
+            "other_instantiations": other,
             "convergence": {k: float(v) for k, v in tot.items()},
             "clocks": t["clocks"],
         }

@@ -228,29 +228,13 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 // block-wide reductions; result valid in every thread.  Contains barriers.
-// Flat pass over n elements, element e = tid, tid + kThreads, ...: the loads of B consecutive elements of a thread are
-// issued together and consumed afterwards.  The plain loop keeps ONE global load in flight per thread — its stores go
-// through pointers the compiler cannot tell from the loads' (shared memory and HBM through generic pointers), so it may
-// not hoist the next element's loads above them — and these passes are then bound by memory latency, not bandwidth.
-// Per-thread order of the elements (and of any sum over them) is unchanged.
-#ifndef HSDDP_FLAT_B
-#define HSDDP_FLAT_B 1
-#endif
-template <int B, class LoadF, class UseF>
+// Flat pass over n elements, element e = tid, tid + kThreads, ...: `load(e)` gathers what the element needs from memory,
+// `use(e, v)` computes and stores.  Measured with the loads of 2 and of 4 consecutive elements of a thread issued together
+// (more loads in flight per thread): 316 and 332 ms per 16,384-problem solve against 300, single solve 6.2 and 5.7 ms
+// against 4.2 (profiles/r02ab_*) -- the larger loop bodies cost more than the memory-level parallelism returns.
+template <class LoadF, class UseF>
 __device__ __forceinline__ void flat_pass(int n, int tid, LoadF&& load, UseF&& use) {
-    for (int e0 = tid; e0 < n; e0 += B * kThreads) {
-        decltype(load(0)) v[B];
-#pragma unroll
-        for (int u = 0; u < B; ++u) {
-            const int e = e0 + u * kThreads;
-            if (e < n) v[u] = load(e);
-        }
-#pragma unroll
-        for (int u = 0; u < B; ++u) {
-            const int e = e0 + u * kThreads;
-            if (e < n) use(e, v[u]);
-        }
-    }
+    for (int e = tid; e < n; e += kThreads) use(e, load(e));
 }
 
 template <int OP>  // 0 sum, 1 min, 2 max
@@ -432,7 +416,7 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
     //      (kept in shared memory next to the states when both fit, else re-read from HBM)
     const bool dev_in_smem = sc.n_nodes * 48 <= kSweepDoubles;
     double* xd = xs + sc.n_nodes * 24;
-    flat_pass<HSDDP_FLAT_B>(sc.n_nodes * 24, tid, [&](int e) { return make_double2(sm.Xbar[e], sm.dX[e]); },
+    flat_pass(sc.n_nodes * 24, tid, [&](int e) { return make_double2(sm.Xbar[e], sm.dX[e]); },
                  [&](int e, const double2& v) {
                      const double x = v.x + eps * v.y;
                      xs[e] = x;
@@ -444,7 +428,7 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
     //     Lane (p, q) = (lane & 7, lane >> 3) accumulates the control pair (2p, 2p+1) over the state
     //     components j = q, q+4, ..: every load is a 16-byte piece of a 384-byte contiguous run of K.
     if (LINEARISED) {
-        flat_pass<HSDDP_FLAT_B>(N * 24, tid,
+        flat_pass(N * 24, tid,
                      [&](int e) {
                          const int s = e / 24, i = e % 24, c = i % 12;
                          const bool stance = (sc.cmask[sc.ph_of_stage[s]] >> (c / 3)) & 1u;
@@ -569,7 +553,7 @@ __device__ inline bool hybrid_rollout_block(Smem& sm, double eps) {
     }
     double gmin = 0.0;
     const double mu = sm.cp.mu;
-    flat_pass<HSDDP_FLAT_B>(N * 24, tid, [&](int e) { return sm.U_t[e]; },
+    flat_pass(N * 24, tid, [&](int e) { return sm.U_t[e]; },
                  [&](int e, double u) {
                      int ph, k;
                      phase_of_stage(sc, e / 24, ph, k);
@@ -632,7 +616,7 @@ __device__ inline void compute_cost_block(Smem& sm) {
     // Every term of the running / terminal costs is a sum over (node or stage, component): the passes below walk
     // those index spaces flat, so all 128 threads work and every global access is coalesced.
     // (1) state tracking, (node, j): running 1/2 dt Q dx^2, terminal 1/2 Qf dx^2
-    flat_pass<HSDDP_FLAT_B>(sc.n_nodes * 24, tid, [&](int e) { return make_double2(sm.X[e], sm.xr[e]); },
+    flat_pass(sc.n_nodes * 24, tid, [&](int e) { return make_double2(sm.X[e], sm.xr[e]); },
                  [&](int e, const double2& v) {
                      const int n = e / 24, j = e % 24;
                      const int ph = sc.ph_of_node[n];
@@ -642,7 +626,7 @@ __device__ inline void compute_cost_block(Smem& sm) {
                      csum += terminal ? 0.5 * ((dx * weight_Qf(j, cm)) * dx) : ((0.5 * dx * weight_Q(j, cm)) * dx) * dt;
                  });
     // (2) control effort, (stage, j)
-    flat_pass<HSDDP_FLAT_B>(N * 24, tid,
+    flat_pass(N * 24, tid,
                  [&](int e) {
                      const int s = e / 24, j = e % 24;
                      int ph, k;
@@ -654,7 +638,7 @@ __device__ inline void compute_cost_block(Smem& sm) {
                      csum += ((0.5 * du * weight_R(e % 24)) * du) * dt;
                  });
     // (3) foot-placement regulariser, (node, leg component)
-    flat_pass<HSDDP_FLAT_B>(sc.n_nodes * 12, tid,
+    flat_pass(sc.n_nodes * 12, tid,
                  [&](int e) {
                      const int n = e / 12, q = e % 12;
                      const double* x = sm.X + 24 * n;
@@ -674,7 +658,7 @@ __device__ inline void compute_cost_block(Smem& sm) {
     // (4) relaxed-barrier terms of the GRF constraints, (stage, row)  (compute_ReB_cost, ConstraintsBase.h:204-222)
     if (sm.opt.ReB_active) {
         const double2* reb2 = reinterpret_cast<const double2*>(sm.reb);
-        flat_pass<HSDDP_FLAT_B>(N * 20, tid,
+        flat_pass(N * 20, tid,
                      [&](int i) {
                          double3 v;
                          v.x = 0.0; v.y = 0.0; v.z = 0.0;
@@ -705,7 +689,7 @@ __device__ inline void compute_cost_block(Smem& sm) {
             }
     }
     double dsum = 0.0;
-    flat_pass<HSDDP_FLAT_B>(sc.n_nodes * 24, tid, [&](int e) { return sm.Defect[e]; }, [&](int, double d) { dsum += d * d; });
+    flat_pass(sc.n_nodes * 24, tid, [&](int e) { return sm.Defect[e]; }, [&](int, double d) { dsum += d * d; });
     const double cost = block_reduce<0>(sm, csum);
     const double f2 = block_reduce<0>(sm, dsum);
     if (tid == 0) { sm.st.actual_cost = cost; sm.st.feas = sqrt(f2); }
@@ -811,7 +795,7 @@ __device__ inline void lq_approximation_block(Smem& sm) {
     // (2) cost gradients, flat over (stage, component), loads batched (flat_pass): the lu of the joint-velocity commands
     //     (12 per stage); lx of every component but the position (21); lx of the position rows (3), which accumulate the
     //     foot-placement regulariser over the legs in order.
-    flat_pass<HSDDP_FLAT_B>(N * 12, tid,
+    flat_pass(N * 12, tid,
                  [&](int e) {
                      const int s = e / 12, i = 12 + e % 12;
                      int ph, k;
@@ -822,7 +806,7 @@ __device__ inline void lq_approximation_block(Smem& sm) {
                      const int s = e / 12, i = 12 + e % 12;
                      sm.lqg[(size_t)s * CR_STRIDE + CR_LU + i] = (dt * weight_R(i)) * (v.x - v.y);
                  });
-    flat_pass<HSDDP_FLAT_B>(N * 21, tid,
+    flat_pass(N * 21, tid,
                  [&](int e) {
                      const int s = e / 21, jr = e % 21, j = jr < 3 ? jr : jr + 3;
                      int ph, k;
@@ -849,7 +833,7 @@ __device__ inline void lq_approximation_block(Smem& sm) {
                  });
     {
         struct PosRow { double xj, xrj, xf[4], pr[4]; };
-        flat_pass<(HSDDP_FLAT_B > 2 ? 2 : HSDDP_FLAT_B)>(N * 3, tid,
+        flat_pass(N * 3, tid,
                      [&](int e) {
                          const int s = e / 3, j = 3 + e % 3;
                          int ph, k;
@@ -923,8 +907,8 @@ __device__ inline void lq_approximation_block(Smem& sm) {
 // update_nominal_trajectory (TrajectoryManagement.cpp:110-115)
 // ---------------------------------------------------------------------------
 __device__ inline void update_nominal_block(Smem& sm) {
-    flat_pass<HSDDP_FLAT_B>(sm.sc.n_nodes * 24, (int)threadIdx.x, [&](int e) { return sm.X[e]; }, [&](int e, double v) { sm.Xbar[e] = v; });
-    flat_pass<HSDDP_FLAT_B>(sm.sc.n_stages * 24, (int)threadIdx.x, [&](int e) { return sm.U[e]; }, [&](int e, double v) { sm.Ubar[e] = v; });
+    flat_pass(sm.sc.n_nodes * 24, (int)threadIdx.x, [&](int e) { return sm.X[e]; }, [&](int e, double v) { sm.Xbar[e] = v; });
+    flat_pass(sm.sc.n_stages * 24, (int)threadIdx.x, [&](int e) { return sm.U[e]; }, [&](int e, double v) { sm.Ubar[e] = v; });
     __syncthreads();
 }
 

@@ -78,9 +78,6 @@ __device__ inline void zero_stage_buffers(Smem& sm) {
 // straight-line code.  The compiler's IEEE division carries a slow-path branch and ~70 cycles of dependent latency in
 // the middle of the serial chain of an elimination step; this form is 13-17 % faster per elimination
 // (tools/microbench/gj_variants.cu) and agrees with the division to the last bit or two.
-#ifdef HSDDP_GJ_IEEE_DIV
-__device__ __forceinline__ double pivot_rcp(double d) { return 1.0 / d; }
-#else
 __device__ __forceinline__ double pivot_rcp(double d) {
     double x;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
@@ -89,7 +86,6 @@ __device__ __forceinline__ double pivot_rcp(double d) {
     e = fma(-d, x, 1.0);
     return fma(x, e, x);
 }
-#endif
 
 // Block Gauss-Jordan with 2x2 pivot blocks on 12 rows, one tableau column per lane (v[0..11]).
 // Lanes 0..11 of the warp hold the columns of the 12x12 pivot matrix.  `sbuf`: 24 doubles per warp.
@@ -99,10 +95,7 @@ __device__ __forceinline__ double pivot_rcp(double d) {
 // Returns false if a negative pivot was met (pivot 1 = a, pivot 2 = det / a), which for the caller
 // that runs Quu_r - 1e-9 I is the reference's LDLT(...).isPositive() verdict (Sylvester's law of
 // inertia).  After the call v = Quu_r^-1 * (original column).
-#ifndef HSDDP_GJ_UNROLL
-#define HSDDP_GJ_UNROLL 1
-#endif
-constexpr int kGjUnroll = HSDDP_GJ_UNROLL;
+constexpr int kGjUnroll = 1;
 #ifdef HSDDP_PROFILE_GJ
 #define GJ_MARK(slot) do { if (threadIdx.x == 0) { const long long t1_ = clock64(); gjacc[slot] += (unsigned long long)(t1_ - gjt0); gjt0 = t1_; } } while (0)
 #else
@@ -149,57 +142,6 @@ __device__ __forceinline__ bool gauss_jordan12(double (&v)[12], double* sbuf, un
 #endif
         __syncwarp();
         GJ_MARK(2);
-    }
-    return ok;
-}
-
-// 4x4 pivot blocks: three sequential steps.  The block is inverted through its 2x2 blocks (A, Schur complement S),
-// and the multipliers t = P^-1 v[0..3] come from the block solve y = A^-1 v01, t23 = S^-1 (v23 - C y), t01 = y - A^-1 B t23,
-// so the two reciprocals are the only long-latency operations of a step.  Columns rotate by four per step.
-// `sbuf`: 48 doubles per warp.  Experiment (-DHSDDP_GJ_BLOCK4), written at the end of round 1 and not yet run on a GPU;
-// tools/microbench/gj_variants.cu variant 6 times it.
-__device__ __forceinline__ bool gauss_jordan12_b4(double (&v)[12], double* sbuf) {
-    const int lane = threadIdx.x & 31;
-    bool ok = true;
-#pragma unroll 1
-    for (int step = 0; step < 3; ++step) {
-        const int pl = lane - 4 * step;
-        if (pl >= 0 && pl < 4) {
-            double2* dst = reinterpret_cast<double2*>(sbuf + 12 * pl);
-#pragma unroll
-            for (int r = 0; r < 12; r += 2) dst[r >> 1] = make_double2(v[r], v[r + 1]);
-        }
-        __syncwarp();
-        // P[i][j] = sbuf[12 j + i]: column j of the pivot block, rows 0..3
-        const double2 c0a = *reinterpret_cast<const double2*>(sbuf), c0b = *reinterpret_cast<const double2*>(sbuf + 2);
-        const double2 c1a = *reinterpret_cast<const double2*>(sbuf + 12), c1b = *reinterpret_cast<const double2*>(sbuf + 14);
-        const double2 c2a = *reinterpret_cast<const double2*>(sbuf + 24), c2b = *reinterpret_cast<const double2*>(sbuf + 26);
-        const double2 c3a = *reinterpret_cast<const double2*>(sbuf + 36), c3b = *reinterpret_cast<const double2*>(sbuf + 38);
-        // A = [c0a.x c1a.x; c0a.y c1a.y], B = [c2a.x c3a.x; c2a.y c3a.y], C = [c0b.x c1b.x; c0b.y c1b.y], D = [c2b.x c3b.x; c2b.y c3b.y]
-        const double detA = c0a.x * c1a.y - c1a.x * c0a.y;
-        const double rA = pivot_rcp(detA);
-        const double i00 = c1a.y * rA, i01 = -c1a.x * rA, i10 = -c0a.y * rA, i11 = c0a.x * rA;      // A^-1
-        const double e00 = fma(i00, c2a.x, i01 * c2a.y), e01 = fma(i00, c3a.x, i01 * c3a.y);          // A^-1 B
-        const double e10 = fma(i10, c2a.x, i11 * c2a.y), e11 = fma(i10, c3a.x, i11 * c3a.y);
-        const double s00 = fma(-c0b.x, e00, fma(-c1b.x, e10, c2b.x)), s01 = fma(-c0b.x, e01, fma(-c1b.x, e11, c3b.x));  // S = D - C A^-1 B
-        const double s10 = fma(-c0b.y, e00, fma(-c1b.y, e10, c2b.y)), s11 = fma(-c0b.y, e01, fma(-c1b.y, e11, c3b.y));
-        const double detS = s00 * s11 - s01 * s10;
-        const double rS = pivot_rcp(detS);
-        if (c0a.x < 0.0 || detA < 0.0 || s00 < 0.0 || detS < 0.0) ok = false;  // the four leading minors, up to positive factors
-        // block solve for this lane's column
-        const double y0 = fma(i00, v[0], i01 * v[1]), y1 = fma(i10, v[0], i11 * v[1]);
-        const double z0 = fma(-c0b.x, y0, fma(-c1b.x, y1, v[2])), z1 = fma(-c0b.y, y0, fma(-c1b.y, y1, v[3]));
-        const double t2 = (s11 * z0 - s01 * z1) * rS, t3 = (s00 * z1 - s10 * z0) * rS;
-        const double t0 = fma(-e00, t2, fma(-e01, t3, y0)), t1 = fma(-e10, t2, fma(-e11, t3, y1));
-#pragma unroll
-        for (int r = 4; r < 12; r += 2) {  // eliminate and rotate in one go
-            const double2 m0 = *reinterpret_cast<const double2*>(sbuf + r), m1 = *reinterpret_cast<const double2*>(sbuf + 12 + r);
-            const double2 m2 = *reinterpret_cast<const double2*>(sbuf + 24 + r), m3 = *reinterpret_cast<const double2*>(sbuf + 36 + r);
-            v[r - 4] = fma(-m3.x, t3, fma(-m2.x, t2, fma(-m1.x, t1, fma(-m0.x, t0, v[r]))));
-            v[r - 3] = fma(-m3.y, t3, fma(-m2.y, t2, fma(-m1.y, t1, fma(-m0.y, t0, v[r + 1]))));
-        }
-        v[8] = t0; v[9] = t1; v[10] = t2; v[11] = t3;
-        __syncwarp();
     }
     return ok;
 }
@@ -469,11 +411,7 @@ __device__ inline bool phase_backward_sweep_block(Smem& sm, int ph, double reg, 
                     for (int r = 0; r < 12; ++r) if (r == lane) col[r] -= 1e-9;
                 }
                 PROF_MARK(sm, 13);
-#ifdef HSDDP_GJ_BLOCK4
-                const bool ok = gauss_jordan12_b4(col, sm.red + 64 * warp);
-#else
                 const bool ok = gauss_jordan12(col, sm.red + 40 * warp, sm.profacc + 10);
-#endif
                 PROF_MARK(sm, 14);
                 if (pass) {
                     if (warp == 1 && lane == 0) sm.ibuf[0] = ok ? 1 : 0;
@@ -825,6 +763,7 @@ __device__ inline void linear_rollout_block(Smem& sm, double eps) {
             if (c0 > 0)
                 for (int e = (c0 - LR_CHUNK) * 24 + tid - 32; e < c0 * 24; e += 96) lr_dv_elem(sm, dt, e / 24, e % 24, dV1, dV2);
         }
+        PROF_MARK(sm, 10);  // (profile build: chunk set-up; 13 = the recursion of the chunk, 11 = the wait at the chunk barrier)
         if (tid < 32) {
             for (int s = c0; s < c1; ++s) {
                 if (ph < 0 || (ph + 1 < sc.n_phases && s >= sc.stage_off[ph + 1])) {
@@ -950,8 +889,10 @@ __device__ inline void linear_rollout_block(Smem& sm, double eps) {
                 __syncwarp();
             }
         }
+        PROF_MARK(sm, 13);
         cp_async_wait_all();
         __syncthreads();
+        PROF_MARK(sm, 11);
     }
     PROF_MARK(sm, 11);
     // ---- expected cost change: what is left (last chunk, terminal terms), all threads ----

@@ -206,3 +206,36 @@ def gait_batch(pkg, w, device=0, cparams=None):
     B.set_problems_from_gaits(refs, [order.index(g) for g, _ in w.keys], [k for _, k in w.keys], w.plan, w.schedule_id, cparams)
     B.set_initial_condition(w.x0)
     return B
+
+
+def random_phase(xs, us, ys, N, seed, n=None):
+    """Synthetic plug-in outputs of one phase (or n phases) of SinglePhase<double, xs, us, ys> for the generic sweeps
+    (the reference ships no model for <12,12,0> and <36,12,12>): near-identity dynamics, positive definite
+    cost Hessians, small defects.  Matrices as [..., row, col]."""
+    rng = np.random.default_rng(seed)
+    lead = () if n is None else (n,)
+
+    def pd(m, shape):
+        M = rng.normal(size=shape + (m, m)) * 0.3
+        return M @ np.swapaxes(M, -1, -2) + np.eye(m)
+    return dict(A=np.eye(xs) + 0.1 * rng.normal(size=lead + (N, xs, xs)), B=0.3 * rng.normal(size=lead + (N, xs, us)),
+                C=0.5 * rng.normal(size=lead + (N, ys, xs)), D=0.5 * rng.normal(size=lead + (N, ys, us)),
+                lx=rng.normal(size=lead + (N, xs)), lu=rng.normal(size=lead + (N, us)), ly=rng.normal(size=lead + (N, ys)),
+                lxx=pd(xs, lead + (N,)), luu=pd(us, lead + (N,)), lux=0.1 * rng.normal(size=lead + (N, us, xs)),
+                lyy=pd(ys, lead + (N,)) if ys else np.zeros(lead + (N, 0, 0)), Phix=rng.normal(size=lead + (xs,)),
+                Phixx=pd(xs, lead), Defect=0.05 * rng.normal(size=lead + (N + 1, xs)))
+
+
+def generic_flop_per_stage(xs, us, ys):
+    """Dense algorithmic FLOP of one Riccati stage with product reuse and Cholesky solves (for any sizes)."""
+    f = 2 * xs * xs + 2 * xs * (xs + us) + 2 * xs * xs * (xs + us) + 2 * xs ** 3 + 2 * us * xs * xs + 2 * us * us * xs + us ** 3 // 3 \
+        + 2 * us * us * (xs + 1) + 2 * xs * us + 2 * xs * xs * us
+    if ys:
+        f += 2 * xs * ys * ys + 2 * us * ys * ys + 2 * xs * xs * ys + 2 * us * xs * ys + 2 * us * us * ys + 2 * xs * ys + 2 * us * ys
+    return f
+
+
+def generic_bytes_per_stage(xs, us, ys):
+    rd = xs * xs + xs * us + ys * xs + ys * us + xs + us + ys + xs * xs + us * us + us * xs + ys * ys + xs
+    wr = us + us * xs + xs + xs * xs
+    return 8 * (rd + wr)

@@ -8,27 +8,13 @@ GPU part: the CUDA sweeps (csrc/hsddp_generic.cu, through the C ABI) against the
 import ctypes as C
 import numpy as np
 import pytest
-from conftest import GAIT_PATH, load_pkg
+from conftest import GAIT_PATH, load_pkg, load_workloads
 
 INSTANTIATIONS = [(12, 12, 0), (36, 12, 12), (24, 24, 0)]  # HSDDPSolver/source/SinglePhase.cpp:538-540
 TOL = 1e-9
 
 
-def random_phase(xs, us, ys, N, seed, n=None):
-    """Plug-in outputs of a well-posed phase: stable-ish dynamics, positive definite cost Hessians."""
-    rng = np.random.default_rng(seed)
-    lead = () if n is None else (n,)
-
-    def pd(m, shape):
-        M = rng.normal(size=shape + (m, m)) * 0.3
-        return M @ np.swapaxes(M, -1, -2) + np.eye(m)
-    d = dict(A=np.eye(xs) + 0.1 * rng.normal(size=lead + (N, xs, xs)), B=0.3 * rng.normal(size=lead + (N, xs, us)),
-             C=0.5 * rng.normal(size=lead + (N, ys, xs)), D=0.5 * rng.normal(size=lead + (N, ys, us)),
-             lx=rng.normal(size=lead + (N, xs)), lu=rng.normal(size=lead + (N, us)), ly=rng.normal(size=lead + (N, ys)),
-             lxx=pd(xs, lead + (N,)), luu=pd(us, lead + (N,)), lux=0.1 * rng.normal(size=lead + (N, us, xs)),
-             lyy=pd(ys, lead + (N,)) if ys else np.zeros(lead + (N, 0, 0)), Phix=rng.normal(size=lead + (xs,)),
-             Phixx=pd(xs, lead), Defect=0.05 * rng.normal(size=lead + (N + 1, xs)))
-    return d
+random_phase = load_workloads().random_phase  # synthetic plug-in outputs (hkd-mpc_b200/workloads.py)
 
 
 def numpy_backward_sweep(xs, us, ys, N, d, reg, Gp, Hp):

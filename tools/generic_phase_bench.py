@@ -5,9 +5,10 @@ instantiation with the dense algorithmic FLOP / byte counts per stage and the fr
 import importlib, json, os, sys
 import numpy as np
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 pkg = importlib.import_module("hkd-mpc_b200")
-from test_generic_phase import random_phase
+wl = importlib.import_module("hkd-mpc_b200.workloads")
+random_phase = wl.random_phase
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 60
@@ -15,18 +16,7 @@ peak = pkg.fp64_peak_tflops(0, 0)
 hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6553.6) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6553.6
 
 
-def flop_per_stage(xs, us, ys):
-    f = 2 * xs * xs + 2 * xs * (xs + us) + 2 * xs * xs * (xs + us) + 2 * xs ** 3 + 2 * us * xs * xs + 2 * us * us * xs + us ** 3 // 3 \
-        + 2 * us * us * (xs + 1) + 2 * xs * us + 2 * xs * xs * us
-    if ys:
-        f += 2 * xs * ys * ys + 2 * us * ys * ys + 2 * xs * xs * ys + 2 * us * xs * ys + 2 * us * us * ys + 2 * xs * ys + 2 * us * ys
-    return f
-
-
-def bytes_per_stage(xs, us, ys):
-    rd = xs * xs + xs * us + ys * xs + ys * us + xs + us + ys + xs * xs + us * us + us * xs + ys * ys + xs
-    wr = us + us * xs + xs + xs * xs
-    return 8 * (rd + wr)
+flop_per_stage, bytes_per_stage = wl.generic_flop_per_stage, wl.generic_bytes_per_stage
 
 
 for xs, us, ys in [(12, 12, 0), (24, 24, 0), (36, 12, 12)]:
