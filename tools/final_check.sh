@@ -6,12 +6,12 @@ python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err || {
 tail -c 1500 gpurun_out/bench_final.json
 python bench.py --steps 2 --warmup 1 --no-latency --no-cpu-baseline > /dev/null 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 6000 --csv \
-  --log-file gpurun_out/r02z_launches.csv python bench.py --steps 2 --warmup 1 --no-latency --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+  --log-file gpurun_out/r02zz_launches.csv python bench.py --steps 2 --warmup 1 --no-latency --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 tail -2 gpurun_out/ncu_bench.log | cut -c1-200
 export HSDDP_SOLVE_MODE=2 HSDDP_PHASED_GROUPS=1
-ncu --set full --clock-control none --import-source on -k regex:"k_phase|k_sweep_w1" --launch-skip 41 -c 4 -f -o gpurun_out/r02z_round \
-  python tools/profile_case.py 8192 config3 1 > gpurun_out/ncu_r02z.log 2>&1
-tail -2 gpurun_out/ncu_r02z.log
+ncu --set full --clock-control none --import-source on -k regex:"k_phase|k_sweep_w1" --launch-skip 41 -c 4 -f -o gpurun_out/r02zz_round \
+  python tools/profile_case.py 8192 config3 1 > gpurun_out/ncu_r02zz.log 2>&1
+tail -2 gpurun_out/ncu_r02zz.log
 unset HSDDP_SOLVE_MODE HSDDP_PHASED_GROUPS
-python tools/config_sweep.py > gpurun_out/r02z_config_sweep.jsonl 2> gpurun_out/config_sweep.err
-cat gpurun_out/r02z_config_sweep.jsonl | cut -c1-330
+python tools/config_sweep.py > gpurun_out/r02zz_config_sweep.jsonl 2> gpurun_out/config_sweep.err
+cat gpurun_out/r02zz_config_sweep.jsonl | cut -c1-330
