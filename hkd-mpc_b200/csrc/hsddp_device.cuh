@@ -146,6 +146,7 @@ struct BatchPtrs {
     int* next_count;
     int* zero_count;                          // counter the first kernel of a round clears for the round after next (nullptr: none)
     int sweep_w1_min;                         // phased driver: rounds with at least this many problems run k_sweep_w1 instead of k_phase<PH_SWEEP> (0: never)
+    int lr_external;                          // phased driver: the linear rollout of the iteration was done by k_lr_w1 (the forward phase skips it)
     int _pad2;
     // concurrent line search of the latency kernel (k_solve_lat4): per problem and step size, the arrays a trial writes
     // (X, Defect, Xsim: [P][4][max_nodes][24]; U, U scratch: [P][4][max_stages][24]; gcon [P][4][max_stages][20];

@@ -15,6 +15,7 @@
 #include "hsddp_device.cuh"
 #include "hsddp_sweep.cuh"
 #include "hsddp_sweep_w1.cuh"
+#include "hsddp_lr_w1.cuh"
 
 // resident blocks per SM the kernels are compiled for (register budget = 65536 / (128 * HSDDP_MIN_BLOCKS))
 #ifndef HSDDP_MIN_BLOCKS
@@ -304,7 +305,7 @@ __device__ inline void iter_forward_block(Smem& sm, const BatchPtrs& bp) {
     const int tid = threadIdx.x;
     const hsddp_options& opt = sm.opt;
     hsddp_iter_record* rec = (sm.ctl.iter <= HSDDP_TRACE_CAP) ? bp.trace + (size_t)sm.pid * HSDDP_TRACE_CAP + sm.ctl.iter - 1 : nullptr;
-    if (opt.MS) linear_rollout_block(sm, 1.0);
+    if (opt.MS && !bp.lr_external) linear_rollout_block(sm, 1.0);  // (phased driver: k_lr_w1 has left dX, K dX, dV_1, dV_2)
     prepare_merit_block(sm);
     const double cost_prev = sm.st.actual_cost, merit_prev = sm.st.merit;
     const double dV_abs = fabs(sm.st.dV_1 + 0.5 * sm.st.dV_2);
@@ -1036,6 +1037,7 @@ struct hsddp_batch {
     // shared-memory wavefronts per stage), four warps below (shorter dependent chain per problem when the GPU is not full)
     int sweep_kind = 2;
     int w1_min_blocks = 1036;      // (one full wave of k_sweep_w1: 148 SMs x 7; measured flat between 800 and 2,072, 2 % worse at 3,000)
+    bool lr_w1 = true;             // phased driver: linear rollout as its own one-warp-per-problem kernel (k_lr_w1) between sweep and forward
     int* d_order = nullptr;        // persistent kernel: queue order by the previous solve's iteration counts (k_order_by_iterations)
     bool have_order = false, use_order = true;
     bool cluster_ls = true;        // latency kernel with the concurrent line search (k_solve_lat4) for batches of at most kClusterLsMax problems
@@ -1171,7 +1173,9 @@ static int batch_init(hsddp_batch* b, int device) {
     if (const char* e = getenv("HSDDP_HYBRID_GROUPS")) { const int v = atoi(e); if (v >= 1 && v <= hsddp_batch::kMaxGroups) b->hybrid_groups = v; }
     if (const char* e = getenv("HSDDP_SWEEP_KIND")) b->sweep_kind = atoi(e);  // tuning / experiments only
     CK(cudaFuncSetAttribute(k_sweep_w1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k_lr_w1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     if (const char* e = getenv("HSDDP_W1_MIN_BLOCKS")) b->w1_min_blocks = atoi(e);  // tuning / experiments only
+    if (const char* e = getenv("HSDDP_LR_W1")) b->lr_w1 = atoi(e) != 0;              // tuning / experiments only
     if (const char* e = getenv("HSDDP_QUEUE_ORDER")) b->use_order = atoi(e) != 0;   // tuning / experiments only
     if (const char* e = getenv("HSDDP_CLUSTER_LS")) b->cluster_ls = atoi(e) != 0;   // tuning / experiments only
     if (const char* e = getenv("HSDDP_SOLVE_MODE")) {  // tuning / experiments only
@@ -1599,6 +1603,7 @@ static int solve_phased(hsddp_batch* b, const hsddp_options& o, bool hybrid) {
         if (cudaStreamWaitEvent(st, b->ev_fork, 0) != cudaSuccess) { rc = HSDDP_ERR_CUDA; break; }
         BatchPtrs bp = b->bp;
         bp.sweep_w1_min = b->sweep_kind == 0 ? 0 : b->sweep_kind == 1 ? 1 : b->w1_min_blocks;
+        bp.lr_external = (b->lr_w1 && o.MS) ? 1 : 0;
         // round 0: begin (initial rollout, first outer iteration set-up) over every problem of the group
         bp.active = list[0]; bp.n_active = nullptr; bp.next_active = list[1]; bp.next_count = cnt[1]; bp.zero_count = nullptr;
         k_phase<PH_BEGIN><<<n, kThreads, 0, st>>>(bp, o);
@@ -1609,8 +1614,9 @@ static int solve_phased(hsddp_batch* b, const hsddp_options& o, bool hybrid) {
             k_phase<PH_PREP><<<n, kThreads, 0, st>>>(bp, o);
             if (use_block) k_phase<PH_SWEEP><<<n, kThreads, 0, st>>>(bp, o);
             if (use_w1) k_sweep_w1<<<n, 32, 0, st>>>(bp, o);
+            if (bp.lr_external) k_lr_w1<<<n, 32, 0, st>>>(bp, o);
             k_phase<PH_FORWARD><<<n, kThreads, 0, st>>>(bp, o);
-            b->n_solve_launches += 3 + (use_block && use_w1 ? 1 : 0);
+            b->n_solve_launches += 3 + (use_block && use_w1 ? 1 : 0) + (bp.lr_external ? 1 : 0);
         }
         if (cudaGetLastError() != cudaSuccess) { rc = HSDDP_ERR_CUDA; g_last_error = "kernel launch failed in the phased driver"; }
         // the survivors of the last round: list / counter the next round would have read
