@@ -69,11 +69,11 @@ def entries_config2(n):
     return [("trot", 0, "default", (i if i >= 1 else None)) for i in range(n)]
 
 
-def entries_config3(n, plan=0.6, first=0):
+def entries_config3(n, plan=0.6, first=0, stride=1):
     sizes = {g: gait_table(g)["body_state"].shape[0] for g in GAITS}
     out = []
     for j in range(n):
-        i = first + j
+        i = first + j * stride
         g = GAITS[i % 3]
         k0 = (7 * (i // 3)) % (sizes[g] - (int(round(plan / 0.01)) + 3))  # (n_samples - 63 for the 0.6 s horizon of SURVEY.md §8d)
         out.append((g, int(k0), "reference", i))
@@ -130,14 +130,14 @@ NAMES = {"config1": "config1: single trot solve", "config2": "config2: {n} trot 
          "config3": "config3: {n} mixed-gait problems (trot/bound/pronk)", "config4": "config4: {n} bound+jump problems"}
 
 
-def define(config, n=None, plan=0.6, first=0):
+def define(config, n=None, plan=0.6, first=0, stride=1):
     """(name, entries) of a configuration — no library needed."""
     if config == "config1":
         e = entries_config1()
     elif config == "config2":
         e = entries_config2(n)
     elif config == "config3":
-        e = entries_config3(n, plan, first)
+        e = entries_config3(n, plan, first, stride)
     elif config == "config4":
         e = entries_config4(n)
     else:
@@ -145,15 +145,15 @@ def define(config, n=None, plan=0.6, first=0):
     return NAMES[config].format(n=len(e)), e
 
 
-def build_cpu(config, hkd_state, n=None, plan=0.6, first=0):
+def build_cpu(config, hkd_state, n=None, plan=0.6, first=0, stride=1):
     """The workload without schedules (CPU arm / oracle side): keys, schedule ids, x0."""
-    name, e = define(config, n, plan, first)
+    name, e = define(config, n, plan, first, stride)
     keys, sid = schedule_keys(e)
     return Workload(name, None, sid, initial_states(e, hkd_state), keys, plan, e)
 
 
-def _build(pkg, config, n=None, plan=0.6, first=0):
-    name, e = define(config, n, plan, first)
+def _build(pkg, config, n=None, plan=0.6, first=0, stride=1):
+    name, e = define(config, n, plan, first, stride)
     return from_entries(pkg, name, e, plan)
 
 
@@ -179,11 +179,11 @@ def config2(pkg, n=1024, plan=0.6):
     return _build(pkg, "config2", n, plan)
 
 
-def config3(pkg, n=16384, plan=0.6, first=0):
+def config3(pkg, n=16384, plan=0.6, first=0, stride=1):
     """n mixed-gait problems: gait i mod 3, window start (7*(i div 3)) mod (n_samples-63),
-    x0 = reference body state at the window start + perturbation.  `first` offsets the
-    problem index (used to shard by index across ranks)."""
-    return _build(pkg, "config3", n, plan, first)
+    x0 = reference body state at the window start + perturbation.  Problem j of the workload is problem
+    i = first + j * stride of the configuration (used to shard by index across ranks: contiguous ranges or interleaved)."""
+    return _build(pkg, "config3", n, plan, first, stride)
 
 
 def config4(pkg, n=4096, plan=0.6):

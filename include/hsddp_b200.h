@@ -190,8 +190,8 @@ int hsddp_batch_sync(hsddp_batch* b);
 /* How solve() is scheduled on the GPU (results agree to rounding; each mode is bitwise reproducible):
  *   1 persistent — one kernel, every block runs whole solves pulled from a queue (small batches, latency).  From the
  *                  second solve of a problem set on, the queue visits the problems in the order of their previous
- *                  iteration counts, longest first (a scheduling hint only: results do not depend on it)
- *   2 phased     — per DDP iteration one kernel per phase (prep / backward sweep / forward sweep) over the problems
+ *                  work (iterations, backward sweeps, trials), longest first (a scheduling hint only: results do not depend on it)
+ *   2 phased     — per DDP iteration one kernel per phase (prep / backward sweep / linear rollout / forward sweep) over the problems
  *                  still running, up to eight index ranges driven concurrently on their own streams.  The list of
  *                  running problems and its length stay in HBM, so the whole solve is queued without a host round trip
  *                  and hsddp_batch_solve_async returns as soon as the launches are queued

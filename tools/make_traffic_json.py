@@ -27,7 +27,7 @@ resets = [i for i in ids if "k_step" in launches[i]["kernel"]]
 steps = [(a, b) for a, b in zip(resets, resets[1:]) if sum("k_iota" in launches[i]["kernel"] or "k_solve" in launches[i]["kernel"] for i in ids if a <= i < b) >= 1]
 a, b = steps[-1]
 names = {"k_phase<0>": "begin", "k_phase<1>": "prep (cost + LQ)", "k_phase<2>": "backward sweep (four warps per problem)", "k_sweep_w1": "backward sweep (one warp per problem)",
-         "k_phase<3>": "forward (linear rollout + line search)", "k_step": "cold-start reset"}
+         "k_phase<3>": "forward (line search; the linear rollout too when k_lr_w1 is off)", "k_lr_w1": "linear rollout (one warp per problem)", "k_step": "cold-start reset"}
 agg = collections.OrderedDict()
 rd = wr = ms = 0.0
 for i in ids:
