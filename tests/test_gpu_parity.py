@@ -243,6 +243,37 @@ def test_solve_modes_agree(pkg, orc, workloads):
         assert rel_err(Bh.get("Xbar")[i], out[2][1][i]) < RTOL, i
 
 
+def test_linear_rollout_kernel_of_the_phased_driver_matches_the_block_version(pkg, orc, workloads, monkeypatch):
+    """The phased driver runs the linear rollout as its own one-warp-per-problem kernel (k_lr_w1); HSDDP_LR_W1=0 leaves it
+    inside the forward kernel (linear_rollout_block).  Same recursion, dV_1 / dV_2 summed in a different order: after ONE
+    DDP iteration the expected cost change, the search direction and the accepted trajectories agree to rounding, and
+    whole solves take the same decisions."""
+    w = workloads.config3(pkg, 96)
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("HSDDP_LR_W1", flag)
+        B = _batch_for(pkg, w)
+        B.set_solve_mode(2)
+        B.solve(pkg.Options(max_AL_iter=1, max_DDP_iter=1))
+        one = (B.trace()[:, 0, :].copy(), B.get("dX").copy(), B.get("Xbar").copy())
+        B.reset()
+        B.solve()
+        res[flag] = one + (B.info().copy(), B.get("Xbar").copy())
+    monkeypatch.delenv("HSDDP_LR_W1")
+    (t1, dx1, x1, i1, xf1), (t0, dx0, x0, i0, xf0) = res["1"], res["0"]
+    cols = [pkg.TRACE_COLS.index(c) for c in ("dV_1", "dV_2", "eps_accepted", "n_trials", "cost_after")]
+    assert np.array_equal(t1[:, cols[2:4]], t0[:, cols[2:4]])  # accepted step and trial count of the first iteration
+    for c in (cols[0], cols[1], cols[4]):
+        assert np.allclose(t1[:, c], t0[:, c], rtol=1e-9, atol=1e-9 * np.abs(t0[:, c]).max()), pkg.TRACE_COLS[c]
+    assert np.array_equal(dx1, dx0)  # the recursion itself is bit-identical
+    assert rel_err(x1, x0) < 1e-12
+    same = (i1["n_iter"] == i0["n_iter"]) & (i1["status"] == i0["status"])
+    assert same.mean() > 0.95, same.mean()
+    for i in np.nonzero(same)[0]:
+        assert rel_err(xf1[i], xf0[i]) < RTOL, i
+    _compare_solution(pkg, orc, w, B, range(0, 6), {}, max_ill_posed=1)
+
+
 def test_mpc_command_extraction(pkg, orc, workloads):
     """What leaves the GPU after a solve (hkd_command_lcmt payload, HKDMPC.cpp:207-298): packed on the device,
     compared with the restated publish_mpc_cmd / update_foot_placement applied to the oracle's trajectories."""

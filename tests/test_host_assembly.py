@@ -106,3 +106,13 @@ def test_cpp_shim_compiles_and_fails_loudly_without_gpu(pkg, tmp_path):
     ref = "/root/reference/Reference/Data/trot/quad_reference.csv"
     r = subprocess.run([exe, ref if os.path.exists(ref) else "/nonexistent"], capture_output=True, text=True)
     assert r.returncode != 0 and "error" in r.stderr
+
+
+def test_config3_shards_by_index_contiguous_and_interleaved(workloads):
+    """Problem j of a shard is problem first + j * stride of the configuration: contiguous ranges (bench.py's strong block)
+    and interleaved shards (tools/strong_shards.py) cover the same 48 problems exactly once."""
+    full = workloads.entries_config3(48)
+    cont = [e for r in range(4) for e in workloads.entries_config3(12, first=12 * r)]
+    inter = [workloads.entries_config3(12, first=r, stride=4) for r in range(4)]
+    assert cont == full
+    assert [inter[j % 4][j // 4] for j in range(48)] == full
