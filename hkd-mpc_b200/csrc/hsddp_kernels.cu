@@ -1655,9 +1655,9 @@ int hsddp_batch_solve_async(hsddp_batch* b, const hsddp_options* opt) {
     // auto: the persistent kernel up to ~7 waves of blocks (its work queue visits the problems longest-first from the second
     // solve on, which keeps the tail short); beyond that the phased driver, whose phase-homogeneous kernels keep the
     // instruction cache hot and whose launch tails are hidden by driving four index ranges on their own streams
-    // (measured on config 3, persistent vs phased, ms: 2,048 problems 57 vs 73, 4,096: 101 vs 108, 8,192: 199 vs 188,
-    // 16,384: 455 vs 336 -- DESIGN.md §4)
-    const bool phased = b->solve_mode == 2 || (b->solve_mode == 0 && b->bp.n_problems >= 7 * b->n_sm * b->blocks_per_sm);
+    // (measured on config 3, persistent vs phased, ms, final code of round 2: 2,048 problems 57 vs 69, 4,096: 98 vs 100,
+    // 5,120: ~121 vs 117, 6,144: 145 vs 135, 8,192: 199 vs 163 -- profiles/r02an_*: the switch is at 5.5 waves of blocks, 4,884 problems)
+    const bool phased = b->solve_mode == 2 || (b->solve_mode == 0 && 2 * b->bp.n_problems >= 11 * b->n_sm * b->blocks_per_sm);
     if (phased) return solve_phased(b, o, false);
     if (b->solve_mode == 3) return solve_phased(b, o, true);
     CK(cudaMemsetAsync(b->bp.work_counter, 0, sizeof(int), b->stream));

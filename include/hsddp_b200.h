@@ -198,7 +198,7 @@ int hsddp_batch_sync(hsddp_batch* b);
  *   3 hybrid     — the phased driver for the first 20 DDP iterations, then a persistent kernel resumes the problems that
  *                  are still running (late phased rounds are latency-bound).  Opt-in: measured 11 % faster than
  *                  persistent at 1,024 problems, 4 % at 4,096, 4 % slower at 2,048
- *   0 auto       — phased when the batch fills the GPU about seven times over (>= 6,216 problems on a B200). */
+ *   0 auto       — phased when the batch fills the GPU five and a half times over (>= 4,884 problems on a B200). */
 int hsddp_batch_set_solve_mode(hsddp_batch* b, int mode);
 /* milliseconds of the last solve kernel, CUDA events on the handle's stream */
 int hsddp_batch_last_solve_ms(hsddp_batch* b, float* ms);
