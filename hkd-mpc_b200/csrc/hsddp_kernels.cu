@@ -1036,7 +1036,7 @@ struct hsddp_batch {
     // 2 auto: one warp per problem for launches of at least `w1_min_blocks` problems (full waves: fewer instructions and
     // shared-memory wavefronts per stage), four warps below (shorter dependent chain per problem when the GPU is not full)
     int sweep_kind = 2;
-    int w1_min_blocks = 1036;      // (one full wave of k_sweep_w1: 148 SMs x 7; measured flat between 800 and 2,072, 2 % worse at 3,000)
+    int w1_min_blocks = 1036;      // (about one wave of k_sweep_w1, 148 SMs x 7 when it was set; measured flat between 800 and 2,072, 2 % worse at 3,000)
     bool lr_w1 = true;             // phased driver: linear rollout as its own one-warp-per-problem kernel (k_lr_w1) between sweep and forward
     int* d_order = nullptr;        // persistent kernel: queue order by the previous solve's iteration counts (k_order_by_iterations)
     bool have_order = false, use_order = true;
