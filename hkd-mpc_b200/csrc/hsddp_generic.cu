@@ -83,13 +83,31 @@ template <int T>
 __device__ __forceinline__ void copy_in(double* dst, const double* __restrict__ src, int n, int tid) {
     for (int e = tid; e < n; e += T) dst[e] = src[e];
 }
+// the same copy as 16-byte cp.async pieces (n even, both sides 16-byte aligned): fire and forget, one wait per stage
+template <int T>
+__device__ __forceinline__ void copy_in_async(double* dst, const double* __restrict__ src, int n, int tid) {
+    for (int e = 2 * tid; e < n; e += 2 * T) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + e);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + e));
+    }
+}
+__device__ __forceinline__ void copy_in_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// 1 / d for a positive pivot: hardware seed and two Newton steps (the IEEE division is ~80 instructions on the elimination's chain)
+__device__ __forceinline__ double pivot_rcp(double d) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-d, x, 1.0);
+    return fma(x, e, x);
+}
 
 // SinglePhase::backward_sweep (SinglePhase.cpp:299-367)
 template <int XS, int US, int YS>
 __global__ void __launch_bounds__(Lay<XS, US, YS>::T) k_generic_backward_sweep(PhasePtrs p, double reg) {
     using L = Lay<XS, US, YS>;
     constexpr int T = L::T;
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, pid = blockIdx.x, N = p.N;
     double* H = smem + L::oH;
     double* AB = smem + L::oAB;   // A (XS x XS) then B (XS x US), column-major
@@ -131,17 +149,22 @@ __global__ void __launch_bounds__(Lay<XS, US, YS>::T) k_generic_backward_sweep(P
     double dV1 = 0.0, dV2 = 0.0;
     bool success = true;
     __syncthreads();
-    for (int k = N - 1; k >= 0; --k) {
-        // ---- stage inputs ----
-        copy_in<T>(AB, p.A + (pN + k) * L::XX, L::XX, tid);
-        copy_in<T>(AB + L::XX, p.B + (pN + k) * L::XU, L::XU, tid);
-        copy_in<T>(dfc, p.Defect + (pN1 + k + 1) * XS, XS, tid);
+    // stage inputs (A, B, C, D, lyy, ly, the defect of the next node) arrive by cp.async: the copies of stage k - 1 are issued
+    // in the middle of stage k, as soon as its Q function is formed and the buffers are dead
+    auto fetch_stage = [&](int k) {
+        copy_in_async<T>(AB, p.A + (pN + k) * L::XX, L::XX, tid);
+        copy_in_async<T>(AB + L::XX, p.B + (pN + k) * L::XU, L::XU, tid);
+        copy_in_async<T>(dfc, p.Defect + (pN1 + k + 1) * XS, XS, tid);
         if (YS > 0) {
-            copy_in<T>(Cm, p.C + (pN + k) * L::YX, L::YX, tid);
-            copy_in<T>(Dm, p.D + (pN + k) * L::YU, L::YU, tid);
-            copy_in<T>(Lyy, p.lyy + (pN + k) * L::YY, L::YY, tid);
-            copy_in<T>(ly, p.ly + (pN + k) * YS, YS, tid);
+            copy_in_async<T>(Cm, p.C + (pN + k) * L::YX, L::YX, tid);
+            copy_in_async<T>(Dm, p.D + (pN + k) * L::YU, L::YU, tid);
+            copy_in_async<T>(Lyy, p.lyy + (pN + k) * L::YY, L::YY, tid);
+            copy_in_async<T>(ly, p.ly + (pN + k) * YS, YS, tid);
         }
+    };
+    fetch_stage(N - 1);
+    for (int k = N - 1; k >= 0; --k) {
+        copy_in_wait();
         __syncthreads();
         // ---- [Y | Z] = H [A | B];  Gnext = G + H Defect[k+1];  C^T lyy, D^T lyy ----
         gemm_tiles<T, XS, XS + US, XS, false>(H, XS, AB, XS, nullptr, 0, YZ, XS, tid);
@@ -155,11 +178,9 @@ __global__ void __launch_bounds__(Lay<XS, US, YS>::T) k_generic_backward_sweep(P
             gemm_tiles<T, US, YS, YS, true>(Dm, YS, Lyy, YS, nullptr, 0, DtL, US, tid);
         }
         __syncthreads();
-        // ---- Q function: the running-cost Hessians are copied in first (coalesced, all loads in flight at once; H is
-        //      dead now and its storage takes Qxx), the products accumulate on top ----
-        copy_in<T>(H, p.lxx + (pN + k) * L::XX, L::XX, tid);
-        copy_in<T>(Qux, p.lux + (pN + k) * L::XU, L::XU, tid);
-        copy_in<T>(Aug, p.luu + (pN + k) * L::UU, L::UU, tid);
+        // ---- Q function.  The running-cost Hessians come straight from HBM as the products' initial values: every thread
+        //      loads the 12 entries of its tile before its inner loop and needs them after it.  H is dead now: its storage
+        //      takes Qxx ----
         for (int i = tid; i < XS + US; i += T) {
             double s = 0.0;
             if (i < XS) {
@@ -175,10 +196,9 @@ __global__ void __launch_bounds__(Lay<XS, US, YS>::T) k_generic_backward_sweep(P
                 Qu[u] = s;
             }
         }
-        __syncthreads();
-        gemm_tiles<T, XS, XS, XS, true>(AB, XS, YZ, XS, H, XS, H, XS, tid);
-        gemm_tiles<T, US, XS, XS, true>(AB + L::XX, XS, YZ, XS, Qux, US, Qux, US, tid);
-        gemm_tiles<T, US, US, XS, true>(AB + L::XX, XS, YZ + L::XX, XS, Aug, US, Aug, US, tid);
+        gemm_tiles<T, XS, XS, XS, true>(AB, XS, YZ, XS, p.lxx + (pN + k) * L::XX, XS, H, XS, tid);
+        gemm_tiles<T, US, XS, XS, true>(AB + L::XX, XS, YZ, XS, p.lux + (pN + k) * L::XU, US, Qux, US, tid);
+        gemm_tiles<T, US, US, XS, true>(AB + L::XX, XS, YZ + L::XX, XS, p.luu + (pN + k) * L::UU, US, Aug, US, tid);
         if (YS > 0) {
             __syncthreads();
             gemm_tiles<T, XS, XS, YS, false>(CtL, XS, Cm, YS, H, XS, H, XS, tid);
@@ -186,6 +206,7 @@ __global__ void __launch_bounds__(Lay<XS, US, YS>::T) k_generic_backward_sweep(P
             gemm_tiles<T, US, US, YS, false>(DtL, US, Dm, YS, Aug, US, Aug, US, tid);
         }
         __syncthreads();
+        if (k > 0) fetch_stage(k - 1);  // (A, B, C, D, lyy, ly, the defect are dead from here on)
         // regularisation; copy of Quu for the exact PD test; Qxx symmetrised in place (each thread owns the pairs (i, j), (j, i))
         for (int e = tid; e < L::XX; e += T) {
             const int i = e % XS, j = e / XS;
@@ -233,7 +254,7 @@ __global__ void __launch_bounds__(Lay<XS, US, YS>::T) k_generic_backward_sweep(P
                 const double pv = cq[q];
                 if (tid == 0 && !(pv > 0.0)) s_flag = 1;
                 if (active) {
-                    const double r = rq[j] / pv;
+                    const double r = rq[j] * pivot_rcp(pv);
 #pragma unroll
                     for (int i = 0; i < RP; ++i) a[i] = (h * RP + i == q) ? r : fma(-cq[h * RP + i], r, a[i]);
                 }
@@ -313,6 +334,7 @@ __global__ void __launch_bounds__(Lay<XS, US, YS>::T) k_generic_backward_sweep(P
         __syncthreads();
     }
     // G[0] += H[0] Defect[0] — runs even after a failed stage, on whatever the storage holds (SinglePhase.cpp:365)
+    copy_in_wait();  // (a failed stage leaves the copies of the next one in flight)
     __syncthreads();
     if (!success) {
         for (int e = tid; e < L::XX; e += T) H[e] = p.H[pN1 * L::XX + e];
