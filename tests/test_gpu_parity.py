@@ -393,12 +393,14 @@ def test_parity_at_scale_config4_all_schedules(pkg, orc, workloads):
     assert np.all(well[conv]) and conv.sum() >= 30
 
 
-def test_receding_horizon_ticks_match_oracle(pkg, orc, workloads):
+@pytest.mark.parametrize("mode", [0, 2], ids=["auto", "phased"])
+def test_receding_horizon_ticks_match_oracle(pkg, orc, workloads, mode):
     """N1: HKDProblem::update on the device + warm re-solve with the reference's MPC budget (2 AL x 1 DDP, HKDMPC.cpp:97-166),
     30 consecutive ticks of nine problems (three gaits, several windows, two problems sharing a schedule), against the oracle's
     restated update.  The windows are chosen so that the ticks exercise: a first phase shrinking to a point and being removed, a
     last phase growing, a phase reaching its end (second touchdown-constraint object: trot window 0 at tick 0), a new last
-    phase with an empty shooting set (horizon 1 and 2), and the shooting set being restored at horizon 3."""
+    phase with an empty shooting set (horizon 1 and 2), and the shooting set being restored at horizon 3.  `phased`: the same
+    ticks through the kernel-per-phase driver (one-warp linear-rollout kernel on the updated schedules)."""
     order = list(workloads.GAITS)
     refs = {g: pkg.QuadReference(workloads.gait_path(g)) for g in order}
     cases = [("trot", 0), ("trot", 0), ("trot", 23), ("bound", 0), ("bound", 5), ("bound", 240), ("pronk", 0), ("pronk", 100), ("pronk", 40)]
@@ -409,6 +411,7 @@ def test_receding_horizon_ticks_match_oracle(pkg, orc, workloads):
         sid.append(keys.index(c))
     B = pkg.MultiPhaseDDPBatch(0)
     B.set_problems_from_gaits([refs[g] for g in order], [order.index(g) for g, _ in keys], [k for _, k in keys], 0.6, sid)
+    B.set_solve_mode(mode)
     tables = {g: _table(orc, g) for g in order}
     models = [orc.default_model()] + ([orc.MODEL_PORT] if orc.ref_available() else [])
     P = [[orc.Problem(tables[g], k0, 0.6, model=m) for m in models] for g, k0 in cases]
