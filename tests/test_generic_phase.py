@@ -216,3 +216,34 @@ def test_gpu_generic_24_24_0_on_hkd_stage_data(orc):
     assert rows_close(B.get("dU")[0], g("dU", s0, s0 + N)) < TOL
     assert rows_close(B.get("H")[0], g("H", n0, n0 + N + 1)) < TOL
     assert rows_close(B.get("G")[0], g("G", n0, n0 + N + 1)) < TOL
+
+
+@pytest.mark.gpu
+def test_gpu_generic_cpp_shim_example_matches_oracle(orc, tmp_path):
+    """examples/generic_sweep.cpp: SinglePhaseSweeps<double,36,12,12> (hkd-mpc_b200/host/MultiPhaseDDP.hpp) over the C ABI."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    pkg = load_pkg()
+    xs, us, ys, N, n = 36, 12, 12, 9, 5
+    d = random_phase(xs, us, ys, N, 77, n=n)
+    mats = {"A", "B", "C", "D", "lxx", "luu", "lux", "lyy", "Phixx"}
+    path = str(tmp_path / "phase.bin")
+    with open(path, "wb") as f:
+        for nm in pkg.SinglePhaseBatch.INPUTS:  # the C ABI's order and layout: column-major matrices
+            a = np.swapaxes(d[nm], -1, -2) if nm in mats else d[nm]
+            f.write(np.ascontiguousarray(a, np.float64).tobytes())
+    exe = str(tmp_path / "generic_sweep")
+    libdir = os.path.dirname(pkg.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", os.path.join(ROOT, "examples", "generic_sweep.cpp"), "-L" + libdir, "-lhsddp_b200",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    out = subprocess.run([exe, path, str(n), str(N), "0.001", "0.5"], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    assert len(out) == n
+    for i, line in enumerate(out):
+        v = dict(t.split("=") for t in line.split())
+        di = {k: a[i] for k, a in d.items()}
+        r = orc.generic_backward_sweep(xs, us, ys, N, di, 0.001)
+        lr = orc.generic_linear_rollout(xs, us, ys, N, di, 0.5, r["dU"], r["K"])
+        assert int(v["ok"]) == int(r["success"]) == 1
+        for got, want in ((v["dV_1"], r["dV_1"]), (v["dV_2"], r["dV_2"]), (v["K00"], r["K"][0, 0, 0]), (v["lr_dV_1"], lr["dV_1"]), (v["dXN0"], lr["dX"][N, 0])):
+            assert abs(float(got) - want) <= TOL * max(abs(want), 1e-3), (i, line)
